@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named in BASELINE.json (3-D diffusion, hex p=4, U=4, E=7):
+
+  * `assembly` (default, BASELINE configs[1]): element-local least-squares assembly fused with the CRS scatter,
+    metric "assembled elements/s";
+  * `matrix_free` (BASELINE configs[2]): sum-factorised operator apply, metric "matrix-free DOFs/s".
+
+One JSON line on stdout (rank 0). The line's `metric`/`value` belong to --workload; the other workload is reported in the
+`also` object of the same line with its own roofline. `--impl reference` times the CPU restatement of the reference
+(oracle/, built -march=native on this host) on a bounded sample of the same workload.
+
+Timing: CUDA events on the library's stream, W warm-up steps, K timed steps between barriers, max over ranks.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P, U, E = 4, 4, 7
+NN = (P + 1) ** 3
+L = NN * U
+Q = (P + 1) ** 3
+# algorithmic work per unit
+ASM_FLOPS_PER_ELEM = Q * (18 * NN + 7 * L * E + (L + 1) ** 2 / 2 * (2 * E + 1))  # 238.7 Mflop, reference's own DPFlops formula
+MF_FLOPS_PER_ELEM = 215e3  # reference formulation: back 45k + QP 120k + forward 45k + geometry 5k
+N_BND_NODES = NN - (P - 1) ** 3
+
+
+def mf_bytes_per_apply(n_dofs, n_elems):
+    return 16 * n_dofs + n_elems * (192 + 4 * (N_BND_NODES + 1))  # x read + y write + vertices + compact node ids
+
+
+def node_dist(n):
+    # benchmarks/Diffusion3D.hpp:11-18: running sum x += 1/n (bit-equal vertices)
+    dx, x, out = 1.0 / n, 0.0, []
+    for _ in range(n + 1):
+        out.append(x)
+        x += dx
+    return np.array(out)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference(workload, n_threads, budget_s=15.0):
+    """The reference's CPU path (oracle restatement, -march=native build on this host), bounded sample."""
+    from oracle import Oracle, build
+
+    build(native=True)
+    orc = Oracle(native=True)
+
+    def make(n):
+        return orc.mesh_cube(node_dist(n), order=P)
+
+    if workload == "assembly":
+        m = make(2)
+        s = m.assembled_system(U)
+        t = s.assemble("bench_diffusion3d", n_threads=n_threads)
+        per_elem = t / 8
+        n = int(max(2, min(8, math.floor((budget_s / per_elem) ** (1 / 3)))))
+        m = make(n)
+        s = m.assembled_system(U)
+        t = s.assemble("bench_diffusion3d", n_threads=n_threads)
+        return dict(value=n**3 / t, unit="elements/s", cores=n_threads, kind="port",
+                    sample=f"oracle assembleGlobalSystem (local assembly + CRS scatter) of {n}^3 hex p=4 elements, {t:.2f} s")
+    m = make(4)
+    s = m.matrix_free_system(U)
+    s.add_kernel("bench_diffusion3d")
+    x = np.random.default_rng(5489).uniform(-1, 1, size=(m.n_nodes * U, 1))
+    s.apply(x, n_threads=n_threads)
+    per_apply = s.last_secs
+    n = int(max(4, min(16, math.floor(4 * (budget_s / 5 / per_apply) ** (1 / 3)))))
+    m = make(n)
+    s = m.matrix_free_system(U)
+    s.add_kernel("bench_diffusion3d")
+    x = np.random.default_rng(5489).uniform(-1, 1, size=(m.n_nodes * U, 1))
+    reps = 5
+    s.apply(x, n_threads=n_threads, repeats=reps)
+    t = s.last_secs
+    return dict(value=m.n_nodes * U * reps / t, unit="DOFs/s", cores=n_threads, kind="port",
+                sample=f"oracle sum-factorised operator apply on {n}^3 hex p=4 elements ({m.n_nodes * U} DOFs), {reps} applies, {t:.2f} s")
+
+
+def physical_cores():
+    try:
+        import psutil
+
+        return psutil.cpu_count(logical=False) or os.cpu_count()
+    except Exception:
+        return os.cpu_count()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="assembly", choices=["assembly", "matrix_free"])
+    ap.add_argument("--n-asm", type=int, default=16, help="elements per edge, assembly workload (per GPU)")
+    ap.add_argument("--n-mf", type=int, default=64, help="elements per edge, matrix-free workload (per GPU)")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary workload")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    metric = {"assembly": ("assembled elements/s (3D diffusion hex p=4, U=4, E=7)", "elements/s"),
+              "matrix_free": ("matrix-free DOFs/s (3D diffusion hex p=4, U=4, E=7)", "DOFs/s")}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = physical_cores()
+        t0 = time.time()
+        vals = []
+        for _ in range(max(1, min(args.steps, 2))):
+            vals.append(cpu_reference(args.workload, cores, budget_s=20.0))
+        best = max(vals, key=lambda d: d["value"])
+        line = {"impl": "reference", "metric": metric[args.workload][0], "value": best["value"], "unit": best["unit"], "n_gpus": args.gpus,
+                "steps": len(vals), "warmup": 0, "ms_per_step": 1e3 * (time.time() - t0) / len(vals), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "mesh": "cube [0,1]^3 hex p=4, benchmarks/Diffusion3D.hpp kernel",
+                           "note": "reference cannot be compiled in this image; CPU restatement (oracle/) timed instead"},
+                "cpu_baseline": best, "e2e": {"value": best["value"], "unit": best["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+
+    import l3ster_b200 as l3b
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: l3ster_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = l3b.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_fn()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, max_over_ranks(1e3 * wall) / steps, clocks
+
+    hbm_peak, hbm_src = measured_peaks()
+
+    # ---- assembly workload ----------------------------------------------------------------------------------------
+    def run_assembly():
+        n = args.n_asm
+        host = l3b.make_cube_mesh(node_dist(n), order=P)
+        mesh = ctx.upload_mesh(host)
+        graph = host.node_graph()
+        sys_ = l3b.AssembledSystem(ctx, mesh, U, 1, graph)
+        n_elems = host.n_elems
+        kernel_ms = []
+
+        def step():
+            sys_.beginAssembly()
+            sys_.assembleProblem("bench_diffusion3d")
+            kernel_ms.append(sys_.last_kernel_ms)
+
+        ms, _, clocks = timed(step, args.steps, args.warmup)
+        k_ms = float(np.mean(kernel_ms[-args.steps:]))
+        # e2e through the C ABI with host buffers: mesh geometry H2D each step, rhs D2H
+        verts, nodes = np.ascontiguousarray(host.verts), np.ascontiguousarray(host.nodes)
+
+        def step_e2e():
+            m2 = l3b.Mesh(ctx, 3, P, verts, nodes, None, host.n_nodes, host.n_nodes)  # H2D of this step's inputs (geometry)
+            sys_.beginAssembly()
+            sys_.assembleProblem("bench_diffusion3d")
+            sys_.download(values=False)  # D2H of the assembled rhs
+            del m2
+
+        _, wall_ms, _ = timed(step_e2e, max(3, args.steps // 2), 1)
+        fp64_fma = ctx.microbench(0)
+        fp64_dmma = ctx.microbench(1)
+        achieved = ASM_FLOPS_PER_ELEM * n_elems / (k_ms * 1e-3) / 1e12
+        return {
+            "value": world * n_elems / (ms * 1e-3), "ms_per_step": ms,
+            "e2e": {"value": world * n_elems / (wall_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": int(verts.nbytes + nodes.nbytes),
+                    "d2h_bytes_per_step": int(sys_.n_dofs * 8),
+                    "what": "mesh geometry H2D + beginAssembly + assembleProblem + rhs D2H through the C ABI, wall clock"},
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_fma, "unit": "TFLOP/s", "frac": achieved / fp64_fma, "traffic": None,
+                         "kernel": "assembleKernel<bench_diffusion3d, hex p=4>", "kernel_ms": k_ms,
+                         "algorithmic_flops_per_element": ASM_FLOPS_PER_ELEM,
+                         "peak_source": "fp64 FMA microkernel measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
+                         "fp64_dmma_tflops_measured": fp64_dmma},
+            "gpu_launches": args.steps, "clocks": clocks,
+            "config": {"workload": f"Diffusion3DBenchmark assembly + CRS scatter: cube [0,1]^3, {n}^3 hex p=4 per GPU, U=4, E=7, nq=5, "
+                                   f"CondensationPolicy::None", "elements_per_gpu": n_elems, "dofs_per_gpu": host.n_nodes * U,
+                       "crs_nnz_per_gpu": sys_.nnz, "l2": "CRS values (%.1f GB) larger than L2" % (sys_.nnz * 8 / 1e9),
+                       "step": "beginAssembly (zero) + assembleProblem", "multi_gpu": "independent z-slab per rank (no interface export yet)"},
+        }
+
+    # ---- matrix-free workload -------------------------------------------------------------------------------------
+    def run_mf():
+        n = args.n_mf
+        host = l3b.make_cube_mesh(node_dist(n), order=P)
+        mesh = ctx.upload_mesh(host)
+        mask = np.zeros(host.n_nodes * U, dtype=np.uint8)
+        mask[host.boundary_nodes([1, 2, 3, 4, 5, 6]) * U] = 1  # Dirichlet T = 0 on the six faces (Diffusion3D.hpp:39-41)
+        sys_ = l3b.MatrixFreeSystem(ctx, mesh, U, 1, mask, None)
+        sys_.assembleProblem("bench_diffusion3d")
+        n_dofs, n_elems = sys_.n_dofs, host.n_elems
+        rng = np.random.default_rng(5489)
+        xh = torch.from_numpy(rng.uniform(-1, 1, size=n_dofs)).pin_memory()
+        yh = torch.empty(n_dofs, dtype=torch.float64).pin_memory()
+        xd = xh.to("cuda")
+        yd = torch.zeros_like(xd)
+        t0 = time.perf_counter()
+        sys_.endAssembly()
+        ctx.synchronize()
+        init_s = time.perf_counter() - t0
+
+        def step():
+            sys_.apply_device(xd.data_ptr(), yd.data_ptr(), 1, 1.0, 0.0)
+
+        steps = max(args.steps, 20)
+        ms, _, clocks = timed(step, steps, args.warmup)
+        launches = sys_.kernel_launches
+
+        def step_e2e():
+            sys_.ctx._chk(l3b.lib().l3b_mf_apply(sys_._h, xh.data_ptr(), yh.data_ptr(), 1, 1.0, 0.0))
+
+        _, wall_ms, _ = timed(step_e2e, max(3, args.steps // 2), 1)
+        gbs = mf_bytes_per_apply(n_dofs, n_elems) / (ms * 1e-3) / 1e9
+        fp64_fma = ctx.microbench(0)
+        return {
+            "value": world * n_dofs / (ms * 1e-3), "ms_per_step": ms,
+            "e2e": {"value": world * n_dofs / (wall_ms * 1e-3), "unit": "DOFs/s", "h2d_bytes_per_step": int(n_dofs * 8), "d2h_bytes_per_step": int(n_dofs * 8),
+                    "what": "l3b_mf_apply with pinned host x/y: H2D x, apply, D2H y, wall clock"},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                         "kernel": "mfSumFactApplyKernel<bench_diffusion3d, hex p=4, nq=5> (+ scale and Dirichlet-row kernels)",
+                         "algorithmic_bytes_per_dof": mf_bytes_per_apply(n_dofs, n_elems) / n_dofs, "peak_source": hbm_src,
+                         "fp64_tflops_reference_formulation": MF_FLOPS_PER_ELEM * n_elems / (ms * 1e-3) / 1e12,
+                         "fp64_fma_peak_tflops_measured": fp64_fma},
+            "gpu_launches": launches * steps, "clocks": clocks, "steps": steps,
+            "config": {"workload": f"Diffusion3DBenchmarkMatrixFree operator apply: cube [0,1]^3, {n}^3 hex p=4 per GPU, U=4, E=7, nq=5, "
+                                   f"Dirichlet T=0 on the six faces", "elements_per_gpu": n_elems, "dofs_per_gpu": n_dofs,
+                       "l2": "x and y (%.0f MB each) larger than L2" % (n_dofs * 8 / 1e6), "init_diag_rhs_s": init_s,
+                       "multi_gpu": "independent z-slab per rank (halo exchange not wired into bench yet)"},
+        }
+
+    runners = {"assembly": run_assembly, "matrix_free": run_mf}
+    main_res = runners[args.workload]()
+    also = None
+    if not args.no_also:
+        other = "matrix_free" if args.workload == "assembly" else "assembly"
+        r = runners[other]()
+        also = {"metric": metric[other][0], "unit": metric[other][1], **r}
+
+    line = {"metric": metric[args.workload][0], "value": main_res["value"], "unit": metric[args.workload][1], "n_gpus": world,
+            "steps": main_res.get("steps", args.steps), "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": main_res["config"],
+            "e2e": main_res["e2e"], "roofline": main_res["roofline"], "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"]}
+    if also:
+        line["also"] = also
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_reference(args.workload, physical_cores())
+        except Exception as exc:  # the baseline is a reported extra; never lose the GPU numbers over it
+            line["cpu_baseline"] = {"error": str(exc)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,166 @@
+/*
+ * l3ster_b200 — C ABI of the B200-native implementation of L3STER's element-local least-squares assembly and
+ * matrix-free operator hot path (BASELINE.json: north_star).
+ *
+ * The reference (kubagalecki/L3STER) has no FFI: its boundary is a header-only C++23 template API. This header is the
+ * boundary a replacement of that path binds to — plain pointers and sizes, opaque handles, int status codes — and each
+ * entry point cites the reference interface it replaces (paths relative to the reference's include/l3ster/).
+ * INTEGRATION.md shows the C++ shim a reference maintainer would put on top.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a non-zero l3b_status otherwise; l3b_last_error(ctx) gives the message.
+ *     The reference signals the same conditions with util::throwingAssert → std::runtime_error (util/Assertion.hpp:85-93).
+ *   - element types: dim 2 = Quad, dim 3 = Hex; local node order lexicographic x-fastest
+ *     (basisfun/ReferenceBasisFunction.hpp:107-117); vertices 2^dim x 3 doubles per element, same order
+ *     (mesh/ElementData.hpp:14-30); sides as mesh/ElementTraits.hpp:88-93.
+ *   - local dof of (local node n, system dof d) = n * dofs_per_node + d (dofs/NodeToDofMap.hpp:249-264 for a single
+ *     domain with all dofs active); vectors are column-major n_local_dofs x n_cols (Tpetra LayoutLeft).
+ *   - all floating point data is fp64 (common/Typedefs.h:23), local node ids u32, local dofs i32, row pointers i64.
+ *   - one host thread drives one context; work is issued on the context's CUDA stream.
+ */
+#ifndef L3STER_B200_H
+#define L3STER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+typedef enum l3b_status
+{
+    L3B_OK                 = 0,
+    L3B_ERR_INVALID_ARG    = 1,
+    L3B_ERR_CUDA           = 2,
+    L3B_ERR_NO_INSTANCE    = 3, /* kernel not compiled for this (order, nq): add it to its L3B_REGISTER_* list */
+    L3B_ERR_DEGENERATE     = 4, /* "Encountered degenerate element ( |J| <= 0 )" (algsys/AssembleLocalSystem.hpp:249) */
+    L3B_ERR_STATE          = 5, /* assembly state machine violated (algsys/AssembledSystem.hpp:455-461) */
+    L3B_ERR_GRAPH          = 6, /* entry not present in the sparsity graph */
+    L3B_ERR_NOT_CONVERGED  = 7,
+    L3B_ERR_NO_DEVICE      = 8
+} l3b_status;
+
+typedef struct l3b_context   l3b_context;
+typedef struct l3b_host_mesh l3b_host_mesh;
+typedef struct l3b_mesh      l3b_mesh;
+typedef struct l3b_fields    l3b_fields;
+typedef struct l3b_asm       l3b_asm;
+typedef struct l3b_mf        l3b_mf;
+
+/* ---- context ----------------------------------------------------------------------------------------------------- */
+/* replaces util::L3sterScopeGuard's device-side duties (util/ScopeGuards.hpp:186-201). Fails with L3B_ERR_NO_DEVICE
+ * when no CUDA device is present: there is no CPU fallback. */
+int         l3b_context_create(int device, l3b_context** out);
+void        l3b_context_destroy(l3b_context* ctx);
+const char* l3b_last_error(const l3b_context* ctx);
+const char* l3b_global_error(void); /* errors raised before a context exists */
+int         l3b_context_synchronize(l3b_context* ctx);
+void*       l3b_context_stream(l3b_context* ctx); /* cudaStream_t */
+
+/* ---- kernel registry (common/KernelInterface.hpp:13-20, 178-190) ---------------------------------------------------- */
+typedef struct l3b_kernel_info
+{
+    char name[64];
+    int  dimension, n_equations, n_unknowns, n_fields, n_rhs, is_boundary;
+    int  n_instances; /* compiled (order, nq) pairs */
+} l3b_kernel_info;
+int l3b_kernel_count(void);
+int l3b_kernel_find(const char* name); /* id or -1 */
+int l3b_kernel_get_info(int kernel_id, l3b_kernel_info* out);
+int l3b_kernel_get_instance(int kernel_id, int i, int* order, int* nq);
+
+/* AssemblyOptions (algsys/AssembleLocalSystem.hpp:24-49). eval_strategy: 0 Auto, 1 LocalElement, 2 SumFactorization,
+ * 3 SumFactorizationOddEvenDecomposition (2 and 3 select the same device kernel: odd-even is a CPU-side optimisation) */
+typedef struct l3b_asm_opts
+{
+    int value_order, derivative_order, eval_strategy;
+} l3b_asm_opts;
+
+/* ---- reference-element tables (basisfun/, quad/, math/), exposed for parity tests ------------------------------------ */
+int l3b_tables_gll(int n_points, double* nodes);                                 /* math/LobattoRuleAbsc.hpp:10-35 */
+int l3b_tables_gauss(int n_points, double* points, double* weights);             /* quad/ReferenceQuadrature.hpp:24-51 */
+int l3b_tables_1d(int order, int nq, double* interp, double* der, double* colloc); /* algsys/SumFactorization.hpp:25-65 */
+/* dense tables at the domain (side < 0) or side quadrature: values [q][a], derivatives [q][d][a];
+ * basisfun/ReferenceElementBasisAtQuadrature.hpp:10-96. Returns the number of points through *n_qp. */
+int l3b_tables_dense(int dim, int order, int nq, int side, int* n_qp, double* points, double* weights, double* values, double* derivatives);
+
+/* ---- host mesh front end (mesh/primitives/CubeMesh.hpp:16-138, SquareMesh.hpp:14-76, ConvertMeshToOrder.hpp:52-104) -- */
+int  l3b_host_mesh_cube(int nx, const double* x, int ny, const double* y, int nz, const double* z, int order, l3b_host_mesh** out);
+int  l3b_host_mesh_square(int nx, const double* x, int ny, const double* y, int order, l3b_host_mesh** out);
+void l3b_host_mesh_destroy(l3b_host_mesh* m);
+/* info: [dim, order, n_nodes, n_elems, nodes_per_elem, n_sides] */
+int l3b_host_mesh_info(const l3b_host_mesh* m, int64_t info[6]);
+/* borrowed pointers, valid until destroy */
+const uint32_t* l3b_host_mesh_nodes(const l3b_host_mesh* m);
+const double*   l3b_host_mesh_verts(const l3b_host_mesh* m);
+const uint16_t* l3b_host_mesh_side_boundaries(const l3b_host_mesh* m); /* 0xFFFF = not on a boundary */
+/* node-level sparsity graph (algsys/SparsityGraph.hpp:25-81, 254-278); expands to the dof-level CRS with
+ * l3b_graph_expand. Arrays are malloc'ed by the library; release with l3b_free. */
+int  l3b_node_graph(int64_t n_nodes, int64_t n_elems, int nodes_per_elem, const uint32_t* nodes, int64_t** ptr, uint32_t** nbr);
+int  l3b_graph_expand(int64_t n_nodes, const int64_t* ptr, const uint32_t* nbr, int dofs_per_node, int64_t* row_ptr, int32_t* col_ind);
+void l3b_free(void* p);
+
+/* ---- device mesh (mesh/LocalMeshView.hpp:13-57: vertices + local node ids + side → boundary id) ---------------------- */
+int  l3b_mesh_upload(l3b_context* ctx, int dim, int order, int64_t n_elems, const double* verts, const uint32_t* nodes,
+                     const uint16_t* side_boundaries /* may be NULL */, int64_t n_local_nodes, int64_t n_owned_nodes, l3b_mesh** out);
+void l3b_mesh_destroy(l3b_mesh* mesh);
+
+/* ---- nodal fields (post/SolutionManager.hpp:54-101, post/FieldAccess.hpp:10-53): field-major [n_fields][n_local_nodes] */
+int  l3b_fields_upload(l3b_context* ctx, int64_t n_local_nodes, int n_fields, const double* data, l3b_fields** out);
+int  l3b_fields_update(l3b_fields* f, const double* data);
+void l3b_fields_destroy(l3b_fields* f);
+
+/* ---- assembled system (algsys/AssembledSystem.hpp:22-83, AssembleGlobalSystem.hpp:13-96, ScatterLocalSystem.hpp:25-54) */
+/* node_ptr/node_nbr: node-level graph of l3b_node_graph (host). The device CRS has the dof-level layout of the reference's
+ * Tpetra graph: row (n, d) holds, for each neighbour node m in ascending order, the dofs_per_node columns of m. */
+int l3b_asm_create(l3b_context* ctx, l3b_mesh* mesh, int dofs_per_node, int n_rhs, const int64_t* node_ptr, const uint32_t* node_nbr,
+                   l3b_asm** out);
+void    l3b_asm_destroy(l3b_asm* sys);
+int64_t l3b_asm_nnz(const l3b_asm* sys);
+int     l3b_asm_begin_assembly(l3b_asm* sys); /* AssembledSystem::beginAssembly: zero matrix and rhs */
+/* AssembledSystem::assembleProblem (:406-436). dof_inds: kernel unknown u → system dof (NULL = identity);
+ * boundary kernels: ids of the boundaries to visit. */
+int l3b_asm_assemble(l3b_asm* sys, int kernel_id, l3b_asm_opts opts, double time, const int* dof_inds, const l3b_fields* fields,
+                     const int* field_inds, const int* boundary_ids, int n_boundary_ids);
+/* AssembledSystem::endAssembly (:373-397) with algebraic Dirichlet BCs (bcs/DirichletBC.hpp:82-150): rows → identity,
+ * columns eliminated into the rhs. vals: n_dirichlet x n_rhs column-major. */
+int l3b_asm_end_assembly(l3b_asm* sys, int64_t n_dirichlet, const int32_t* dirichlet_dofs, const double* dirichlet_vals);
+int l3b_asm_download(l3b_asm* sys, double* values /* nnz, may be NULL */, double* rhs /* n_dofs x n_rhs, may be NULL */);
+double* l3b_asm_device_values(l3b_asm* sys);
+/* y = A x on the device CRS (Tpetra::CrsMatrix::apply), host buffers */
+int l3b_asm_spmv(l3b_asm* sys, const double* x, double* y);
+/* CG + native Jacobi on the assembled matrix (solve/BelosSolvers.hpp:116-123, NativePreconditioners.hpp:36-100) */
+int l3b_asm_solve_cg(l3b_asm* sys, double tol, int max_iters, double* x /* host, n_dofs */, double* achieved_tol, int* iters);
+/* timing of the last l3b_asm_assemble kernel launches (ms, CUDA events on the context stream) */
+double l3b_asm_last_kernel_ms(const l3b_asm* sys);
+
+/* ---- matrix-free system (algsys/MatrixFreeSystem.hpp:47-120) -------------------------------------------------------- */
+/* dirichlet_mask: n_local_dofs bytes (bcs/LocalDirichletBC.hpp), may be NULL; dirichlet_vals: n_local_dofs x n_rhs */
+int  l3b_mf_create(l3b_context* ctx, l3b_mesh* mesh, int dofs_per_node, int n_rhs, const uint8_t* dirichlet_mask,
+                   const double* dirichlet_vals, l3b_mf** out);
+void l3b_mf_destroy(l3b_mf* sys);
+/* MatrixFreeSystem::assembleProblem: registers the kernel for init and apply (:585-787) */
+int l3b_mf_assemble(l3b_mf* sys, int kernel_id, l3b_asm_opts opts, double time, const int* dof_inds, const l3b_fields* fields,
+                    const int* field_inds, const int* boundary_ids, int n_boundary_ids);
+/* MatrixFreeSystem::endAssembly → computeDiagAndRhs (:877-941) */
+int l3b_mf_end_assembly(l3b_mf* sys);
+int l3b_mf_download(l3b_mf* sys, double* diag, double* rhs);
+/* Tpetra::Operator::apply → MatrixFreeSystem::applyImpl (:34-41, 1019-1140): y = alpha A x + beta y.
+ * _device: x, y are device pointers (column-major, ld = n_local_dofs), asynchronous on the context stream.
+ * host version: copies x (and y if beta != 0) in, y out. */
+int l3b_mf_apply_device(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta);
+int l3b_mf_apply(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta);
+/* CG + native Jacobi, x0 = 0, rhs = system rhs column 0 (benchmarks/Diffusion3D.hpp:115-118) */
+int l3b_mf_solve_cg(l3b_mf* sys, double tol, int max_iters, double* x /* host */, double* achieved_tol, int* iters);
+int64_t l3b_mf_num_dofs(const l3b_mf* sys);
+int     l3b_mf_kernel_launches(const l3b_mf* sys); /* device kernels launched by the last apply */
+
+/* ---- roofline denominators measured in place (MEASURED_PEAKS.json has no fp64 figure) ------------------------------ */
+/* mode 0: fp64 FMA TFLOP/s (CUDA cores); 1: fp64 DMMA TFLOP/s (mma.sync.m8n8k4.f64); 2: HBM copy GB/s (read + write) */
+int l3b_microbench(l3b_context* ctx, int mode, double* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

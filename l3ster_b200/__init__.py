@@ -1,0 +1,516 @@
+"""l3ster_b200 — B200-native (sm_100a) implementation of L3STER's element-local least-squares assembly and matrix-free
+operator hot path, behind the C ABI declared in ``include/l3ster_b200.h``.
+
+This package is the thin Python host layer used by the tests and ``bench.py``: it loads ``libl3ster_b200.so`` with ctypes
+and mirrors the reference's system API names (``beginAssembly / assembleProblem / endAssembly / solve`` of
+``algsys/AssembledSystem.hpp:22-83`` and ``algsys/MatrixFreeSystem.hpp:47-120``).  There is no CPU fallback: creating a
+:class:`Context` without a CUDA device raises, and a missing extension raises at import of :func:`lib`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "libl3ster_b200.so")
+
+QUAD, HEX = 2, 3
+NO_BOUNDARY = 0xFFFF
+
+
+class L3BError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[l3b status {code}] {msg}")
+        self.code, self.msg = code, msg
+
+
+class _KernelInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("dimension", C.c_int), ("n_equations", C.c_int), ("n_unknowns", C.c_int), ("n_fields", C.c_int),
+                ("n_rhs", C.c_int), ("is_boundary", C.c_int), ("n_instances", C.c_int)]
+
+
+class _AsmOpts(C.Structure):
+    _fields_ = [("value_order", C.c_int), ("derivative_order", C.c_int), ("eval_strategy", C.c_int)]
+
+
+@dataclass(frozen=True)
+class AssemblyOptions:
+    """algsys/AssembleLocalSystem.hpp:24-49"""
+    value_order: int = 1
+    derivative_order: int = 0
+    eval_strategy: int = 0  # 0 Auto, 1 LocalElement, 2 SumFactorization, 3 SumFactorizationOddEvenDecomposition
+
+    def _c(self):
+        return _AsmOpts(self.value_order, self.derivative_order, self.eval_strategy)
+
+
+_lib = None
+
+# every symbol include/l3ster_b200.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "l3b_context_create", "l3b_context_destroy", "l3b_last_error", "l3b_global_error", "l3b_context_synchronize", "l3b_context_stream",
+    "l3b_kernel_count", "l3b_kernel_find", "l3b_kernel_get_info", "l3b_kernel_get_instance",
+    "l3b_tables_gll", "l3b_tables_gauss", "l3b_tables_1d", "l3b_tables_dense",
+    "l3b_host_mesh_cube", "l3b_host_mesh_square", "l3b_host_mesh_destroy", "l3b_host_mesh_info", "l3b_host_mesh_nodes",
+    "l3b_host_mesh_verts", "l3b_host_mesh_side_boundaries", "l3b_node_graph", "l3b_graph_expand", "l3b_free",
+    "l3b_mesh_upload", "l3b_mesh_destroy", "l3b_fields_upload", "l3b_fields_update", "l3b_fields_destroy",
+    "l3b_asm_create", "l3b_asm_destroy", "l3b_asm_nnz", "l3b_asm_begin_assembly", "l3b_asm_assemble", "l3b_asm_end_assembly",
+    "l3b_asm_download", "l3b_asm_device_values", "l3b_asm_spmv", "l3b_asm_solve_cg", "l3b_asm_last_kernel_ms",
+    "l3b_mf_create", "l3b_mf_destroy", "l3b_mf_assemble", "l3b_mf_end_assembly", "l3b_mf_download", "l3b_mf_apply_device", "l3b_mf_apply",
+    "l3b_mf_solve_cg", "l3b_mf_num_dofs", "l3b_mf_kernel_launches", "l3b_microbench",
+]
+
+
+def lib():
+    """Load the CUDA extension. Fails loudly when it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(or `make -C l3ster_b200/csrc`). l3ster_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    L.l3b_last_error.restype = C.c_char_p
+    L.l3b_last_error.argtypes = [vp]
+    L.l3b_global_error.restype = C.c_char_p
+    L.l3b_context_create.argtypes = [i32, C.POINTER(vp)]
+    L.l3b_context_destroy.argtypes = [vp]
+    L.l3b_context_destroy.restype = None
+    L.l3b_context_synchronize.argtypes = [vp]
+    L.l3b_context_stream.argtypes = [vp]
+    L.l3b_context_stream.restype = vp
+    L.l3b_kernel_find.argtypes = [C.c_char_p]
+    L.l3b_kernel_get_info.argtypes = [i32, C.POINTER(_KernelInfo)]
+    L.l3b_kernel_get_instance.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.l3b_tables_gll.argtypes = [i32, vp]
+    L.l3b_tables_gauss.argtypes = [i32, vp, vp]
+    L.l3b_tables_1d.argtypes = [i32, i32, vp, vp, vp]
+    L.l3b_tables_dense.argtypes = [i32, i32, i32, i32, C.POINTER(i32), vp, vp, vp, vp]
+    L.l3b_host_mesh_cube.argtypes = [i32, vp, i32, vp, i32, vp, i32, C.POINTER(vp)]
+    L.l3b_host_mesh_square.argtypes = [i32, vp, i32, vp, i32, C.POINTER(vp)]
+    L.l3b_host_mesh_destroy.argtypes = [vp]
+    L.l3b_host_mesh_destroy.restype = None
+    L.l3b_host_mesh_info.argtypes = [vp, vp]
+    for f in ("l3b_host_mesh_nodes", "l3b_host_mesh_verts", "l3b_host_mesh_side_boundaries"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = vp
+    L.l3b_node_graph.argtypes = [i64, i64, i32, vp, C.POINTER(vp), C.POINTER(vp)]
+    L.l3b_graph_expand.argtypes = [i64, vp, vp, i32, vp, vp]
+    L.l3b_free.argtypes = [vp]
+    L.l3b_free.restype = None
+    L.l3b_mesh_upload.argtypes = [vp, i32, i32, i64, vp, vp, vp, i64, i64, C.POINTER(vp)]
+    L.l3b_mesh_destroy.argtypes = [vp]
+    L.l3b_mesh_destroy.restype = None
+    L.l3b_fields_upload.argtypes = [vp, i64, i32, vp, C.POINTER(vp)]
+    L.l3b_fields_update.argtypes = [vp, vp]
+    L.l3b_fields_destroy.argtypes = [vp]
+    L.l3b_fields_destroy.restype = None
+    L.l3b_asm_create.argtypes = [vp, vp, i32, i32, vp, vp, C.POINTER(vp)]
+    L.l3b_asm_destroy.argtypes = [vp]
+    L.l3b_asm_destroy.restype = None
+    L.l3b_asm_nnz.argtypes = [vp]
+    L.l3b_asm_nnz.restype = i64
+    L.l3b_asm_begin_assembly.argtypes = [vp]
+    L.l3b_asm_assemble.argtypes = [vp, i32, _AsmOpts, dbl, vp, vp, vp, vp, i32]
+    L.l3b_asm_end_assembly.argtypes = [vp, i64, vp, vp]
+    L.l3b_asm_download.argtypes = [vp, vp, vp]
+    L.l3b_asm_device_values.argtypes = [vp]
+    L.l3b_asm_device_values.restype = vp
+    L.l3b_asm_spmv.argtypes = [vp, vp, vp]
+    L.l3b_asm_solve_cg.argtypes = [vp, dbl, i32, vp, C.POINTER(dbl), C.POINTER(i32)]
+    L.l3b_asm_last_kernel_ms.argtypes = [vp]
+    L.l3b_asm_last_kernel_ms.restype = dbl
+    L.l3b_mf_create.argtypes = [vp, vp, i32, i32, vp, vp, C.POINTER(vp)]
+    L.l3b_mf_destroy.argtypes = [vp]
+    L.l3b_mf_destroy.restype = None
+    L.l3b_mf_assemble.argtypes = [vp, i32, _AsmOpts, dbl, vp, vp, vp, vp, i32]
+    L.l3b_mf_end_assembly.argtypes = [vp]
+    L.l3b_mf_download.argtypes = [vp, vp, vp]
+    L.l3b_mf_apply_device.argtypes = [vp, vp, vp, i32, dbl, dbl]
+    L.l3b_mf_apply.argtypes = [vp, vp, vp, i32, dbl, dbl]
+    L.l3b_mf_solve_cg.argtypes = [vp, dbl, i32, vp, C.POINTER(dbl), C.POINTER(i32)]
+    L.l3b_mf_num_dofs.argtypes = [vp]
+    L.l3b_mf_num_dofs.restype = i64
+    L.l3b_mf_kernel_launches.argtypes = [vp]
+    L.l3b_microbench.argtypes = [vp, i32, C.POINTER(dbl)]
+    _lib = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _iarr(v, n=None):
+    if v is None:
+        return None
+    a = np.ascontiguousarray(v, dtype=np.int32)
+    if n is not None and len(a) != n:
+        raise ValueError(f"expected {n} indices, got {len(a)}")
+    return a
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def kernel_id(name: str) -> int:
+    kid = lib().l3b_kernel_find(name.encode())
+    if kid < 0:
+        raise KeyError(f"kernel '{name}' is not registered")
+    return kid
+
+
+def kernel_info(name_or_id):
+    kid = kernel_id(name_or_id) if isinstance(name_or_id, str) else name_or_id
+    info = _KernelInfo()
+    if lib().l3b_kernel_get_info(kid, C.byref(info)) != 0:
+        raise KeyError(kid)
+    inst = []
+    for i in range(info.n_instances):
+        o, q = C.c_int(), C.c_int()
+        lib().l3b_kernel_get_instance(kid, i, C.byref(o), C.byref(q))
+        inst.append((o.value, q.value))
+    return dict(id=kid, name=info.name.decode(), dimension=info.dimension, n_equations=info.n_equations, n_unknowns=info.n_unknowns,
+                n_fields=info.n_fields, n_rhs=info.n_rhs, is_boundary=bool(info.is_boundary), instances=inst)
+
+
+def list_kernels():
+    return [kernel_info(i) for i in range(lib().l3b_kernel_count())]
+
+
+# ---- tables (host-only entry points; usable without a GPU)
+def tables_gll(n):
+    out = np.zeros(n)
+    lib().l3b_tables_gll(n, _p(out))
+    return out
+
+
+def tables_gauss(n):
+    p, w = np.zeros(n), np.zeros(n)
+    lib().l3b_tables_gauss(n, _p(p), _p(w))
+    return p, w
+
+
+def tables_1d(order, nq):
+    a, b, c = np.zeros((order + 1, nq)), np.zeros((order + 1, nq)), np.zeros((nq, nq))
+    lib().l3b_tables_1d(order, nq, _p(a), _p(b), _p(c))
+    return a, b, c
+
+
+def tables_dense(dim, order, nq, side=-1):
+    nb = (order + 1) ** dim
+    q = nq**dim if side < 0 else nq ** (dim - 1)
+    pts, wts, vals, ders = np.zeros((q, dim)), np.zeros(q), np.zeros((q, nb)), np.zeros((q, dim, nb))
+    n = C.c_int()
+    rc = lib().l3b_tables_dense(dim, order, nq, side, C.byref(n), _p(pts), _p(wts), _p(vals), _p(ders))
+    if rc != 0 or n.value != q:
+        raise L3BError(rc, lib().l3b_global_error().decode())
+    return pts, wts, vals, ders
+
+
+# ---- host mesh front end
+class HostMesh:
+    """Structured quad/hex mesh with the reference's order-p node numbering (mesh/primitives/*, ConvertMeshToOrder.hpp)."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+        info = np.zeros(6, dtype=np.int64)
+        lib().l3b_host_mesh_info(self._h, _p(info))
+        self.dim, self.order, self.n_nodes, self.n_elems, self.nodes_per_elem, self.n_sides = map(int, info)
+        L = lib()
+
+        def view(ptr, dtype, shape):
+            n = int(np.prod(shape))
+            buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+        self.nodes = view(L.l3b_host_mesh_nodes(self._h), np.uint32, (self.n_elems, self.nodes_per_elem))
+        self.verts = view(L.l3b_host_mesh_verts(self._h), np.float64, (self.n_elems, 2**self.dim, 3))
+        self.side_boundaries = view(L.l3b_host_mesh_side_boundaries(self._h), np.uint16, (self.n_elems, self.n_sides))
+
+    def __del__(self):
+        try:
+            lib().l3b_host_mesh_destroy(self._h)
+        except Exception:
+            pass
+
+    def node_graph(self):
+        return node_graph(self.n_nodes, self.nodes)
+
+    def boundary_nodes(self, boundary_ids):
+        """Local node ids on the sides carrying one of `boundary_ids` (bcs/LocalDirichletBC.hpp:86-105)."""
+        nb = self.order + 1
+        sel = np.zeros(self.n_nodes, dtype=bool)
+        for side in range(self.n_sides):
+            on = np.isin(self.side_boundaries[:, side], list(boundary_ids))
+            if on.any():
+                sel[self.nodes[on][:, side_node_inds(self.dim, self.order, side)].ravel()] = True
+        return np.nonzero(sel)[0]
+
+
+def side_node_inds(dim, order, side):
+    """mesh/ElementTraits.hpp:72-98, 118-137"""
+    n = order + 1
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    i, j = i.ravel(), j.ravel()
+    if dim == 3:
+        nps = n * n
+        return [i * n + j, i * n + j + nps * (n - 1), i * nps + j, i * nps + j + n * (n - 1), i * nps + j * n, i * nps + j * n + n - 1][side]
+    k = np.arange(n)
+    return [k, k + n * (n - 1), k * n, k * n + n - 1][side]
+
+
+def make_cube_mesh(x, y=None, z=None, order=1) -> HostMesh:
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = x if y is None else np.ascontiguousarray(y, dtype=np.float64)
+    z = x if z is None else np.ascontiguousarray(z, dtype=np.float64)
+    h = C.c_void_p()
+    rc = lib().l3b_host_mesh_cube(len(x), _p(x), len(y), _p(y), len(z), _p(z), order, C.byref(h))
+    if rc != 0:
+        raise L3BError(rc, lib().l3b_global_error().decode())
+    return HostMesh(h.value)
+
+
+def make_square_mesh(x, y=None, order=1) -> HostMesh:
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = x if y is None else np.ascontiguousarray(y, dtype=np.float64)
+    h = C.c_void_p()
+    rc = lib().l3b_host_mesh_square(len(x), _p(x), len(y), _p(y), order, C.byref(h))
+    if rc != 0:
+        raise L3BError(rc, lib().l3b_global_error().decode())
+    return HostMesh(h.value)
+
+
+def node_graph(n_nodes, nodes):
+    """Node-level sparsity graph (algsys/SparsityGraph.hpp:25-81): returns (ptr, nbr) numpy arrays."""
+    nodes = np.ascontiguousarray(nodes, dtype=np.uint32)
+    ptr, nbr = C.c_void_p(), C.c_void_p()
+    rc = lib().l3b_node_graph(n_nodes, nodes.shape[0], nodes.shape[1], _p(nodes), C.byref(ptr), C.byref(nbr))
+    if rc != 0:
+        raise L3BError(rc, lib().l3b_global_error().decode())
+    try:
+        p = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int64)), shape=(n_nodes + 1,)).copy()
+        n = np.ctypeslib.as_array(C.cast(nbr, C.POINTER(C.c_uint32)), shape=(max(int(p[-1]), 1),)).copy()[: int(p[-1])]
+    finally:
+        lib().l3b_free(ptr)
+        lib().l3b_free(nbr)
+    return p, n
+
+
+def expand_graph(ptr, nbr, dofs_per_node, with_cols=True):
+    """dof-level CRS (row_ptr, col_ind) of the reference's Tpetra graph (SparsityGraph.hpp:254-278)."""
+    n_nodes = len(ptr) - 1
+    row_ptr = np.zeros(n_nodes * dofs_per_node + 1, dtype=np.int64)
+    col_ind = np.zeros(int(ptr[-1]) * dofs_per_node**2, dtype=np.int32) if with_cols else None
+    lib().l3b_graph_expand(n_nodes, _p(ptr), _p(nbr), dofs_per_node, _p(row_ptr), _p(col_ind))
+    return row_ptr, col_ind
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class Context:
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().l3b_context_create(device, C.byref(self._h))
+        if rc != 0:
+            raise L3BError(rc, lib().l3b_global_error().decode())
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise L3BError(rc, lib().l3b_last_error(self._h).decode())
+
+    def synchronize(self):
+        self._chk(lib().l3b_context_synchronize(self._h))
+
+    @property
+    def stream(self):
+        return lib().l3b_context_stream(self._h)
+
+    def __del__(self):
+        try:
+            lib().l3b_context_destroy(self._h)
+        except Exception:
+            pass
+
+    def microbench(self, mode):
+        """0: fp64 FMA TFLOP/s, 1: fp64 DMMA TFLOP/s, 2: HBM copy GB/s"""
+        out = C.c_double()
+        self._chk(lib().l3b_microbench(self._h, mode, C.byref(out)))
+        return out.value
+
+    def upload_mesh(self, mesh: HostMesh, n_owned_nodes=None):
+        return Mesh(self, mesh.dim, mesh.order, mesh.verts, mesh.nodes, mesh.side_boundaries, mesh.n_nodes,
+                    mesh.n_nodes if n_owned_nodes is None else n_owned_nodes)
+
+    def upload_fields(self, data):
+        """data: (n_fields, n_local_nodes) — post/SolutionManager.hpp:83-101 layout"""
+        return Fields(self, data)
+
+
+class Mesh:
+    def __init__(self, ctx: Context, dim, order, verts, nodes, side_boundaries, n_local_nodes, n_owned_nodes):
+        self.ctx, self.dim, self.order = ctx, dim, order
+        verts = np.ascontiguousarray(verts, dtype=np.float64)
+        nodes = np.ascontiguousarray(nodes, dtype=np.uint32)
+        sb = None if side_boundaries is None else np.ascontiguousarray(side_boundaries, dtype=np.uint16)
+        self.n_elems, self.nodes_per_elem = nodes.shape
+        self.n_local_nodes = int(n_local_nodes)
+        self.nodes = nodes
+        self._h = C.c_void_p()
+        ctx._chk(lib().l3b_mesh_upload(ctx._h, dim, order, self.n_elems, _p(verts), _p(nodes), _p(sb), n_local_nodes, n_owned_nodes,
+                                       C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            lib().l3b_mesh_destroy(self._h)
+        except Exception:
+            pass
+
+
+class Fields:
+    def __init__(self, ctx: Context, data):
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        self.ctx, self.n_fields, self.n_nodes = ctx, data.shape[0], data.shape[1]
+        self._h = C.c_void_p()
+        ctx._chk(lib().l3b_fields_upload(ctx._h, self.n_nodes, self.n_fields, _p(data), C.byref(self._h)))
+
+    def update(self, data):
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        self.ctx._chk(lib().l3b_fields_update(self._h, _p(data)))
+
+    def __del__(self):
+        try:
+            lib().l3b_fields_destroy(self._h)
+        except Exception:
+            pass
+
+
+def _kernel_args(kernel, dof_inds, fields, field_inds, boundary_ids):
+    info = kernel_info(kernel)
+    di = _iarr(dof_inds, info["n_unknowns"])
+    fi = _iarr(field_inds, info["n_fields"])
+    bi = _iarr(list(boundary_ids))
+    return info["id"], di, (fields._h if fields is not None else None), fi, bi, (0 if bi is None else len(bi))
+
+
+class AssembledSystem:
+    """algsys/AssembledSystem.hpp:22-83 on the device: node-block CRS values + rhs."""
+
+    def __init__(self, ctx: Context, mesh: Mesh, dofs_per_node, n_rhs=1, graph=None):
+        self.ctx, self.mesh, self.dofs_per_node, self.n_rhs = ctx, mesh, dofs_per_node, n_rhs
+        self.node_ptr, self.node_nbr = graph if graph is not None else node_graph(mesh.n_local_nodes, mesh.nodes)
+        self.n_dofs = mesh.n_local_nodes * dofs_per_node
+        self._h = C.c_void_p()
+        ctx._chk(lib().l3b_asm_create(ctx._h, mesh._h, dofs_per_node, n_rhs, _p(self.node_ptr), _p(self.node_nbr), C.byref(self._h)))
+        self.nnz = int(lib().l3b_asm_nnz(self._h))
+
+    def __del__(self):
+        try:
+            lib().l3b_asm_destroy(self._h)
+        except Exception:
+            pass
+
+    def beginAssembly(self):
+        self.ctx._chk(lib().l3b_asm_begin_assembly(self._h))
+
+    def assembleProblem(self, kernel, boundary_ids=(), fields=None, field_inds=None, dof_inds=None, asm_opts=AssemblyOptions(), time=0.0):
+        kid, di, fh, fi, bi, nb = _kernel_args(kernel, dof_inds, fields, field_inds, boundary_ids)
+        self.ctx._chk(lib().l3b_asm_assemble(self._h, kid, asm_opts._c(), time, _p(di), fh, _p(fi), _p(bi), nb))
+
+    def endAssembly(self, dirichlet_dofs=None, dirichlet_vals=None):
+        n = 0 if dirichlet_dofs is None else len(dirichlet_dofs)
+        d = None if n == 0 else np.ascontiguousarray(dirichlet_dofs, dtype=np.int32)
+        v = None if n == 0 else np.ascontiguousarray(np.asarray(dirichlet_vals, dtype=np.float64).reshape(n, -1).T)
+        self.ctx._chk(lib().l3b_asm_end_assembly(self._h, n, _p(d), _p(v)))
+
+    def graph(self):
+        return expand_graph(self.node_ptr, self.node_nbr, self.dofs_per_node)
+
+    def download(self, values=True):
+        vals = np.zeros(self.nnz) if values else None
+        rhs = np.zeros((self.n_rhs, self.n_dofs))
+        self.ctx._chk(lib().l3b_asm_download(self._h, _p(vals), _p(rhs)))
+        return vals, rhs.T.copy()
+
+    def getMatrix(self):
+        import scipy.sparse as sp
+        row_ptr, col_ind = self.graph()
+        vals, _ = self.download()
+        return sp.csr_matrix((vals, col_ind, row_ptr), shape=(self.n_dofs, self.n_dofs))
+
+    def spmv(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros_like(x)
+        self.ctx._chk(lib().l3b_asm_spmv(self._h, _p(x), _p(y)))
+        return y
+
+    def solve(self, tol=1e-6, max_iters=10000):
+        x = np.zeros(self.n_dofs)
+        at, it = C.c_double(), C.c_int()
+        self.ctx._chk(lib().l3b_asm_solve_cg(self._h, tol, max_iters, _p(x), C.byref(at), C.byref(it)))
+        return x, at.value, it.value
+
+    @property
+    def last_kernel_ms(self):
+        return lib().l3b_asm_last_kernel_ms(self._h)
+
+
+class MatrixFreeSystem:
+    """algsys/MatrixFreeSystem.hpp:47-120 on the device."""
+
+    def __init__(self, ctx: Context, mesh: Mesh, dofs_per_node, n_rhs=1, dirichlet_mask=None, dirichlet_vals=None):
+        self.ctx, self.mesh, self.dofs_per_node, self.n_rhs = ctx, mesh, dofs_per_node, n_rhs
+        self.n_dofs = mesh.n_local_nodes * dofs_per_node
+        m = None if dirichlet_mask is None else np.ascontiguousarray(dirichlet_mask, dtype=np.uint8)
+        v = None
+        if dirichlet_vals is not None:
+            v = np.ascontiguousarray(np.asarray(dirichlet_vals, dtype=np.float64).reshape(self.n_dofs, -1).T)
+        self._h = C.c_void_p()
+        ctx._chk(lib().l3b_mf_create(ctx._h, mesh._h, dofs_per_node, n_rhs, _p(m), _p(v), C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            lib().l3b_mf_destroy(self._h)
+        except Exception:
+            pass
+
+    def assembleProblem(self, kernel, boundary_ids=(), fields=None, field_inds=None, dof_inds=None, asm_opts=AssemblyOptions(), time=0.0):
+        kid, di, fh, fi, bi, nb = _kernel_args(kernel, dof_inds, fields, field_inds, boundary_ids)
+        self.ctx._chk(lib().l3b_mf_assemble(self._h, kid, asm_opts._c(), time, _p(di), fh, _p(fi), _p(bi), nb))
+
+    def endAssembly(self):
+        self.ctx._chk(lib().l3b_mf_end_assembly(self._h))
+
+    def download(self):
+        diag = np.zeros(self.n_dofs)
+        rhs = np.zeros((self.n_rhs, self.n_dofs))
+        self.ctx._chk(lib().l3b_mf_download(self._h, _p(diag), _p(rhs)))
+        return diag, rhs.T.copy()
+
+    def apply(self, x, y=None, alpha=1.0, beta=0.0):
+        """y = alpha A x + beta y with host buffers (x, y: n_dofs x n_cols)."""
+        x = np.asarray(x, dtype=np.float64)
+        nc = 1 if x.ndim == 1 else x.shape[1]
+        x = x.reshape(self.n_dofs, nc)
+        xf = np.ascontiguousarray(x.T)
+        yf = np.zeros_like(xf) if y is None else np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(self.n_dofs, nc).T)
+        self.ctx._chk(lib().l3b_mf_apply(self._h, _p(xf), _p(yf), nc, alpha, beta))
+        return yf.T.copy()
+
+    def apply_raw(self, xf, yf, n_cols=1, alpha=1.0, beta=0.0):
+        """host buffers already in the C ABI layout (column-major, contiguous): no numpy copies in the timed region"""
+        self.ctx._chk(lib().l3b_mf_apply(self._h, xf.ctypes.data, yf.ctypes.data, n_cols, alpha, beta))
+
+    def apply_device(self, x_ptr, y_ptr, n_cols=1, alpha=1.0, beta=0.0):
+        self.ctx._chk(lib().l3b_mf_apply_device(self._h, x_ptr, y_ptr, n_cols, alpha, beta))
+
+    def solve(self, tol=1e-6, max_iters=10000):
+        x = np.zeros(self.n_dofs)
+        at, it = C.c_double(), C.c_int()
+        self.ctx._chk(lib().l3b_mf_solve_cg(self._h, tol, max_iters, _p(x), C.byref(at), C.byref(it)))
+        return x, at.value, it.value
+
+    @property
+    def kernel_launches(self):
+        return lib().l3b_mf_kernel_launches(self._h)

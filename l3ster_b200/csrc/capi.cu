@@ -1,0 +1,1292 @@
+// C ABI implementation (include/l3ster_b200.h): contexts, device meshes, the assembled and the matrix-free system, and the
+// Krylov layer. Host orchestration only — all element math lives in the kernels instantiated through register_kernel.cuh.
+#include "../../include/l3ster_b200.h"
+
+#include "mesh_host.hpp"
+#include "registry.hpp"
+#include "tables.hpp"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace l3b
+{
+std::vector< KernelEntry >& kernelRegistry()
+{
+    static std::vector< KernelEntry > registry;
+    return registry;
+}
+int findKernel(const std::string& name)
+{
+    const auto& r = kernelRegistry();
+    for (size_t i = 0; i < r.size(); ++i)
+        if (r[i].info.name == name)
+            return static_cast< int >(i);
+    return -1;
+}
+} // namespace l3b
+
+using namespace l3b;
+
+namespace
+{
+std::string g_global_error;
+
+struct Error
+{
+    int         code;
+    std::string msg;
+};
+[[noreturn]] void fail(int code, std::string msg)
+{
+    throw Error{code, std::move(msg)};
+}
+void cudaCheck(cudaError_t err, const char* what)
+{
+    if (err != cudaSuccess)
+        fail(L3B_ERR_CUDA, std::string{what} + ": " + cudaGetErrorString(err));
+}
+
+template < typename T >
+struct DevBuf
+{
+    T*     ptr = nullptr;
+    size_t n   = 0;
+    DevBuf()   = default;
+    explicit DevBuf(size_t n_) { alloc(n_); }
+    DevBuf(const DevBuf&)            = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : ptr{o.ptr}, n{o.n} { o.ptr = nullptr, o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept
+    {
+        release();
+        ptr   = o.ptr;
+        n     = o.n;
+        o.ptr = nullptr;
+        o.n   = 0;
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t n_)
+    {
+        release();
+        n = n_;
+        if (n > 0)
+            cudaCheck(cudaMalloc(&ptr, n * sizeof(T)), "cudaMalloc");
+    }
+    void release()
+    {
+        if (ptr)
+            cudaFree(ptr);
+        ptr = nullptr;
+        n   = 0;
+    }
+    void upload(const T* src, size_t count, cudaStream_t s)
+    {
+        if (count > 0)
+            cudaCheck(cudaMemcpyAsync(ptr, src, count * sizeof(T), cudaMemcpyHostToDevice, s), "H2D copy");
+    }
+    void download(T* dst, size_t count, cudaStream_t s) const
+    {
+        if (count > 0)
+            cudaCheck(cudaMemcpyAsync(dst, ptr, count * sizeof(T), cudaMemcpyDeviceToHost, s), "D2H copy");
+    }
+    void zero(cudaStream_t s)
+    {
+        if (n > 0)
+            cudaCheck(cudaMemsetAsync(ptr, 0, n * sizeof(T), s), "memset");
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// vector kernels
+__global__ void scaleKernel(double* y, long long n, double beta)
+{
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
+        y[i] = beta == 0. ? 0. : beta * y[i];
+}
+// Dirichlet rows are identity rows: y[d] += alpha x[d] (MatrixFreeSystem.hpp:1087-1103)
+__global__ void dirichletRowsKernel(const uint8_t* mask, const double* x, double* y, long long n, long long ld, int n_cols, double alpha)
+{
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
+        if (mask[i])
+            for (int c = 0; c < n_cols; ++c)
+                y[i + c * ld] += alpha * x[i + c * ld];
+}
+// handle_dirichlet_dof (MatrixFreeSystem.hpp:911-915)
+__global__ void dirichletInitKernel(const uint8_t* mask, const double* vals, double* diag, double* rhs, long long n, long long ld, int n_rhs)
+{
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
+        if (mask[i])
+        {
+            diag[i] = 1.;
+            for (int c = 0; c < n_rhs; ++c)
+                rhs[i + c * ld] = vals[i + c * ld];
+        }
+}
+// native Jacobi: M^-1 = damping * sign(d) / max(|d|, threshold) (solve/NativePreconditioners.hpp:86-100)
+__global__ void jacobiInvertKernel(const double* diag, double* minv, long long n, double damping, double threshold)
+{
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
+    {
+        const double v = diag[i];
+        minv[i]        = (v < 0 ? -damping : damping) / fmax(fabs(v), threshold);
+    }
+}
+__device__ __forceinline__ double blockSum(double v)
+{
+    __shared__ double s[32];
+    for (int off = 16; off > 0; off >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0)
+        s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    v = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.;
+    if (threadIdx.x < 32)
+        for (int off = 16; off > 0; off >>= 1)
+            v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    return v;
+}
+// out[0] += a.b ; out[1] += c.d (either pair may alias)
+__global__ void dot2Kernel(const double* a, const double* b, const double* c, const double* d, long long n, double* out)
+{
+    double s0 = 0., s1 = 0.;
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
+    {
+        s0 = fma(a[i], b[i], s0);
+        if (c)
+            s1 = fma(c[i], d[i], s1);
+    }
+    s0 = blockSum(s0);
+    s1 = blockSum(s1);
+    if (threadIdx.x == 0)
+    {
+        atomicAdd(out, s0);
+        if (c)
+            atomicAdd(out + 1, s1);
+    }
+}
+// x += a p ; r -= a Ap ; z = minv r ; out[0] += r.r ; out[1] += r.z     (a = rz / pAp read from device scalars)
+__global__ void cgUpdateKernel(double* x, double* r, double* z, const double* p, const double* Ap, const double* minv, long long n,
+                               const double* scal /* [rz, pAp] */, double* out)
+{
+    const double a  = scal[0] / scal[1];
+    double       s0 = 0., s1 = 0.;
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
+    {
+        x[i] = fma(a, p[i], x[i]);
+        const double ri = fma(-a, Ap[i], r[i]);
+        r[i]            = ri;
+        const double zi = minv[i] * ri;
+        z[i]            = zi;
+        s0              = fma(ri, ri, s0);
+        s1              = fma(ri, zi, s1);
+    }
+    s0 = blockSum(s0);
+    s1 = blockSum(s1);
+    if (threadIdx.x == 0)
+    {
+        atomicAdd(out, s0);
+        atomicAdd(out + 1, s1);
+    }
+}
+// p = z + (rz_new / rz_old) p
+__global__ void cgDirectionKernel(double* p, const double* z, long long n, const double* rz_new, const double* rz_old)
+{
+    const double b = rz_new[0] / rz_old[0];
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
+        p[i] = fma(b, p[i], z[i]);
+}
+__global__ void hadamardKernel(double* z, const double* minv, const double* r, long long n)
+{
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
+        z[i] = minv[i] * r[i];
+}
+// dof-level CRS helpers on the node-block layout: row (n, d) = for each neighbour m (ascending): dofs_per_node entries
+__global__ void rowPtrKernel(const long long* node_ptr, long long n_nodes, int dpn, long long* row_ptr)
+{
+    const long long row = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x;
+    if (row > n_nodes * dpn)
+        return;
+    if (row == n_nodes * dpn)
+    {
+        row_ptr[row] = node_ptr[n_nodes] * dpn * dpn;
+        return;
+    }
+    const long long n = row / dpn, d = row % dpn, deg = node_ptr[n + 1] - node_ptr[n];
+    row_ptr[row] = dpn * (dpn * node_ptr[n] + d * deg);
+}
+// slot map from the node graph: pos[e][a][b] = index of node b in the sorted neighbour list of node a
+__global__ void slotMapKernel(const uint32_t* nodes, long long n_elems, int nn, const long long* node_ptr, const uint32_t* node_nbr,
+                              uint16_t* pos, int* status)
+{
+    const long long idx = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x;
+    if (idx >= n_elems * nn * nn)
+        return;
+    const long long e    = idx / (static_cast< long long >(nn) * nn);
+    const int       a    = static_cast< int >((idx / nn) % nn), b = static_cast< int >(idx % nn);
+    const long long na   = nodes[e * nn + a];
+    const uint32_t  want = nodes[e * nn + b];
+    long long       lo = node_ptr[na], hi = node_ptr[na + 1];
+    const long long beg = lo, end = hi;
+    while (lo < hi)
+    {
+        const long long mid = (lo + hi) / 2;
+        if (node_nbr[mid] < want)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    if (lo >= end or node_nbr[lo] != want)
+    {
+        atomicOr(status, 2);
+        return;
+    }
+    pos[idx] = static_cast< uint16_t >(lo - beg);
+}
+// y = A x, one warp per row, node-block layout
+__global__ void spmvKernel(const long long* node_ptr, const uint32_t* node_nbr, const double* vals, long long n_nodes, int dpn, const double* x,
+                           double* y)
+{
+    const long long row  = (blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x) / 32;
+    const int       lane = threadIdx.x & 31;
+    if (row >= n_nodes * dpn)
+        return;
+    const long long n = row / dpn, d = row % dpn, deg = node_ptr[n + 1] - node_ptr[n];
+    const long long beg = dpn * (dpn * node_ptr[n] + d * deg);
+    double          acc = 0.;
+    for (long long k = lane; k < deg * dpn; k += 32)
+        acc = fma(vals[beg + k], x[static_cast< long long >(node_nbr[node_ptr[n] + k / dpn]) * dpn + k % dpn], acc);
+    for (int off = 16; off > 0; off >>= 1)
+        acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0)
+        y[row] = acc;
+}
+// algebraic Dirichlet BCs (bcs/DirichletBC.hpp:82-150), one warp per row
+__global__ void dirichletAlgebraicKernel(const long long* node_ptr, const uint32_t* node_nbr, double* vals, long long n_nodes, int dpn,
+                                         const uint8_t* is_bc, const double* bc_vals, double* rhs, long long ld, int n_rhs)
+{
+    const long long row  = (blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x) / 32;
+    const int       lane = threadIdx.x & 31;
+    if (row >= n_nodes * dpn)
+        return;
+    const long long n = row / dpn, d = row % dpn, deg = node_ptr[n + 1] - node_ptr[n];
+    const long long beg = dpn * (dpn * node_ptr[n] + d * deg);
+    if (is_bc[row])
+    {
+        for (long long k = lane; k < deg * dpn; k += 32)
+        {
+            const long long col = static_cast< long long >(node_nbr[node_ptr[n] + k / dpn]) * dpn + k % dpn;
+            vals[beg + k]       = col == row ? 1. : 0.;
+        }
+        if (lane == 0)
+            for (int c = 0; c < n_rhs; ++c)
+                rhs[row + c * ld] = bc_vals[row + c * ld];
+        return;
+    }
+    for (int c = 0; c < n_rhs; ++c)
+    {
+        double acc = 0.;
+        for (long long k = lane; k < deg * dpn; k += 32)
+        {
+            const long long col = static_cast< long long >(node_nbr[node_ptr[n] + k / dpn]) * dpn + k % dpn;
+            if (is_bc[col])
+                acc = fma(vals[beg + k], bc_vals[col + c * ld], acc);
+        }
+        for (int off = 16; off > 0; off >>= 1)
+            acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0)
+            rhs[row + c * ld] -= acc;
+    }
+    for (long long k = lane; k < deg * dpn; k += 32)
+    {
+        const long long col = static_cast< long long >(node_nbr[node_ptr[n] + k / dpn]) * dpn + k % dpn;
+        if (is_bc[col])
+            vals[beg + k] = 0.;
+    }
+}
+__global__ void extractDiagKernel(const long long* node_ptr, const uint32_t* node_nbr, const double* vals, long long n_nodes, int dpn,
+                                  double* diag)
+{
+    const long long row = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x;
+    if (row >= n_nodes * dpn)
+        return;
+    const long long n = row / dpn, d = row % dpn, deg = node_ptr[n + 1] - node_ptr[n];
+    const long long beg = dpn * (dpn * node_ptr[n] + d * deg);
+    long long       lo = 0, hi = deg;
+    while (lo < hi)
+    {
+        const long long mid = (lo + hi) / 2;
+        if (node_nbr[node_ptr[n] + mid] < n)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    diag[row] = vals[beg + lo * dpn + d];
+}
+
+unsigned gridFor(long long n, int block = 256)
+{
+    const long long g = (n + block - 1) / block;
+    return static_cast< unsigned >(std::max< long long >(1, std::min< long long >(g, 148ll * 32)));
+}
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct l3b_context
+{
+    int                 device = 0;
+    cudaStream_t        stream = nullptr;
+    mutable std::string err;
+    DevBuf< int >       status;
+    DevBuf< double >    scalars; // Krylov scalars
+    int                 sm_count = 148;
+    std::map< std::pair< int, int >, tables::Tables1D > tab1d;
+    struct DenseDev
+    {
+        int              n_qp = 0;
+        DevBuf< double > vals, ders, pts, wts; // domain: one table; boundary: n_sides tables back to back
+    };
+    std::map< std::tuple< int, int, int, bool >, std::unique_ptr< DenseDev > > dense;
+
+    const tables::Tables1D& tables1d(int order, int nq)
+    {
+        auto it = tab1d.find({order, nq});
+        if (it == tab1d.end())
+            it = tab1d.emplace(std::make_pair(order, nq), tables::makeTables1D(order, nq)).first;
+        return it->second;
+    }
+    const DenseDev& denseTables(int dim, int order, int nq, bool boundary)
+    {
+        const auto key = std::make_tuple(dim, order, nq, boundary);
+        auto       it  = dense.find(key);
+        if (it != dense.end())
+            return *it->second;
+        auto                    d = std::make_unique< DenseDev >();
+        std::vector< double >   vals, ders, pts, wts;
+        const int               n_tab = boundary ? 2 * dim : 1;
+        for (int s = 0; s < n_tab; ++s)
+        {
+            std::vector< tables::ld > p, w;
+            if (boundary)
+                tables::sideQuadrature(dim, nq, s, p, w);
+            else
+                tables::domainQuadrature(dim, nq, p, w);
+            const auto t = tables::makeDenseTables(dim, order, p, w);
+            d->n_qp      = t.n_qp;
+            vals.insert(vals.end(), t.values.begin(), t.values.end());
+            ders.insert(ders.end(), t.derivatives.begin(), t.derivatives.end());
+            pts.insert(pts.end(), t.points.begin(), t.points.end());
+            wts.insert(wts.end(), t.weights.begin(), t.weights.end());
+        }
+        d->vals.alloc(vals.size());
+        d->ders.alloc(ders.size());
+        d->pts.alloc(pts.size());
+        d->wts.alloc(wts.size());
+        d->vals.upload(vals.data(), vals.size(), stream);
+        d->ders.upload(ders.data(), ders.size(), stream);
+        d->pts.upload(pts.data(), pts.size(), stream);
+        d->wts.upload(wts.data(), wts.size(), stream);
+        cudaCheck(cudaStreamSynchronize(stream), "table upload");
+        return *dense.emplace(key, std::move(d)).first->second;
+    }
+    // read-and-clear the device status word; translate to the reference's exceptions
+    void checkStatus()
+    {
+        int st = 0;
+        status.download(&st, 1, stream);
+        cudaCheck(cudaStreamSynchronize(stream), "status read");
+        if (st != 0)
+        {
+            status.zero(stream);
+            if (st & status_degenerate_element)
+                fail(L3B_ERR_DEGENERATE, "Encountered degenerate element ( |J| <= 0 )");
+            fail(L3B_ERR_GRAPH, "entry not present in the sparsity graph");
+        }
+    }
+};
+
+struct l3b_host_mesh
+{
+    host::Mesh mesh;
+};
+
+struct l3b_mesh
+{
+    l3b_context*        ctx = nullptr;
+    int                 dim = 0, order = 0, nn = 0, n_sides = 0;
+    long long           n_elems = 0, n_local_nodes = 0, n_owned_nodes = 0;
+    DevBuf< double >    verts;
+    DevBuf< uint32_t >  nodes;
+    std::vector< uint16_t > side_bnd; // host copy, used to build boundary work lists
+};
+
+struct l3b_fields
+{
+    l3b_context*     ctx = nullptr;
+    long long        n_nodes = 0;
+    int              n_fields = 0;
+    DevBuf< double > data;
+};
+
+namespace
+{
+struct WorkList
+{
+    long long          n = 0;
+    DevBuf< int32_t >  elems;
+    DevBuf< uint8_t >  sides;
+};
+struct KernelUse
+{
+    int                         kernel_id = -1;
+    const KernelInstance*       inst      = nullptr;
+    l3b_asm_opts                opts{};
+    int                         nq = 0;
+    double                      time = 0.;
+    int                         dof_inds[max_unknowns]{};
+    const l3b_fields*           fields = nullptr;
+    int                         field_inds[max_fields]{};
+    std::shared_ptr< WorkList > boundary_work; // boundary kernels only
+};
+
+KernelUse makeUse(l3b_mesh* mesh, int dofs_per_node, int n_rhs, int kernel_id, l3b_asm_opts opts, double time, const int* dof_inds,
+                  const l3b_fields* fields, const int* field_inds, const int* boundary_ids, int n_boundary_ids)
+{
+    auto& reg = kernelRegistry();
+    if (kernel_id < 0 or kernel_id >= static_cast< int >(reg.size()))
+        fail(L3B_ERR_INVALID_ARG, "invalid kernel id");
+    const auto& entry = reg[kernel_id];
+    const auto& info  = entry.info;
+    if (info.dim != mesh->dim)
+        fail(L3B_ERR_INVALID_ARG, "The dimensions of the kernel do not match the dimensions of the domain");
+    if (info.n_rhs != n_rhs)
+        fail(L3B_ERR_INVALID_ARG, "kernel n_rhs does not match the system's n_rhs");
+    if (info.n_unknowns > dofs_per_node)
+        fail(L3B_ERR_INVALID_ARG, "kernel has more unknowns than the system has dofs per node");
+    if (opts.value_order < 1)
+        fail(L3B_ERR_INVALID_ARG, "value_order must be >= 1");
+    KernelUse use;
+    use.kernel_id = kernel_id;
+    use.opts      = opts;
+    AssemblyOptions ao;
+    ao.value_order      = opts.value_order;
+    ao.derivative_order = opts.derivative_order;
+    use.nq              = ao.nq1d(mesh->order);
+    use.inst            = entry.find(mesh->order, use.nq);
+    if (not use.inst)
+        fail(L3B_ERR_NO_INSTANCE, "kernel '" + info.name + "' is not compiled for order " + std::to_string(mesh->order) + ", nq " +
+                                      std::to_string(use.nq) + " — add L3B_PQ(" + std::to_string(mesh->order) + ", " +
+                                      std::to_string(use.nq) + ") to its registration");
+    use.time = time;
+    for (int u = 0; u < info.n_unknowns; ++u)
+    {
+        use.dof_inds[u] = dof_inds ? dof_inds[u] : u;
+        if (use.dof_inds[u] < 0 or use.dof_inds[u] >= dofs_per_node)
+            fail(L3B_ERR_INVALID_ARG, "dof index out of range");
+    }
+    if (info.n_fields > 0)
+    {
+        if (not fields)
+            fail(L3B_ERR_INVALID_ARG, "kernel needs external fields but none were passed");
+        if (fields->n_nodes != mesh->n_local_nodes)
+            fail(L3B_ERR_INVALID_ARG, "field storage does not match the mesh's local node count");
+        for (int f = 0; f < info.n_fields; ++f)
+        {
+            use.field_inds[f] = field_inds ? field_inds[f] : f;
+            if (use.field_inds[f] < 0 or use.field_inds[f] >= fields->n_fields)
+                fail(L3B_ERR_INVALID_ARG, "field index out of range");
+        }
+        use.fields = fields;
+    }
+    if (info.is_boundary)
+    {
+        if (mesh->side_bnd.empty())
+            fail(L3B_ERR_INVALID_ARG, "boundary kernel on a mesh without side boundary ids");
+        std::vector< int32_t > el;
+        std::vector< uint8_t > sd;
+        for (long long e = 0; e < mesh->n_elems; ++e)
+            for (int s = 0; s < mesh->n_sides; ++s)
+            {
+                const auto id = mesh->side_bnd[e * mesh->n_sides + s];
+                if (id == host::no_boundary)
+                    continue;
+                for (int k = 0; k < n_boundary_ids; ++k)
+                    if (boundary_ids[k] == id)
+                    {
+                        el.push_back(static_cast< int32_t >(e));
+                        sd.push_back(static_cast< uint8_t >(s));
+                        break;
+                    }
+            }
+        auto wl = std::make_shared< WorkList >();
+        wl->n   = static_cast< long long >(el.size());
+        wl->elems.alloc(el.size());
+        wl->sides.alloc(sd.size());
+        wl->elems.upload(el.data(), el.size(), mesh->ctx->stream);
+        wl->sides.upload(sd.data(), sd.size(), mesh->ctx->stream);
+        cudaCheck(cudaStreamSynchronize(mesh->ctx->stream), "work list upload");
+        use.boundary_work = std::move(wl);
+    }
+    return use;
+}
+
+ElemArgs baseArgs(l3b_mesh* mesh, const KernelUse& use, int dofs_per_node, long long ld)
+{
+    ElemArgs a{};
+    a.verts         = mesh->verts.ptr;
+    a.nodes         = mesh->nodes.ptr;
+    a.dofs_per_node = dofs_per_node;
+    a.ld            = ld;
+    std::memcpy(a.dof_inds, use.dof_inds, sizeof(a.dof_inds));
+    std::memcpy(a.field_inds, use.field_inds, sizeof(a.field_inds));
+    if (use.fields)
+    {
+        a.fields       = use.fields->data.ptr;
+        a.field_stride = use.fields->n_nodes;
+    }
+    a.time   = use.time;
+    a.status = mesh->ctx->status.ptr;
+    if (use.boundary_work)
+    {
+        a.n_work     = use.boundary_work->n;
+        a.work_elems = use.boundary_work->elems.ptr;
+        a.work_sides = use.boundary_work->sides.ptr;
+    }
+    else
+    {
+        a.n_work     = mesh->n_elems;
+        a.first_elem = 0;
+    }
+    return a;
+}
+void setDense(ElemArgs& a, l3b_mesh* mesh, const KernelUse& use, bool boundary)
+{
+    const auto& d = mesh->ctx->denseTables(mesh->dim, mesh->order, use.nq, boundary);
+    a.tab_vals    = d.vals.ptr;
+    a.tab_ders    = d.ders.ptr;
+    a.tab_pts     = d.pts.ptr;
+    a.tab_wts     = d.wts.ptr;
+    a.n_qp        = d.n_qp;
+}
+} // namespace
+
+struct l3b_asm
+{
+    l3b_context*        ctx  = nullptr;
+    l3b_mesh*           mesh = nullptr;
+    int                 dpn = 0, n_rhs = 1;
+    long long           n_dofs = 0, nnz = 0;
+    DevBuf< long long > node_ptr, row_ptr;
+    DevBuf< uint32_t >  node_nbr;
+    DevBuf< uint16_t >  slot_pos;
+    DevBuf< double >    values, rhs;
+    bool                open = false;
+    cudaEvent_t         ev0 = nullptr, ev1 = nullptr;
+    double              last_ms = 0.;
+    ~l3b_asm()
+    {
+        if (ev0)
+            cudaEventDestroy(ev0);
+        if (ev1)
+            cudaEventDestroy(ev1);
+    }
+};
+
+struct l3b_mf
+{
+    l3b_context*             ctx  = nullptr;
+    l3b_mesh*                mesh = nullptr;
+    int                      dpn = 0, n_rhs = 1;
+    long long                n_dofs = 0;
+    DevBuf< uint8_t >        dir_mask;
+    DevBuf< double >         dir_vals, diag, rhs;
+    bool                     has_bc = false, closed = false;
+    std::vector< KernelUse > uses;
+    DevBuf< double >         work_x, work_y; // staging for the host-buffer apply
+    int                      last_launches = 0;
+};
+
+namespace
+{
+template < typename F >
+int guardedCtx(const l3b_context* ctx, F&& f)
+{
+    try
+    {
+        f();
+        return L3B_OK;
+    }
+    catch (const Error& e)
+    {
+        if (ctx)
+            ctx->err = e.msg;
+        g_global_error = e.msg;
+        return e.code;
+    }
+    catch (const std::exception& e)
+    {
+        if (ctx)
+            ctx->err = e.what();
+        g_global_error = e.what();
+        return L3B_ERR_INVALID_ARG;
+    }
+}
+
+// y = alpha A x + beta y on device pointers
+void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta)
+{
+    auto* ctx = sys->ctx;
+    if (not sys->closed)
+        fail(L3B_ERR_STATE, "`apply` was called before `endAssembly()`");
+    if (n_cols != sys->n_rhs and n_cols != 1)
+        fail(L3B_ERR_INVALID_ARG, "n_cols must equal the system's n_rhs or 1");
+    int launches = 0;
+    scaleKernel<<< gridFor(sys->n_dofs * n_cols), 256, 0, ctx->stream >>>(y, sys->n_dofs * n_cols, beta);
+    ++launches;
+    for (const auto& use : sys->uses)
+    {
+        const auto& info = kernelRegistry()[use.kernel_id].info;
+        ElemArgs    a    = baseArgs(sys->mesh, use, sys->dpn, sys->n_dofs);
+        a.x              = x;
+        a.y              = y;
+        a.n_cols         = n_cols;
+        a.alpha          = alpha;
+        a.dir_mask       = sys->has_bc ? sys->dir_mask.ptr : nullptr;
+        const bool full  = n_cols == sys->n_rhs;
+        const bool sf    = not info.is_boundary and use.opts.eval_strategy != 1;
+        cudaError_t err;
+        if (sf)
+        {
+            const auto& t = ctx->tables1d(sys->mesh->order, use.nq);
+            err           = (full ? use.inst->mf_sumfact_full : use.inst->mf_sumfact_one)(kernelRegistry()[use.kernel_id].object.get(), a, t,
+                                                                                ctx->stream);
+        }
+        else
+        {
+            setDense(a, sys->mesh, use, info.is_boundary);
+            err = (full ? use.inst->local_apply_full : use.inst->local_apply_one)(kernelRegistry()[use.kernel_id].object.get(), a, ctx->stream);
+        }
+        cudaCheck(err, "operator apply launch");
+        if (a.n_work > 0)
+            ++launches;
+    }
+    if (sys->has_bc)
+    {
+        dirichletRowsKernel<<< gridFor(sys->n_dofs), 256, 0, ctx->stream >>>(sys->dir_mask.ptr, x, y, sys->n_dofs, sys->n_dofs, n_cols, alpha);
+        ++launches;
+    }
+    cudaCheck(cudaGetLastError(), "operator apply");
+    sys->last_launches = launches;
+}
+
+// Preconditioned CG, Belos "Block CG" semantics for block size 1 (solve/BelosSolvers.hpp:76-89): left preconditioner,
+// absolute 2-norm of the (unpreconditioned) residual against `tol`, x0 = 0. One fused vector kernel and one 2-scalar
+// read-back per iteration.
+template < typename Apply >
+void pcg(l3b_context* ctx, long long n, Apply&& apply, const double* diag, const double* b, double* x /* device */, double tol,
+         int max_iters, double* achieved, int* iters)
+{
+    DevBuf< double > r(n), z(n), p(n), Ap(n), minv(n);
+    if (ctx->scalars.n < 8)
+        ctx->scalars.alloc(8);
+    double*    sc = ctx->scalars.ptr; // [0] rz, [1] pAp, [2] rr, [3] rz_new
+    const auto s  = ctx->stream;
+    const auto g  = gridFor(n);
+    jacobiInvertKernel<<< g, 256, 0, s >>>(diag, minv.ptr, n, 1., 0.);
+    cudaCheck(cudaMemsetAsync(x, 0, n * sizeof(double), s), "memset");
+    cudaCheck(cudaMemcpyAsync(r.ptr, b, n * sizeof(double), cudaMemcpyDeviceToDevice, s), "copy");
+    hadamardKernel<<< g, 256, 0, s >>>(z.ptr, minv.ptr, r.ptr, n);
+    cudaCheck(cudaMemcpyAsync(p.ptr, z.ptr, n * sizeof(double), cudaMemcpyDeviceToDevice, s), "copy");
+    cudaCheck(cudaMemsetAsync(sc, 0, 8 * sizeof(double), s), "memset");
+    dot2Kernel<<< g, 256, 0, s >>>(r.ptr, r.ptr, r.ptr, z.ptr, n, sc + 2); // rr → sc[2], rz → sc[3]
+    double h[2];
+    cudaCheck(cudaMemcpyAsync(h, sc + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, s), "copy");
+    cudaCheck(cudaStreamSynchronize(s), "sync");
+    double rnorm = std::sqrt(h[0]);
+    int    it    = 0;
+    if (rnorm > tol)
+    {
+        cudaCheck(cudaMemcpyAsync(sc, sc + 3, sizeof(double), cudaMemcpyDeviceToDevice, s), "copy"); // rz
+        while (it < max_iters)
+        {
+            apply(p.ptr, Ap.ptr);
+            cudaCheck(cudaMemsetAsync(sc + 1, 0, 3 * sizeof(double), s), "memset");
+            dot2Kernel<<< g, 256, 0, s >>>(p.ptr, Ap.ptr, nullptr, nullptr, n, sc + 1);
+            cgUpdateKernel<<< g, 256, 0, s >>>(x, r.ptr, z.ptr, p.ptr, Ap.ptr, minv.ptr, n, sc, sc + 2);
+            cudaCheck(cudaMemcpyAsync(h, sc + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, s), "copy");
+            cudaCheck(cudaStreamSynchronize(s), "sync");
+            ++it;
+            rnorm = std::sqrt(h[0]);
+            if (not(rnorm > tol))
+                break;
+            cgDirectionKernel<<< g, 256, 0, s >>>(p.ptr, z.ptr, n, sc + 3, sc);
+            cudaCheck(cudaMemcpyAsync(sc, sc + 3, sizeof(double), cudaMemcpyDeviceToDevice, s), "copy");
+        }
+    }
+    cudaCheck(cudaGetLastError(), "pcg");
+    *achieved = rnorm;
+    *iters    = it;
+}
+} // namespace
+
+extern "C"
+{
+// ---- context
+int l3b_context_create(int device, l3b_context** out)
+{
+    return guardedCtx(nullptr, [&] {
+        int n_dev = 0;
+        if (cudaGetDeviceCount(&n_dev) != cudaSuccess or n_dev == 0)
+            fail(L3B_ERR_NO_DEVICE, "no CUDA device available: l3ster_b200 has no CPU fallback");
+        if (device < 0 or device >= n_dev)
+            fail(L3B_ERR_INVALID_ARG, "invalid device ordinal");
+        cudaCheck(cudaSetDevice(device), "cudaSetDevice");
+        auto ctx    = std::make_unique< l3b_context >();
+        ctx->device = device;
+        cudaCheck(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "stream create");
+        ctx->status.alloc(1);
+        ctx->status.zero(ctx->stream);
+        cudaDeviceProp prop{};
+        cudaCheck(cudaGetDeviceProperties(&prop, device), "device properties");
+        ctx->sm_count = prop.multiProcessorCount;
+        *out          = ctx.release();
+    });
+}
+void l3b_context_destroy(l3b_context* ctx)
+{
+    if (not ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    ctx->dense.clear();
+    ctx->status.release();
+    ctx->scalars.release();
+    if (ctx->stream)
+        cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+const char* l3b_last_error(const l3b_context* ctx)
+{
+    return ctx ? ctx->err.c_str() : g_global_error.c_str();
+}
+const char* l3b_global_error(void)
+{
+    return g_global_error.c_str();
+}
+int l3b_context_synchronize(l3b_context* ctx)
+{
+    return guardedCtx(ctx, [&] { cudaCheck(cudaStreamSynchronize(ctx->stream), "synchronize"); });
+}
+void* l3b_context_stream(l3b_context* ctx)
+{
+    return ctx->stream;
+}
+
+// ---- registry
+int l3b_kernel_count(void)
+{
+    return static_cast< int >(kernelRegistry().size());
+}
+int l3b_kernel_find(const char* name)
+{
+    return findKernel(name);
+}
+int l3b_kernel_get_info(int id, l3b_kernel_info* out)
+{
+    const auto& r = kernelRegistry();
+    if (id < 0 or id >= static_cast< int >(r.size()))
+        return L3B_ERR_INVALID_ARG;
+    const auto& i = r[id].info;
+    std::memset(out, 0, sizeof(*out));
+    std::strncpy(out->name, i.name.c_str(), sizeof(out->name) - 1);
+    out->dimension   = i.dim;
+    out->n_equations = i.n_equations;
+    out->n_unknowns  = i.n_unknowns;
+    out->n_fields    = i.n_fields;
+    out->n_rhs       = i.n_rhs;
+    out->is_boundary = i.is_boundary;
+    out->n_instances = static_cast< int >(r[id].instances.size());
+    return L3B_OK;
+}
+int l3b_kernel_get_instance(int id, int i, int* order, int* nq)
+{
+    const auto& r = kernelRegistry();
+    if (id < 0 or id >= static_cast< int >(r.size()) or i < 0 or i >= static_cast< int >(r[id].instances.size()))
+        return L3B_ERR_INVALID_ARG;
+    *order = r[id].instances[i].order;
+    *nq    = r[id].instances[i].nq;
+    return L3B_OK;
+}
+
+// ---- tables
+int l3b_tables_gll(int n, double* nodes)
+{
+    return guardedCtx(nullptr, [&] {
+        const auto x = tables::gllNodes(n);
+        for (int i = 0; i < n; ++i)
+            nodes[i] = static_cast< double >(x[i]);
+    });
+}
+int l3b_tables_gauss(int n, double* points, double* weights)
+{
+    return guardedCtx(nullptr, [&] {
+        std::vector< tables::ld > x, w;
+        tables::glRule(n, x, w);
+        for (int i = 0; i < n; ++i)
+        {
+            points[i]  = static_cast< double >(x[i]);
+            weights[i] = static_cast< double >(w[i]);
+        }
+    });
+}
+int l3b_tables_1d(int order, int nq, double* interp, double* der, double* colloc)
+{
+    return guardedCtx(nullptr, [&] {
+        const auto t = tables::makeTables1D(order, nq);
+        std::copy(t.interp.begin(), t.interp.end(), interp);
+        std::copy(t.der.begin(), t.der.end(), der);
+        if (colloc)
+            std::copy(t.colloc.begin(), t.colloc.end(), colloc);
+    });
+}
+int l3b_tables_dense(int dim, int order, int nq, int side, int* n_qp, double* points, double* weights, double* values, double* derivatives)
+{
+    return guardedCtx(nullptr, [&] {
+        std::vector< tables::ld > p, w;
+        if (side < 0)
+            tables::domainQuadrature(dim, nq, p, w);
+        else
+            tables::sideQuadrature(dim, nq, side, p, w);
+        const auto t = tables::makeDenseTables(dim, order, p, w);
+        *n_qp        = t.n_qp;
+        if (points)
+            std::copy(t.points.begin(), t.points.end(), points);
+        if (weights)
+            std::copy(t.weights.begin(), t.weights.end(), weights);
+        if (values)
+            std::copy(t.values.begin(), t.values.end(), values);
+        if (derivatives)
+            std::copy(t.derivatives.begin(), t.derivatives.end(), derivatives);
+    });
+}
+
+// ---- host mesh
+int l3b_host_mesh_cube(int nx, const double* x, int ny, const double* y, int nz, const double* z, int order, l3b_host_mesh** out)
+{
+    return guardedCtx(nullptr, [&] {
+        if (order < 1)
+            fail(L3B_ERR_INVALID_ARG, "order must be >= 1");
+        *out = new l3b_host_mesh{host::makeStructured(3, {x, x + nx}, {y, y + ny}, {z, z + nz}, order)};
+    });
+}
+int l3b_host_mesh_square(int nx, const double* x, int ny, const double* y, int order, l3b_host_mesh** out)
+{
+    return guardedCtx(nullptr, [&] {
+        if (order < 1)
+            fail(L3B_ERR_INVALID_ARG, "order must be >= 1");
+        *out = new l3b_host_mesh{host::makeStructured(2, {x, x + nx}, {y, y + ny}, {}, order)};
+    });
+}
+void l3b_host_mesh_destroy(l3b_host_mesh* m)
+{
+    delete m;
+}
+int l3b_host_mesh_info(const l3b_host_mesh* m, int64_t info[6])
+{
+    info[0] = m->mesh.dim;
+    info[1] = m->mesh.order;
+    info[2] = m->mesh.n_nodes;
+    info[3] = m->mesh.n_elems;
+    info[4] = m->mesh.nodes_per_elem;
+    info[5] = m->mesh.n_sides;
+    return L3B_OK;
+}
+const uint32_t* l3b_host_mesh_nodes(const l3b_host_mesh* m)
+{
+    return m->mesh.nodes.data();
+}
+const double* l3b_host_mesh_verts(const l3b_host_mesh* m)
+{
+    return m->mesh.verts.data();
+}
+const uint16_t* l3b_host_mesh_side_boundaries(const l3b_host_mesh* m)
+{
+    return m->mesh.side_bnd.data();
+}
+int l3b_node_graph(int64_t n_nodes, int64_t n_elems, int nn, const uint32_t* nodes, int64_t** ptr, uint32_t** nbr)
+{
+    return guardedCtx(nullptr, [&] {
+        const auto g = host::makeNodeGraph(n_nodes, n_elems, nn, nodes);
+        *ptr         = static_cast< int64_t* >(std::malloc(g.ptr.size() * sizeof(int64_t)));
+        *nbr         = static_cast< uint32_t* >(std::malloc(std::max< size_t >(1, g.nbr.size()) * sizeof(uint32_t)));
+        if (not *ptr or not *nbr)
+            fail(L3B_ERR_INVALID_ARG, "out of host memory");
+        for (size_t i = 0; i < g.ptr.size(); ++i)
+            (*ptr)[i] = g.ptr[i];
+        std::copy(g.nbr.begin(), g.nbr.end(), *nbr);
+    });
+}
+int l3b_graph_expand(int64_t n_nodes, const int64_t* ptr, const uint32_t* nbr, int dpn, int64_t* row_ptr, int32_t* col_ind)
+{
+    for (int64_t n = 0; n < n_nodes; ++n)
+    {
+        const int64_t deg = ptr[n + 1] - ptr[n];
+        for (int d = 0; d < dpn; ++d)
+        {
+            const int64_t beg    = dpn * (dpn * ptr[n] + d * deg);
+            row_ptr[n * dpn + d] = beg;
+            if (col_ind)
+                for (int64_t k = 0; k < deg; ++k)
+                    for (int v = 0; v < dpn; ++v)
+                        col_ind[beg + k * dpn + v] = static_cast< int32_t >(nbr[ptr[n] + k]) * dpn + v;
+        }
+    }
+    row_ptr[n_nodes * dpn] = ptr[n_nodes] * dpn * dpn;
+    return L3B_OK;
+}
+void l3b_free(void* p)
+{
+    std::free(p);
+}
+
+// ---- device mesh
+int l3b_mesh_upload(l3b_context* ctx, int dim, int order, int64_t n_elems, const double* verts, const uint32_t* nodes,
+                    const uint16_t* side_boundaries, int64_t n_local_nodes, int64_t n_owned_nodes, l3b_mesh** out)
+{
+    return guardedCtx(ctx, [&] {
+        if (dim != 2 and dim != 3)
+            fail(L3B_ERR_INVALID_ARG, "only quad (dim 2) and hex (dim 3) elements are supported");
+        auto m           = std::make_unique< l3b_mesh >();
+        m->ctx           = ctx;
+        m->dim           = dim;
+        m->order         = order;
+        m->nn            = cpow(order + 1, dim);
+        m->n_sides       = 2 * dim;
+        m->n_elems       = n_elems;
+        m->n_local_nodes = n_local_nodes;
+        m->n_owned_nodes = n_owned_nodes;
+        const size_t nv  = static_cast< size_t >(n_elems) * (1 << dim) * 3;
+        m->verts.alloc(nv);
+        m->verts.upload(verts, nv, ctx->stream);
+        m->nodes.alloc(static_cast< size_t >(n_elems) * m->nn);
+        m->nodes.upload(nodes, static_cast< size_t >(n_elems) * m->nn, ctx->stream);
+        if (side_boundaries)
+            m->side_bnd.assign(side_boundaries, side_boundaries + n_elems * m->n_sides);
+        cudaCheck(cudaStreamSynchronize(ctx->stream), "mesh upload");
+        *out = m.release();
+    });
+}
+void l3b_mesh_destroy(l3b_mesh* mesh)
+{
+    delete mesh;
+}
+
+// ---- fields
+int l3b_fields_upload(l3b_context* ctx, int64_t n_local_nodes, int n_fields, const double* data, l3b_fields** out)
+{
+    return guardedCtx(ctx, [&] {
+        auto f      = std::make_unique< l3b_fields >();
+        f->ctx      = ctx;
+        f->n_nodes  = n_local_nodes;
+        f->n_fields = n_fields;
+        f->data.alloc(static_cast< size_t >(n_local_nodes) * n_fields);
+        f->data.upload(data, f->data.n, ctx->stream);
+        cudaCheck(cudaStreamSynchronize(ctx->stream), "fields upload");
+        *out = f.release();
+    });
+}
+int l3b_fields_update(l3b_fields* f, const double* data)
+{
+    return guardedCtx(f->ctx, [&] {
+        f->data.upload(data, f->data.n, f->ctx->stream);
+        cudaCheck(cudaStreamSynchronize(f->ctx->stream), "fields upload");
+    });
+}
+void l3b_fields_destroy(l3b_fields* f)
+{
+    delete f;
+}
+
+// ---- assembled system
+int l3b_asm_create(l3b_context* ctx, l3b_mesh* mesh, int dpn, int n_rhs, const int64_t* node_ptr, const uint32_t* node_nbr, l3b_asm** out)
+{
+    return guardedCtx(ctx, [&] {
+        auto s       = std::make_unique< l3b_asm >();
+        s->ctx       = ctx;
+        s->mesh      = mesh;
+        s->dpn       = dpn;
+        s->n_rhs     = n_rhs;
+        const auto N = mesh->n_local_nodes;
+        s->n_dofs    = N * dpn;
+        s->nnz       = node_ptr[N] * dpn * dpn;
+        s->node_ptr.alloc(N + 1);
+        s->node_nbr.alloc(node_ptr[N]);
+        static_assert(sizeof(long long) == sizeof(int64_t));
+        s->node_ptr.upload(reinterpret_cast< const long long* >(node_ptr), N + 1, ctx->stream);
+        s->node_nbr.upload(node_nbr, node_ptr[N], ctx->stream);
+        s->row_ptr.alloc(s->n_dofs + 1);
+        rowPtrKernel<<< static_cast< unsigned >((s->n_dofs + 1 + 255) / 256), 256, 0, ctx->stream >>>(s->node_ptr.ptr, N, dpn, s->row_ptr.ptr);
+        s->values.alloc(s->nnz);
+        s->rhs.alloc(s->n_dofs * n_rhs);
+        const long long n_pos = mesh->n_elems * mesh->nn * mesh->nn;
+        s->slot_pos.alloc(n_pos);
+        slotMapKernel<<< static_cast< unsigned >((n_pos + 255) / 256), 256, 0, ctx->stream >>>(mesh->nodes.ptr, mesh->n_elems, mesh->nn,
+                                                                                           s->node_ptr.ptr, s->node_nbr.ptr,
+                                                                                           s->slot_pos.ptr, ctx->status.ptr);
+        cudaCheck(cudaGetLastError(), "slot map");
+        ctx->checkStatus();
+        cudaCheck(cudaEventCreate(&s->ev0), "event");
+        cudaCheck(cudaEventCreate(&s->ev1), "event");
+        *out = s.release();
+    });
+}
+void l3b_asm_destroy(l3b_asm* sys)
+{
+    delete sys;
+}
+int64_t l3b_asm_nnz(const l3b_asm* sys)
+{
+    return sys->nnz;
+}
+int l3b_asm_begin_assembly(l3b_asm* sys)
+{
+    return guardedCtx(sys->ctx, [&] {
+        sys->values.zero(sys->ctx->stream);
+        sys->rhs.zero(sys->ctx->stream);
+        sys->open = true;
+    });
+}
+int l3b_asm_assemble(l3b_asm* sys, int kernel_id, l3b_asm_opts opts, double time, const int* dof_inds, const l3b_fields* fields,
+                     const int* field_inds, const int* boundary_ids, int n_boundary_ids)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (not sys->open)
+            fail(L3B_ERR_STATE, "`assembleProblem()` was called before `beginAssembly()`");
+        const auto  use  = makeUse(sys->mesh, sys->dpn, sys->n_rhs, kernel_id, opts, time, dof_inds, fields, field_inds, boundary_ids, n_boundary_ids);
+        const auto& info = kernelRegistry()[kernel_id].info;
+        ElemArgs    a    = baseArgs(sys->mesh, use, sys->dpn, sys->n_dofs);
+        setDense(a, sys->mesh, use, info.is_boundary);
+        a.row_ptr  = sys->row_ptr.ptr;
+        a.slot_pos = sys->slot_pos.ptr;
+        a.crs_vals = sys->values.ptr;
+        a.rhs      = sys->rhs.ptr;
+        cudaCheck(cudaEventRecord(sys->ev0, sys->ctx->stream), "event record");
+        cudaCheck(use.inst->assemble(kernelRegistry()[kernel_id].object.get(), a, sys->ctx->stream), "assembly launch");
+        cudaCheck(cudaEventRecord(sys->ev1, sys->ctx->stream), "event record");
+        sys->ctx->checkStatus();
+        float ms = 0.f;
+        cudaCheck(cudaEventElapsedTime(&ms, sys->ev0, sys->ev1), "event elapsed");
+        sys->last_ms = ms;
+    });
+}
+int l3b_asm_end_assembly(l3b_asm* sys, int64_t n_dir, const int32_t* dofs, const double* vals)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (not sys->open)
+            fail(L3B_ERR_STATE, "`endAssembly()` was called more than once");
+        if (n_dir > 0)
+        {
+            std::vector< uint8_t > mask(sys->n_dofs, 0);
+            std::vector< double >  bc(static_cast< size_t >(sys->n_dofs) * sys->n_rhs, 0.);
+            for (int64_t i = 0; i < n_dir; ++i)
+            {
+                if (dofs[i] < 0 or dofs[i] >= sys->n_dofs)
+                    fail(L3B_ERR_INVALID_ARG, "Dirichlet dof out of range");
+                mask[dofs[i]] = 1;
+                for (int c = 0; c < sys->n_rhs; ++c)
+                    bc[dofs[i] + static_cast< size_t >(c) * sys->n_dofs] = vals[i + c * n_dir];
+            }
+            DevBuf< uint8_t > d_mask(mask.size());
+            DevBuf< double >  d_bc(bc.size());
+            d_mask.upload(mask.data(), mask.size(), sys->ctx->stream);
+            d_bc.upload(bc.data(), bc.size(), sys->ctx->stream);
+            const long long threads = sys->n_dofs * 32;
+            dirichletAlgebraicKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
+                sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, d_mask.ptr, d_bc.ptr, sys->rhs.ptr,
+                sys->n_dofs, sys->n_rhs);
+            cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "Dirichlet BC application");
+        }
+        sys->open = false;
+    });
+}
+int l3b_asm_download(l3b_asm* sys, double* values, double* rhs)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (values)
+            sys->values.download(values, sys->nnz, sys->ctx->stream);
+        if (rhs)
+            sys->rhs.download(rhs, sys->rhs.n, sys->ctx->stream);
+        cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "download");
+    });
+}
+double* l3b_asm_device_values(l3b_asm* sys)
+{
+    return sys->values.ptr;
+}
+int l3b_asm_spmv(l3b_asm* sys, const double* x, double* y)
+{
+    return guardedCtx(sys->ctx, [&] {
+        DevBuf< double > dx(sys->n_dofs), dy(sys->n_dofs);
+        dx.upload(x, sys->n_dofs, sys->ctx->stream);
+        const long long threads = sys->n_dofs * 32;
+        spmvKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
+            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, dx.ptr, dy.ptr);
+        dy.download(y, sys->n_dofs, sys->ctx->stream);
+        cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "spmv");
+    });
+}
+int l3b_asm_solve_cg(l3b_asm* sys, double tol, int max_iters, double* x, double* achieved_tol, int* iters)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (sys->open)
+            fail(L3B_ERR_STATE, "`solve()` was called before `endAssembly()`");
+        const auto       n = sys->n_dofs;
+        DevBuf< double > diag(n), dx(n);
+        extractDiagKernel<<< static_cast< unsigned >((n + 255) / 256), 256, 0, sys->ctx->stream >>>(
+            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, diag.ptr);
+        const long long threads = n * 32;
+        pcg(
+            sys->ctx, n,
+            [&](const double* in, double* out) {
+                spmvKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
+                    sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, in, out);
+            },
+            diag.ptr, sys->rhs.ptr, dx.ptr, tol, max_iters, achieved_tol, iters);
+        dx.download(x, n, sys->ctx->stream);
+        cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "solve");
+    });
+}
+double l3b_asm_last_kernel_ms(const l3b_asm* sys)
+{
+    return sys->last_ms;
+}
+
+// ---- matrix-free system
+int l3b_mf_create(l3b_context* ctx, l3b_mesh* mesh, int dpn, int n_rhs, const uint8_t* mask, const double* vals, l3b_mf** out)
+{
+    return guardedCtx(ctx, [&] {
+        auto s    = std::make_unique< l3b_mf >();
+        s->ctx    = ctx;
+        s->mesh   = mesh;
+        s->dpn    = dpn;
+        s->n_rhs  = n_rhs;
+        s->n_dofs = mesh->n_local_nodes * dpn;
+        s->diag.alloc(s->n_dofs);
+        s->rhs.alloc(s->n_dofs * n_rhs);
+        if (mask)
+        {
+            s->has_bc = true;
+            s->dir_mask.alloc(s->n_dofs);
+            s->dir_mask.upload(mask, s->n_dofs, ctx->stream);
+            s->dir_vals.alloc(s->n_dofs * n_rhs);
+            if (vals)
+                s->dir_vals.upload(vals, s->dir_vals.n, ctx->stream);
+            else
+                s->dir_vals.zero(ctx->stream);
+            cudaCheck(cudaStreamSynchronize(ctx->stream), "Dirichlet upload");
+        }
+        *out = s.release();
+    });
+}
+void l3b_mf_destroy(l3b_mf* sys)
+{
+    delete sys;
+}
+int l3b_mf_assemble(l3b_mf* sys, int kernel_id, l3b_asm_opts opts, double time, const int* dof_inds, const l3b_fields* fields,
+                    const int* field_inds, const int* boundary_ids, int n_boundary_ids)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (sys->closed)
+            fail(L3B_ERR_STATE, "`assembleProblem()` was called after `endAssembly()`");
+        sys->uses.push_back(makeUse(sys->mesh, sys->dpn, sys->n_rhs, kernel_id, opts, time, dof_inds, fields, field_inds, boundary_ids, n_boundary_ids));
+    });
+}
+int l3b_mf_end_assembly(l3b_mf* sys)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (sys->closed)
+            fail(L3B_ERR_STATE, "`endAssembly()` was called more than once");
+        auto* ctx = sys->ctx;
+        sys->diag.zero(ctx->stream);
+        sys->rhs.zero(ctx->stream);
+        for (const auto& use : sys->uses)
+        {
+            const auto& info = kernelRegistry()[use.kernel_id].info;
+            ElemArgs    a    = baseArgs(sys->mesh, use, sys->dpn, sys->n_dofs);
+            setDense(a, sys->mesh, use, info.is_boundary);
+            a.dir_mask = sys->has_bc ? sys->dir_mask.ptr : nullptr;
+            a.dir_vals = sys->has_bc ? sys->dir_vals.ptr : nullptr;
+            a.diag     = sys->diag.ptr;
+            a.rhs      = sys->rhs.ptr;
+            cudaCheck(use.inst->init(kernelRegistry()[use.kernel_id].object.get(), a, ctx->stream), "init launch");
+        }
+        if (sys->has_bc)
+            dirichletInitKernel<<< gridFor(sys->n_dofs), 256, 0, ctx->stream >>>(sys->dir_mask.ptr, sys->dir_vals.ptr, sys->diag.ptr, sys->rhs.ptr,
+                                                                             sys->n_dofs, sys->n_dofs, sys->n_rhs);
+        cudaCheck(cudaGetLastError(), "init");
+        ctx->checkStatus();
+        sys->closed = true;
+    });
+}
+int l3b_mf_download(l3b_mf* sys, double* diag, double* rhs)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (diag)
+            sys->diag.download(diag, sys->n_dofs, sys->ctx->stream);
+        if (rhs)
+            sys->rhs.download(rhs, sys->rhs.n, sys->ctx->stream);
+        cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "download");
+    });
+}
+int l3b_mf_apply_device(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta)
+{
+    return guardedCtx(sys->ctx, [&] { mfApplyDevice(sys, x, y, n_cols, alpha, beta); });
+}
+int l3b_mf_apply(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta)
+{
+    return guardedCtx(sys->ctx, [&] {
+        const size_t n = static_cast< size_t >(sys->n_dofs) * n_cols;
+        if (sys->work_x.n < n)
+        {
+            sys->work_x.alloc(n);
+            sys->work_y.alloc(n);
+        }
+        sys->work_x.upload(x, n, sys->ctx->stream);
+        if (beta != 0.)
+            sys->work_y.upload(y, n, sys->ctx->stream);
+        mfApplyDevice(sys, sys->work_x.ptr, sys->work_y.ptr, n_cols, alpha, beta);
+        sys->work_y.download(y, n, sys->ctx->stream);
+        cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "apply");
+        sys->ctx->checkStatus();
+    });
+}
+int l3b_mf_solve_cg(l3b_mf* sys, double tol, int max_iters, double* x, double* achieved_tol, int* iters)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (not sys->closed)
+            fail(L3B_ERR_STATE, "`solve()` was called before `endAssembly()`");
+        if (sys->n_rhs != 1)
+            fail(L3B_ERR_INVALID_ARG, "the CG driver handles one right-hand side");
+        DevBuf< double > dx(sys->n_dofs);
+        pcg(
+            sys->ctx, sys->n_dofs, [&](const double* in, double* out) { mfApplyDevice(sys, in, out, 1, 1., 0.); }, sys->diag.ptr, sys->rhs.ptr,
+            dx.ptr, tol, max_iters, achieved_tol, iters);
+        dx.download(x, sys->n_dofs, sys->ctx->stream);
+        cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "solve");
+    });
+}
+int64_t l3b_mf_num_dofs(const l3b_mf* sys)
+{
+    return sys->n_dofs;
+}
+int l3b_mf_kernel_launches(const l3b_mf* sys)
+{
+    return sys->last_launches;
+}
+} // extern "C"

@@ -1,0 +1,218 @@
+// Device-callable mirror of the reference's user-kernel API (include/l3ster/common/KernelInterface.hpp:13-204).
+//
+// The parameter structure is the reference's: a kernel is a callable `(const Input&, Result&) -> void` that fills
+// `A0, A1..AD` (E x U each) and `rhs` (E x n_rhs) per quadrature point, starting from a zero-initialised Result.
+// The same source idiom works on the device:
+//
+//     auto& [operators, rhs] = out;  auto& [A0, Ax, Ay, Az] = operators;  Ax(0, 1) = -k;  rhs[0] = s;
+//     const auto& [vals, ders, point] = in;   in.normal[0];   in.point.space.x();
+//
+// Differences forced by the device: the callable is a by-value functor whose operator() is `__host__ __device__`
+// (reference kernels are host lambdas, some capturing by reference), and Eigen types are replaced by the tiny fixed-size
+// types below (same element access syntax, same column-major storage).
+#ifndef L3B_KERNEL_INTERFACE_CUH
+#define L3B_KERNEL_INTERFACE_CUH
+
+#include <cstddef>
+#include <tuple>
+#include <type_traits>
+#include <utility>
+
+#ifdef __CUDACC__
+#define L3B_HD __host__ __device__ __forceinline__
+#else
+#define L3B_HD inline
+#endif
+
+namespace l3b
+{
+using val_t = double;
+using dim_t = unsigned char;
+using std::size_t;
+
+// common/KernelInterface.hpp:13-20
+struct KernelParams
+{
+    int    dimension;
+    size_t n_equations;
+    size_t n_unknowns = 1;
+    size_t n_fields   = 0;
+    size_t n_rhs      = 1;
+};
+
+// fixed-size array with the tuple protocol (structured bindings on host and device)
+template < typename T, size_t N >
+struct Array
+{
+    T                       v[N > 0 ? N : 1];
+    L3B_HD constexpr T&       operator[](size_t i) { return v[i]; }
+    L3B_HD constexpr const T& operator[](size_t i) const { return v[i]; }
+    L3B_HD static constexpr size_t size() { return N; }
+    template < size_t I >
+    L3B_HD constexpr T& get()
+    {
+        static_assert(I < N);
+        return v[I];
+    }
+    template < size_t I >
+    L3B_HD constexpr const T& get() const
+    {
+        static_assert(I < N);
+        return v[I];
+    }
+};
+
+// column-major R x C matrix: the storage order of Eigen::Matrix<val_t, R, C> (KernelInterface.hpp:32-33)
+template < size_t R, size_t C >
+struct Matrix
+{
+    val_t                       v[R * C > 0 ? R * C : 1];
+    L3B_HD constexpr val_t&       operator()(size_t i, size_t j) { return v[i + j * R]; }
+    L3B_HD constexpr const val_t& operator()(size_t i, size_t j) const { return v[i + j * R]; }
+    L3B_HD constexpr val_t&       operator[](size_t i) { return v[i]; } // vector-style access, as Eigen allows for C == 1
+    L3B_HD constexpr const val_t& operator[](size_t i) const { return v[i]; }
+    L3B_HD constexpr void         setZero()
+    {
+        for (size_t i = 0; i < R * C; ++i)
+            v[i] = 0.;
+    }
+    static constexpr size_t rows = R, cols = C;
+};
+
+// common/Structs.hpp:10-86
+template < size_t DIM >
+struct Point
+{
+    val_t                       coords[DIM];
+    L3B_HD constexpr val_t        operator[](size_t i) const { return coords[i]; }
+    L3B_HD constexpr val_t&       operator[](size_t i) { return coords[i]; }
+    L3B_HD constexpr val_t        x() const { return coords[0]; }
+    L3B_HD constexpr val_t        y() const
+    {
+        static_assert(DIM >= 2);
+        return coords[1];
+    }
+    L3B_HD constexpr val_t z() const
+    {
+        static_assert(DIM >= 3);
+        return coords[2];
+    }
+};
+struct SpaceTimePoint
+{
+    Point< 3 > space;
+    val_t      time;
+};
+
+// common/KernelInterface.hpp:29-57
+template < KernelParams params >
+struct KernelInterface
+{
+    using Operator = Matrix< params.n_equations, params.n_unknowns >;
+    using Rhs      = Matrix< params.n_equations, params.n_rhs >;
+    struct Result
+    {
+        Array< Operator, params.dimension + 1 > operators;
+        Rhs                                     rhs;
+    };
+    using FieldVals = Array< val_t, params.n_fields >;
+    using FieldDers = Array< FieldVals, params.dimension >;
+    using Normal    = Array< val_t, params.dimension >;
+    struct DomainInput
+    {
+        FieldVals      field_vals;
+        FieldDers      field_ders;
+        SpaceTimePoint point;
+    };
+    struct BoundaryInput
+    {
+        FieldVals      field_vals;
+        FieldDers      field_ders;
+        SpaceTimePoint point;
+        Normal         normal;
+    };
+};
+
+// common/KernelInterface.hpp:102-138: wrappers zero-initialise the result, then invoke the user callable
+template < typename Kernel, KernelParams params >
+struct DomainEquationKernel
+{
+    static constexpr auto parameters  = params;
+    static constexpr bool is_boundary = false;
+    using Input                       = typename KernelInterface< params >::DomainInput;
+    using Result                      = typename KernelInterface< params >::Result;
+    constexpr DomainEquationKernel(Kernel kernel) : m_kernel{kernel} {}
+    L3B_HD Result operator()(const Input& input) const
+    {
+        Result retval;
+        for (size_t i = 0; i <= static_cast< size_t >(params.dimension); ++i)
+            retval.operators[i].setZero();
+        retval.rhs.setZero();
+        m_kernel(input, retval);
+        return retval;
+    }
+    Kernel m_kernel;
+};
+template < typename Kernel, KernelParams params >
+struct BoundaryEquationKernel
+{
+    static constexpr auto parameters  = params;
+    static constexpr bool is_boundary = true;
+    using Input                       = typename KernelInterface< params >::BoundaryInput;
+    using Result                      = typename KernelInterface< params >::Result;
+    constexpr BoundaryEquationKernel(Kernel kernel) : m_kernel{kernel} {}
+    L3B_HD Result operator()(const Input& input) const
+    {
+        Result retval;
+        for (size_t i = 0; i <= static_cast< size_t >(params.dimension); ++i)
+            retval.operators[i].setZero();
+        retval.rhs.setZero();
+        m_kernel(input, retval);
+        return retval;
+    }
+    Kernel m_kernel;
+};
+
+// common/KernelInterface.hpp:178-190
+template < KernelParams params, typename Kernel >
+constexpr auto wrapDomainEquationKernel(Kernel kernel)
+{
+    return DomainEquationKernel< Kernel, params >{kernel};
+}
+template < KernelParams params, typename Kernel >
+constexpr auto wrapBoundaryEquationKernel(Kernel kernel)
+{
+    return BoundaryEquationKernel< Kernel, params >{kernel};
+}
+
+// algsys/AssembleLocalSystem.hpp:16-49
+enum struct LocalEvalStrategy : int
+{
+    Auto                                 = 0,
+    LocalElement                         = 1,
+    SumFactorization                     = 2,
+    SumFactorizationOddEvenDecomposition = 3
+};
+struct AssemblyOptions
+{
+    int               value_order      = 1;
+    int               derivative_order = 0;
+    LocalEvalStrategy eval_strategy    = LocalEvalStrategy::Auto;
+    constexpr int     order(int elem_order) const { return value_order * elem_order + derivative_order * (elem_order - 1); }
+    // quad/ReferenceQuadrature.hpp:13-22 applied to QO = 2 * order(EO) (algsys/AssembleGlobalSystem.hpp:42)
+    constexpr int nq1d(int elem_order) const { return (2 * order(elem_order)) / 2 + 1; }
+};
+} // namespace l3b
+
+namespace std
+{
+template < typename T, size_t N >
+struct tuple_size< l3b::Array< T, N > > : integral_constant< size_t, N >
+{};
+template < size_t I, typename T, size_t N >
+struct tuple_element< I, l3b::Array< T, N > >
+{
+    using type = T;
+};
+} // namespace std
+#endif

@@ -1,0 +1,275 @@
+// Device-callable restatements of the equation kernels used by the reference's tests, benchmarks and examples, written in
+// the reference's own idiom (structured bindings on `out`, `A(i, j) = ...`). Each is registered for the element orders
+// the parity tests and the benchmarks need (see the .cu files next to this header).
+#ifndef L3B_BUILTIN_KERNELS_CUH
+#define L3B_BUILTIN_KERNELS_CUH
+
+#include "../kernel_interface.cuh"
+
+namespace l3b::kernels
+{
+// tests/Kernels.hpp:5-25
+struct Diffusion2D
+{
+    template < typename In, typename Out >
+    L3B_HD void operator()(const In&, Out& out) const
+    {
+        auto& [operators, rhs] = out;
+        auto& [A0, Ax, Ay]     = operators;
+        constexpr double lambda = 1.;
+        Ax(0, 1) = -lambda;
+        Ay(0, 2) = -lambda;
+        A0(1, 1) = -1.;
+        Ax(1, 0) = 1.;
+        A0(2, 2) = -1.;
+        Ay(2, 0) = 1.;
+        Ax(3, 2) = 1.;
+        Ay(3, 1) = -1.;
+    }
+};
+
+// tests/Kernels.hpp:27-54
+struct Diffusion2DVar
+{
+    template < typename In, typename Out >
+    L3B_HD void operator()(const In& in, Out& out) const
+    {
+        const auto& [field_vals, field_ders, _] = in;
+        const auto lambda                       = field_vals[0];
+        const auto& [dx, dy]                    = field_ders;
+        const auto dl_dx                        = dx[0];
+        const auto dl_dy                        = dy[0];
+        auto& [operators, rhs] = out;
+        auto& [A0, Ax, Ay]     = operators;
+        A0(0, 1) = -dl_dx;
+        A0(0, 2) = -dl_dy;
+        Ax(0, 1) = -lambda;
+        Ay(0, 2) = -lambda;
+        A0(1, 1) = -1.;
+        Ax(1, 0) = 1.;
+        A0(2, 2) = -1.;
+        Ay(2, 0) = 1.;
+        Ax(3, 2) = 1.;
+        Ay(3, 1) = -1.;
+    }
+};
+
+// tests/Kernels.hpp:56-83; with `source`: benchmarks/Diffusion3D.hpp:50-79 and benchmarks/Kernels.hpp:91-118
+template < bool with_source >
+struct Diffusion3D
+{
+    template < typename In, typename Out >
+    L3B_HD void operator()(const In&, Out& out) const
+    {
+        auto& [operators, rhs] = out;
+        auto& [A0, Ax, Ay, Az] = operators;
+        constexpr double k = 1.; // diffusivity
+        constexpr double s = 1.; // source
+        // -k * div q = s
+        Ax(0, 1) = -k;
+        Ay(0, 2) = -k;
+        Az(0, 3) = -k;
+        if constexpr (with_source)
+            rhs[0] = s;
+        // grad T = q
+        A0(1, 1) = -1.;
+        Ax(1, 0) = 1.;
+        A0(2, 2) = -1.;
+        Ay(2, 0) = 1.;
+        A0(3, 3) = -1.;
+        Az(3, 0) = 1.;
+        // rot q = 0
+        Ay(4, 3) = 1.;
+        Az(4, 2) = -1.;
+        Ax(5, 3) = -1.;
+        Az(5, 1) = 1.;
+        Ax(6, 2) = 1.;
+        Ay(6, 1) = -1.;
+    }
+};
+
+// tests/Kernels.hpp:85-118
+struct Diffusion3DVar
+{
+    template < typename In, typename Out >
+    L3B_HD void operator()(const In& in, Out& out) const
+    {
+        const auto& [field_vals, field_ders, _] = in;
+        const auto lambda                       = field_vals[0];
+        const auto& [dx, dy, dz]                = field_ders;
+        const auto dl_dx                        = dx[0];
+        const auto dl_dy                        = dy[0];
+        const auto dl_dz                        = dz[0];
+        auto& [operators, rhs] = out;
+        auto& [A0, Ax, Ay, Az] = operators;
+        A0(0, 1) = -dl_dx;
+        A0(0, 2) = -dl_dy;
+        A0(0, 3) = -dl_dz;
+        Ax(0, 1) = -lambda;
+        Ay(0, 2) = -lambda;
+        Az(0, 3) = -lambda;
+        A0(1, 1) = -1.;
+        Ax(1, 0) = 1.;
+        A0(2, 2) = -1.;
+        Ay(2, 0) = 1.;
+        A0(3, 3) = -1.;
+        Az(3, 0) = 1.;
+        Ay(4, 3) = 1.;
+        Az(4, 2) = -1.;
+        Ax(5, 3) = -1.;
+        Az(5, 1) = 1.;
+        Ax(6, 2) = 1.;
+        Ay(6, 1) = -1.;
+    }
+};
+
+// tests/Kernels.hpp:120-128
+struct AdiabaticBC2D
+{
+    template < typename In, typename Out >
+    L3B_HD void operator()(const In& in, Out& out) const
+    {
+        const auto& [vals, ders, point, normal] = in;
+        auto& [operators, rhs]                  = out;
+        auto& [A0, A1, A2]                      = operators;
+        A0(0, 1) = normal[0];
+        A0(0, 2) = normal[1];
+    }
+};
+
+// examples/02-diffusion-2D/source.cpp:45-67
+struct Example02Domain
+{
+    template < typename In, typename Out >
+    L3B_HD void operator()(const In&, Out& out) const
+    {
+        auto& [operators, rhs] = out;
+        auto& [A0, A1, A2]     = operators;
+        A1(0, 1) = -1.;
+        A2(0, 2) = -1.;
+        rhs[0]   = 1.;
+        A0(1, 1) = -1.;
+        A1(1, 0) = 1.;
+        A0(2, 2) = -1.;
+        A2(2, 0) = 1.;
+        A1(3, 2) = 1.;
+        A2(3, 1) = -1.;
+    }
+};
+
+// examples/02-diffusion-2D/source.cpp:68-81
+struct Example02BC
+{
+    template < typename In, typename Out >
+    L3B_HD void operator()(const In& in, Out& out) const
+    {
+        const auto& normal = in.normal;
+        const auto  nx     = normal[0];
+        const auto  ny     = normal[1];
+        auto& [operators, rhs] = out;
+        auto& [A0, A1, A2]     = operators;
+        A0(0, 0) = 1.;
+        A0(0, 1) = nx;
+        A0(0, 2) = ny;
+    }
+};
+
+// benchmarks/Kernels.hpp:3-65
+struct NS3D
+{
+    template < typename In, typename Out >
+    L3B_HD void operator()(const In& in, Out& out) const
+    {
+        const auto& [vals, ders, point]             = in;
+        const auto& [u, v, w, p, ox, oy, oz]        = vals;
+        const auto& [x_ders, y_ders, z_ders]        = ders;
+        const auto& [ux, vx, wx, px, oxx, oyx, ozx] = x_ders;
+        const auto& [uy, vy, wy, py, oxy, oyy, ozy] = y_ders;
+        const auto& [uz, vz, wz, pz, oxz, oyz, ozz] = z_ders;
+        auto& [operators, rhs] = out;
+        auto& [A0, A1, A2, A3] = operators;
+        constexpr double Re_inv = 1e-3;
+        A0(0, 0) = ux;
+        A0(0, 1) = uy;
+        A0(0, 2) = uz;
+        A0(1, 0) = vx;
+        A0(1, 1) = vy;
+        A0(1, 2) = vz;
+        A0(2, 0) = wx;
+        A0(2, 1) = wy;
+        A0(2, 2) = wz;
+        A0(3, 4) = 1.;
+        A0(4, 5) = 1.;
+        A0(5, 6) = 1.;
+        A1(0, 0) = u;
+        A1(0, 3) = 1.;
+        A1(1, 1) = u;
+        A1(1, 6) = -Re_inv;
+        A1(2, 2) = u;
+        A1(2, 5) = Re_inv;
+        A1(4, 2) = -1.;
+        A1(5, 1) = 1.;
+        A1(6, 0) = 1.;
+        A1(7, 4) = 1.;
+        A2(0, 0) = v;
+        A2(0, 3) = 1.;
+        A2(0, 6) = Re_inv;
+        A2(1, 1) = v;
+        A2(2, 2) = v;
+        A2(2, 4) = -Re_inv;
+        A2(3, 2) = 1.;
+        A2(5, 0) = -1.;
+        A2(6, 1) = 1.;
+        A2(7, 5) = 1.;
+        A3(0, 0) = w;
+        A3(0, 3) = 1.;
+        A3(0, 5) = -Re_inv;
+        A3(1, 1) = w;
+        A3(1, 4) = Re_inv;
+        A3(2, 2) = w;
+        A3(3, 1) = -1.;
+        A3(4, 0) = 1.;
+        A3(6, 2) = 1.;
+        A3(7, 6) = 1.;
+        rhs[0] = u * ux + v * uy + w * uz;
+        rhs[1] = u * vx + v * vy + w * vz;
+        rhs[2] = u * wx + v * wy + w * wz;
+    }
+};
+
+// Not in the reference: dense, space-/time-/field-dependent probes (same formulas as oracle/kernels.cpp) that leave no
+// structural zero for an indexing or layout mistake to hide behind.
+struct DenseProbe3D
+{
+    template < typename In, typename Out >
+    L3B_HD void operator()(const In& in, Out& out) const
+    {
+        constexpr int E = 5, U = 3;
+        for (int i = 0; i <= 3; ++i)
+            for (int e = 0; e < E; ++e)
+                for (int u = 0; u < U; ++u)
+                    out.operators[i](e, u) = 0.1 * (i + 1) + 0.01 * (e + 1) * (u + 2) + 0.3 * in.point.space[0] -
+                                             0.2 * in.point.space[1] * (i == 2) + 0.05 * in.field_vals[0] * (e == u) +
+                                             0.07 * in.field_ders[(e + u) % 3][1] + 0.01 * in.point.time;
+        for (int e = 0; e < E; ++e)
+            out.rhs[e] = 1. + 0.5 * e + in.point.space[0] * in.field_vals[1];
+    }
+};
+struct DenseProbe2D
+{
+    template < typename In, typename Out >
+    L3B_HD void operator()(const In& in, Out& out) const
+    {
+        constexpr int E = 4, U = 2;
+        for (int i = 0; i <= 2; ++i)
+            for (int e = 0; e < E; ++e)
+                for (int u = 0; u < U; ++u)
+                    out.operators[i](e, u) = 0.1 * (i + 1) + 0.01 * (e + 1) * (u + 2) + 0.3 * in.point.space[0] -
+                                             0.2 * in.point.space[1] * (i == 2) + 0.05 * in.field_vals[0] * (e == u) +
+                                             0.07 * in.field_ders[(e + u) % 2][1] + 0.01 * in.point.time;
+        for (int e = 0; e < E; ++e)
+            out.rhs[e] = 1. + 0.5 * e + in.point.space[1] * in.field_vals[1];
+    }
+};
+} // namespace l3b::kernels
+#endif

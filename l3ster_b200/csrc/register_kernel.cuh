@@ -1,0 +1,136 @@
+// Instantiation + registration of a user kernel for a list of (order, nq) pairs. Include from a .cu file:
+//
+//     struct MyKernel { template <class In, class Out> __host__ __device__ void operator()(const In& in, Out& out) const {...} };
+//     L3B_REGISTER_DOMAIN_KERNEL(my_kernel, MyKernel, (l3b::KernelParams{.dimension = 3, .n_equations = 7, .n_unknowns = 4}),
+//                                L3B_PQ(4, 5), L3B_PQ(6, 7));
+//
+// mirrors `wrapDomainEquationKernel<params>(lambda)` / `wrapBoundaryEquationKernel<params>(lambda)` of the reference
+// (common/KernelInterface.hpp:178-190), plus the explicit list of element orders the reference gets implicitly from the
+// mesh type.
+#ifndef L3B_REGISTER_KERNEL_CUH
+#define L3B_REGISTER_KERNEL_CUH
+
+#include "assemble.cuh"
+#include "local_element.cuh"
+#include "mf_sumfact.cuh"
+#include "registry.hpp"
+
+#include <algorithm>
+
+namespace l3b
+{
+template < auto KernelFn >
+cudaError_t raiseSmemLimit(size_t bytes)
+{
+    static size_t current = 48 * 1024;
+    if (bytes > current)
+    {
+        const auto err = cudaFuncSetAttribute(KernelFn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(bytes));
+        if (err != cudaSuccess)
+            return err;
+        current = bytes;
+    }
+    return cudaSuccess;
+}
+
+template < typename KernelT, int DIM, int P, int NQ, int NC >
+cudaError_t launchMfSumFact(const void* obj, const ElemArgs& args, const tables::Tables1D& t, cudaStream_t stream)
+{
+    using Cfg = MfSumFactCfg< KernelT, DIM, P, NQ, NC >;
+    if (args.n_work == 0)
+        return cudaSuccess;
+    SumFactTables< P + 1, NQ > tab;
+    std::copy(t.interp.begin(), t.interp.end(), tab.interp);
+    std::copy(t.der.begin(), t.der.end(), tab.der);
+    std::copy(t.colloc.begin(), t.colloc.end(), tab.colloc);
+    std::copy(t.w.begin(), t.w.end(), tab.w);
+    std::copy(t.pts.begin(), t.pts.end(), tab.pts);
+    constexpr auto fn = mfSumFactApplyKernel< KernelT, DIM, P, NQ, NC >;
+    if (const auto err = raiseSmemLimit< fn >(Cfg::smem_bytes); err != cudaSuccess)
+        return err;
+    const auto grid = static_cast< unsigned >((args.n_work + Cfg::EPB - 1) / Cfg::EPB);
+    fn<<< grid, Cfg::threads, Cfg::smem_bytes, stream >>>(*static_cast< const KernelT* >(obj), args, tab);
+    return cudaGetLastError();
+}
+
+template < typename KernelT, int DIM, int P, int NC, int MODE >
+cudaError_t launchLocal(const void* obj, const ElemArgs& args, cudaStream_t stream)
+{
+    using Cfg = LocalCfg< KernelT, DIM, P, NC, MODE >;
+    if (args.n_work == 0)
+        return cudaSuccess;
+    constexpr auto fn = localElementKernel< KernelT, DIM, P, NC, MODE >;
+    if (const auto err = raiseSmemLimit< fn >(Cfg::smem_bytes); err != cudaSuccess)
+        return err;
+    fn<<< static_cast< unsigned >(args.n_work), local_threads, Cfg::smem_bytes, stream >>>(*static_cast< const KernelT* >(obj), args);
+    return cudaGetLastError();
+}
+
+template < typename KernelT, int DIM, int P >
+cudaError_t launchAssemble(const void* obj, const ElemArgs& args, cudaStream_t stream)
+{
+    using Cfg = AsmCfg< KernelT, DIM, P >;
+    if (args.n_work == 0)
+        return cudaSuccess;
+    constexpr auto fn = assembleKernel< KernelT, DIM, P >;
+    if (const auto err = raiseSmemLimit< fn >(Cfg::smem_bytes); err != cudaSuccess)
+        return err;
+    fn<<< static_cast< unsigned >(args.n_work * Cfg::n_pairs), asm_threads, Cfg::smem_bytes, stream >>>(*static_cast< const KernelT* >(obj), args);
+    return cudaGetLastError();
+}
+
+template < int P_, int NQ_ >
+struct PQ
+{
+    static constexpr int P = P_, NQ = NQ_;
+};
+
+template < typename KernelT, int DIM, typename pq >
+KernelInstance makeInstance()
+{
+    constexpr int  P = pq::P, NQ = pq::NQ;
+    constexpr int  NRHS = KernelT::parameters.n_rhs;
+    KernelInstance inst;
+    inst.order = P;
+    inst.nq    = NQ;
+    if constexpr (not KernelT::is_boundary)
+    {
+        inst.mf_sumfact_full    = launchMfSumFact< KernelT, DIM, P, NQ, NRHS >;
+        inst.mf_sumfact_one     = launchMfSumFact< KernelT, DIM, P, NQ, 1 >;
+        inst.mf_elems_per_block = MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::EPB;
+    }
+    inst.local_apply_full    = launchLocal< KernelT, DIM, P, NRHS, MODE_APPLY >;
+    inst.local_apply_one     = launchLocal< KernelT, DIM, P, 1, MODE_APPLY >;
+    inst.init                = launchLocal< KernelT, DIM, P, NRHS, MODE_INIT >;
+    inst.assemble            = launchAssemble< KernelT, DIM, P >;
+    inst.asm_blocks_per_elem = AsmCfg< KernelT, DIM, P >::n_pairs;
+    return inst;
+}
+
+template < typename KernelT, typename... pqs >
+int registerKernel(const char* name, const KernelT& kernel)
+{
+    constexpr auto params = KernelT::parameters;
+    KernelEntry    entry;
+    entry.info.name        = name;
+    entry.info.dim         = params.dimension;
+    entry.info.n_equations = static_cast< int >(params.n_equations);
+    entry.info.n_unknowns  = static_cast< int >(params.n_unknowns);
+    entry.info.n_fields    = static_cast< int >(params.n_fields);
+    entry.info.n_rhs       = static_cast< int >(params.n_rhs);
+    entry.info.is_boundary = KernelT::is_boundary;
+    entry.object           = std::make_shared< KernelT >(kernel);
+    (entry.instances.push_back(makeInstance< KernelT, params.dimension, pqs >()), ...);
+    kernelRegistry().push_back(std::move(entry));
+    return static_cast< int >(kernelRegistry().size()) - 1;
+}
+} // namespace l3b
+
+#define L3B_PQ(P, NQ) ::l3b::PQ< P, NQ >
+#define L3B_REGISTER_DOMAIN_KERNEL(NAME, FUNCTOR, PARAMS, ...)                                                                  \
+    static const int l3b_registered_##NAME =                                                                                   \
+        ::l3b::registerKernel< ::l3b::DomainEquationKernel< FUNCTOR, PARAMS >, __VA_ARGS__ >(#NAME, ::l3b::wrapDomainEquationKernel< PARAMS >(FUNCTOR{}))
+#define L3B_REGISTER_BOUNDARY_KERNEL(NAME, FUNCTOR, PARAMS, ...)                                                                \
+    static const int l3b_registered_##NAME =                                                                                   \
+        ::l3b::registerKernel< ::l3b::BoundaryEquationKernel< FUNCTOR, PARAMS >, __VA_ARGS__ >(#NAME, ::l3b::wrapBoundaryEquationKernel< PARAMS >(FUNCTOR{}))
+#endif

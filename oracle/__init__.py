@@ -289,6 +289,11 @@ class OracleMesh:
         except Exception:
             pass
 
+    def set_verts(self, verts):
+        verts = np.ascontiguousarray(verts, dtype=np.float64).reshape(self.elem_verts.shape)
+        self.orc.lib.orc_mesh_set_verts(self.h, _ptr(verts))
+        self.elem_verts = verts.copy()
+
     def assembled_system(self, U, n_rhs=1):
         return OracleAssembled(self, U, n_rhs)
 

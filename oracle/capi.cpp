@@ -362,6 +362,12 @@ void orc_mesh_boundary(void* h, int* domain, long long* parent, int* side, unsig
                 nodes[k++] = n;
     }
 }
+// overwrite the element vertices (tests distort the structured meshes); boundary matching is node-based and unaffected
+void orc_mesh_set_verts(void* h, const double* elem_verts)
+{
+    auto& m = static_cast< MeshHandle* >(h)->mesh;
+    std::copy(elem_verts, elem_verts + m.elem_verts.size(), m.elem_verts.begin());
+}
 int orc_side_node_inds(int et, int order, int side, int* out)
 {
     const auto v = sideNodeInds(static_cast< ElementType >(et), order, side);

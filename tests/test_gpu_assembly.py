@@ -1,0 +1,147 @@
+"""GPU parity: element-local least-squares assembly fused with the CRS scatter, algebraic Dirichlet BCs and the assembled
+solve, against the CPU oracle on identical inputs (through the C ABI). Sparsity is compared bit-exactly, values to 1e-12."""
+import numpy as np
+import pytest
+
+import l3ster_b200 as l3b
+from common import PairedMesh, default_dists, oracle, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return l3b.Context(0)
+
+
+CASES = [
+    ("bench_diffusion3d", "bench_diffusion3d", 3, 2, 4, l3b.AssemblyOptions(), 1),
+    ("bench_diffusion3d", "bench_diffusion3d", 3, 3, 2, l3b.AssemblyOptions(), 1),
+    ("bench_diffusion3d", "bench_diffusion3d", 3, 2, 1, l3b.AssemblyOptions(), 1),
+    ("bench_diffusion3d", "bench_diffusion3d", 3, 1, 6, l3b.AssemblyOptions(), 1),
+    ("diffusion_kernel_3D", "diffusion_kernel_3D", 3, 2, 3, l3b.AssemblyOptions(value_order=2), 3),
+    ("diffusion_kernel_3D_var", "diffusion_kernel_3D_var", 3, 2, 3, l3b.AssemblyOptions(value_order=2), 2),
+    ("dense_probe_3D", "dense_probe_3D", 3, 2, 2, l3b.AssemblyOptions(), 1),
+    ("diffusion_kernel_2D", "diffusion_kernel_2D", 2, 3, 4, l3b.AssemblyOptions(value_order=2), 2),
+    ("diffusion_kernel_2D_var", "diffusion_kernel_2D_var", 2, 3, 3, l3b.AssemblyOptions(), 2),
+    ("dense_probe_2D", "dense_probe_2D", 2, 4, 2, l3b.AssemblyOptions(value_order=1, derivative_order=1), 1),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-d{c[2]}-n{c[3]}-p{c[4]}")
+def test_assembled_system_matches_oracle(ctx, case):
+    kname, oname, dim, n, p, opts, n_rhs = case
+    info = l3b.kernel_info(kname)
+    U, NF = info["n_unknowns"], info["n_fields"]
+    pm = PairedMesh(dim, default_dists(dim, n), p)
+    mesh = pm.upload(ctx)
+    fdata = np.random.default_rng(7).uniform(-1, 1, size=(NF, pm.n_nodes)) if NF else None
+    time = 0.21
+    sys_g = l3b.AssembledSystem(ctx, mesh, U, n_rhs)
+    sys_o = pm.orc.assembled_system(U, n_rhs)
+    # sparsity graph: bit-exact (tests/SparsityGraphTest.cpp contract)
+    row_ptr, col_ind = sys_g.graph()
+    assert np.array_equal(row_ptr, sys_o.row_ptr) and np.array_equal(col_ind, sys_o.col_ind)
+    for _ in range(2):  # beginAssembly must re-zero
+        sys_g.beginAssembly()
+        sys_g.assembleProblem(kname, fields=ctx.upload_fields(fdata) if NF else None, asm_opts=opts, time=time)
+    sys_o.assemble(oname, opts.value_order, opts.derivative_order, time, fdata, n_threads=4)
+    vals_o, rhs_o = sys_o.get()
+    vals_g, rhs_g = sys_g.download()
+    assert rel_err(vals_g, vals_o) < TOL
+    assert np.linalg.norm(rhs_g - rhs_o) <= TOL * max(np.linalg.norm(rhs_o), 1.0)
+    # Dirichlet BCs on two faces, dof 0 and the last dof (bcs/DirichletBC.hpp:82-150)
+    nodes = pm.host.boundary_nodes([1, 2 * dim])
+    dofs = np.sort(np.concatenate([nodes * U, nodes * U + U - 1])).astype(np.int32)
+    dvals = np.random.default_rng(3).uniform(-1, 1, size=(len(dofs), n_rhs))
+    sys_g.endAssembly(dofs, dvals)
+    sys_o.apply_dirichlet(dofs, dvals)
+    vals_o, rhs_o = sys_o.get()
+    vals_g, rhs_g = sys_g.download()
+    assert rel_err(vals_g, vals_o) < TOL
+    assert rel_err(rhs_g, rhs_o) < TOL
+    x = np.random.default_rng(4).uniform(-1, 1, size=sys_g.n_dofs)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((vals_o, col_ind, row_ptr), shape=(sys_g.n_dofs,) * 2)
+    assert rel_err(sys_g.spmv(x), A @ x) < TOL
+
+
+def test_assembled_matches_matrix_free(ctx):
+    """The two evaluation strategies describe the same operator: A_assembled x == matrix-free apply (no BCs)."""
+    pm = PairedMesh(3, default_dists(3, 2), 4)
+    mesh = pm.upload(ctx)
+    a = l3b.AssembledSystem(ctx, mesh, 4)
+    a.beginAssembly()
+    a.assembleProblem("bench_diffusion3d")
+    a.endAssembly()
+    m = l3b.MatrixFreeSystem(ctx, mesh, 4)
+    m.assembleProblem("bench_diffusion3d")
+    m.endAssembly()
+    x = np.random.default_rng(0).uniform(-1, 1, size=a.n_dofs)
+    assert rel_err(a.spmv(x), m.apply(x)[:, 0]) < TOL
+    diag, rhs = m.download()
+    _, rhs_a = a.download(values=False)
+    assert rel_err(rhs_a, rhs) < TOL
+    assert rel_err(a.getMatrix().diagonal(), diag) < TOL
+
+
+def test_diffusion2d_assembled_end_to_end(ctx):
+    """tests/Diffusion2DAssembledTest.cpp via tests/Diffusion2D.hpp:23-120 and BASELINE config 1's ingredients (domain +
+    boundary kernel assembled into one CRS matrix): 4x4 quads p=2, Dirichlet T = x left/right, adiabatic top/bottom."""
+    node_dist = np.linspace(0.0, 1.0, 5)
+    host = l3b.make_square_mesh(node_dist, order=2)
+    orc_mesh = oracle().mesh_square(node_dist, order=2)
+    mesh = ctx.upload_mesh(host)
+    U = 3
+    gll = oracle().lobatto(3)
+    xs = np.zeros(host.n_nodes)
+    for e in range(host.n_elems):
+        for a_ in range(9):
+            xs[host.nodes[e, a_]] = oracle().map_to_physical(2, host.verts[e], [gll[a_ % 3], gll[a_ // 3]])[0]
+    bc_nodes = host.boundary_nodes([3, 4])
+    dofs = (bc_nodes * U).astype(np.int32)
+    vals = xs[bc_nodes][:, None]
+    s = l3b.AssembledSystem(ctx, mesh, U)
+    s.beginAssembly()
+    s.assembleProblem("diffusion_kernel_2D_r1")
+    s.assembleProblem("adiabatic_bc_2D", boundary_ids=[1, 2])
+    so = orc_mesh.assembled_system(U)
+    so.assemble("diffusion_kernel_2D")
+    so.assemble("adiabatic_bc_2D", boundary_ids=[1, 2])
+    v_g, r_g = s.download()
+    v_o, r_o = so.get()
+    assert rel_err(v_g, v_o) < TOL
+    s.endAssembly(dofs, vals)
+    sol, tol, iters = s.solve(tol=1e-10)
+    assert tol <= 1e-10
+    assert np.abs(sol[0::3] - xs).max() < 1e-8
+    assert np.abs(sol[1::3] - 1.0).max() < 1e-8
+    assert np.abs(sol[2::3]).max() < 1e-8
+
+
+def test_example02_diffusion2d(ctx):
+    """BASELINE config 1 (examples/02-diffusion-2D/source.cpp:10-81) at reduced size: quad p=4, domain kernel with source
+    + Robin-type boundary kernel on all four sides, assembled; matrix and rhs against the oracle, solve against a direct
+    solve of the oracle system (the reference uses KLU2)."""
+    node_dist = np.linspace(0.0, 1.0, 6)
+    host = l3b.make_square_mesh(node_dist, order=4)
+    orc_mesh = oracle().mesh_square(node_dist, order=4)
+    mesh = ctx.upload_mesh(host)
+    s = l3b.AssembledSystem(ctx, mesh, 3)
+    s.beginAssembly()
+    s.assembleProblem("example02_domain")
+    s.assembleProblem("example02_bc", boundary_ids=[1, 2, 3, 4])
+    s.endAssembly()
+    so = orc_mesh.assembled_system(3)
+    so.assemble("example02_domain")
+    so.assemble("example02_bc", boundary_ids=[1, 2, 3, 4])
+    v_o, r_o = so.get()
+    v_g, r_g = s.download()
+    assert rel_err(v_g, v_o) < TOL and rel_err(r_g, r_o) < TOL
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    A = sp.csr_matrix((v_o, so.col_ind, so.row_ptr), shape=(so.n_dofs,) * 2).tocsc()
+    ref = spla.spsolve(A, r_o[:, 0])
+    sol, tol, iters = s.solve(tol=1e-12, max_iters=20000)
+    assert np.abs(sol - ref).max() < 1e-8 * max(1.0, np.abs(ref).max())
