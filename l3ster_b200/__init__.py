@@ -416,6 +416,7 @@ class AssembledSystem:
 
     def assembleProblem(self, kernel, boundary_ids=(), fields=None, field_inds=None, dof_inds=None, asm_opts=AssemblyOptions(), time=0.0):
         kid, di, fh, fi, bi, nb = _kernel_args(kernel, dof_inds, fields, field_inds, boundary_ids)
+        self._keepalive = fields  # the launch is asynchronous w.r.t. Python object lifetimes
         self.ctx._chk(lib().l3b_asm_assemble(self._h, kid, asm_opts._c(), time, _p(di), fh, _p(fi), _p(bi), nb))
 
     def endAssembly(self, dirichlet_dofs=None, dirichlet_vals=None):
@@ -467,6 +468,7 @@ class MatrixFreeSystem:
         if dirichlet_vals is not None:
             v = np.ascontiguousarray(np.asarray(dirichlet_vals, dtype=np.float64).reshape(self.n_dofs, -1).T)
         self._h = C.c_void_p()
+        self._keepalive = []
         ctx._chk(lib().l3b_mf_create(ctx._h, mesh._h, dofs_per_node, n_rhs, _p(m), _p(v), C.byref(self._h)))
 
     def __del__(self):
@@ -477,6 +479,7 @@ class MatrixFreeSystem:
 
     def assembleProblem(self, kernel, boundary_ids=(), fields=None, field_inds=None, dof_inds=None, asm_opts=AssemblyOptions(), time=0.0):
         kid, di, fh, fi, bi, nb = _kernel_args(kernel, dof_inds, fields, field_inds, boundary_ids)
+        self._keepalive.append(fields)  # the system stores the device pointer (like FieldAccess references SolutionManager)
         self.ctx._chk(lib().l3b_mf_assemble(self._h, kid, asm_opts._c(), time, _p(di), fh, _p(fi), _p(bi), nb))
 
     def endAssembly(self):
@@ -494,7 +497,7 @@ class MatrixFreeSystem:
         nc = 1 if x.ndim == 1 else x.shape[1]
         x = x.reshape(self.n_dofs, nc)
         xf = np.ascontiguousarray(x.T)
-        yf = np.zeros_like(xf) if y is None else np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(self.n_dofs, nc).T)
+        yf = np.zeros_like(xf) if y is None else np.array(np.asarray(y, dtype=np.float64).reshape(self.n_dofs, nc).T, order="C", copy=True)
         self.ctx._chk(lib().l3b_mf_apply(self._h, _p(xf), _p(yf), nc, alpha, beta))
         return yf.T.copy()
 

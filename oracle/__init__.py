@@ -380,7 +380,7 @@ class OracleMatrixFree:
         x = np.asarray(x, dtype=np.float64).reshape(self.n_dofs, -1)
         nc = x.shape[1]
         xf = np.ascontiguousarray(x.T)
-        yf = np.zeros_like(xf) if y is None else np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(self.n_dofs, -1).T)
+        yf = np.zeros_like(xf) if y is None else np.array(np.asarray(y, dtype=np.float64).reshape(self.n_dofs, -1).T, order="C", copy=True)
         secs = C.c_double()
         self.mesh.orc._chk(self.lib.orc_mf_apply(self.h, _ptr(xf), _ptr(yf), nc, C.c_double(alpha), C.c_double(beta), n_threads, repeats,
                                                  C.byref(secs)))
