@@ -38,7 +38,8 @@ typedef enum l3b_status
     L3B_ERR_STATE          = 5, /* assembly state machine violated (algsys/AssembledSystem.hpp:455-461) */
     L3B_ERR_GRAPH          = 6, /* entry not present in the sparsity graph */
     L3B_ERR_NOT_CONVERGED  = 7,
-    L3B_ERR_NO_DEVICE      = 8
+    L3B_ERR_NO_DEVICE      = 8,
+    L3B_ERR_SPARSITY       = 9 /* run-time guard of the compile-time operator sparsity probe tripped (kernel_interface.cuh) */
 } l3b_status;
 
 typedef struct l3b_context   l3b_context;

@@ -407,6 +407,9 @@ struct l3b_context
             status.zero(stream);
             if (st & status_degenerate_element)
                 fail(L3B_ERR_DEGENERATE, "Encountered degenerate element ( |J| <= 0 )");
+            if (st & status_sparsity_violation)
+                fail(L3B_ERR_SPARSITY, "an operator entry found structurally zero by the compile-time probe was non-zero at run time: "
+                                       "register the kernel with a functor that is not constexpr-evaluable, or fix the probe");
             fail(L3B_ERR_GRAPH, "entry not present in the sparsity graph");
         }
     }
@@ -659,6 +662,10 @@ void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double a
         a.n_cols         = n_cols;
         a.alpha          = alpha;
         a.dir_mask       = sys->has_bc ? sys->dir_mask.ptr : nullptr;
+        bool contiguous  = info.n_unknowns == sys->dpn and reinterpret_cast< uintptr_t >(x) % 16 == 0 and sys->n_dofs % 2 == 0;
+        for (int u = 0; u < info.n_unknowns; ++u)
+            contiguous = contiguous and use.dof_inds[u] == u;
+        a.contiguous_dofs = contiguous;
         const bool full  = n_cols == sys->n_rhs;
         const bool sf    = not info.is_boundary and use.opts.eval_strategy != 1;
         cudaError_t err;

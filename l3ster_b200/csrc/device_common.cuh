@@ -27,7 +27,9 @@ constexpr int max_fields   = 8;
 // status word bits written by the device (mirrors the reference's exceptions, see l3ster_b200.h)
 enum StatusBits : int
 {
-    status_degenerate_element = 1 // "Encountered degenerate element ( |J| <= 0 )" (AssembleLocalSystem.hpp:249)
+    status_degenerate_element = 1, // "Encountered degenerate element ( |J| <= 0 )" (AssembleLocalSystem.hpp:249)
+    status_graph_entry_missing = 2,
+    status_sparsity_violation  = 4 // an operator entry the compile-time probe found structurally zero was non-zero at run time
 };
 
 // Everything an element kernel needs. Plain pointers and sizes only.
@@ -44,6 +46,7 @@ struct ElemArgs
     // DOF layout: local dof of (node, kernel unknown u) = node * dofs_per_node + dof_inds[u]
     int dofs_per_node;
     int dof_inds[max_unknowns];
+    int contiguous_dofs; // dofs_per_node == n_unknowns, dof_inds == identity, x 16-byte aligned: vectorised gathers allowed
     // operand / result (column-major, leading dimension ld)
     const double* x;
     double*       y;

@@ -141,10 +141,11 @@ struct DomainEquationKernel
     static constexpr bool is_boundary = false;
     using Input                       = typename KernelInterface< params >::DomainInput;
     using Result                      = typename KernelInterface< params >::Result;
+    using functor_type                = Kernel;
     constexpr DomainEquationKernel(Kernel kernel) : m_kernel{kernel} {}
-    L3B_HD Result operator()(const Input& input) const
+    L3B_HD constexpr Result operator()(const Input& input) const
     {
-        Result retval;
+        Result retval{};
         for (size_t i = 0; i <= static_cast< size_t >(params.dimension); ++i)
             retval.operators[i].setZero();
         retval.rhs.setZero();
@@ -160,10 +161,11 @@ struct BoundaryEquationKernel
     static constexpr bool is_boundary = true;
     using Input                       = typename KernelInterface< params >::BoundaryInput;
     using Result                      = typename KernelInterface< params >::Result;
+    using functor_type                = Kernel;
     constexpr BoundaryEquationKernel(Kernel kernel) : m_kernel{kernel} {}
-    L3B_HD Result operator()(const Input& input) const
+    L3B_HD constexpr Result operator()(const Input& input) const
     {
-        Result retval;
+        Result retval{};
         for (size_t i = 0; i <= static_cast< size_t >(params.dimension); ++i)
             retval.operators[i].setZero();
         retval.rhs.setZero();
@@ -183,6 +185,94 @@ template < KernelParams params, typename Kernel >
 constexpr auto wrapBoundaryEquationKernel(Kernel kernel)
 {
     return BoundaryEquationKernel< Kernel, params >{kernel};
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Structural sparsity of a kernel's operators, discovered at compile time.
+//
+// Least-squares kernels fill a handful of the (D+1) x E x U operator entries (15 of 112 for 3-D diffusion) on top of the
+// zero-initialised Result. IEEE arithmetic forbids the compiler from dropping `0.0 * x`, so the device kernels skip the
+// dead multiply-adds explicitly: the kernel functor is evaluated *at compile time* on two generic probe inputs, entries
+// that are exactly zero for both are treated as structurally zero, and every device evaluation re-checks that those
+// entries really are zero (a check the compiler folds away for entries it can prove constant) — a violation raises
+// L3B_ERR_SPARSITY instead of producing a wrong result. Kernels whose functor is not constexpr-evaluable (e.g. it calls
+// a transcendental) simply get the dense mask.
+template < typename KernelT >
+constexpr auto makeProbeInput(int variant)
+{
+    typename KernelT::Input in{};
+    constexpr auto          params = KernelT::parameters;
+    const val_t             s      = variant == 0 ? 1. : -1.37;
+    for (size_t f = 0; f < params.n_fields; ++f)
+    {
+        in.field_vals[f] = s * (0.37 + 0.11 * static_cast< val_t >(f));
+        for (size_t d = 0; d < static_cast< size_t >(params.dimension); ++d)
+            in.field_ders[d][f] = s * (-0.23 + 0.07 * static_cast< val_t >(d) + 0.13 * static_cast< val_t >(f));
+    }
+    in.point.space.coords[0] = 0.123 * s;
+    in.point.space.coords[1] = 0.456 * s;
+    in.point.space.coords[2] = 0.789 * s;
+    in.point.time            = 0.31 * s;
+    if constexpr (KernelT::is_boundary)
+        for (size_t d = 0; d < static_cast< size_t >(params.dimension); ++d)
+            in.normal[d] = s * (0.48 + 0.16 * static_cast< val_t >(d));
+    return in;
+}
+
+template < typename KernelT >
+constexpr auto probeOperatorMask()
+{
+    constexpr auto params = KernelT::parameters;
+    constexpr size_t n    = (params.dimension + 1) * params.n_equations * params.n_unknowns;
+    Array< bool, n > mask{};
+    for (int variant = 0; variant < 2; ++variant)
+    {
+        const KernelT kernel{typename KernelT::functor_type{}};
+        const auto    res = kernel(makeProbeInput< KernelT >(variant));
+        for (size_t i = 0; i <= static_cast< size_t >(params.dimension); ++i)
+            for (size_t k = 0; k < params.n_equations * params.n_unknowns; ++k)
+                mask[i * params.n_equations * params.n_unknowns + k] =
+                    mask[i * params.n_equations * params.n_unknowns + k] or res.operators[i].v[k] != 0.;
+    }
+    return mask;
+}
+
+template < typename KernelT >
+concept ConstexprProbeable = requires { typename std::integral_constant< size_t, (probeOperatorMask< KernelT >(), size_t{0}) >; };
+
+template < typename KernelT >
+struct KernelSparsity
+{
+    static constexpr auto   params = KernelT::parameters;
+    static constexpr size_t E = params.n_equations, U = params.n_unknowns, n = (params.dimension + 1) * E * U;
+    static constexpr bool   probed = ConstexprProbeable< KernelT >;
+    static constexpr auto   mask   = [] {
+        if constexpr (ConstexprProbeable< KernelT >)
+            return probeOperatorMask< KernelT >();
+        else
+        {
+            Array< bool, n > m{};
+            for (size_t i = 0; i < n; ++i)
+                m[i] = true;
+            return m;
+        }
+    }();
+    // is operator `op` entry (eq, u) structurally non-zero?
+    static constexpr bool nz(size_t op, size_t eq, size_t u) { return mask[op * E * U + eq + u * E]; }
+    static constexpr size_t count()
+    {
+        size_t c = 0;
+        for (size_t i = 0; i < n; ++i)
+            c += mask[i];
+        return c;
+    }
+};
+
+// compile-time loop: f(std::integral_constant<int, I>{}) for I in [0, N)
+template < int N, typename F >
+L3B_HD constexpr void staticFor(F&& f)
+{
+    [&]< int... I >(std::integer_sequence< int, I... >) { (f(std::integral_constant< int, I >{}), ...); }(std::make_integer_sequence< int, N >{});
 }
 
 // algsys/AssembleLocalSystem.hpp:16-49

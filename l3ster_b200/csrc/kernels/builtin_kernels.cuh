@@ -12,7 +12,7 @@ namespace l3b::kernels
 struct Diffusion2D
 {
     template < typename In, typename Out >
-    L3B_HD void operator()(const In&, Out& out) const
+    L3B_HD constexpr void operator()(const In&, Out& out) const
     {
         auto& [operators, rhs] = out;
         auto& [A0, Ax, Ay]     = operators;
@@ -32,7 +32,7 @@ struct Diffusion2D
 struct Diffusion2DVar
 {
     template < typename In, typename Out >
-    L3B_HD void operator()(const In& in, Out& out) const
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
     {
         const auto& [field_vals, field_ders, _] = in;
         const auto lambda                       = field_vals[0];
@@ -59,7 +59,7 @@ template < bool with_source >
 struct Diffusion3D
 {
     template < typename In, typename Out >
-    L3B_HD void operator()(const In&, Out& out) const
+    L3B_HD constexpr void operator()(const In&, Out& out) const
     {
         auto& [operators, rhs] = out;
         auto& [A0, Ax, Ay, Az] = operators;
@@ -92,7 +92,7 @@ struct Diffusion3D
 struct Diffusion3DVar
 {
     template < typename In, typename Out >
-    L3B_HD void operator()(const In& in, Out& out) const
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
     {
         const auto& [field_vals, field_ders, _] = in;
         const auto lambda                       = field_vals[0];
@@ -127,7 +127,7 @@ struct Diffusion3DVar
 struct AdiabaticBC2D
 {
     template < typename In, typename Out >
-    L3B_HD void operator()(const In& in, Out& out) const
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
     {
         const auto& [vals, ders, point, normal] = in;
         auto& [operators, rhs]                  = out;
@@ -141,7 +141,7 @@ struct AdiabaticBC2D
 struct Example02Domain
 {
     template < typename In, typename Out >
-    L3B_HD void operator()(const In&, Out& out) const
+    L3B_HD constexpr void operator()(const In&, Out& out) const
     {
         auto& [operators, rhs] = out;
         auto& [A0, A1, A2]     = operators;
@@ -161,7 +161,7 @@ struct Example02Domain
 struct Example02BC
 {
     template < typename In, typename Out >
-    L3B_HD void operator()(const In& in, Out& out) const
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
     {
         const auto& normal = in.normal;
         const auto  nx     = normal[0];
@@ -178,7 +178,7 @@ struct Example02BC
 struct NS3D
 {
     template < typename In, typename Out >
-    L3B_HD void operator()(const In& in, Out& out) const
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
     {
         const auto& [vals, ders, point]             = in;
         const auto& [u, v, w, p, ox, oy, oz]        = vals;
@@ -242,7 +242,7 @@ struct NS3D
 struct DenseProbe3D
 {
     template < typename In, typename Out >
-    L3B_HD void operator()(const In& in, Out& out) const
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
     {
         constexpr int E = 5, U = 3;
         for (int i = 0; i <= 3; ++i)
@@ -258,7 +258,7 @@ struct DenseProbe3D
 struct DenseProbe2D
 {
     template < typename In, typename Out >
-    L3B_HD void operator()(const In& in, Out& out) const
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
     {
         constexpr int E = 4, U = 2;
         for (int i = 0; i <= 2; ++i)

@@ -48,6 +48,10 @@ cudaError_t launchMfSumFact(const void* obj, const ElemArgs& args, const tables:
     constexpr auto fn = mfSumFactApplyKernel< KernelT, DIM, P, NQ, NC >;
     if (const auto err = raiseSmemLimit< fn >(Cfg::smem_bytes); err != cudaSuccess)
         return err;
+    static const cudaError_t carveout =
+        cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, static_cast< int >(cudaSharedmemCarveoutMaxShared));
+    if (carveout != cudaSuccess)
+        return carveout;
     const auto grid = static_cast< unsigned >((args.n_work + Cfg::EPB - 1) / Cfg::EPB);
     fn<<< grid, Cfg::threads, Cfg::smem_bytes, stream >>>(*static_cast< const KernelT* >(obj), args, tab);
     return cudaGetLastError();
