@@ -84,12 +84,18 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        def num(s):
+            try:
+                return float(s.split()[0])
+            except Exception:
+                return None
+
+        sm = [num(r[0]) for r in self.rows if len(r) >= 7 and num(r[0]) is not None]
+        mx = [num(r[1]) for r in self.rows if len(r) >= 7 and num(r[1]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "raw_first": self.rows[0] if self.rows and not sm else None}
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -20,8 +20,12 @@
 //   * the hex path hands the user kernel point.space = (x, y, 0), replicating SumFactorization.hpp:732.
 //
 // Thread mapping: TPE = nq^D threads per element (one per Gauss point / node), EPB elements per CTA. All tensors of an
-// element live in shared memory; every sweep assigns one 1-D line to a thread. Shared memory per element: two F x Q
-// ping-pong buffers (+ extra when D*F0 > 2F), reused for the D x F0 x Q flux arrays r_d of the transposed stage.
+// element live in shared memory: (D+1) x F arrays (values + D reference derivatives) in a padded nq^D layout in which
+// every sweep runs in place — one 1-D line per thread, loaded into registers, transformed with constant-bank
+// coefficients, stored back. The last interpolation sweep also differentiates its own direction, the remaining
+// derivatives are line sweeps over the interpolated values, the per-point stage overwrites its own entries with the
+// fluxes r_0..r_D, and the transposed stage mirrors all of it. Shared-memory traffic — the binding resource of the v1/v2
+// kernels, which read 15 neighbour values + 15 table entries per field and point — drops to ~128 KB per p=4 element.
 #ifndef L3B_MF_SUMFACT_CUH
 #define L3B_MF_SUMFACT_CUH
 
@@ -46,42 +50,102 @@ struct MfSumFactCfg
     static constexpr int  E = params.n_equations, U = params.n_unknowns, NF = params.n_fields;
     static constexpr int  NB = P + 1;
     static constexpr int  F0 = U * NRHS, F = F0 + NF;
-    static constexpr int  NN = cpow(NB, DIM), Q = cpow(NQ, DIM), M = Q;
-    static constexpr int  TPE = Q;
-    static constexpr int  EPB = cmax(1, 128 / TPE);
-    static constexpr int  threads = TPE * EPB;
+    static constexpr int  NN = cpow(NB, DIM), Q = cpow(NQ, DIM);
+    // shared-memory tensor layout of one field: idx(qx, qy, qz) = qz * PS + qy * LS + qx. The line stride is padded to an
+    // odd number of doubles so that the x-lines of one half-warp fall into distinct banks for every nq.
+    static constexpr int LS = NQ % 2 == 0 ? NQ + 1 : NQ;
+    static constexpr int PS = LS * NQ;
+    static constexpr int AQ = DIM == 3 ? PS * NQ : PS; // doubles per field array
+    static constexpr int TPE = Q;
+    static constexpr int EPB = cmax(1, 128 / TPE);
+    static constexpr int threads = TPE * EPB;
     // resident CTAs per SM the register allocator should leave room for (~20 warps per SM)
     static constexpr int warps      = (threads + 31) / 32;
     static constexpr int min_blocks = cmax(1, 20 / warps);
-    // the D*F0 flux arrays are laid over the two ping-pong buffers; anything beyond 2F arrays needs extra room
-    static constexpr int extra_q     = cmax(0, DIM * F0 - 2 * F);
-    static constexpr int geo_doubles = (1 << DIM) * 3;
-    static constexpr int tab_doubles = NQ * NQ + 2 * NQ; // colloc, pts, w
-    static constexpr int smem_doubles_per_elem = (2 * F + extra_q) * Q + geo_doubles;
-    static constexpr size_t smem_bytes = (static_cast< size_t >(EPB) * smem_doubles_per_elem + tab_doubles) * sizeof(double);
+    // per element: values + DIM reference derivatives of all F fields (the DIM+1 flux arrays of the transposed stage
+    // overwrite them in place), the geometry coefficients and, for affine elements, the shared inverse Jacobian
+    static constexpr int geo_doubles = (1 << DIM) * 3 + DIM * DIM + 2;
+    static constexpr int smem_doubles_per_elem = (DIM + 1) * F * AQ + geo_doubles;
+    static constexpr size_t smem_bytes = static_cast< size_t >(EPB) * smem_doubles_per_elem * sizeof(double);
     static_assert(params.dimension == DIM);
     static_assert(NQ >= NB, "collocation differentiation at the Gauss points needs nq >= nb (value_order >= 1)");
     static_assert(threads <= 1024, "element too large for one thread per tensor entry");
 };
 
-// out[o] = sum_i in[i] * tab; one thread per 1-D line
-template < int N_IN, int N_OUT, bool TRANSPOSED_TABLE >
-__device__ __forceinline__ void sweepLine(const double* __restrict__ in, int in_stride, double* __restrict__ out, int out_stride,
-                                          const double* __restrict__ tab /* [N_IN][N_OUT] or transposed [N_OUT][N_IN] */)
+// ---- 1-D line kernels. A line lives in shared memory at `p[i * stride]`; each is processed by one thread, entirely in
+// registers, and written back in place (or to a second array). Table indices are compile-time after unrolling, so the
+// coefficients become constant-bank operands of the DFMAs.
+template < int NB, int NQ >
+__device__ __forceinline__ void loadLine(const double* __restrict__ p, int stride, double (&v)[NQ], int n)
 {
-    double v[N_IN];
 #pragma unroll
-    for (int i = 0; i < N_IN; ++i)
-        v[i] = in[i * in_stride];
+    for (int i = 0; i < NQ; ++i)
+        if (i < n)
+            v[i] = p[i * stride];
+}
+// nodes → Gauss points: out[q] = sum_i v[i] interp[i][q]
+template < int NB, int NQ >
+__device__ __forceinline__ void interpolate(const double (&v)[NQ], double (&out)[NQ], const double* __restrict__ interp)
+{
 #pragma unroll
-    for (int o = 0; o < N_OUT; ++o)
+    for (int q = 0; q < NQ; ++q)
     {
-        double acc = v[0] * (TRANSPOSED_TABLE ? tab[o * N_IN] : tab[o]);
+        double acc = v[0] * interp[q];
 #pragma unroll
-        for (int i = 1; i < N_IN; ++i)
-            acc = fma(v[i], TRANSPOSED_TABLE ? tab[o * N_IN + i] : tab[i * N_OUT + o], acc);
-        out[o * out_stride] = acc;
+        for (int i = 1; i < NB; ++i)
+            acc = fma(v[i], interp[i * NQ + q], acc);
+        out[q] = acc;
     }
+}
+// Gauss points → nodes (transpose): out[i] = sum_q v[q] interp[i][q]
+template < int NB, int NQ >
+__device__ __forceinline__ void interpolateT(const double (&v)[NQ], double (&out)[NQ], const double* __restrict__ interp)
+{
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+    {
+        double acc = v[0] * interp[i * NQ];
+#pragma unroll
+        for (int q = 1; q < NQ; ++q)
+            acc = fma(v[q], interp[i * NQ + q], acc);
+        out[i] = acc;
+    }
+}
+// collocation derivative at the Gauss points: out[q] = sum_m colloc[m][q] v[m]
+template < int NQ >
+__device__ __forceinline__ void differentiate(const double (&v)[NQ], double (&out)[NQ], const double* __restrict__ colloc)
+{
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+    {
+        double acc = v[0] * colloc[q];
+#pragma unroll
+        for (int m = 1; m < NQ; ++m)
+            acc = fma(v[m], colloc[m * NQ + q], acc);
+        out[q] = acc;
+    }
+}
+// its transpose, accumulated: acc[m] += sum_q colloc[m][q] r[q]
+template < int NQ >
+__device__ __forceinline__ void differentiateTAccumulate(const double (&r)[NQ], double (&acc)[NQ], const double* __restrict__ colloc)
+{
+#pragma unroll
+    for (int m = 0; m < NQ; ++m)
+    {
+        double a = acc[m];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+            a = fma(r[q], colloc[m * NQ + q], a);
+        acc[m] = a;
+    }
+}
+template < int NQ >
+__device__ __forceinline__ void storeLine(double* __restrict__ p, int stride, const double (&v)[NQ], int n)
+{
+#pragma unroll
+    for (int i = 0; i < NQ; ++i)
+        if (i < n)
+            p[i * stride] = v[i];
 }
 
 // monomial coefficients of the multilinear map: x(xi) = sum_m c_m prod_{d in m} xi_d, m = bitmask over directions
@@ -142,36 +206,31 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
 {
     using Cfg = MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >;
     using Sp  = KernelSparsity< KernelT >;
-    constexpr int E = Cfg::E, U = Cfg::U, NF = Cfg::NF, NB = Cfg::NB, F0 = Cfg::F0, F = Cfg::F, NN = Cfg::NN, Q = Cfg::Q;
+    constexpr int E = Cfg::E, U = Cfg::U, NF = Cfg::NF, NB = Cfg::NB, F0 = Cfg::F0, F = Cfg::F, NN = Cfg::NN;
+    constexpr int LS = Cfg::LS, PS = Cfg::PS, AQ = Cfg::AQ, TPE = Cfg::TPE;
+    constexpr int nv = 1 << DIM;
     extern __shared__ double smem[];
-    double*         s_colloc = smem; // [m][q]
-    double*         s_pts    = s_colloc + NQ * NQ;
-    double*         s_w      = s_pts + NQ;
-    const int       slot     = threadIdx.x / Cfg::TPE;
-    const int       t        = threadIdx.x % Cfg::TPE;
-    const long long wi       = static_cast< long long >(blockIdx.x) * Cfg::EPB + slot;
-    const bool      active   = wi < args.n_work;
-    const long long e        = active ? (args.work_elems ? args.work_elems[wi] : args.first_elem + wi) : 0;
-    double*         bufA     = s_w + NQ + static_cast< size_t >(slot) * Cfg::smem_doubles_per_elem;
-    double*         bufB     = bufA + F * Q;
-    double*         s_geo    = bufB + F * Q + Cfg::extra_q * Q;
+    const int       slot   = threadIdx.x / TPE;
+    const int       t      = threadIdx.x % TPE;
+    const long long wi     = static_cast< long long >(blockIdx.x) * Cfg::EPB + slot;
+    const bool      active = wi < args.n_work;
+    const long long e      = active ? (args.work_elems ? args.work_elems[wi] : args.first_elem + wi) : 0;
+    // field arrays: s_val[f], s_der[d][f] (f < F), each AQ doubles
+    double* const   s_val  = smem + static_cast< size_t >(slot) * Cfg::smem_doubles_per_elem;
+    double* const   s_der  = s_val + F * AQ;
+    double* const   s_geo  = s_val + (DIM + 1) * F * AQ; // [2^D][3] monomial coefficients, then Jti[D][D], detJ, affine flag
     const uint32_t* el_nodes = args.nodes + e * NN;
+    const auto      der_arr = [&](int d, int f) { return s_der + (d * F + f) * AQ; };
 
-    for (int i = threadIdx.x; i < NQ * NQ; i += Cfg::threads)
-        s_colloc[i] = tab.colloc[i];
-    for (int i = threadIdx.x; i < NQ; i += Cfg::threads)
-    {
-        s_pts[i] = tab.pts[i];
-        s_w[i]   = tab.w[i];
-    }
     if (active)
-        buildGeometryCoefs< DIM >(args.verts + e * (1 << DIM) * 3, s_geo, t, Cfg::TPE);
+        buildGeometryCoefs< DIM >(args.verts + e * nv * 3, s_geo, t, TPE);
 
-    // ---- gather (MatrixFreeSystem.hpp:421-467): bufA[f][a], f = rhs*U + u, then the NF external fields
+    // ---- gather (MatrixFreeSystem.hpp:421-467) into s_val[f], f = rhs*U + u, then the NF external fields
     if (active)
-        for (int a = t; a < NN; a += Cfg::TPE)
+        for (int a = t; a < NN; a += TPE)
         {
             const long long node = el_nodes[a];
+            const int       pos  = DIM == 3 ? (a / (NB * NB)) * PS + ((a / NB) % NB) * LS + a % NB : (a / NB) * LS + a % NB;
             if (U % 2 == 0 and args.contiguous_dofs)
             {
                 // dofs of a node are the U contiguous entries node*U .. node*U+U-1: vectorised 16-byte loads
@@ -190,8 +249,8 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
                             if (args.dir_mask[node * U + 2 * u2 + 1])
                                 v.y = 0.;
                         }
-                        bufA[(r * U + 2 * u2) * Q + a]     = v.x;
-                        bufA[(r * U + 2 * u2 + 1) * Q + a] = v.y;
+                        s_val[(r * U + 2 * u2) * AQ + pos]     = v.x;
+                        s_val[(r * U + 2 * u2 + 1) * AQ + pos] = v.y;
                     }
                 }
             }
@@ -204,100 +263,160 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
                     const bool      dir = isDirichlet(args.dir_mask, dof);
 #pragma unroll
                     for (int r = 0; r < NRHS; ++r)
-                        bufA[(r * U + u) * Q + a] = dir ? 0. : args.x[dof + r * args.ld];
+                        s_val[(r * U + u) * AQ + pos] = dir ? 0. : args.x[dof + r * args.ld];
                 }
             }
 #pragma unroll
             for (int f = 0; f < NF; ++f)
-                bufA[(F0 + f) * Q + a] = args.fields[node + args.field_inds[f] * args.field_stride];
+                s_val[(F0 + f) * AQ + pos] = args.fields[node + args.field_inds[f] * args.field_stride];
         }
     __syncthreads();
-
-    // ---- interpolate to the Gauss points, one direction at a time (bufA → bufB → bufA [→ bufB])
-    if constexpr (DIM == 2)
+    // affine element (all mixed monomial coefficients vanish): one thread inverts the constant Jacobian for everybody
+    if (active and t == 0)
     {
-        for (int l = t; l < F * NB; l += Cfg::TPE)
+        bool affine = true;
+        for (int m = 0; m < nv; ++m)
+            if (__popc(m) > 1)
+                for (int s = 0; s < 3; ++s)
+                    affine = affine and s_geo[m * 3 + s] == 0.;
+        double* g = s_geo + nv * 3;
+        g[DIM * DIM + 1] = affine ? 1. : 0.;
+        if (affine)
         {
-            const int f = l / NB, j = l % NB;
-            sweepLine< NB, NQ, false >(bufA + f * Q + j * NB, 1, bufB + f * Q + j * NQ, 1, tab.interp);
+            double Jt[DIM][DIM], Jti[DIM][DIM];
+            for (int d = 0; d < DIM; ++d)
+                for (int s = 0; s < DIM; ++s)
+                    Jt[d][s] = s_geo[(1 << d) * 3 + s];
+            g[DIM * DIM] = invert< DIM >(Jt, Jti);
+            for (int s = 0; s < DIM; ++s)
+                for (int d = 0; d < DIM; ++d)
+                    g[s * DIM + d] = Jti[s][d];
+        }
+    }
+
+    // ---- nodes → Gauss points, in place, one direction at a time; the last sweep also differentiates along its direction
+    {
+        double v[NQ], o[NQ];
+        // x: lines (f, k, j), j, k < NB
+        constexpr int n_x = DIM == 3 ? F * NB * NB : F * NB;
+        for (int l = t; l < n_x; l += TPE)
+        {
+            const int f = l / (n_x / F), r = l % (n_x / F);
+            double*   p = s_val + f * AQ + (DIM == 3 ? (r / NB) * PS + (r % NB) * LS : r * LS);
+            if (active)
+            {
+                loadLine< NB, NQ >(p, 1, v, NB);
+                interpolate< NB, NQ >(v, o, tab.interp);
+                if constexpr (DIM == 2)
+                    ; // y is the last direction in 2-D
+                storeLine< NQ >(p, 1, o, NQ);
+            }
         }
         __syncthreads();
-        for (int l = t; l < F * NQ; l += Cfg::TPE)
+        if constexpr (DIM == 3)
         {
-            const int f = l / NQ, qx = l % NQ;
-            sweepLine< NB, NQ, false >(bufB + f * Q + qx, NQ, bufA + f * Q + qx, NQ, tab.interp);
+            // y: lines (f, k, qx), k < NB
+            for (int l = t; l < F * NB * NQ; l += TPE)
+            {
+                const int f = l / (NB * NQ), r = l % (NB * NQ);
+                double*   p = s_val + f * AQ + (r / NQ) * PS + r % NQ;
+                if (active)
+                {
+                    loadLine< NB, NQ >(p, LS, v, NB);
+                    interpolate< NB, NQ >(v, o, tab.interp);
+                    storeLine< NQ >(p, LS, o, NQ);
+                }
+            }
+            __syncthreads();
+        }
+        // last direction (y in 2-D, z in 3-D): lines over all (qx[, qy]); interpolate and differentiate in one pass
+        constexpr int n_l    = DIM == 3 ? NQ * NQ : NQ;
+        constexpr int stride = DIM == 3 ? PS : LS;
+        for (int l = t; l < F * n_l; l += TPE)
+        {
+            const int f = l / n_l, r = l % n_l;
+            const int off = DIM == 3 ? (r / NQ) * LS + r % NQ : r;
+            if (active)
+            {
+                loadLine< NB, NQ >(s_val + f * AQ + off, stride, v, NB);
+                interpolate< NB, NQ >(v, o, tab.interp);
+                storeLine< NQ >(s_val + f * AQ + off, stride, o, NQ);
+                differentiate< NQ >(o, v, tab.colloc);
+                storeLine< NQ >(der_arr(DIM - 1, f) + off, stride, v, NQ);
+            }
+        }
+        __syncthreads();
+        // remaining reference derivatives: x (and y in 3-D) lines of the interpolated values
+        constexpr int n_dl = DIM == 3 ? NQ * NQ : NQ;
+        for (int l = t; l < (DIM - 1) * F * n_dl; l += TPE)
+        {
+            const int d = l / (F * n_dl), f = (l / n_dl) % F, r = l % n_dl;
+            int       off, st;
+            if (d == 0) // x-lines (qy[, qz])
+            {
+                off = DIM == 3 ? (r / NQ) * PS + (r % NQ) * LS : r * LS;
+                st  = 1;
+            }
+            else // y-lines (qx, qz), 3-D only
+            {
+                off = (r / NQ) * PS + r % NQ;
+                st  = LS;
+            }
+            if (active)
+            {
+                loadLine< NQ, NQ >(s_val + f * AQ + off, st, v, NQ);
+                differentiate< NQ >(v, o, tab.colloc);
+                storeLine< NQ >(der_arr(d, f) + off, st, o, NQ);
+            }
         }
         __syncthreads();
     }
-    else
-    {
-        for (int l = t; l < F * NB * NB; l += Cfg::TPE)
-        {
-            const int f = l / (NB * NB), kj = l % (NB * NB);
-            sweepLine< NB, NQ, false >(bufA + f * Q + kj * NB, 1, bufB + f * Q + kj * NQ, 1, tab.interp);
-        }
-        __syncthreads();
-        for (int l = t; l < F * NB * NQ; l += Cfg::TPE)
-        {
-            const int f = l / (NB * NQ), k = (l / NQ) % NB, qx = l % NQ;
-            sweepLine< NB, NQ, false >(bufB + f * Q + k * NB * NQ + qx, NQ, bufA + f * Q + k * NQ * NQ + qx, NQ, tab.interp);
-        }
-        __syncthreads();
-        for (int l = t; l < F * NQ * NQ; l += Cfg::TPE)
-        {
-            const int f = l / (NQ * NQ), qyx = l % (NQ * NQ);
-            sweepLine< NB, NQ, false >(bufA + f * Q + qyx, NQ * NQ, bufB + f * Q + qyx, NQ * NQ, tab.interp);
-        }
-        __syncthreads();
-    }
-    double* uq = DIM == 2 ? bufA : bufB; // values at the Gauss points, [f][q], q = (qz*NQ + qy)*NQ + qx
-    double* vq = DIM == 2 ? bufB : bufA; // the other ping-pong buffer
-    // flux arrays r_d (d = 1..DIM), each F0 x Q: laid over [vq | uq | extra] *after* every thread has read uq
-    double* const region2 = bufB + F * Q;
-    const auto    r_ptr   = [&](int d, int f) -> double* {
-        const int idx = d * F0 + f; // position in the virtual list of D*F0 arrays
-        if (idx < F)
-            return vq + idx * Q;
-        if (idx < 2 * F)
-            return uq + (idx - F) * Q;
-        return region2 + (idx - 2 * F) * Q;
-    };
 
-    // ---- quadrature point stage (SumFactorization.hpp:614-756); one point per thread (TPE == Q)
+    // ---- quadrature point stage (SumFactorization.hpp:614-756); one point per thread, in place on its own entries
     const int q     = t;
     const int qi[3] = {q % NQ, (q / NQ) % NQ, DIM == 3 ? q / (NQ * NQ) : 0};
-    double    r0[F0], rd[DIM][F0];
+    const int qpos  = qi[2] * PS + qi[1] * LS + qi[0];
     if (active)
     {
         double val[F], dref[DIM][F];
 #pragma unroll
         for (int f = 0; f < F; ++f)
         {
-            const double* line = uq + f * Q;
-            val[f]             = line[q];
-            int stride         = 1;
+            val[f] = s_val[f * AQ + qpos];
 #pragma unroll
             for (int d = 0; d < DIM; ++d)
-            {
-                const int base = q - qi[d] * stride;
-                double    acc  = s_colloc[qi[d]] * line[base];
-#pragma unroll
-                for (int m = 1; m < NQ; ++m)
-                    acc = fma(s_colloc[m * NQ + qi[d]], line[base + m * stride], acc);
-                dref[d][f] = acc;
-                stride *= NQ;
-            }
+                dref[d][f] = der_arr(d, f)[qpos];
         }
-        double xi[DIM], xs[3], Jt[DIM][DIM], Jti[DIM][DIM];
+        double xi[DIM], xs[3], Jt[DIM][DIM], Jti[DIM][DIM], detJ;
         double wq = 1.;
+        // table entries by run-time index: tiny select chains over constant-bank operands
 #pragma unroll
         for (int d = 0; d < DIM; ++d)
         {
-            xi[d] = s_pts[qi[d]];
-            wq *= s_w[qi[d]];
+            double pt = tab.pts[0], w = tab.w[0];
+#pragma unroll
+            for (int k = 1; k < NQ; ++k)
+                if (qi[d] == k)
+                {
+                    pt = tab.pts[k];
+                    w  = tab.w[k];
+                }
+            xi[d] = pt;
+            wq *= w;
         }
         geometryFromCoefs< DIM >(s_geo, xi, xs, Jt);
-        const double detJ = invert< DIM >(Jt, Jti);
+        const double* g = s_geo + nv * 3;
+        if (g[DIM * DIM + 1] != 0.)
+        {
+            detJ = g[DIM * DIM];
+#pragma unroll
+            for (int s = 0; s < DIM; ++s)
+#pragma unroll
+                for (int d = 0; d < DIM; ++d)
+                    Jti[s][d] = g[s * DIM + d];
+        }
+        else
+            detJ = invert< DIM >(Jt, Jti);
         // Jt[d][s] = dx_s/dxi_d, so Jti[s][d] = dxi_d/dx_s = the reference's jac_inv(d, s)
         typename KernelT::Input in;
 #pragma unroll
@@ -335,7 +454,7 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
 #pragma unroll
         for (int r = 0; r < NRHS; ++r)
         {
-            double g[DIM][U]; // physical gradients of the operand
+            double g_phys[DIM][U]; // physical gradients of the operand
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -345,7 +464,7 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
 #pragma unroll
                     for (int d = 1; d < DIM; ++d)
                         acc = fma(Jti[s][d], dref[d][r * U + u], acc);
-                    g[s][u] = acc;
+                    g_phys[s][u] = acc;
                 }
             double tv[E];
             staticFor< E >([&](auto eq) {
@@ -355,7 +474,7 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
                         acc = fma(res.operators[0](eq, u), val[r * U + u], acc);
                     staticFor< DIM >([&](auto s) {
                         if constexpr (Sp::nz(s + 1, eq, u))
-                            acc = fma(res.operators[s + 1](eq, u), g[s][u], acc);
+                            acc = fma(res.operators[s + 1](eq, u), g_phys[s][u], acc);
                     });
                 });
                 tv[eq] = acc * wgt;
@@ -373,7 +492,8 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
                             ps[s] = fma(res.operators[s + 1](eq, u), tv[eq], ps[s]);
                     });
                 });
-                r0[r * U + u] = a0;
+                // fluxes overwrite this thread's own entries: r0 → values, r_d → derivative arrays
+                s_val[(r * U + u) * AQ + qpos] = a0;
 #pragma unroll
                 for (int d = 0; d < DIM; ++d)
                 {
@@ -381,94 +501,99 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
 #pragma unroll
                     for (int s = 1; s < DIM; ++s)
                         acc = fma(Jti[s][d], ps[s], acc);
-                    rd[d][r * U + u] = acc;
+                    der_arr(d, r * U + u)[qpos] = acc;
                 }
             });
         }
     }
-    __syncthreads(); // every thread is done reading uq: its storage may now be overwritten by the fluxes
-    if (active)
-#pragma unroll
-        for (int d = 0; d < DIM; ++d)
-#pragma unroll
-            for (int f = 0; f < F0; ++f)
-                r_ptr(d, f)[q] = rd[d][f];
     __syncthreads();
 
-    // ---- transposed collocation derivative: v(q) = r0(q) + sum_d sum_n colloc[q_d][n] r_d(.., n, ..); kept in registers
-    double vreg[F0];
-    if (active)
+    // ---- transposed stage: v = r0 + sum_d D_d^T r_d, then Gauss points → nodes; all in place on s_val[f < F0]
     {
-#pragma unroll
-        for (int f = 0; f < F0; ++f)
+        double v[NQ], r[NQ], o[NQ];
+        constexpr int n_dl = DIM == 3 ? NQ * NQ : NQ;
+        // x- (and, in 3-D, y-) derivative transposes, one direction per phase (both update s_val)
+        for (int d = 0; d < DIM - 1; ++d)
         {
-            double acc    = r0[f];
-            int    stride = 1;
-#pragma unroll
-            for (int d = 0; d < DIM; ++d)
+            for (int l = t; l < F0 * n_dl; l += TPE)
             {
-                const double* line = r_ptr(d, f) + (q - qi[d] * stride);
-#pragma unroll
-                for (int n = 0; n < NQ; ++n)
-                    acc = fma(s_colloc[qi[d] * NQ + n], line[n * stride], acc);
-                stride *= NQ;
+                const int f = l / n_dl, rr = l % n_dl;
+                int       off, st;
+                if (d == 0)
+                {
+                    off = DIM == 3 ? (rr / NQ) * PS + (rr % NQ) * LS : rr * LS;
+                    st  = 1;
+                }
+                else
+                {
+                    off = (rr / NQ) * PS + rr % NQ;
+                    st  = LS;
+                }
+                if (active)
+                {
+                    loadLine< NQ, NQ >(s_val + f * AQ + off, st, v, NQ);
+                    loadLine< NQ, NQ >(der_arr(d, f) + off, st, r, NQ);
+                    differentiateTAccumulate< NQ >(r, v, tab.colloc);
+                    storeLine< NQ >(s_val + f * AQ + off, st, v, NQ);
+                }
             }
-            vreg[f] = acc;
+            __syncthreads();
         }
-    }
-    __syncthreads(); // all flux reads done: vq is free again
-    if (active)
-#pragma unroll
-        for (int f = 0; f < F0; ++f)
-            vq[f * Q + q] = vreg[f];
-    __syncthreads();
-
-    // ---- project back to the nodes (transposed interpolation sweeps), last direction first
-    double* res_nodes;
-    if constexpr (DIM == 2)
-    {
-        for (int l = t; l < F0 * NQ; l += Cfg::TPE)
+        // last direction: derivative transpose fused with the projection to the nodes
+        constexpr int n_l    = DIM == 3 ? NQ * NQ : NQ;
+        constexpr int stride = DIM == 3 ? PS : LS;
+        for (int l = t; l < F0 * n_l; l += TPE)
         {
-            const int f = l / NQ, qx = l % NQ;
-            sweepLine< NQ, NB, true >(vq + f * Q + qx, NQ, uq + f * Q + qx, NQ, tab.interp);
+            const int f = l / n_l, rr = l % n_l;
+            const int off = DIM == 3 ? (rr / NQ) * LS + rr % NQ : rr;
+            if (active)
+            {
+                loadLine< NQ, NQ >(s_val + f * AQ + off, stride, v, NQ);
+                loadLine< NQ, NQ >(der_arr(DIM - 1, f) + off, stride, r, NQ);
+                differentiateTAccumulate< NQ >(r, v, tab.colloc);
+                interpolateT< NB, NQ >(v, o, tab.interp);
+                storeLine< NQ >(s_val + f * AQ + off, stride, o, NB);
+            }
         }
         __syncthreads();
-        for (int l = t; l < F0 * NB; l += Cfg::TPE)
+        if constexpr (DIM == 3)
         {
-            const int f = l / NB, j = l % NB;
-            sweepLine< NQ, NB, true >(uq + f * Q + j * NQ, 1, vq + f * Q + j * NB, 1, tab.interp);
+            // y: lines (f, k, qx), k < NB
+            for (int l = t; l < F0 * NB * NQ; l += TPE)
+            {
+                const int f = l / (NB * NQ), rr = l % (NB * NQ);
+                double*   p = s_val + f * AQ + (rr / NQ) * PS + rr % NQ;
+                if (active)
+                {
+                    loadLine< NQ, NQ >(p, LS, v, NQ);
+                    interpolateT< NB, NQ >(v, o, tab.interp);
+                    storeLine< NQ >(p, LS, o, NB);
+                }
+            }
+            __syncthreads();
+        }
+        // x: lines (f, k, j), j, k < NB
+        constexpr int n_x = DIM == 3 ? F0 * NB * NB : F0 * NB;
+        for (int l = t; l < n_x; l += TPE)
+        {
+            const int f = l / (n_x / F0), rr = l % (n_x / F0);
+            double*   p = s_val + f * AQ + (DIM == 3 ? (rr / NB) * PS + (rr % NB) * LS : rr * LS);
+            if (active)
+            {
+                loadLine< NQ, NQ >(p, 1, v, NQ);
+                interpolateT< NB, NQ >(v, o, tab.interp);
+                storeLine< NQ >(p, 1, o, NB);
+            }
         }
         __syncthreads();
-        res_nodes = vq;
-    }
-    else
-    {
-        for (int l = t; l < F0 * NQ * NQ; l += Cfg::TPE)
-        {
-            const int f = l / (NQ * NQ), qyx = l % (NQ * NQ);
-            sweepLine< NQ, NB, true >(vq + f * Q + qyx, NQ * NQ, uq + f * Q + qyx, NQ * NQ, tab.interp);
-        }
-        __syncthreads();
-        for (int l = t; l < F0 * NB * NQ; l += Cfg::TPE)
-        {
-            const int f = l / (NB * NQ), k = (l / NQ) % NB, qx = l % NQ;
-            sweepLine< NQ, NB, true >(uq + f * Q + k * NQ * NQ + qx, NQ, vq + f * Q + k * NB * NQ + qx, NQ, tab.interp);
-        }
-        __syncthreads();
-        for (int l = t; l < F0 * NB * NB; l += Cfg::TPE)
-        {
-            const int f = l / (NB * NB), kj = l % (NB * NB);
-            sweepLine< NQ, NB, true >(vq + f * Q + kj * NQ, 1, uq + f * Q + kj * NB, 1, tab.interp);
-        }
-        __syncthreads();
-        res_nodes = uq;
     }
 
     // ---- scatter (MatrixFreeSystem.hpp:494-537): relaxed fp64 atomics, Dirichlet rows skipped
     if (active)
-        for (int a = t; a < NN; a += Cfg::TPE)
+        for (int a = t; a < NN; a += TPE)
         {
             const long long node = el_nodes[a];
+            const int       pos  = DIM == 3 ? (a / (NB * NB)) * PS + ((a / NB) % NB) * LS + a % NB : (a / NB) * LS + a % NB;
 #pragma unroll
             for (int u = 0; u < U; ++u)
             {
@@ -477,7 +602,7 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
                     continue;
 #pragma unroll
                 for (int r = 0; r < NRHS; ++r)
-                    atomicAdd(args.y + dof + r * args.ld, args.alpha * res_nodes[(r * U + u) * Q + a]);
+                    atomicAdd(args.y + dof + r * args.ld, args.alpha * s_val[(r * U + u) * AQ + pos]);
             }
         }
 }
