@@ -55,7 +55,10 @@ struct MfSumFactCfg
     // odd number of doubles so that the x-lines of one half-warp fall into distinct banks for every nq.
     static constexpr int LS = NQ % 2 == 0 ? NQ + 1 : NQ;
     static constexpr int PS = LS * NQ;
-    static constexpr int AQ = DIM == 3 ? PS * NQ : PS; // doubles per field array
+    static constexpr int AQ_raw = DIM == 3 ? PS * NQ : PS;
+    // doubles per field array, padded to AQ ≡ NQ (mod 16): lanes ordered (qx fastest, then field) then hit consecutive
+    // even banks in the sweeps whose lines start at (qx, k) — the y-type sweeps, which conflicted 2-way in v3
+    static constexpr int AQ = AQ_raw + ((NQ - AQ_raw) % 16 + 16) % 16;
     static constexpr int TPE = Q;
     static constexpr int EPB = cmax(1, 128 / TPE);
     static constexpr int threads = TPE * EPB;
@@ -225,51 +228,30 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
     if (active)
         buildGeometryCoefs< DIM >(args.verts + e * nv * 3, s_geo, t, TPE);
 
-    // ---- gather (MatrixFreeSystem.hpp:421-467) into s_val[f], f = rhs*U + u, then the NF external fields
+    // ---- gather (MatrixFreeSystem.hpp:421-467) into s_val[f], f = rhs*U + u, then the NF external fields.
+    // One lane per (node, unknown): the U dofs of a node are adjacent in x, so a warp touches ~32/U sectors per load
+    // instead of 32 (thread-per-node would).
     if (active)
-        for (int a = t; a < NN; a += TPE)
+    {
+        for (int i = t; i < NN * U; i += TPE)
         {
+            const int       a = i / U, u = i % U;
             const long long node = el_nodes[a];
             const int       pos  = DIM == 3 ? (a / (NB * NB)) * PS + ((a / NB) % NB) * LS + a % NB : (a / NB) * LS + a % NB;
-            if (U % 2 == 0 and args.contiguous_dofs)
-            {
-                // dofs of a node are the U contiguous entries node*U .. node*U+U-1: vectorised 16-byte loads
+            const long long dof  = node * args.dofs_per_node + args.dof_inds[u];
+            const bool      dir  = isDirichlet(args.dir_mask, dof);
 #pragma unroll
-                for (int r = 0; r < NRHS; ++r)
-                {
-                    const double2* src = reinterpret_cast< const double2* >(args.x + node * U + r * args.ld);
-#pragma unroll
-                    for (int u2 = 0; u2 < U / 2; ++u2)
-                    {
-                        double2 v = __ldg(src + u2);
-                        if (args.dir_mask)
-                        {
-                            if (args.dir_mask[node * U + 2 * u2])
-                                v.x = 0.;
-                            if (args.dir_mask[node * U + 2 * u2 + 1])
-                                v.y = 0.;
-                        }
-                        s_val[(r * U + 2 * u2) * AQ + pos]     = v.x;
-                        s_val[(r * U + 2 * u2 + 1) * AQ + pos] = v.y;
-                    }
-                }
-            }
-            else
-            {
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                {
-                    const long long dof = node * args.dofs_per_node + args.dof_inds[u];
-                    const bool      dir = isDirichlet(args.dir_mask, dof);
-#pragma unroll
-                    for (int r = 0; r < NRHS; ++r)
-                        s_val[(r * U + u) * AQ + pos] = dir ? 0. : args.x[dof + r * args.ld];
-                }
-            }
-#pragma unroll
-            for (int f = 0; f < NF; ++f)
-                s_val[(F0 + f) * AQ + pos] = args.fields[node + args.field_inds[f] * args.field_stride];
+            for (int r = 0; r < NRHS; ++r)
+                s_val[(r * U + u) * AQ + pos] = dir ? 0. : __ldg(args.x + dof + r * args.ld);
         }
+        if constexpr (NF > 0)
+            for (int i = t; i < NN * NF; i += TPE)
+            {
+                const int       a = i % NN, f = i / NN;
+                const int       pos = DIM == 3 ? (a / (NB * NB)) * PS + ((a / NB) % NB) * LS + a % NB : (a / NB) * LS + a % NB;
+                s_val[(F0 + f) * AQ + pos] = __ldg(args.fields + el_nodes[a] + args.field_inds[f] * args.field_stride);
+            }
+    }
     __syncthreads();
     // affine element (all mixed monomial coefficients vanish): one thread inverts the constant Jacobian for everybody
     if (active and t == 0)
@@ -315,11 +297,11 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
         __syncthreads();
         if constexpr (DIM == 3)
         {
-            // y: lines (f, k, qx), k < NB
+            // y: lines (qx fastest, then f, then k < NB)
             for (int l = t; l < F * NB * NQ; l += TPE)
             {
-                const int f = l / (NB * NQ), r = l % (NB * NQ);
-                double*   p = s_val + f * AQ + (r / NQ) * PS + r % NQ;
+                const int qx = l % NQ, f = (l / NQ) % F, k = l / (NQ * F);
+                double*   p = s_val + f * AQ + k * PS + qx;
                 if (active)
                 {
                     loadLine< NB, NQ >(p, LS, v, NB);
@@ -350,17 +332,21 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
         constexpr int n_dl = DIM == 3 ? NQ * NQ : NQ;
         for (int l = t; l < (DIM - 1) * F * n_dl; l += TPE)
         {
-            const int d = l / (F * n_dl), f = (l / n_dl) % F, r = l % n_dl;
-            int       off, st;
-            if (d == 0) // x-lines (qy[, qz])
+            const int d = l / (F * n_dl);
+            int       f, off, st;
+            if (d == 0) // x-lines (qy[, qz]); tasks ordered (line, f)
             {
-                off = DIM == 3 ? (r / NQ) * PS + (r % NQ) * LS : r * LS;
-                st  = 1;
+                const int r = l % n_dl;
+                f           = (l / n_dl) % F;
+                off         = DIM == 3 ? (r / NQ) * PS + (r % NQ) * LS : r * LS;
+                st          = 1;
             }
-            else // y-lines (qx, qz), 3-D only
+            else // y-lines, 3-D only; tasks ordered (qx fastest, then f, then qz)
             {
-                off = (r / NQ) * PS + r % NQ;
-                st  = LS;
+                const int ll = l - F * n_dl;
+                f            = (ll / NQ) % F;
+                off          = (ll / (NQ * F)) * PS + ll % NQ;
+                st           = LS;
             }
             if (active)
             {
@@ -517,16 +503,18 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
         {
             for (int l = t; l < F0 * n_dl; l += TPE)
             {
-                const int f = l / n_dl, rr = l % n_dl;
-                int       off, st;
+                int f, off, st;
                 if (d == 0)
                 {
-                    off = DIM == 3 ? (rr / NQ) * PS + (rr % NQ) * LS : rr * LS;
-                    st  = 1;
+                    const int rr = l % n_dl;
+                    f            = l / n_dl;
+                    off          = DIM == 3 ? (rr / NQ) * PS + (rr % NQ) * LS : rr * LS;
+                    st           = 1;
                 }
                 else
                 {
-                    off = (rr / NQ) * PS + rr % NQ;
+                    f   = (l / NQ) % F0;
+                    off = (l / (NQ * F0)) * PS + l % NQ;
                     st  = LS;
                 }
                 if (active)
@@ -558,11 +546,11 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
         __syncthreads();
         if constexpr (DIM == 3)
         {
-            // y: lines (f, k, qx), k < NB
+            // y: lines (qx fastest, then f, then k < NB)
             for (int l = t; l < F0 * NB * NQ; l += TPE)
             {
-                const int f = l / (NB * NQ), rr = l % (NB * NQ);
-                double*   p = s_val + f * AQ + (rr / NQ) * PS + rr % NQ;
+                const int qx = l % NQ, f = (l / NQ) % F0, k = l / (NQ * F0);
+                double*   p = s_val + f * AQ + k * PS + qx;
                 if (active)
                 {
                     loadLine< NQ, NQ >(p, LS, v, NQ);
@@ -588,22 +576,19 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
         __syncthreads();
     }
 
-    // ---- scatter (MatrixFreeSystem.hpp:494-537): relaxed fp64 atomics, Dirichlet rows skipped
+    // ---- scatter (MatrixFreeSystem.hpp:494-537): relaxed fp64 atomics, Dirichlet rows skipped; one lane per (node, unknown)
     if (active)
-        for (int a = t; a < NN; a += TPE)
+        for (int i = t; i < NN * U; i += TPE)
         {
+            const int       a = i / U, u = i % U;
             const long long node = el_nodes[a];
             const int       pos  = DIM == 3 ? (a / (NB * NB)) * PS + ((a / NB) % NB) * LS + a % NB : (a / NB) * LS + a % NB;
+            const long long dof  = node * args.dofs_per_node + args.dof_inds[u];
+            if (isDirichlet(args.dir_mask, dof))
+                continue;
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-            {
-                const long long dof = node * args.dofs_per_node + args.dof_inds[u];
-                if (isDirichlet(args.dir_mask, dof))
-                    continue;
-#pragma unroll
-                for (int r = 0; r < NRHS; ++r)
-                    atomicAdd(args.y + dof + r * args.ld, args.alpha * s_val[(r * U + u) * AQ + pos]);
-            }
+            for (int r = 0; r < NRHS; ++r)
+                atomicAdd(args.y + dof + r * args.ld, args.alpha * s_val[(r * U + u) * AQ + pos]);
         }
 }
 } // namespace l3b
