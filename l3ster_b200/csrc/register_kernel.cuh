@@ -12,10 +12,12 @@
 
 #include "assemble.cuh"
 #include "local_element.cuh"
+#include "mf_hex_planes.cuh"
 #include "mf_sumfact.cuh"
 #include "registry.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace l3b
 {
@@ -46,6 +48,42 @@ cudaError_t launchMfSumFact(const void* obj, const ElemArgs& args, const tables:
     std::copy(t.w.begin(), t.w.end(), tab.w);
     std::copy(t.pts.begin(), t.pts.end(), tab.pts);
     constexpr auto fn = mfSumFactApplyKernel< KernelT, DIM, P, NQ, NC >;
+    if (const auto err = raiseSmemLimit< fn >(Cfg::smem_bytes); err != cudaSuccess)
+        return err;
+    static const cudaError_t carveout =
+        cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, static_cast< int >(cudaSharedmemCarveoutMaxShared));
+    if (carveout != cudaSuccess)
+        return carveout;
+    const auto grid = static_cast< unsigned >((args.n_work + Cfg::EPB - 1) / Cfg::EPB);
+    fn<<< grid, Cfg::threads, Cfg::smem_bytes, stream >>>(*static_cast< const KernelT* >(obj), args, tab);
+    return cudaGetLastError();
+}
+
+// hexahedra: planes + columns kernel (mf_hex_planes.cuh) when its register tiles fit, else the line-per-thread kernel.
+// L3B_MF_LINES=1 in the environment forces the line-per-thread kernel (A/B measurements, parity of both paths).
+inline bool forceLineKernel()
+{
+    static const bool force = [] {
+        const char* e = std::getenv("L3B_MF_LINES");
+        return e != nullptr and e[0] == '1';
+    }();
+    return force;
+}
+template < typename KernelT, int P, int NQ, int NC >
+cudaError_t launchMfHex(const void* obj, const ElemArgs& args, const tables::Tables1D& t, cudaStream_t stream)
+{
+    using Cfg = MfHexCfg< KernelT, P, NQ, NC >;
+    if (forceLineKernel())
+        return launchMfSumFact< KernelT, 3, P, NQ, NC >(obj, args, t, stream);
+    if (args.n_work == 0)
+        return cudaSuccess;
+    SumFactTables< P + 1, NQ > tab;
+    std::copy(t.interp.begin(), t.interp.end(), tab.interp);
+    std::copy(t.der.begin(), t.der.end(), tab.der);
+    std::copy(t.colloc.begin(), t.colloc.end(), tab.colloc);
+    std::copy(t.w.begin(), t.w.end(), tab.w);
+    std::copy(t.pts.begin(), t.pts.end(), tab.pts);
+    constexpr auto fn = mfHexPlanesKernel< KernelT, P, NQ, NC >;
     if (const auto err = raiseSmemLimit< fn >(Cfg::smem_bytes); err != cudaSuccess)
         return err;
     static const cudaError_t carveout =
@@ -99,9 +137,19 @@ KernelInstance makeInstance()
     inst.nq    = NQ;
     if constexpr (not KernelT::is_boundary)
     {
-        inst.mf_sumfact_full    = launchMfSumFact< KernelT, DIM, P, NQ, NRHS >;
-        inst.mf_sumfact_one     = launchMfSumFact< KernelT, DIM, P, NQ, 1 >;
-        inst.mf_elems_per_block = MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::EPB;
+        if constexpr (DIM == 3 and NQ * NQ <= 49)
+        {
+            static_assert(MfHexCfg< KernelT, P, NQ, NRHS >::supported);
+            inst.mf_sumfact_full    = launchMfHex< KernelT, P, NQ, NRHS >;
+            inst.mf_sumfact_one     = launchMfHex< KernelT, P, NQ, 1 >;
+            inst.mf_elems_per_block = MfHexCfg< KernelT, P, NQ, NRHS >::EPB;
+        }
+        else
+        {
+            inst.mf_sumfact_full    = launchMfSumFact< KernelT, DIM, P, NQ, NRHS >;
+            inst.mf_sumfact_one     = launchMfSumFact< KernelT, DIM, P, NQ, 1 >;
+            inst.mf_elems_per_block = MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::EPB;
+        }
     }
     inst.local_apply_full    = launchLocal< KernelT, DIM, P, NRHS, MODE_APPLY >;
     inst.local_apply_one     = launchLocal< KernelT, DIM, P, 1, MODE_APPLY >;
