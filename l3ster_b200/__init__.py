@@ -15,7 +15,8 @@ from dataclasses import dataclass
 import numpy as np
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "libl3ster_b200.so")
+# L3B_LIB_PATH: load an experiment build (csrc/Makefile: EXTRA/BUILD/OUT) instead of the product library
+LIB_PATH = os.environ.get("L3B_LIB_PATH") or os.path.join(_DIR, "libl3ster_b200.so")
 
 QUAD, HEX = 2, 3
 NO_BOUNDARY = 0xFFFF

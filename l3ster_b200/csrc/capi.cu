@@ -3,6 +3,7 @@
 #include "../../include/l3ster_b200.h"
 
 #include "mesh_host.hpp"
+#include "mf_hex_planes.cuh"
 #include "registry.hpp"
 #include "tables.hpp"
 
@@ -117,6 +118,57 @@ __global__ void dirichletRowsKernel(const uint8_t* mask, const double* x, double
         if (mask[i])
             for (int c = 0; c < n_cols; ++c)
                 y[i + c * ld] += alpha * x[i + c * ld];
+}
+// per element: any Dirichlet dof on any of its nodes? (lets the apply kernels skip the mask for interior elements)
+__global__ void elemDirichletFlagKernel(const uint32_t* nodes, long long n_elems, int nn, int dpn, const uint8_t* mask, uint32_t* flag)
+{
+    for (long long e = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; e < n_elems; e += static_cast< long long >(gridDim.x) * blockDim.x)
+    {
+        uint32_t f = 0;
+        for (int a = 0; a < nn; ++a)
+            for (int d = 0; d < dpn; ++d)
+                f |= mask[static_cast< long long >(nodes[e * nn + a]) * dpn + d];
+        flag[e] = f != 0;
+    }
+}
+// hex geometry record (mf_hex_planes.cuh): monomial coefficients of the trilinear map, and for affine elements the constant
+// inverse Jacobian, its determinant and the affine flag
+__global__ void hexGeometryKernel(const double* verts, long long n_elems, double* geo)
+{
+    for (long long e = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; e < n_elems; e += static_cast< long long >(gridDim.x) * blockDim.x)
+    {
+        double* g = geo + e * hex_geo_doubles;
+        for (int i = 0; i < hex_geo_doubles; ++i)
+            g[i] = 0.;
+        buildGeometryCoefs< 3 >(verts + e * 24, g, 0, 1);
+        bool affine = true;
+        for (int m = 0; m < 8; ++m)
+            if (__popc(m) > 1)
+                for (int s = 0; s < 3; ++s)
+                    affine = affine and g[m * 3 + s] == 0.;
+        g[hex_geo_affine] = affine ? 1. : 0.;
+        if (affine)
+        {
+            double Jt[3][3], Jti[3][3];
+            for (int d = 0; d < 3; ++d)
+                for (int s = 0; s < 3; ++s)
+                    Jt[d][s] = g[(1 << d) * 3 + s];
+            g[hex_geo_det] = invert< 3 >(Jt, Jti);
+            for (int s = 0; s < 3; ++s)
+                for (int d = 0; d < 3; ++d)
+                    g[hex_geo_jti + s * 3 + d] = Jti[s][d];
+        }
+    }
+}
+// the same over a compact list of the Dirichlet dofs (O(surface) instead of a pass over the whole vector)
+__global__ void dirichletRowsListKernel(const int32_t* dofs, long long n_dir, const double* x, double* y, long long ld, int n_cols, double alpha)
+{
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n_dir; i += static_cast< long long >(gridDim.x) * blockDim.x)
+    {
+        const long long d = dofs[i];
+        for (int c = 0; c < n_cols; ++c)
+            y[d + c * ld] += alpha * x[d + c * ld];
+    }
 }
 // handle_dirichlet_dof (MatrixFreeSystem.hpp:911-915)
 __global__ void dirichletInitKernel(const uint8_t* mask, const double* vals, double* diag, double* rhs, long long n, long long ld, int n_rhs)
@@ -427,6 +479,7 @@ struct l3b_mesh
     long long           n_elems = 0, n_local_nodes = 0, n_owned_nodes = 0;
     DevBuf< double >    verts;
     DevBuf< uint32_t >  nodes;
+    DevBuf< double >    hex_geo; // dim 3: per-element geometry record of the planes + columns apply kernel
     std::vector< uint16_t > side_bnd; // host copy, used to build boundary work lists
 };
 
@@ -545,6 +598,7 @@ ElemArgs baseArgs(l3b_mesh* mesh, const KernelUse& use, int dofs_per_node, long 
     ElemArgs a{};
     a.verts         = mesh->verts.ptr;
     a.nodes         = mesh->nodes.ptr;
+    a.hex_geo       = mesh->hex_geo.ptr;
     a.dofs_per_node = dofs_per_node;
     a.ld            = ld;
     std::memcpy(a.dof_inds, use.dof_inds, sizeof(a.dof_inds));
@@ -609,6 +663,9 @@ struct l3b_mf
     int                      dpn = 0, n_rhs = 1;
     long long                n_dofs = 0;
     DevBuf< uint8_t >        dir_mask;
+    DevBuf< uint32_t >       elem_dir;
+    DevBuf< int32_t >        dir_list; // the Dirichlet dofs, ascending
+    long long                n_dir = 0;
     DevBuf< double >         dir_vals, diag, rhs;
     bool                     has_bc = false, closed = false;
     std::vector< KernelUse > uses;
@@ -651,8 +708,13 @@ void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double a
     if (n_cols != sys->n_rhs and n_cols != 1)
         fail(L3B_ERR_INVALID_ARG, "n_cols must equal the system's n_rhs or 1");
     int launches = 0;
-    scaleKernel<<< gridFor(sys->n_dofs * n_cols), 256, 0, ctx->stream >>>(y, sys->n_dofs * n_cols, beta);
-    ++launches;
+    if (beta == 0.)
+        cudaCheck(cudaMemsetAsync(y, 0, sizeof(double) * sys->n_dofs * n_cols, ctx->stream), "memset");
+    else
+    {
+        scaleKernel<<< gridFor(sys->n_dofs * n_cols), 256, 0, ctx->stream >>>(y, sys->n_dofs * n_cols, beta);
+        ++launches;
+    }
     for (const auto& use : sys->uses)
     {
         const auto& info = kernelRegistry()[use.kernel_id].info;
@@ -662,6 +724,7 @@ void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double a
         a.n_cols         = n_cols;
         a.alpha          = alpha;
         a.dir_mask       = sys->has_bc ? sys->dir_mask.ptr : nullptr;
+        a.elem_dir       = sys->has_bc ? sys->elem_dir.ptr : nullptr;
         bool contiguous  = info.n_unknowns == sys->dpn and reinterpret_cast< uintptr_t >(x) % 16 == 0 and sys->n_dofs % 2 == 0;
         for (int u = 0; u < info.n_unknowns; ++u)
             contiguous = contiguous and use.dof_inds[u] == u;
@@ -684,9 +747,9 @@ void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double a
         if (a.n_work > 0)
             ++launches;
     }
-    if (sys->has_bc)
+    if (sys->has_bc and sys->n_dir > 0)
     {
-        dirichletRowsKernel<<< gridFor(sys->n_dofs), 256, 0, ctx->stream >>>(sys->dir_mask.ptr, x, y, sys->n_dofs, sys->n_dofs, n_cols, alpha);
+        dirichletRowsListKernel<<< gridFor(sys->n_dir), 256, 0, ctx->stream >>>(sys->dir_list.ptr, sys->n_dir, x, y, sys->n_dofs, n_cols, alpha);
         ++launches;
     }
     cudaCheck(cudaGetLastError(), "operator apply");
@@ -985,6 +1048,12 @@ int l3b_mesh_upload(l3b_context* ctx, int dim, int order, int64_t n_elems, const
         m->nodes.upload(nodes, static_cast< size_t >(n_elems) * m->nn, ctx->stream);
         if (side_boundaries)
             m->side_bnd.assign(side_boundaries, side_boundaries + n_elems * m->n_sides);
+        if (dim == 3 and n_elems > 0)
+        {
+            m->hex_geo.alloc(static_cast< size_t >(n_elems) * hex_geo_doubles);
+            hexGeometryKernel<<< gridFor(n_elems), 256, 0, ctx->stream >>>(m->verts.ptr, n_elems, m->hex_geo.ptr);
+            cudaCheck(cudaGetLastError(), "hex geometry");
+        }
         cudaCheck(cudaStreamSynchronize(ctx->stream), "mesh upload");
         *out = m.release();
     });
@@ -1191,11 +1260,25 @@ int l3b_mf_create(l3b_context* ctx, l3b_mesh* mesh, int dpn, int n_rhs, const ui
             s->has_bc = true;
             s->dir_mask.alloc(s->n_dofs);
             s->dir_mask.upload(mask, s->n_dofs, ctx->stream);
+            std::vector< int32_t > list;
+            for (long long i = 0; i < s->n_dofs; ++i)
+                if (mask[i])
+                    list.push_back(static_cast< int32_t >(i));
+            s->n_dir = static_cast< long long >(list.size());
+            s->dir_list.alloc(list.size());
+            s->dir_list.upload(list.data(), list.size(), ctx->stream);
             s->dir_vals.alloc(s->n_dofs * n_rhs);
             if (vals)
                 s->dir_vals.upload(vals, s->dir_vals.n, ctx->stream);
             else
                 s->dir_vals.zero(ctx->stream);
+            if (mesh->n_elems > 0)
+            {
+                s->elem_dir.alloc(mesh->n_elems);
+                elemDirichletFlagKernel<<< gridFor(mesh->n_elems), 256, 0, ctx->stream >>>(mesh->nodes.ptr, mesh->n_elems, mesh->nn, dpn,
+                                                                                       s->dir_mask.ptr, s->elem_dir.ptr);
+                cudaCheck(cudaGetLastError(), "element Dirichlet flags");
+            }
             cudaCheck(cudaStreamSynchronize(ctx->stream), "Dirichlet upload");
         }
         *out = s.release();

@@ -56,6 +56,10 @@ struct ElemArgs
     // Dirichlet mask per local dof (may be null) and prescribed values (ld-strided, may be null)
     const uint8_t* dir_mask;
     const double*  dir_vals;
+    // per element: does any dof of any of its nodes carry a Dirichlet condition? (may be null = unknown, always look)
+    const uint32_t* elem_dir;
+    // hexahedra: per-element geometry record (mf_hex_planes.cuh: hex_geo_doubles), built at mesh upload
+    const double* hex_geo;
     // init outputs
     double* diag;
     double* rhs;

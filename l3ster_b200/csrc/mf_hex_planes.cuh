@@ -25,6 +25,18 @@
 // 4 barriers and ~64 KB of shared-memory traffic per p=4 element; 46 k DFMA per element (15 k per transform direction
 // pair, 16 k in the point stage) is what remains, i.e. the kernel is built to be bound by the fp64 pipe.
 //
+// HBM side (v7): the kernel is persistent (one CTA per resident slot, batches of EPB elements strided over the grid) and
+// software-pipelined so that no warp waits on HBM inside the loop (ncu r1_v5: 44 % of the stall samples sat on the
+// Dirichlet-mask and x loads of the gather/scatter):
+//   iteration i   runs A..E on batch i;
+//                 after the first barrier it issues, with cp.async (LDGSTS), the geometry record of batch i+1 and the
+//                 node ids + element flags of batch i+2 (coalesced 4-byte copies into a 3-deep ring);
+//                 at the start of D it issues the indexed gather of batch i+1 — one 256-bit load per node through the
+//                 ids that arrived an iteration earlier — into registers that are only consumed by A of iteration i+1
+//                 (D and E are the phases with register head-room; v6 staged x through cp.async instead, which cost one
+//                 shared-memory wavefront per 16-byte piece: 45 % of all shared-memory traffic, ncu r1_v6).
+// Dirichlet mask bytes are only looked at for elements flagged at system creation (elemDirichletFlagKernel).
+//
 // Shared-memory layout (doubles): three arrays V, DX, DY of [plane = f * NQ + qz][element slot][PSZ], PSZ = NQ^2 rounded
 // up to an odd number. A column thread (slot, c) addresses plane * EPB * PSZ + slot * PSZ + c: consecutive threads →
 // consecutive words, conflict-free. A plane thread w = plane * EPB + slot addresses PSZ * w + n: odd stride →
@@ -36,6 +48,11 @@
 
 namespace l3b
 {
+// per-element geometry record built once at mesh upload (hexGeometryKernel): monomial coefficients of the trilinear map
+// [8][3], then — for affine elements — the constant inverse Jacobian Jti[s][d] = dxi_d/dx_s, detJ, and the affine flag
+constexpr int hex_geo_doubles = 36;
+constexpr int hex_geo_jti = 24, hex_geo_det = 33, hex_geo_affine = 34;
+
 template < typename KernelT, int P, int NQ, int NRHS >
 struct MfHexCfg
 {
@@ -46,17 +63,31 @@ struct MfHexCfg
     static constexpr int  NN  = NB * NB * NB;
     static constexpr int  CT  = NQ * NQ;                    // column threads per element
     static constexpr int  PSZ = CT % 2 == 0 ? CT + 1 : CT;  // plane stride
-    static constexpr int  EPB = cmax(1, 128 / CT);          // elements per CTA
+    // elements per batch: fill ~128 threads, but keep the batch's tensors within ~100 KB of shared memory
+    static constexpr int  EPB = [] {
+        int epb = cmax(1, 128 / CT);
+        while (epb > 1 and 3 * F * NQ * epb * PSZ * 8 > 100 * 1024)
+            --epb;
+        return epb;
+    }();
     static constexpr int  threads = ((EPB * CT + 31) / 32) * 32;
     static constexpr int  NPL     = F * NQ;                 // planes per element, back transform
     static constexpr int  NPLF    = F0 * NQ;                // planes per element, transposed transform
     static constexpr int  AS      = NPL * EPB * PSZ;        // doubles per array
-    static constexpr int  geo_doubles = 36;                 // 8 x 3 monomial coefficients, Jti[3][3], detJ, affine flag (+1 pad)
-    static constexpr size_t smem_bytes = (3 * static_cast< size_t >(AS) + EPB * geo_doubles) * sizeof(double);
-    // registers: the point stage keeps a z-column of values and of accumulators for U unknowns + the NF field values
-    static constexpr int col_doubles = (2 * U + NF) * NQ + NQ * NQ / 2;
-    static constexpr int min_blocks  = col_doubles <= 56 and smem_bytes <= 72 * 1024 ? 3 : smem_bytes <= 110 * 1024 ? 2 : 1;
-    static constexpr bool supported  = CT <= 49 and smem_bytes <= 200 * 1024;
+    static constexpr int  RING    = 3;                      // node-id / element-flag prefetch depth
+    // shared memory map, in doubles: V, DX, DY | geometry x 2 | then u32: node ids x RING | mask words | flags x RING
+    static constexpr int off_geo   = 3 * AS + (3 * AS) % 2; // 16-byte aligned: target of 16-byte cp.async
+    static constexpr int off_u32   = off_geo + 2 * EPB * hex_geo_doubles; // doubles
+    static constexpr int ids_words = RING * EPB * NN, mask_words = threads * NB, flag_words = RING * EPB + 1;
+    static constexpr size_t smem_bytes = static_cast< size_t >(off_u32) * sizeof(double) + (ids_words + mask_words + flag_words) * sizeof(uint32_t);
+#ifdef L3B_HEX_MIN_BLOCKS
+    static constexpr int  min_blocks  = L3B_HEX_MIN_BLOCKS; // experiment override
+#else
+    // 2 CTAs/SM: at 3 (168 registers) the point stage spills, and the shared-memory carve-out leaves the spills no L1
+    static constexpr int  min_blocks  = smem_bytes <= 112 * 1024 ? 2 : 1;
+#endif
+    static constexpr bool supported   = CT <= 49 and smem_bytes <= 220 * 1024;
+    static constexpr bool mask_bits_fit = NB * U <= 64;
     static_assert(params.dimension == 3);
     static_assert(NQ >= NB, "collocation differentiation at the Gauss points needs nq >= nb (value_order >= 1)");
 };
@@ -72,75 +103,242 @@ constexpr bool gradNeeded(int s, int u)
     return false;
 }
 
+__device__ __forceinline__ void cpAsync4(void* smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast< unsigned >(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cpAsync16(void* smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast< unsigned >(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
+}
+// gather loads of the software pipeline: volatile so that they stay where they are issued (far ahead of their use)
+__device__ __forceinline__ void ldNc256(const double* p, double& a, double& b, double& c, double& d)
+{
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void ldNc128(const double* p, double& a, double& b)
+{
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+}
+__device__ __forceinline__ double ldNc64(const double* p)
+{
+    double a;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(a) : "l"(p));
+    return a;
+}
+// predicated fire-and-forget fp64 atomic add: no divergent branch around the RED
+__device__ __forceinline__ void redAddIf(double* p, double v, int go)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p red.global.add.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"(go) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cpAsyncWaitAll()
+{
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 template < typename KernelT, int P, int NQ, int NRHS >
 __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfHexCfg< KernelT, P, NQ, NRHS >::min_blocks)
     mfHexPlanesKernel(const KernelT kernel, const __grid_constant__ ElemArgs args, const __grid_constant__ SumFactTables< P + 1, NQ > tab)
 {
     using Cfg = MfHexCfg< KernelT, P, NQ, NRHS >;
     using Sp  = KernelSparsity< KernelT >;
-    constexpr int E = Cfg::E, U = Cfg::U, NF = Cfg::NF, NB = Cfg::NB, F0 = Cfg::F0, F = Cfg::F, NN = Cfg::NN;
+    constexpr int E = Cfg::E, U = Cfg::U, NF = Cfg::NF, NB = Cfg::NB, F0 = Cfg::F0, NN = Cfg::NN;
     constexpr int CT = Cfg::CT, PSZ = Cfg::PSZ, EPB = Cfg::EPB, AS = Cfg::AS, NPL = Cfg::NPL, NPLF = Cfg::NPLF;
-    constexpr int T = Cfg::threads;
+    constexpr int T = Cfg::threads, RING = Cfg::RING;
     extern __shared__ double smem[];
-    double* const s_V   = smem;
-    double* const s_DX  = smem + AS;
-    double* const s_DY  = smem + 2 * AS;
-    double* const s_geo = smem + 3 * AS;
+    double* const   s_V     = smem;
+    double* const   s_DX    = smem + AS;
+    double* const   s_DY    = smem + 2 * AS;
+    double* const   s_geo   = smem + Cfg::off_geo;
+    uint32_t* const s_ids   = reinterpret_cast< uint32_t* >(smem + Cfg::off_u32);
+    uint32_t* const s_mask  = s_ids + Cfg::ids_words;
+    uint32_t* const s_flag  = s_mask + Cfg::mask_words;
 
-    const int       tid      = threadIdx.x;
-    const long long wi0      = static_cast< long long >(blockIdx.x) * EPB;
-    const int       n_active = static_cast< int >(args.n_work - wi0 < EPB ? args.n_work - wi0 : EPB); // elements of this CTA
+    const int       tid       = threadIdx.x;
+    const long long n_batches = (args.n_work + EPB - 1) / EPB;
+    const int       n_it      = static_cast< int >((n_batches - blockIdx.x + gridDim.x - 1) / gridDim.x);
     // column role
     const int  slot    = tid / CT;
     const int  cc      = tid % CT;
-    const bool col_on  = tid < EPB * CT and slot < n_active;
     const int  ci      = cc % NQ, cj = cc / NQ;
-    const long long ce = col_on ? (args.work_elems ? args.work_elems[wi0 + slot] : args.first_elem + wi0 + slot) : 0;
-    const uint32_t* el_nodes = args.nodes + ce * NN;
-    double* const   geo      = s_geo + slot * Cfg::geo_doubles;
-    const int       col_off  = slot * PSZ + cc; // + plane * EPB * PSZ
+    const bool col_thr = tid < EPB * CT;
+    const bool node_thr = col_thr and ci < NB and cj < NB; // owns the nodal z-column (ci, cj)
+    const int  col_off = slot * PSZ + cc;                   // + plane * EPB * PSZ
+    // vector gather when the dofs of a node are contiguous and aligned; then (U == 4) one 4-byte mask word per node
+    const bool vec_vals   = args.contiguous_dofs != 0 and U % 2 == 0;
+    const bool stage_mask = vec_vals and U == 4 and args.dir_mask != nullptr;
 
-    // ---- A: gather (MatrixFreeSystem.hpp:421-467) + z-interpolation
-    if (col_on)
-    {
-        buildGeometryCoefs< 3 >(args.verts + ce * 24, geo, cc, CT);
-        if (ci < NB and cj < NB)
+    const auto batchOf = [&](int i) { return static_cast< long long >(blockIdx.x) + static_cast< long long >(i) * gridDim.x; };
+    // element handled by this thread's slot in iteration i, or -1
+    const auto elemOf = [&](int i) -> long long {
+        const long long wi = batchOf(i) * EPB + slot;
+        if (not col_thr or wi >= args.n_work)
+            return -1;
+        return args.work_elems ? args.work_elems[wi] : args.first_elem + wi;
+    };
+    const auto activeIn = [&](int i) { // number of elements in batch i
+        const long long left = args.n_work - batchOf(i) * EPB;
+        return static_cast< int >(left < EPB ? left : EPB);
+    };
+    // node ids (coalesced over the batch) and element flags of iteration i → ring slot i % RING
+    const auto prefetchIds = [&](int i) {
+        const int       ring  = i % RING;
+        const int       n_act = activeIn(i);
+        const long long wi0   = batchOf(i) * EPB;
+        if (args.work_elems == nullptr)
         {
-            long long node[NB];
+            const uint32_t* src = args.nodes + (args.first_elem + wi0) * NN;
+#pragma unroll 1
+            for (int w = tid; w < n_act * NN; w += T)
+                cpAsync4(s_ids + ring * EPB * NN + w, src + w);
+        }
+        else
+#pragma unroll 1
+            for (int w = tid; w < n_act * NN; w += T)
+                cpAsync4(s_ids + ring * EPB * NN + w, args.nodes + static_cast< long long >(args.work_elems[wi0 + w / NN]) * NN + w % NN);
+        if (args.elem_dir != nullptr and tid < n_act)
+            cpAsync4(s_flag + ring * EPB + tid, args.elem_dir + (args.work_elems ? args.work_elems[wi0 + tid] : args.first_elem + wi0 + tid));
+    };
+    const auto flagOf = [&](int i) -> bool { // does the element of iteration i touch a Dirichlet dof?
+        if (args.dir_mask == nullptr)
+            return false;
+        return args.elem_dir == nullptr or s_flag[(i % RING) * EPB + slot] != 0;
+    };
+    const auto nodeOf = [&](int i, int k) -> uint32_t { return s_ids[((i % RING) * EPB + slot) * NN + k * NB * NB + cj * NB + ci]; };
+    // geometry record of iteration i
+    const auto prefetchGeo = [&](int i) {
+        const long long e = elemOf(i);
+        if (e < 0)
+            return;
+        for (int c = cc; c < hex_geo_doubles / 2; c += CT)
+            cpAsync16(s_geo + ((i & 1) * EPB + slot) * hex_geo_doubles + c * 2, args.hex_geo + e * hex_geo_doubles + c * 2);
+    };
+    // the nodal z-column of this thread in iteration i: x → registers, mask words of flagged elements → shared memory
+    double     xn[NRHS][NB][U];
+    const auto loadX = [&](int i) {
+        if (not(node_thr and slot < activeIn(i)))
+            return;
+        const bool flagged = stage_mask and flagOf(i);
 #pragma unroll
-            for (int k = 0; k < NB; ++k)
-                node[k] = el_nodes[k * NB * NB + cj * NB + ci];
+        for (int k = 0; k < NB; ++k)
+        {
+            const long long node = nodeOf(i, k);
 #pragma unroll
             for (int r = 0; r < NRHS; ++r)
             {
-                double v[U][NB];
-                if (args.contiguous_dofs and U % 2 == 0)
+                if (vec_vals)
                 {
-#pragma unroll
-                    for (int k = 0; k < NB; ++k)
+                    const double* src = args.x + node * U + r * args.ld;
+                    if constexpr (U % 4 == 0)
                     {
-                        const long long dof = node[k] * U;
-                        const double2*  src = reinterpret_cast< const double2* >(args.x + dof + r * args.ld);
+                        if (args.ld % 4 == 0 and reinterpret_cast< uintptr_t >(args.x) % 32 == 0)
+                        {
+#pragma unroll
+                            for (int u4 = 0; u4 < U / 4; ++u4)
+                                ldNc256(src + 4 * u4, xn[r][k][4 * u4], xn[r][k][4 * u4 + 1], xn[r][k][4 * u4 + 2], xn[r][k][4 * u4 + 3]);
+                            continue;
+                        }
+                    }
+                    if constexpr (U % 2 == 0)
+                    {
 #pragma unroll
                         for (int u2 = 0; u2 < U / 2; ++u2)
-                        {
-                            const double2 val = __ldg(src + u2);
-                            v[2 * u2][k]      = isDirichlet(args.dir_mask, dof + 2 * u2) ? 0. : val.x;
-                            v[2 * u2 + 1][k]  = isDirichlet(args.dir_mask, dof + 2 * u2 + 1) ? 0. : val.y;
-                        }
+                            ldNc128(src + 2 * u2, xn[r][k][2 * u2], xn[r][k][2 * u2 + 1]);
                     }
                 }
                 else
                 {
 #pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        xn[r][k][u] = ldNc64(args.x + node * args.dofs_per_node + args.dof_inds[u] + r * args.ld);
+                }
+            }
+            if (flagged)
+                cpAsync4(s_mask + k * T + tid, args.dir_mask + node * U);
+        }
+    };
+
+    // ---- prologue (the only exposed HBM latency of the CTA)
+    if (n_it <= 0)
+        return;
+    prefetchIds(0);
+    prefetchGeo(0);
+    cpAsyncCommit();
+    cpAsyncWaitAll();
+    __syncthreads();
+#ifndef L3B_HEX_NO_X_PREFETCH
+    loadX(0);
+#endif
+    if (n_it > 1)
+        prefetchIds(1);
+    cpAsyncCommit();
+
+    for (int it = 0; it < n_it; ++it)
+    {
+        const int       n_active = activeIn(it);
+        const bool      col_on   = col_thr and slot < n_active;
+        const double*   geo      = s_geo + ((it & 1) * EPB + slot) * hex_geo_doubles;
+        unsigned long long dirbits = 0; // bit k * U + u: dof (node k of this column, unknown u) is a Dirichlet dof
+
+#ifdef L3B_HEX_NO_X_PREFETCH
+        loadX(it);
+        cpAsyncCommit();
+#endif
+        cpAsyncWaitAll();
+        // ---- A: gather (MatrixFreeSystem.hpp:421-467) + z-interpolation
+        if (col_on and node_thr)
+        {
+            const bool flagged = flagOf(it);
+            if (flagged)
+            {
+                if (stage_mask)
+                {
+                    if constexpr (U == 4)
+                    {
+#pragma unroll
+                        for (int k = 0; k < NB; ++k)
+                        {
+                            const uint32_t m = s_mask[k * T + tid]; // the node's 4 mask bytes, staged by loadX
+#pragma unroll
+                            for (int b = 0; b < 4; ++b)
+                                if ((m >> (8 * b)) & 0xffu)
+                                    dirbits |= 1ull << (k * U + b);
+                        }
+                    }
+                }
+                else if constexpr (Cfg::mask_bits_fit)
+                {
+#pragma unroll
                     for (int k = 0; k < NB; ++k)
+                    {
+                        const long long node = nodeOf(it, k);
 #pragma unroll
                         for (int u = 0; u < U; ++u)
-                        {
-                            const long long dof = node[k] * args.dofs_per_node + args.dof_inds[u];
-                            v[u][k]             = isDirichlet(args.dir_mask, dof) ? 0. : __ldg(args.x + dof + r * args.ld);
-                        }
+                            if (args.dir_mask[node * args.dofs_per_node + args.dof_inds[u]] != 0)
+                                dirbits |= 1ull << (k * U + u);
+                    }
                 }
+            }
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r)
+            {
+                double v[U][NB];
+#pragma unroll
+                for (int k = 0; k < NB; ++k)
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                    {
+                        bool dir;
+                        if constexpr (Cfg::mask_bits_fit)
+                            dir = ((dirbits >> (k * U + u)) & 1ull) != 0;
+                        else
+                            dir = flagged and args.dir_mask[static_cast< long long >(nodeOf(it, k)) * args.dofs_per_node + args.dof_inds[u]] != 0;
+                        v[u][k] = dir ? 0. : xn[r][k][u];
+                    }
 #pragma unroll
                 for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -161,7 +359,7 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
                     double v[NB];
 #pragma unroll
                     for (int k = 0; k < NB; ++k)
-                        v[k] = __ldg(args.fields + node[k] + args.field_inds[f] * args.field_stride);
+                        v[k] = __ldg(args.fields + nodeOf(it, k) + args.field_inds[f] * args.field_stride);
 #pragma unroll
                     for (int q = 0; q < NQ; ++q)
                     {
@@ -174,345 +372,380 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
                 }
             }
         }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    // affine element (all mixed monomial coefficients vanish): one thread inverts the constant Jacobian for everybody
-    if (col_on and cc == 0)
-    {
-        bool affine = true;
-#pragma unroll
-        for (int m = 0; m < 8; ++m)
-            if (__popc(m) > 1)
-                for (int s = 0; s < 3; ++s)
-                    affine = affine and geo[m * 3 + s] == 0.;
-        geo[34] = affine ? 1. : 0.;
-        if (affine)
-        {
-            double Jt[3][3], Jti[3][3];
-            for (int d = 0; d < 3; ++d)
-                for (int s = 0; s < 3; ++s)
-                    Jt[d][s] = geo[(1 << d) * 3 + s];
-            geo[33] = invert< 3 >(Jt, Jti);
-            for (int s = 0; s < 3; ++s)
-                for (int d = 0; d < 3; ++d)
-                    geo[24 + s * 3 + d] = Jti[s][d];
-        }
-    }
+        // ---- software pipeline: geometry of the next batch, node ids of the one after
+        if (it + 1 < n_it)
+            prefetchGeo(it + 1);
+        if (it + 2 < n_it)
+            prefetchIds(it + 2);
+        cpAsyncCommit();
 
-    // ---- B: xy-planes: interpolate along x and y, differentiate along x and y
-    for (int w = tid; w < NPL * EPB; w += T)
-    {
-        if (w % EPB >= n_active)
-            continue;
-        double* const pv = s_V + w * PSZ;
-        double        a[NQ][NQ];
-#pragma unroll
-        for (int j = 0; j < NB; ++j)
-#pragma unroll
-            for (int i = 0; i < NB; ++i)
-                a[j][i] = pv[j * NQ + i];
-#pragma unroll
-        for (int j = 0; j < NB; ++j) // x
+        // ---- B: xy-planes: interpolate along x and y, differentiate along x and y
+        for (int w = tid; w < NPL * EPB; w += T)
         {
-            double o[NQ];
+            if (w % EPB >= n_active)
+                continue;
+            double* const pv = s_V + w * PSZ;
+            double        a[NQ][NQ];
 #pragma unroll
-            for (int q = 0; q < NQ; ++q)
+            for (int j = 0; j < NB; ++j)
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+                    a[j][i] = pv[j * NQ + i];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) // x
             {
-                double acc = a[j][0] * tab.interp[q];
-#pragma unroll
-                for (int i = 1; i < NB; ++i)
-                    acc = fma(a[j][i], tab.interp[i * NQ + q], acc);
-                o[q] = acc;
-            }
-#pragma unroll
-            for (int q = 0; q < NQ; ++q)
-                a[j][q] = o[q];
-        }
-#pragma unroll
-        for (int qx = 0; qx < NQ; ++qx) // y
-        {
-            double o[NQ];
-#pragma unroll
-            for (int q = 0; q < NQ; ++q)
-            {
-                double acc = a[0][qx] * tab.interp[q];
-#pragma unroll
-                for (int j = 1; j < NB; ++j)
-                    acc = fma(a[j][qx], tab.interp[j * NQ + q], acc);
-                o[q] = acc;
-            }
-#pragma unroll
-            for (int q = 0; q < NQ; ++q)
-                a[q][qx] = o[q];
-        }
-        double* const px = s_DX + w * PSZ;
-        double* const py = s_DY + w * PSZ;
-#pragma unroll
-        for (int qy = 0; qy < NQ; ++qy)
-#pragma unroll
-            for (int qx = 0; qx < NQ; ++qx)
-            {
-                pv[qy * NQ + qx] = a[qy][qx];
-                double dx = a[qy][0] * tab.colloc[qx], dy = a[0][qx] * tab.colloc[qy];
-#pragma unroll
-                for (int m = 1; m < NQ; ++m)
-                {
-                    dx = fma(a[qy][m], tab.colloc[m * NQ + qx], dx);
-                    dy = fma(a[m][qx], tab.colloc[m * NQ + qy], dy);
-                }
-                px[qy * NQ + qx] = dx;
-                py[qy * NQ + qx] = dy;
-            }
-    }
-    __syncthreads();
-
-    // ---- C: quadrature-point stage along the z-column (SumFactorization.hpp:614-756)
-    if (col_on)
-    {
-        const bool   affine = geo[34] != 0.;
-        const double wxy    = tab.w[ci] * tab.w[cj];
-        double       Jti[3][3], detJ = 0.;
-        if (affine)
-        {
-            detJ = geo[33];
-#pragma unroll
-            for (int s = 0; s < 3; ++s)
-#pragma unroll
-                for (int d = 0; d < 3; ++d)
-                    Jti[s][d] = geo[24 + s * 3 + d];
-        }
-        double fval[NF > 0 ? NF : 1][NQ];
-        if constexpr (NF > 0)
-        {
-#pragma unroll
-            for (int f = 0; f < NF; ++f)
-#pragma unroll
-                for (int q = 0; q < NQ; ++q)
-                    fval[f][q] = s_V[((F0 + f) * NQ + q) * (EPB * PSZ) + col_off];
-        }
-        bool violated = false;
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r)
-        {
-            double val[U][NQ], wacc[U][NQ];
-#pragma unroll
-            for (int u = 0; u < U; ++u)
+                double o[NQ];
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
                 {
-                    val[u][q]  = s_V[((r * U + u) * NQ + q) * (EPB * PSZ) + col_off];
-                    wacc[u][q] = 0.;
+                    double acc = a[j][0] * tab.interp[q];
+#pragma unroll
+                    for (int i = 1; i < NB; ++i)
+                        acc = fma(a[j][i], tab.interp[i * NQ + q], acc);
+                    o[q] = acc;
                 }
 #pragma unroll
-            for (int qz = 0; qz < NQ; ++qz)
+                for (int q = 0; q < NQ; ++q)
+                    a[j][q] = o[q];
+            }
+#pragma unroll
+            for (int qx = 0; qx < NQ; ++qx) // y
             {
-                // geometry + user kernel at (ci, cj, qz)
-                typename KernelT::Input in;
-                {
-                    const double xi[3] = {tab.pts[ci], tab.pts[cj], tab.pts[qz]};
-                    double       xs[3], Jt[3][3];
-                    geometryFromCoefs< 3 >(geo, xi, xs, Jt); // dead code for affine elements whose kernel ignores the point
-                    if (not affine)
-                        detJ = invert< 3 >(Jt, Jti);
-                    in.point.space.coords[0] = xs[0];
-                    in.point.space.coords[1] = xs[1];
-                    in.point.space.coords[2] = 0.; // SumFactorization.hpp:656, :732
-                }
-                in.point.time = args.time;
+                double o[NQ];
 #pragma unroll
-                for (int f = 0; f < NF; ++f)
+                for (int q = 0; q < NQ; ++q)
                 {
-                    const int    off = ((F0 + f) * NQ + qz) * (EPB * PSZ) + col_off;
-                    const double dxf = s_DX[off], dyf = s_DY[off];
-                    double       dzf = fval[f][0] * tab.colloc[qz];
+                    double acc = a[0][qx] * tab.interp[q];
+#pragma unroll
+                    for (int j = 1; j < NB; ++j)
+                        acc = fma(a[j][qx], tab.interp[j * NQ + q], acc);
+                    o[q] = acc;
+                }
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+                    a[q][qx] = o[q];
+            }
+            double* const px = s_DX + w * PSZ;
+            double* const py = s_DY + w * PSZ;
+#pragma unroll
+            for (int qy = 0; qy < NQ; ++qy)
+#pragma unroll
+                for (int qx = 0; qx < NQ; ++qx)
+                {
+                    pv[qy * NQ + qx] = a[qy][qx];
+                    double dx = a[qy][0] * tab.colloc[qx], dy = a[0][qx] * tab.colloc[qy];
 #pragma unroll
                     for (int m = 1; m < NQ; ++m)
-                        dzf = fma(fval[f][m], tab.colloc[m * NQ + qz], dzf);
-                    in.field_vals[f] = fval[f][qz];
-#pragma unroll
-                    for (int s = 0; s < 3; ++s)
-                        in.field_ders[s][f] = fma(Jti[s][2], dzf, fma(Jti[s][1], dyf, Jti[s][0] * dxf));
+                    {
+                        dx = fma(a[qy][m], tab.colloc[m * NQ + qx], dx);
+                        dy = fma(a[m][qx], tab.colloc[m * NQ + qy], dy);
+                    }
+                    px[qy * NQ + qx] = dx;
+                    py[qy * NQ + qx] = dy;
                 }
-                const auto   res = kernel(in);
-                const double wgt = wxy * tab.w[qz] * detJ;
-                staticFor< 4 >([&](auto op) {
-                    staticFor< E >([&](auto eq) {
-                        staticFor< U >([&](auto u) {
-                            if constexpr (not Sp::nz(op, eq, u))
-                                violated |= res.operators[op](eq, u) != 0.;
+        }
+        __syncthreads();
+
+        // ---- C: quadrature-point stage along the z-column (SumFactorization.hpp:614-756)
+        if (col_on)
+        {
+            const bool   affine = geo[hex_geo_affine] != 0.;
+            const double wxy    = tab.w[ci] * tab.w[cj];
+            double       Jti[3][3], detJ = 0.;
+            if (affine)
+            {
+                detJ = geo[hex_geo_det];
+#pragma unroll
+                for (int s = 0; s < 3; ++s)
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+                        Jti[s][d] = geo[hex_geo_jti + s * 3 + d];
+            }
+            double fval[NF > 0 ? NF : 1][NQ];
+            if constexpr (NF > 0)
+            {
+#pragma unroll
+                for (int f = 0; f < NF; ++f)
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+                        fval[f][q] = s_V[((F0 + f) * NQ + q) * (EPB * PSZ) + col_off];
+            }
+            bool violated = false;
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r)
+            {
+                double val[U][NQ], wacc[U][NQ];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+                    {
+                        val[u][q]  = s_V[((r * U + u) * NQ + q) * (EPB * PSZ) + col_off];
+                        wacc[u][q] = 0.;
+                    }
+#pragma unroll
+                for (int qz = 0; qz < NQ; ++qz)
+                {
+                    // geometry + user kernel at (ci, cj, qz)
+                    typename KernelT::Input in;
+                    {
+                        const double xi[3] = {tab.pts[ci], tab.pts[cj], tab.pts[qz]};
+                        double       xs[3], Jt[3][3];
+                        geometryFromCoefs< 3 >(geo, xi, xs, Jt); // dead code for affine elements whose kernel ignores the point
+                        if (not affine)
+                            detJ = invert< 3 >(Jt, Jti);
+                        in.point.space.coords[0] = xs[0];
+                        in.point.space.coords[1] = xs[1];
+                        in.point.space.coords[2] = 0.; // SumFactorization.hpp:656, :732
+                    }
+                    in.point.time = args.time;
+#pragma unroll
+                    for (int f = 0; f < NF; ++f)
+                    {
+                        const int    off = ((F0 + f) * NQ + qz) * (EPB * PSZ) + col_off;
+                        const double dxf = s_DX[off], dyf = s_DY[off];
+                        double       dzf = fval[f][0] * tab.colloc[qz];
+#pragma unroll
+                        for (int m = 1; m < NQ; ++m)
+                            dzf = fma(fval[f][m], tab.colloc[m * NQ + qz], dzf);
+                        in.field_vals[f] = fval[f][qz];
+#pragma unroll
+                        for (int s = 0; s < 3; ++s)
+                            in.field_ders[s][f] = fma(Jti[s][2], dzf, fma(Jti[s][1], dyf, Jti[s][0] * dxf));
+                    }
+                    const auto   res = kernel(in);
+                    const double wgt = wxy * tab.w[qz] * detJ;
+                    staticFor< 4 >([&](auto op) {
+                        staticFor< E >([&](auto eq) {
+                            staticFor< U >([&](auto u) {
+                                if constexpr (not Sp::nz(op, eq, u))
+                                    violated |= res.operators[op](eq, u) != 0.;
+                            });
                         });
                     });
-                });
-                // reference derivatives of the operand at this point
-                double dref[3][U];
+                    // reference derivatives of the operand at this point
+                    double dref[3][U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                    {
+                        const int off = ((r * U + u) * NQ + qz) * (EPB * PSZ) + col_off;
+                        dref[0][u]    = s_DX[off];
+                        dref[1][u]    = s_DY[off];
+                        double dz     = val[u][0] * tab.colloc[qz];
+#pragma unroll
+                        for (int m = 1; m < NQ; ++m)
+                            dz = fma(val[u][m], tab.colloc[m * NQ + qz], dz);
+                        dref[2][u] = dz;
+                    }
+                    double g_phys[3][U];
+                    staticFor< U >([&](auto u) {
+                        staticFor< 3 >([&](auto s) {
+                            if constexpr (gradNeeded< KernelT >(s, u))
+                                g_phys[s][u] = fma(Jti[s][2], dref[2][u], fma(Jti[s][1], dref[1][u], Jti[s][0] * dref[0][u]));
+                        });
+                    });
+                    double tv[E];
+                    staticFor< E >([&](auto eq) {
+                        double acc = 0.;
+                        staticFor< U >([&](auto u) {
+                            if constexpr (Sp::nz(0, eq, u))
+                                acc = fma(res.operators[0](eq, u), val[u][qz], acc);
+                            staticFor< 3 >([&](auto s) {
+                                if constexpr (Sp::nz(s + 1, eq, u))
+                                    acc = fma(res.operators[s + 1](eq, u), g_phys[s][u], acc);
+                            });
+                        });
+                        tv[eq] = acc * wgt;
+                    });
+                    staticFor< U >([&](auto u) {
+                        double a0 = 0., ps[3] = {0., 0., 0.};
+                        staticFor< E >([&](auto eq) {
+                            if constexpr (Sp::nz(0, eq, u))
+                                a0 = fma(res.operators[0](eq, u), tv[eq], a0);
+                            staticFor< 3 >([&](auto s) {
+                                if constexpr (Sp::nz(s + 1, eq, u))
+                                    ps[s] = fma(res.operators[s + 1](eq, u), tv[eq], ps[s]);
+                            });
+                        });
+                        // r_d = sum_s Ji(d, s) p_s, only over the directions s this unknown is differentiated along
+                        double rd[3] = {0., 0., 0.};
+                        staticFor< 3 >([&](auto s) {
+                            if constexpr (gradNeeded< KernelT >(s, u))
+                            {
+#pragma unroll
+                                for (int d = 0; d < 3; ++d)
+                                    rd[d] = fma(Jti[s][d], ps[s], rd[d]);
+                            }
+                        });
+                        const int off = ((r * U + u) * NQ + qz) * (EPB * PSZ) + col_off;
+                        s_DX[off]     = rd[0];
+                        s_DY[off]     = rd[1];
+                        wacc[u][qz] += a0;
+#pragma unroll
+                        for (int m = 0; m < NQ; ++m)
+                            wacc[u][m] = fma(tab.colloc[m * NQ + qz], rd[2], wacc[u][m]);
+                    });
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+                        s_V[((r * U + u) * NQ + q) * (EPB * PSZ) + col_off] = wacc[u][q];
+            }
+            if (violated)
+                atomicOr(args.status, status_sparsity_violation);
+        }
+        __syncthreads();
+
+        // ---- software pipeline: gather of the next batch into registers (consumed by A of the next iteration)
+#ifndef L3B_HEX_NO_X_PREFETCH
+        if (it + 1 < n_it)
+            loadX(it + 1);
+        cpAsyncCommit();
+#endif
+
+        // ---- D: xy-planes: transposed derivatives, projection to the nodes along y and x
+        for (int w = tid; w < NPLF * EPB; w += T)
+        {
+            if (w % EPB >= n_active)
+                continue;
+            double* const       pv = s_V + w * PSZ;
+            const double* const px = s_DX + w * PSZ;
+            const double* const py = s_DY + w * PSZ;
+            double              t[NQ][NQ];
+#pragma unroll
+            for (int qy = 0; qy < NQ; ++qy)
+#pragma unroll
+                for (int qx = 0; qx < NQ; ++qx)
+                    t[qy][qx] = pv[qy * NQ + qx];
+#pragma unroll
+            for (int qy = 0; qy < NQ; ++qy)
+#pragma unroll
+                for (int qx = 0; qx < NQ; ++qx)
+                {
+                    const double rx = px[qy * NQ + qx], ry = py[qy * NQ + qx];
+#pragma unroll
+                    for (int m = 0; m < NQ; ++m)
+                    {
+                        t[qy][m] = fma(tab.colloc[m * NQ + qx], rx, t[qy][m]);
+                        t[m][qx] = fma(tab.colloc[m * NQ + qy], ry, t[m][qx]);
+                    }
+                }
+#pragma unroll
+            for (int qx = 0; qx < NQ; ++qx) // y: Gauss points → nodes
+            {
+                double o[NB];
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                {
+                    double acc = t[0][qx] * tab.interp[j * NQ];
+#pragma unroll
+                    for (int q = 1; q < NQ; ++q)
+                        acc = fma(t[q][qx], tab.interp[j * NQ + q], acc);
+                    o[j] = acc;
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                    t[j][qx] = o[j];
+            }
+#pragma unroll
+            for (int j = 0; j < NB; ++j) // x
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+                {
+                    double acc = t[j][0] * tab.interp[i * NQ];
+#pragma unroll
+                    for (int q = 1; q < NQ; ++q)
+                        acc = fma(t[j][q], tab.interp[i * NQ + q], acc);
+                    pv[j * NQ + i] = acc;
+                }
+        }
+        __syncthreads();
+
+#ifdef L3B_HEX_SCATTER_TASKS
+        // ---- E: z-projection + scatter (MatrixFreeSystem.hpp:494-537): relaxed fp64 atomics (RED), Dirichlet rows skipped.
+        // One task per (nodal column (i, j), unknown u), unknown fastest: the U lanes of a node hit one 32-byte sector, so a
+        // warp's RED touches 32 / U sectors instead of 32 (ncu r1_v6: the scatter held 19 % of the stall samples).
+        {
+            const int n_tasks = n_active * NB * NB * U;
+#pragma unroll 1
+            for (int w = tid; w < n_tasks; w += T)
+            {
+                const int  u = w % U, ij = (w / U) % (NB * NB), sl = w / (U * NB * NB);
+                const int  i = ij % NB, j = ij / NB;
+                const bool flagged = args.dir_mask != nullptr and (args.elem_dir == nullptr or s_flag[(it % RING) * EPB + sl] != 0);
+                const uint32_t* ids = s_ids + ((it % RING) * EPB + sl) * NN + j * NB + i;
+                const long long dof_stride = vec_vals ? U : args.dofs_per_node;
+                const int       dof_off    = vec_vals ? u : args.dof_inds[u];
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r)
+                {
+                    double v[NQ];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+                        v[q] = s_V[((r * U + u) * NQ + q) * (EPB * PSZ) + sl * PSZ + j * NQ + i];
+#pragma unroll
+                    for (int k = 0; k < NB; ++k)
+                    {
+                        double acc = v[0] * tab.interp[k * NQ];
+#pragma unroll
+                        for (int q = 1; q < NQ; ++q)
+                            acc = fma(v[q], tab.interp[k * NQ + q], acc);
+                        const long long dof = ids[k * NB * NB] * dof_stride + dof_off;
+                        const int       go  = not(flagged and args.dir_mask[dof] != 0);
+                        redAddIf(args.y + dof + r * args.ld, acc * args.alpha, go);
+                    }
+                }
+            }
+        }
+#else
+        // ---- E: z-projection + scatter (MatrixFreeSystem.hpp:494-537): relaxed fp64 atomics (RED), Dirichlet rows skipped
+        if (col_on and node_thr)
+        {
+            const bool flagged = flagOf(it);
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r)
+            {
+                double out[U][NB];
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                 {
-                    const int off = ((r * U + u) * NQ + qz) * (EPB * PSZ) + col_off;
-                    dref[0][u]    = s_DX[off];
-                    dref[1][u]    = s_DY[off];
-                    double dz     = val[u][0] * tab.colloc[qz];
+                    double v[NQ];
 #pragma unroll
-                    for (int m = 1; m < NQ; ++m)
-                        dz = fma(val[u][m], tab.colloc[m * NQ + qz], dz);
-                    dref[2][u] = dz;
+                    for (int q = 0; q < NQ; ++q)
+                        v[q] = s_V[((r * U + u) * NQ + q) * (EPB * PSZ) + col_off];
+#pragma unroll
+                    for (int k = 0; k < NB; ++k)
+                    {
+                        double acc = v[0] * tab.interp[k * NQ];
+#pragma unroll
+                        for (int q = 1; q < NQ; ++q)
+                            acc = fma(v[q], tab.interp[k * NQ + q], acc);
+                        out[u][k] = acc * args.alpha;
+                    }
                 }
-                double g_phys[3][U];
-                staticFor< U >([&](auto u) {
-                    staticFor< 3 >([&](auto s) {
-                        if constexpr (gradNeeded< KernelT >(s, u))
-                            g_phys[s][u] = fma(Jti[s][2], dref[2][u], fma(Jti[s][1], dref[1][u], Jti[s][0] * dref[0][u]));
-                    });
-                });
-                double tv[E];
-                staticFor< E >([&](auto eq) {
-                    double acc = 0.;
-                    staticFor< U >([&](auto u) {
-                        if constexpr (Sp::nz(0, eq, u))
-                            acc = fma(res.operators[0](eq, u), val[u][qz], acc);
-                        staticFor< 3 >([&](auto s) {
-                            if constexpr (Sp::nz(s + 1, eq, u))
-                                acc = fma(res.operators[s + 1](eq, u), g_phys[s][u], acc);
-                        });
-                    });
-                    tv[eq] = acc * wgt;
-                });
-                staticFor< U >([&](auto u) {
-                    double a0 = 0., ps[3] = {0., 0., 0.};
-                    staticFor< E >([&](auto eq) {
-                        if constexpr (Sp::nz(0, eq, u))
-                            a0 = fma(res.operators[0](eq, u), tv[eq], a0);
-                        staticFor< 3 >([&](auto s) {
-                            if constexpr (Sp::nz(s + 1, eq, u))
-                                ps[s] = fma(res.operators[s + 1](eq, u), tv[eq], ps[s]);
-                        });
-                    });
-                    // r_d = sum_s Ji(d, s) p_s, only over the directions s this unknown is differentiated along
-                    double rd[3] = {0., 0., 0.};
-                    staticFor< 3 >([&](auto s) {
-                        if constexpr (gradNeeded< KernelT >(s, u))
-                        {
-#pragma unroll
-                            for (int d = 0; d < 3; ++d)
-                                rd[d] = fma(Jti[s][d], ps[s], rd[d]);
-                        }
-                    });
-                    const int off = ((r * U + u) * NQ + qz) * (EPB * PSZ) + col_off;
-                    s_DX[off]     = rd[0];
-                    s_DY[off]     = rd[1];
-                    wacc[u][qz] += a0;
-#pragma unroll
-                    for (int m = 0; m < NQ; ++m)
-                        wacc[u][m] = fma(tab.colloc[m * NQ + qz], rd[2], wacc[u][m]);
-                });
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int q = 0; q < NQ; ++q)
-                    s_V[((r * U + u) * NQ + q) * (EPB * PSZ) + col_off] = wacc[u][q];
-        }
-        if (violated)
-            atomicOr(args.status, status_sparsity_violation);
-    }
-    __syncthreads();
-
-    // ---- D: xy-planes: transposed derivatives, projection to the nodes along y and x
-    for (int w = tid; w < NPLF * EPB; w += T)
-    {
-        if (w % EPB >= n_active)
-            continue;
-        double* const       pv = s_V + w * PSZ;
-        const double* const px = s_DX + w * PSZ;
-        const double* const py = s_DY + w * PSZ;
-        double              t[NQ][NQ];
-#pragma unroll
-        for (int qy = 0; qy < NQ; ++qy)
-#pragma unroll
-            for (int qx = 0; qx < NQ; ++qx)
-                t[qy][qx] = pv[qy * NQ + qx];
-#pragma unroll
-        for (int qy = 0; qy < NQ; ++qy)
-#pragma unroll
-            for (int qx = 0; qx < NQ; ++qx)
-            {
-                const double rx = px[qy * NQ + qx], ry = py[qy * NQ + qx];
-#pragma unroll
-                for (int m = 0; m < NQ; ++m)
-                {
-                    t[qy][m] = fma(tab.colloc[m * NQ + qx], rx, t[qy][m]);
-                    t[m][qx] = fma(tab.colloc[m * NQ + qy], ry, t[m][qx]);
-                }
-            }
-#pragma unroll
-        for (int qx = 0; qx < NQ; ++qx) // y: Gauss points → nodes
-        {
-            double o[NB];
-#pragma unroll
-            for (int j = 0; j < NB; ++j)
-            {
-                double acc = t[0][qx] * tab.interp[j * NQ];
-#pragma unroll
-                for (int q = 1; q < NQ; ++q)
-                    acc = fma(t[q][qx], tab.interp[j * NQ + q], acc);
-                o[j] = acc;
-            }
-#pragma unroll
-            for (int j = 0; j < NB; ++j)
-                t[j][qx] = o[j];
-        }
-#pragma unroll
-        for (int j = 0; j < NB; ++j) // x
-#pragma unroll
-            for (int i = 0; i < NB; ++i)
-            {
-                double acc = t[j][0] * tab.interp[i * NQ];
-#pragma unroll
-                for (int q = 1; q < NQ; ++q)
-                    acc = fma(t[j][q], tab.interp[i * NQ + q], acc);
-                pv[j * NQ + i] = acc;
-            }
-    }
-    __syncthreads();
-
-    // ---- E: z-projection + scatter (MatrixFreeSystem.hpp:494-537): relaxed fp64 atomics, Dirichlet rows skipped
-    if (col_on and ci < NB and cj < NB)
-    {
-#pragma unroll
-        for (int r = 0; r < NRHS; ++r)
-        {
-            double out[U][NB];
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-            {
-                double v[NQ];
-#pragma unroll
-                for (int q = 0; q < NQ; ++q)
-                    v[q] = s_V[((r * U + u) * NQ + q) * (EPB * PSZ) + col_off];
 #pragma unroll
                 for (int k = 0; k < NB; ++k)
                 {
-                    double acc = v[0] * tab.interp[k * NQ];
+                    const long long node = nodeOf(it, k);
 #pragma unroll
-                    for (int q = 1; q < NQ; ++q)
-                        acc = fma(v[q], tab.interp[k * NQ + q], acc);
-                    out[u][k] = acc * args.alpha;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < NB; ++k)
-            {
-                const long long node = el_nodes[k * NB * NB + cj * NB + ci];
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                {
-                    const long long dof = node * args.dofs_per_node + args.dof_inds[u];
-                    if (not isDirichlet(args.dir_mask, dof))
-                        atomicAdd(args.y + dof + r * args.ld, out[u][k]);
+                    for (int u = 0; u < U; ++u)
+                    {
+                        const long long dof = vec_vals ? node * U + u : node * args.dofs_per_node + args.dof_inds[u];
+                        bool dir; // dirbits: set in A from the staged mask words, no HBM access here
+                        if constexpr (Cfg::mask_bits_fit)
+                            dir = ((dirbits >> (k * U + u)) & 1ull) != 0;
+                        else
+                            dir = flagged and args.dir_mask[dof] != 0;
+                        if (not dir)
+                            atomicAdd(args.y + dof + r * args.ld, out[u][k]);
+                    }
                 }
             }
         }
+#endif
     }
 }
 } // namespace l3b

@@ -90,7 +90,16 @@ cudaError_t launchMfHex(const void* obj, const ElemArgs& args, const tables::Tab
         cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, static_cast< int >(cudaSharedmemCarveoutMaxShared));
     if (carveout != cudaSuccess)
         return carveout;
-    const auto grid = static_cast< unsigned >((args.n_work + Cfg::EPB - 1) / Cfg::EPB);
+    // persistent grid: one CTA per resident slot of the device, batches strided over the grid
+    static const int resident = [] {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, Cfg::threads, Cfg::smem_bytes);
+        return std::max(1, sms * std::max(1, per_sm));
+    }();
+    const long long n_batches = (args.n_work + Cfg::EPB - 1) / Cfg::EPB;
+    const auto      grid      = static_cast< unsigned >(std::min< long long >(n_batches, resident));
     fn<<< grid, Cfg::threads, Cfg::smem_bytes, stream >>>(*static_cast< const KernelT* >(obj), args, tab);
     return cudaGetLastError();
 }
@@ -137,18 +146,18 @@ KernelInstance makeInstance()
     inst.nq    = NQ;
     if constexpr (not KernelT::is_boundary)
     {
-        if constexpr (DIM == 3 and NQ * NQ <= 49)
+        inst.mf_sumfact_full    = launchMfSumFact< KernelT, DIM, P, NQ, NRHS >;
+        inst.mf_sumfact_one     = launchMfSumFact< KernelT, DIM, P, NQ, 1 >;
+        inst.mf_elems_per_block = MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::EPB;
+        if constexpr (DIM == 3)
         {
-            static_assert(MfHexCfg< KernelT, P, NQ, NRHS >::supported);
-            inst.mf_sumfact_full    = launchMfHex< KernelT, P, NQ, NRHS >;
-            inst.mf_sumfact_one     = launchMfHex< KernelT, P, NQ, 1 >;
-            inst.mf_elems_per_block = MfHexCfg< KernelT, P, NQ, NRHS >::EPB;
-        }
-        else
-        {
-            inst.mf_sumfact_full    = launchMfSumFact< KernelT, DIM, P, NQ, NRHS >;
-            inst.mf_sumfact_one     = launchMfSumFact< KernelT, DIM, P, NQ, 1 >;
-            inst.mf_elems_per_block = MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::EPB;
+            if constexpr (MfHexCfg< KernelT, P, NQ, NRHS >::supported)
+            {
+                inst.mf_sumfact_full    = launchMfHex< KernelT, P, NQ, NRHS >;
+                inst.mf_elems_per_block = MfHexCfg< KernelT, P, NQ, NRHS >::EPB;
+            }
+            if constexpr (MfHexCfg< KernelT, P, NQ, 1 >::supported)
+                inst.mf_sumfact_one = launchMfHex< KernelT, P, NQ, 1 >;
         }
     }
     inst.local_apply_full    = launchLocal< KernelT, DIM, P, NRHS, MODE_APPLY >;
