@@ -11,6 +11,7 @@
 #define L3B_REGISTER_KERNEL_CUH
 
 #include "assemble.cuh"
+#include "assemble_dmma.cuh"
 #include "local_element.cuh"
 #include "mf_hex_planes.cuh"
 #include "mf_sumfact.cuh"
@@ -117,12 +118,34 @@ cudaError_t launchLocal(const void* obj, const ElemArgs& args, cudaStream_t stre
     return cudaGetLastError();
 }
 
+// L3B_ASM_FMA=1 in the environment selects the register-tiled DFMA kernel (assemble.cuh) instead of the DMMA kernel
+inline bool forceFmaAssembly()
+{
+    static const bool force = [] {
+        const char* e = std::getenv("L3B_ASM_FMA");
+        return e != nullptr and e[0] == '1';
+    }();
+    return force;
+}
 template < typename KernelT, int DIM, int P >
 cudaError_t launchAssemble(const void* obj, const ElemArgs& args, cudaStream_t stream)
 {
     using Cfg = AsmCfg< KernelT, DIM, P >;
     if (args.n_work == 0)
         return cudaSuccess;
+    if (not forceFmaAssembly())
+    {
+        using DCfg                  = AsmDmmaCfg< KernelT, DIM, P >;
+        static const AsmPairs pairs = DCfg::makePairs();
+        if (pairs.tiles_per_elem == 0)
+            return cudaSuccess;
+        constexpr auto dfn = assembleDmmaKernel< KernelT, DIM, P >;
+        if (const auto err = raiseSmemLimit< dfn >(DCfg::smem_bytes); err != cudaSuccess)
+            return err;
+        dfn<<< static_cast< unsigned >(args.n_work * pairs.tiles_per_elem), DCfg::threads, DCfg::smem_bytes, stream >>>(
+            *static_cast< const KernelT* >(obj), args, pairs);
+        return cudaGetLastError();
+    }
     constexpr auto fn = assembleKernel< KernelT, DIM, P >;
     if (const auto err = raiseSmemLimit< fn >(Cfg::smem_bytes); err != cudaSuccess)
         return err;
