@@ -13,10 +13,15 @@
 // 16 x 7 = 112 products, and only the pairs u <= v are computed (K_e is symmetric, the reference mirrors the lower
 // triangle, :176-182). The sqrt(w) split is the reference's own (:189-195); weights are positive wherever |J| > 0.
 //
-// One CTA owns one (element, unknown pair, TB x TB node tile). Quadrature points are streamed in chunks: the two panels
-// sqrt(w) B[.,(a,u)] and sqrt(w) B[.,(b,v)] of chunk c+1 are built in shared memory (per-point mapping + user kernel one
-// chunk further ahead) while the warps contract chunk c with DMMA — 32 x 32 accumulator tile per warp, fragments read
-// with conflict-free 8-byte loads (panel leading dimension ≡ 4 mod 16 doubles) — one barrier per chunk.
+// One CTA owns one (element, unknown pair, TM x TN node tile), 128 x 128 nodes and 16 warps for NN > 64. Quadrature
+// points are streamed in chunks: the two panels
+// sqrt(w) B[.,(a,u)] and sqrt(w) B[.,(b,v)] of chunk c+1 are built in shared memory while the warps contract chunk c with
+// DMMA — 32 x 32 accumulator tile per warp, fragments read with conflict-free 8-byte loads (panel leading dimension
+// ≡ 4 mod 16 doubles) — one barrier per chunk. The per-point stage (mapping, user kernel, two chunks ahead) folds
+// J^-1 and sqrt(w) into four coefficients per (point, equation, panel),
+//     sqrt(w) B[e,(a,u)] = c0 N_a + sum_d c_d dN_a/dxi_d,   c0 = sqrt(w) A0(e,u),  c_d = sqrt(w) sum_s A_s(e,u) Jinv(s,d),
+// so a panel entry costs 4 fp64 operations on the (L2-resident) reference tables. For u == v the warp tiles above the
+// diagonal are skipped and the lower triangle is mirrored by the scatter.
 // The DMMA and DFMA instructions share the fp64 pipe on B200 (bench microkernels: 33.7 DFMA, 37.1 DMMA, 34.9 TFLOP/s
 // interleaved), so the win over the register-tiled FMA kernel (assemble.cuh) is issue bandwidth and registers, not peak:
 // one DMMA retires 256 multiply-adds for 2 fragment loads.
@@ -39,6 +44,7 @@ struct AsmPairs
         uint8_t  u, v, n_eq, pad;
         uint16_t tile0, n_tiles;
         uint8_t  eq[asm_max_equations];
+        int8_t   ei_of_eq[asm_max_equations]; // position of an equation in `eq`, or -1
     } p[asm_max_pairs];
 };
 
@@ -58,20 +64,29 @@ struct AsmDmmaCfg
     static constexpr auto params = KernelT::parameters;
     static constexpr int  E = params.n_equations, U = params.n_unknowns, NF = params.n_fields, NRHS = params.n_rhs;
     static constexpr int  NN = cpow(P + 1, DIM), L = NN * U;
-    static constexpr int  TB      = NN > 64 ? 128 : NN > 32 ? 64 : 32; // node tile edge
-    static constexpr int  WR      = TB / 32;                            // warps per tile edge
-    static constexpr int  threads = WR * WR * 32;
-    static constexpr int  n_nb    = (NN + TB - 1) / TB;                 // node blocks
-    static constexpr int  LD      = TB + 4;                             // panel leading dimension, ≡ 4 (mod 16)
-    static constexpr int  KCMAX   = cmax(32, 4 * E);                    // panel rows (quadrature points x equations) per chunk
-    static constexpr int  QCMAX   = 16;                                 // quadrature points per chunk, at most
-    static constexpr int  qp_doubles = DIM * DIM + 2 + (DIM + 1) * E * U + E * NRHS; // Jti, sqrt(w), w, A, f
-    // smem (doubles): panel A x 2 | panel B x 2 | per-point data x 2 | node field values | vertices
-    static constexpr int    off_b = 2 * KCMAX * LD, off_qp = 4 * KCMAX * LD, off_nv = off_qp + 2 * QCMAX * qp_doubles,
-                         off_verts = off_nv + NN * NF, total = off_verts + 8 * 3;
+    static constexpr int  TN      = NN > 64 ? 128 : NN > 32 ? 64 : 32; // tile columns (nodes b)
+#ifdef L3B_ASM_RECT
+    static constexpr int  TM      = NN > 64 ? 64 : TN; // experiment: 64 x 128 tiles, two 256-thread CTAs per SM (129 k vs 158 k elements/s)
+#else
+    static constexpr int  TM      = TN;                // tile rows (nodes a); TN is a multiple of TM
+#endif
+    static constexpr int  WM = TM / 32, WN = TN / 32;                  // warps along rows / columns, 32 x 32 each
+    static constexpr int  threads = WM * WN * 32;
+    static constexpr int  n_rb = (NN + TM - 1) / TM, n_cb = (NN + TN - 1) / TN; // row / column blocks
+    static constexpr int  LDA = TM + 4, LDB = TN + 4;                  // panel leading dimensions, ≡ 4 (mod 16)
+    static constexpr int  KCMAX = cmax(32, 4 * E);                     // panel rows (quadrature points x equations) per chunk
+    static constexpr int  QCMAX = 16;                                  // quadrature points per chunk, at most
+    // smem (doubles): panel A x 2 | panel B x 2 | coefficients A x 2 | coefficients B x 2 | rhs coefficients x 2 |
+    // node field values | vertices
+    static constexpr int off_b = 2 * KCMAX * LDA, off_ca = off_b + 2 * KCMAX * LDB, off_cb = off_ca + 2 * KCMAX * 4,
+                         off_cr = off_cb + 2 * KCMAX * 4, off_nv = off_cr + 2 * QCMAX * NRHS * 4, off_verts = off_nv + NN * NF,
+                         total = off_verts + 8 * 3;
     static constexpr size_t smem_bytes = static_cast< size_t >(total) * sizeof(double);
+    static constexpr int    min_blocks = smem_bytes <= 112 * 1024 and threads <= 256 ? 2 : 1;
     static_assert(E <= asm_max_equations and U <= max_unknowns);
 
+    // tiles of the pair (u, v): all n_rb x n_cb for u != v; for u == v those that touch the lower triangle
+    static constexpr bool tileNeeded(bool diag_pair, int rb, int cb) { return not diag_pair or cb * TN <= rb * TM + TM - 1; }
     static constexpr AsmPairs makePairs()
     {
         AsmPairs out{};
@@ -82,14 +97,23 @@ struct AsmDmmaCfg
                 AsmPairs::Pair pr{};
                 pr.u = static_cast< uint8_t >(u);
                 pr.v = static_cast< uint8_t >(v);
+                for (int eq = 0; eq < asm_max_equations; ++eq)
+                    pr.ei_of_eq[eq] = -1;
                 for (int eq = 0; eq < E; ++eq)
                     if (unknownInEquation< KernelT >(u, eq) and unknownInEquation< KernelT >(v, eq))
+                    {
+                        pr.ei_of_eq[eq]  = static_cast< int8_t >(pr.n_eq);
                         pr.eq[pr.n_eq++] = static_cast< uint8_t >(eq);
+                    }
                 if (pr.n_eq == 0)
                     continue;
+                int n = 0;
+                for (int rb = 0; rb < n_rb; ++rb)
+                    for (int cb = 0; cb < n_cb; ++cb)
+                        n += tileNeeded(u == v, rb, cb);
                 pr.tile0   = static_cast< uint16_t >(tile);
-                pr.n_tiles = static_cast< uint16_t >(u == v ? n_nb * (n_nb + 1) / 2 : n_nb * n_nb);
-                tile += pr.n_tiles;
+                pr.n_tiles = static_cast< uint16_t >(n);
+                tile += n;
                 out.p[out.n_pairs++] = pr;
             }
         out.tiles_per_elem = tile;
@@ -103,19 +127,22 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 }
 
 template < typename KernelT, int DIM, int P >
-__global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads)
+__global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmmaCfg< KernelT, DIM, P >::min_blocks)
     assembleDmmaKernel(const KernelT kernel, const __grid_constant__ ElemArgs args, const __grid_constant__ AsmPairs pairs)
 {
     using Cfg = AsmDmmaCfg< KernelT, DIM, P >;
     using Sp  = KernelSparsity< KernelT >;
-    constexpr int  E = Cfg::E, U = Cfg::U, NF = Cfg::NF, NRHS = Cfg::NRHS, NN = Cfg::NN, TB = Cfg::TB, LD = Cfg::LD;
-    constexpr int  T = Cfg::threads, n_warps = T / 32, n_nb = Cfg::n_nb;
+    constexpr int  E = Cfg::E, U = Cfg::U, NF = Cfg::NF, NRHS = Cfg::NRHS, NN = Cfg::NN, TM = Cfg::TM, TN = Cfg::TN;
+    constexpr int  LDA = Cfg::LDA, LDB = Cfg::LDB, KCMAX = Cfg::KCMAX, QCMAX = Cfg::QCMAX;
+    constexpr int  T = Cfg::threads, n_warps = T / 32;
     constexpr bool is_bnd = KernelT::is_boundary;
     constexpr int  nv     = 1 << DIM;
     extern __shared__ double smem[];
     double* const s_pa    = smem;
     double* const s_pb    = smem + Cfg::off_b;
-    double* const s_qp    = smem + Cfg::off_qp;
+    double* const s_ca    = smem + Cfg::off_ca; // [buf][k][4]
+    double* const s_cb    = smem + Cfg::off_cb;
+    double* const s_cr    = smem + Cfg::off_cr; // [buf][qc][r][4]
     double* const s_nv    = smem + Cfg::off_nv;
     double* const s_verts = smem + Cfg::off_verts;
 
@@ -128,27 +155,22 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads)
         ++pi;
     const AsmPairs::Pair& pr = pairs.p[pi];
     t -= pr.tile0;
-    const int u = pr.u, v = pr.v, n_eq = pr.n_eq;
-    int       bi, bj;
-    if (u != v)
-    {
-        bi = t / n_nb;
-        bj = t % n_nb;
-    }
-    else
-    {
-        bi = 0;
-        while (t >= bi + 1)
+    const int  u = pr.u, v = pr.v, n_eq = pr.n_eq;
+    const bool diag_pair = u == v;
+    int        rb = 0, cb = 0;
+    for (int i = 0, n = 0; i < Cfg::n_rb * Cfg::n_cb; ++i) // t-th needed tile of the pair
+        if (Cfg::tileNeeded(diag_pair, i / Cfg::n_cb, i % Cfg::n_cb) and n++ == t)
         {
-            t -= bi + 1;
-            ++bi;
+            rb = i / Cfg::n_cb;
+            cb = i % Cfg::n_cb;
+            break;
         }
-        bj = t;
-    }
-    const bool      same_panel = u == v and bi == bj; // the tile is a diagonal block: one panel serves as both operands
-    const long long e          = args.work_elems ? args.work_elems[wi] : args.first_elem + wi;
-    const int       side       = is_bnd ? args.work_sides[wi] : -1;
-    const uint32_t* el_nodes   = args.nodes + e * NN;
+    const int row0 = rb * TM, col0 = cb * TN;
+    // u == v and the row block lies inside the column block: panel A is a window of panel B
+    const bool      a_in_b   = diag_pair and row0 >= col0 and row0 + TM <= col0 + TN;
+    const long long e        = args.work_elems ? args.work_elems[wi] : args.first_elem + wi;
+    const int       side     = is_bnd ? args.work_sides[wi] : -1;
+    const uint32_t* el_nodes = args.nodes + e * NN;
 
     for (int i = tid; i < nv * 3; i += T)
         s_verts[i] = args.verts[e * nv * 3 + i];
@@ -163,22 +185,30 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads)
     const double*   tab_wts  = args.tab_wts + tab_off;
 
     // quadrature points per chunk: as many as fit KCMAX panel rows, a multiple of 4 (DMMA k = 4), at most QCMAX
-    int QC = (Cfg::KCMAX / n_eq) & ~3;
-    QC     = QC > Cfg::QCMAX ? Cfg::QCMAX : QC;
-    const int n_chunks = (args.n_qp + QC - 1) / QC;
-    const int n_k4     = QC * n_eq / 4;
+    int QC = (KCMAX / n_eq) & ~3;
+    QC     = QC > QCMAX ? QCMAX : QC;
+    const int  n_chunks = (args.n_qp + QC - 1) / QC;
+    const int  n_k4     = QC * n_eq / 4;
+    const bool rhs_duty = diag_pair and cb == 0; // this CTA also owns F_e[(a, u)] for the nodes a of row block rb
 
-    // ---- per-point data of chunk c → s_qp[c & 1]: warp w handles point c * QC + w (mapping, fields, user kernel)
+    // ---- per-point stage of chunk c → coefficient tables [c & 1]. One warp (rotating with c), one lane per point:
+    // mapping, user kernel, then — through compile-time loops over the structurally non-zero operator entries only —
+    //     c0 = sqrt(w) A0(e,u),  c_d = sqrt(w) sum_s A_s(e,u) Jinv(s,d)        for the equations e of the pair and u, v.
     const auto perPoint = [&](int c) {
-        double* const base = s_qp + (c & 1) * Cfg::QCMAX * Cfg::qp_doubles;
-        for (int qc = warp; qc < QC; qc += n_warps)
+        if (warp != c % n_warps)
+            return;
+        double* const ca  = s_ca + (c & 1) * KCMAX * 4;
+        double* const cbp = s_cb + (c & 1) * KCMAX * 4;
+        double* const cr  = s_cr + (c & 1) * QCMAX * NRHS * 4;
+        for (int qc = lane; qc < QC; qc += 32)
         {
-            const int q  = c * QC + qc;
-            double*   qd = base + qc * Cfg::qp_doubles;
-            if (q >= args.n_qp)
+            const int q = c * QC + qc;
+            if (q >= args.n_qp) // padding point: zero coefficients zero its panel rows
             {
-                if (lane == 0)
-                    qd[DIM * DIM] = 0.; // padding point: sqrt(w) = 0 zeroes its panel rows
+                for (int i = 0; i < n_eq * 4; ++i)
+                    ca[qc * n_eq * 4 + i] = cbp[qc * n_eq * 4 + i] = 0.;
+                for (int i = 0; i < NRHS * 4; ++i)
+                    cr[qc * NRHS * 4 + i] = 0.;
                 continue;
             }
             double xi[DIM], xs[3], Jt[DIM][DIM], Jti[DIM][DIM], nrm[DIM];
@@ -189,143 +219,193 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads)
             double       jac  = detJ;
             if constexpr (is_bnd)
                 jac = boundaryMeasureAndNormal< DIM >(side, Jt, nrm);
-            else if (not(detJ > 0.) and lane == 0)
+            else if (not(detJ > 0.))
                 atomicOr(args.status, status_degenerate_element); // AssembleLocalSystem.hpp:249
             typename KernelT::Input in;
             if constexpr (NF > 0)
             {
-                double        fred[NF * (DIM + 1)];
+                // reference-space sums over the nodes first, then one J^-1 per field (AssembleLocalSystem.hpp:54-75)
+                double        sv[NF], sd[DIM][NF];
                 const double* bv = tab_vals + static_cast< long long >(q) * NN;
                 const double* bd = tab_ders + static_cast< long long >(q) * DIM * NN;
-                for (int i = 0; i < NF * (DIM + 1); ++i)
-                    fred[i] = 0.;
-                for (int a = lane; a < NN; a += 32)
+                for (int f = 0; f < NF; ++f)
                 {
-                    double pd[DIM];
-                    for (int s = 0; s < DIM; ++s)
-                    {
-                        double val = 0.;
-                        for (int d = 0; d < DIM; ++d)
-                            val = fma(Jti[s][d], bd[d * NN + a], val);
-                        pd[s] = val;
-                    }
+                    sv[f] = 0.;
+                    for (int d = 0; d < DIM; ++d)
+                        sd[d][f] = 0.;
+                }
+                for (int a = 0; a < NN; ++a)
+                {
+                    const double n = bv[a];
+                    double       dr[DIM];
+                    for (int d = 0; d < DIM; ++d)
+                        dr[d] = bd[d * NN + a];
+#pragma unroll
                     for (int f = 0; f < NF; ++f)
                     {
                         const double val = s_nv[a * NF + f];
-                        fred[f]          = fma(bv[a], val, fred[f]);
-                        for (int s = 0; s < DIM; ++s)
-                            fred[NF * (s + 1) + f] = fma(pd[s], val, fred[NF * (s + 1) + f]);
+                        sv[f]            = fma(n, val, sv[f]);
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d)
+                            sd[d][f] = fma(dr[d], val, sd[d][f]);
                     }
                 }
-                for (int i = 0; i < NF * (DIM + 1); ++i)
-                    for (int off = 16; off > 0; off >>= 1)
-                        fred[i] += __shfl_xor_sync(0xffffffffu, fred[i], off);
+#pragma unroll
                 for (int f = 0; f < NF; ++f)
                 {
-                    in.field_vals[f] = fred[f];
-                    for (int s = 0; s < DIM; ++s)
-                        in.field_ders[s][f] = fred[NF * (s + 1) + f];
+                    in.field_vals[f] = sv[f];
+#pragma unroll
+                    for (int s_ = 0; s_ < DIM; ++s_)
+                    {
+                        double acc = 0.;
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d)
+                            acc = fma(Jti[s_][d], sd[d][f], acc);
+                        in.field_ders[s_][f] = acc;
+                    }
                 }
             }
-            if (lane == 0)
-            {
-                for (int s = 0; s < 3; ++s)
-                    in.point.space.coords[s] = xs[s];
-                in.point.time = args.time;
-                if constexpr (is_bnd)
-                    for (int s = 0; s < DIM; ++s)
-                        in.normal[s] = nrm[s];
-                const auto res = kernel(in);
-                // guard: entries the compile-time probe declared structurally zero must be zero
-                bool violated = false;
-                staticFor< DIM + 1 >([&](auto op) {
-                    staticFor< E >([&](auto eq) {
-                        staticFor< U >([&](auto uu) {
-                            if constexpr (not Sp::nz(op, eq, uu))
-                                violated |= res.operators[op](eq, uu) != 0.;
-                        });
+            for (int s_ = 0; s_ < 3; ++s_)
+                in.point.space.coords[s_] = xs[s_];
+            in.point.time = args.time;
+            if constexpr (is_bnd)
+                for (int s_ = 0; s_ < DIM; ++s_)
+                    in.normal[s_] = nrm[s_];
+            const auto res = kernel(in);
+            // guard: entries the compile-time probe declared structurally zero must be zero
+            bool violated = false;
+            staticFor< DIM + 1 >([&](auto op) {
+                staticFor< E >([&](auto eq) {
+                    staticFor< U >([&](auto uu) {
+                        if constexpr (not Sp::nz(op, eq, uu))
+                            violated |= res.operators[op](eq, uu) != 0.;
                     });
                 });
-                if (violated)
-                    atomicOr(args.status, status_sparsity_violation);
-                for (int s = 0; s < DIM; ++s)
-                    for (int d = 0; d < DIM; ++d)
-                        qd[s * DIM + d] = Jti[s][d];
-                const double w    = jac * tab_wts[q];
-                qd[DIM * DIM]     = sqrt(fabs(w)); // AssembleLocalSystem.hpp:189-195
-                qd[DIM * DIM + 1] = w;
-                double* qa        = qd + DIM * DIM + 2;
-                for (int i = 0; i <= DIM; ++i)
-                    for (int k = 0; k < E * U; ++k)
-                        qa[i * E * U + k] = res.operators[i].v[k];
-                for (int k = 0; k < E * NRHS; ++k)
-                    qa[(DIM + 1) * E * U + k] = res.rhs.v[k];
-            }
+            });
+            if (violated)
+                atomicOr(args.status, status_sparsity_violation);
+            const double w  = jac * tab_wts[q];
+            const double sw = sqrt(fabs(w)); // AssembleLocalSystem.hpp:189-195
+            double       racc[NRHS][4];
+            for (int r = 0; r < NRHS; ++r)
+                for (int j = 0; j < 4; ++j)
+                    racc[r][j] = 0.;
+            staticFor< U >([&](auto uu) {
+                if (uu != u and uu != v)
+                    return;
+                staticFor< E >([&](auto eq) {
+                    if constexpr (unknownInEquation< KernelT >(uu, eq))
+                    {
+                        const int ei = pr.ei_of_eq[eq];
+                        if (ei < 0)
+                            return;
+                        double cf[4] = {0., 0., 0., 0.};
+                        if constexpr (Sp::nz(0, eq, uu))
+                            cf[0] = sw * res.operators[0](eq, uu);
+                        staticFor< DIM >([&](auto s_) {
+                            if constexpr (Sp::nz(s_ + 1, eq, uu))
+                            {
+#pragma unroll
+                                for (int d = 0; d < DIM; ++d)
+                                    cf[1 + d] = fma(sw * res.operators[s_ + 1](eq, uu), Jti[s_][d], cf[1 + d]);
+                            }
+                        });
+                        if (uu == u)
+                        {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                ca[(qc * n_eq + ei) * 4 + j] = cf[j];
+                            // rhs: F_e[(a,u)] += sum_e w B[e,(a,u)] f_e = sum_e (sqrt(w) f_e) (sqrt(w) B[e,(a,u)])
+#pragma unroll
+                            for (int r = 0; r < NRHS; ++r)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    racc[r][j] = fma(sw * res.rhs(eq, r), cf[j], racc[r][j]);
+                        }
+                        if (uu == v)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                cbp[(qc * n_eq + ei) * 4 + j] = cf[j];
+                    }
+                });
+            });
+            if (rhs_duty)
+                for (int r = 0; r < NRHS; ++r)
+                    for (int j = 0; j < 4; ++j)
+                        cr[(qc * NRHS + r) * 4 + j] = racc[r][j];
         }
     };
 
-    // ---- panels of chunk c → s_pa/s_pb[c & 1]: rows k = qc * n_eq + ei, columns = the TB nodes of block bi (resp. bj)
-    // work item ↔ (panel column = node of block bi or bj, point of the chunk); a thread always meets the same A column
-    const int  n_cols      = same_panel ? TB : 2 * TB;
-    const int  my_a_col    = tid % n_cols;          // the panel-A column of this thread, if < TB
-    const bool rhs_duty    = u == v and bj == 0;    // this CTA also owns F_e[(a, u)] for the nodes a of block bi
-    double     f_acc[NRHS];
+    // ---- panels of chunk c → s_pa/s_pb[c & 1]: rows k = qc * n_eq + ei, columns = the nodes of the row / column block.
+    // Work item ↔ (panel column, point of the chunk); with T a multiple of the column count a thread keeps its column.
+    // A thread owns one panel column (several when T < n_pcols) and a share `part` of the chunk's points, so at most one
+    // A-side node — the one whose rhs entry it accumulates.
+    const int n_pcols = a_in_b ? TN : TM + TN;
+    const int n_parts = T >= n_pcols ? T / n_pcols : 1;
+    double    f_acc[NRHS];
     for (int r = 0; r < NRHS; ++r)
         f_acc[r] = 0.;
     const auto build = [&](int c) {
-        const double* const qbase = s_qp + (c & 1) * Cfg::QCMAX * Cfg::qp_doubles;
-        for (int w = tid; w < n_cols * QC; w += T)
+        const double* const ca  = s_ca + (c & 1) * KCMAX * 4;
+        const double* const cbp = s_cb + (c & 1) * KCMAX * 4;
+        const double* const cr  = s_cr + (c & 1) * QCMAX * NRHS * 4;
+        for (int pc = tid; pc < n_pcols * n_parts; pc += T)
         {
-            const int     pcol = w % n_cols, qc = w / n_cols;
-            const bool    is_a = pcol < TB;
-            const int     prow = pcol % TB;
-            const int     pa   = (is_a ? bi : bj) * TB + prow; // local node
-            const int     pu   = is_a ? u : v;
-            double* const dst  = (is_a ? s_pa : s_pb) + (c & 1) * Cfg::KCMAX * LD + prow;
-            const int     q    = c * QC + qc;
-            const double* qd   = qbase + qc * Cfg::qp_doubles;
-            const double  sw   = qd[DIM * DIM];
-            if (q < args.n_qp and pa < NN)
+            const int  pcol = pc % n_pcols, part = pc / n_pcols;
+            const bool is_b = pcol < TN; // panel B columns first (they exist in both layouts)
+            const int  prow = is_b ? pcol : pcol - TN;
+            const int  node = (is_b ? col0 : row0) + prow;
+            double*    dst  = is_b ? s_pb + (c & 1) * KCMAX * LDB + prow : s_pa + (c & 1) * KCMAX * LDA + prow;
+            const int  ld   = is_b ? LDB : LDA;
+            // rhs rows: the A-side nodes (row block); with a_in_b they are the window [row0, row0 + TM) of panel B
+            const bool rhs_row = rhs_duty and (a_in_b ? (node >= row0 and node < row0 + TM) : not is_b);
+#pragma unroll 4
+            for (int qc = part; qc < QC; qc += n_parts)
             {
-                const double* qa = qd + DIM * DIM + 2;
-                const double  wq = qd[DIM * DIM + 1];
-                const double  n  = __ldg(tab_vals + static_cast< long long >(q) * NN + pa);
-                double        der[DIM], pd[DIM];
-#pragma unroll
-                for (int d = 0; d < DIM; ++d)
-                    der[d] = __ldg(tab_ders + (static_cast< long long >(q) * DIM + d) * NN + pa);
-#pragma unroll
-                for (int s = 0; s < DIM; ++s)
+                const int q = c * QC + qc;
+                if (q < args.n_qp and node < NN)
                 {
-                    double val = qd[s * DIM] * der[0];
+                    double bas[4] = {__ldg(tab_vals + q * NN + node), 0., 0., 0.};
 #pragma unroll
-                    for (int d = 1; d < DIM; ++d)
-                        val = fma(qd[s * DIM + d], der[d], val);
-                    pd[s] = val;
-                }
-                for (int ei = 0; ei < n_eq; ++ei)
-                {
-                    const int eq = pr.eq[ei];
-                    double    b  = n * qa[eq + pu * E];
+                    for (int d = 0; d < DIM; ++d)
+                        bas[1 + d] = __ldg(tab_ders + (q * DIM + d) * NN + node);
+                    const double* cf = (is_b ? cbp : ca) + qc * n_eq * 4;
+                    for (int ei = 0; ei < n_eq; ++ei)
+                    {
+                        const double2 c01 = *reinterpret_cast< const double2* >(cf + ei * 4);
+                        const double2 c23 = *reinterpret_cast< const double2* >(cf + ei * 4 + 2);
+                        double        b   = c01.x * bas[0];
+                        b                 = fma(c01.y, bas[1], b);
+                        if constexpr (DIM >= 2)
+                            b = fma(c23.x, bas[2], b);
+                        if constexpr (DIM >= 3)
+                            b = fma(c23.y, bas[3], b);
+                        dst[(qc * n_eq + ei) * ld] = b;
+                    }
+                    if (rhs_row)
 #pragma unroll
-                    for (int s = 0; s < DIM; ++s)
-                        b = fma(pd[s], qa[(s + 1) * E * U + eq + pu * E], b);
-                    if (rhs_duty and is_a)
                         for (int r = 0; r < NRHS; ++r)
-                            f_acc[r] = fma(b * wq, qa[(DIM + 1) * E * U + eq + r * E], f_acc[r]);
-                    dst[(qc * n_eq + ei) * LD] = b * sw;
+                        {
+                            const double* c4  = cr + (qc * NRHS + r) * 4;
+                            double        acc = c4[0] * bas[0];
+#pragma unroll
+                            for (int d = 0; d < DIM; ++d)
+                                acc = fma(c4[1 + d], bas[1 + d], acc);
+                            f_acc[r] += acc;
+                        }
                 }
+                else
+                    for (int ei = 0; ei < n_eq; ++ei)
+                        dst[(qc * n_eq + ei) * ld] = 0.;
             }
-            else
-                for (int ei = 0; ei < n_eq; ++ei)
-                    dst[(qc * n_eq + ei) * LD] = 0.;
         }
     };
 
     // ---- accumulators: warp (wy, wx) owns rows wy*32 .. +32, columns wx*32 .. +32 of the tile as 4 x 4 DMMA tiles
-    const int wy = warp / Cfg::WR, wx = warp % Cfg::WR;
-    const int g = lane >> 2, tq = lane & 3;
-    double    acc[4][4][2];
+    const int  wy = warp / Cfg::WN, wx = warp % Cfg::WN;
+    const int  g = lane >> 2, tq = lane & 3;
+    const bool warp_live = not diag_pair or col0 + wx * 32 <= row0 + wy * 32 + 31; // not strictly above the diagonal
+    double     acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -345,65 +425,86 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads)
             build(c + 1);
         if (c + 2 < n_chunks)
             perPoint(c + 2);
-        const double* const pa_c = s_pa + (c & 1) * Cfg::KCMAX * LD + wy * 32 + g;
-        const double* const pb_c = (same_panel ? s_pa : s_pb) + (c & 1) * Cfg::KCMAX * LD + wx * 32 + g;
-#pragma unroll 2
-        for (int k4 = 0; k4 < n_k4; ++k4)
+        if (warp_live)
         {
-            double a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
+            const double* const pb_c = s_pb + (c & 1) * KCMAX * LDB + wx * 32 + g;
+            const double* const pa_c = a_in_b ? s_pb + (c & 1) * KCMAX * LDB + (row0 - col0) + wy * 32 + g : s_pa + (c & 1) * KCMAX * LDA + wy * 32 + g;
+            const int           lda  = a_in_b ? LDB : LDA;
+#pragma unroll 2
+            for (int k4 = 0; k4 < n_k4; ++k4)
             {
-                a[i] = pa_c[(k4 * 4 + tq) * LD + i * 8];
-                b[i] = pb_c[(k4 * 4 + tq) * LD + i * 8];
+                double a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                {
+                    a[i] = pa_c[(k4 * 4 + tq) * lda + i * 8];
+                    b[i] = pb_c[(k4 * 4 + tq) * LDB + i * 8];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
         __syncthreads();
     }
 
     // ---- scatter into the CRS values: slot(row (a,u), col (b,v)) = row_ptr[dof(a,u)] + pos[e][a][b] * dofs_per_node + dof_inds[v]
-    // DMMA accumulator layout: acc[i][j][h] = tile(row i*8 + g, column j*8 + 2*tq + h)
-    const uint16_t* pos = args.slot_pos + e * static_cast< long long >(NN) * NN;
-    const int       du = args.dof_inds[u], dv = args.dof_inds[v];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
+    // DMMA accumulator layout: acc[i][j][h] = tile(row i*8 + g, column j*8 + 2*tq + h). For u == v only b <= a is
+    // scattered, with its mirror image when b < a; for u != v every entry and its mirror K_e[(b,v)][(a,u)].
+    if (warp_live)
     {
-        const int a = bi * TB + wy * 32 + i * 8 + g;
-        if (a >= NN)
-            continue;
-        const long long node_a = el_nodes[a];
-        const long long rbeg   = args.row_ptr[node_a * args.dofs_per_node + du];
+        const uint16_t* pos = args.slot_pos + e * static_cast< long long >(NN) * NN;
+        const int       dpn = args.dofs_per_node, du = args.dof_inds[u], dv = args.dof_inds[v];
+        long long       cbeg[4][2]; // row starts of the mirrored entries: rows (b, v)
+        int             bcol[4][2];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int h = 0; h < 2; ++h)
             {
-                const int b = bj * TB + wx * 32 + j * 8 + 2 * tq + h;
-                if (b >= NN)
-                    continue;
-                const double val = acc[i][j][h];
-                atomicAdd(args.crs_vals + rbeg + static_cast< long long >(pos[a * NN + b]) * args.dofs_per_node + dv, val);
-                if (not same_panel) // mirrored entry K_e[(b,v)][(a,u)]
-                {
-                    const long long node_b = el_nodes[b];
-                    atomicAdd(args.crs_vals + args.row_ptr[node_b * args.dofs_per_node + dv] +
-                                  static_cast< long long >(pos[b * NN + a]) * args.dofs_per_node + du,
-                              val);
-                }
+                const int b = col0 + wx * 32 + j * 8 + 2 * tq + h;
+                bcol[j][h]  = b;
+                cbeg[j][h]  = b < NN ? args.row_ptr[static_cast< long long >(el_nodes[b]) * dpn + dv] + du : 0;
             }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            const int a = row0 + wy * 32 + i * 8 + g;
+            if (a >= NN)
+                continue;
+            double* const   rowp = args.crs_vals + args.row_ptr[static_cast< long long >(el_nodes[a]) * dpn + du] + dv;
+            const uint16_t* pa_  = pos + a * NN;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                {
+                    const int b = bcol[j][h];
+                    if (b >= NN or (diag_pair and b > a))
+                        continue;
+                    const double val = acc[i][j][h];
+                    atomicAdd(rowp + static_cast< int >(pa_[b]) * dpn, val);
+                    if (not diag_pair or b < a)
+                        atomicAdd(args.crs_vals + cbeg[j][h] + static_cast< int >(pos[b * NN + a]) * dpn, val);
+                }
+        }
     }
-    // ---- rhs (ScatterLocalSystem.hpp:47-52)
-    if (rhs_duty and my_a_col < TB and bi * TB + my_a_col < NN and (T >= n_cols or tid < TB))
-    {
-        const long long grow = static_cast< long long >(el_nodes[bi * TB + my_a_col]) * args.dofs_per_node + du;
-        for (int r = 0; r < NRHS; ++r)
-            atomicAdd(args.rhs + grow + r * args.ld, f_acc[r]);
-    }
+    // ---- rhs (ScatterLocalSystem.hpp:47-52): the A-side node this thread met in `build`
+    if (rhs_duty)
+        for (int pc = tid; pc < n_pcols * n_parts; pc += T)
+        {
+            const int  pcol = pc % n_pcols;
+            const bool is_b = pcol < TN;
+            const int  node = (is_b ? col0 : row0) + (is_b ? pcol : pcol - TN);
+            if ((a_in_b ? (node >= row0 and node < row0 + TM) : not is_b) and node < NN)
+            {
+                const long long grow = static_cast< long long >(el_nodes[node]) * args.dofs_per_node + args.dof_inds[u];
+                for (int r = 0; r < NRHS; ++r)
+                    atomicAdd(args.rhs + grow + r * args.ld, f_acc[r]);
+            }
+        }
 }
 } // namespace l3b
 #endif
