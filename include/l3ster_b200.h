@@ -154,6 +154,25 @@ int l3b_mf_apply_device(l3b_mf* sys, const double* x, double* y, int n_cols, dou
 int l3b_mf_apply(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta);
 /* CG + native Jacobi, x0 = 0, rhs = system rhs column 0 (benchmarks/Diffusion3D.hpp:115-118) */
 int l3b_mf_solve_cg(l3b_mf* sys, double tol, int max_iters, double* x /* host */, double* achieved_tol, int* iters);
+/* The same apply split into the phases MatrixFreeSystem::applyImpl overlaps with its halo exchange (:1046-1122):
+ *   L3B_APPLY_INIT     y <- beta y                                   (:1038)
+ *   L3B_APPLY_ELEMENTS y[dofs(e)] += alpha K_e x[dofs(e)] for the domain elements e in [elem_begin, elem_end) — the caller passes
+ *                      its interior range while comm::Import (owner -> ghost copies of x) is in flight, then the border range;
+ *                      boundary kernels run with the range that contains element 0
+ *   L3B_APPLY_FINISH   Dirichlet identity rows y[d] += alpha x[d]    (:1087-1103)
+ * All phases are asynchronous on the context stream; x, y are device pointers over the LOCAL dofs [owned | ghost]. */
+enum
+{
+    L3B_APPLY_INIT     = 1,
+    L3B_APPLY_ELEMENTS = 2,
+    L3B_APPLY_FINISH   = 4
+};
+int l3b_mf_apply_phase_device(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta, int phases,
+                              int64_t elem_begin, int64_t elem_end);
+/* halo packing for comm::Import / comm::Export (comm/ImportExport.hpp:29-472) with device index lists:
+ * gather: dst[i + c n] = src[idx[i] + c ld];  scatter_add: dst[idx[i] + c ld] += src[i + c n]. Asynchronous on the context stream. */
+int l3b_vec_gather(l3b_context* ctx, const double* src, int64_t ld, const int32_t* idx, int64_t n, int n_cols, double* dst);
+int l3b_vec_scatter_add(l3b_context* ctx, double* dst, int64_t ld, const int32_t* idx, int64_t n, int n_cols, const double* src);
 int64_t l3b_mf_num_dofs(const l3b_mf* sys);
 int     l3b_mf_kernel_launches(const l3b_mf* sys); /* device kernels launched by the last apply */
 

@@ -49,6 +49,7 @@ class AssemblyOptions:
 
 
 _lib = None
+APPLY_INIT, APPLY_ELEMENTS, APPLY_FINISH = 1, 2, 4
 
 # every symbol include/l3ster_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
@@ -62,6 +63,7 @@ EXPORTED_SYMBOLS = [
     "l3b_asm_download", "l3b_asm_device_values", "l3b_asm_spmv", "l3b_asm_solve_cg", "l3b_asm_last_kernel_ms",
     "l3b_mf_create", "l3b_mf_destroy", "l3b_mf_assemble", "l3b_mf_end_assembly", "l3b_mf_download", "l3b_mf_apply_device", "l3b_mf_apply",
     "l3b_mf_solve_cg", "l3b_mf_num_dofs", "l3b_mf_kernel_launches", "l3b_microbench",
+    "l3b_mf_apply_phase_device", "l3b_vec_gather", "l3b_vec_scatter_add",
 ]
 
 
@@ -132,6 +134,9 @@ def lib():
     L.l3b_mf_end_assembly.argtypes = [vp]
     L.l3b_mf_download.argtypes = [vp, vp, vp]
     L.l3b_mf_apply_device.argtypes = [vp, vp, vp, i32, dbl, dbl]
+    L.l3b_mf_apply_phase_device.argtypes = [vp, vp, vp, i32, dbl, dbl, i32, i64, i64]
+    L.l3b_vec_gather.argtypes = [vp, vp, i64, vp, i64, i32, vp]
+    L.l3b_vec_scatter_add.argtypes = [vp, vp, i64, vp, i64, i32, vp]
     L.l3b_mf_apply.argtypes = [vp, vp, vp, i32, dbl, dbl]
     L.l3b_mf_solve_cg.argtypes = [vp, dbl, i32, vp, C.POINTER(dbl), C.POINTER(i32)]
     L.l3b_mf_num_dofs.argtypes = [vp]
@@ -340,6 +345,12 @@ class Context:
         self._chk(lib().l3b_microbench(self._h, mode, C.byref(out)))
         return out.value
 
+    def vec_gather(self, src_ptr, ld, idx_ptr, n, dst_ptr, n_cols=1):
+        self._chk(lib().l3b_vec_gather(self._h, src_ptr, ld, idx_ptr, n, n_cols, dst_ptr))
+
+    def vec_scatter_add(self, dst_ptr, ld, idx_ptr, n, src_ptr, n_cols=1):
+        self._chk(lib().l3b_vec_scatter_add(self._h, dst_ptr, ld, idx_ptr, n, n_cols, src_ptr))
+
     def upload_mesh(self, mesh: HostMesh, n_owned_nodes=None):
         return Mesh(self, mesh.dim, mesh.order, mesh.verts, mesh.nodes, mesh.side_boundaries, mesh.n_nodes,
                     mesh.n_nodes if n_owned_nodes is None else n_owned_nodes)
@@ -508,6 +519,11 @@ class MatrixFreeSystem:
 
     def apply_device(self, x_ptr, y_ptr, n_cols=1, alpha=1.0, beta=0.0):
         self.ctx._chk(lib().l3b_mf_apply_device(self._h, x_ptr, y_ptr, n_cols, alpha, beta))
+
+    def apply_phase_device(self, x_ptr, y_ptr, phases, elem_begin=0, elem_end=None, n_cols=1, alpha=1.0, beta=0.0):
+        """One phase of the apply (APPLY_INIT | APPLY_ELEMENTS | APPLY_FINISH) on device pointers over [owned | ghost] dofs."""
+        end = self.mesh.n_elems if elem_end is None else elem_end
+        self.ctx._chk(lib().l3b_mf_apply_phase_device(self._h, x_ptr, y_ptr, n_cols, alpha, beta, phases, elem_begin, end))
 
     def solve(self, tol=1e-6, max_iters=10000):
         x = np.zeros(self.n_dofs)

@@ -170,6 +170,17 @@ __global__ void dirichletRowsListKernel(const int32_t* dofs, long long n_dir, co
             y[d + c * ld] += alpha * x[d + c * ld];
     }
 }
+// halo packing (comm/ImportExport.hpp): gather / scatter-add through a device index list
+__global__ void vecGatherKernel(const double* src, long long ld, const int32_t* idx, long long n, int n_cols, double* dst)
+{
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n * n_cols; i += static_cast< long long >(gridDim.x) * blockDim.x)
+        dst[i] = src[idx[i % n] + (i / n) * ld];
+}
+__global__ void vecScatterAddKernel(double* dst, long long ld, const int32_t* idx, long long n, int n_cols, const double* src)
+{
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n * n_cols; i += static_cast< long long >(gridDim.x) * blockDim.x)
+        dst[idx[i % n] + (i / n) * ld] += src[i];
+}
 // handle_dirichlet_dof (MatrixFreeSystem.hpp:911-915)
 __global__ void dirichletInitKernel(const uint8_t* mask, const double* vals, double* diag, double* rhs, long long n, long long ld, int n_rhs)
 {
@@ -699,61 +710,82 @@ int guardedCtx(const l3b_context* ctx, F&& f)
     }
 }
 
-// y = alpha A x + beta y on device pointers
-void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta)
+// y = alpha A x + beta y on device pointers, in the phases of l3b_mf_apply_phase_device
+void mfApplyPhases(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta, int phases, long long elem_begin,
+                   long long elem_end)
 {
     auto* ctx = sys->ctx;
     if (not sys->closed)
         fail(L3B_ERR_STATE, "`apply` was called before `endAssembly()`");
     if (n_cols != sys->n_rhs and n_cols != 1)
         fail(L3B_ERR_INVALID_ARG, "n_cols must equal the system's n_rhs or 1");
+    if (elem_begin < 0 or elem_end > sys->mesh->n_elems or elem_begin > elem_end)
+        fail(L3B_ERR_INVALID_ARG, "element range out of bounds");
     int launches = 0;
-    if (beta == 0.)
-        cudaCheck(cudaMemsetAsync(y, 0, sizeof(double) * sys->n_dofs * n_cols, ctx->stream), "memset");
-    else
+    if (phases & L3B_APPLY_INIT)
     {
-        scaleKernel<<< gridFor(sys->n_dofs * n_cols), 256, 0, ctx->stream >>>(y, sys->n_dofs * n_cols, beta);
-        ++launches;
-    }
-    for (const auto& use : sys->uses)
-    {
-        const auto& info = kernelRegistry()[use.kernel_id].info;
-        ElemArgs    a    = baseArgs(sys->mesh, use, sys->dpn, sys->n_dofs);
-        a.x              = x;
-        a.y              = y;
-        a.n_cols         = n_cols;
-        a.alpha          = alpha;
-        a.dir_mask       = sys->has_bc ? sys->dir_mask.ptr : nullptr;
-        a.elem_dir       = sys->has_bc ? sys->elem_dir.ptr : nullptr;
-        bool contiguous  = info.n_unknowns == sys->dpn and reinterpret_cast< uintptr_t >(x) % 16 == 0 and sys->n_dofs % 2 == 0;
-        for (int u = 0; u < info.n_unknowns; ++u)
-            contiguous = contiguous and use.dof_inds[u] == u;
-        a.contiguous_dofs = contiguous;
-        const bool full  = n_cols == sys->n_rhs;
-        const bool sf    = not info.is_boundary and use.opts.eval_strategy != 1;
-        cudaError_t err;
-        if (sf)
-        {
-            const auto& t = ctx->tables1d(sys->mesh->order, use.nq);
-            err           = (full ? use.inst->mf_sumfact_full : use.inst->mf_sumfact_one)(kernelRegistry()[use.kernel_id].object.get(), a, t,
-                                                                                ctx->stream);
-        }
+        if (beta == 0.)
+            cudaCheck(cudaMemsetAsync(y, 0, sizeof(double) * sys->n_dofs * n_cols, ctx->stream), "memset");
         else
         {
-            setDense(a, sys->mesh, use, info.is_boundary);
-            err = (full ? use.inst->local_apply_full : use.inst->local_apply_one)(kernelRegistry()[use.kernel_id].object.get(), a, ctx->stream);
-        }
-        cudaCheck(err, "operator apply launch");
-        if (a.n_work > 0)
+            scaleKernel<<< gridFor(sys->n_dofs * n_cols), 256, 0, ctx->stream >>>(y, sys->n_dofs * n_cols, beta);
             ++launches;
+        }
     }
-    if (sys->has_bc and sys->n_dir > 0)
+    if (phases & L3B_APPLY_ELEMENTS)
+        for (const auto& use : sys->uses)
+        {
+            const auto& info = kernelRegistry()[use.kernel_id].info;
+            ElemArgs    a    = baseArgs(sys->mesh, use, sys->dpn, sys->n_dofs);
+            if (info.is_boundary)
+            {
+                if (elem_begin != 0) // the side work list is not split: it runs with the range that contains element 0
+                    continue;
+            }
+            else
+            {
+                a.first_elem = elem_begin;
+                a.n_work     = elem_end - elem_begin;
+            }
+            a.x              = x;
+            a.y              = y;
+            a.n_cols         = n_cols;
+            a.alpha          = alpha;
+            a.dir_mask       = sys->has_bc ? sys->dir_mask.ptr : nullptr;
+            a.elem_dir       = sys->has_bc ? sys->elem_dir.ptr : nullptr;
+            bool contiguous  = info.n_unknowns == sys->dpn and reinterpret_cast< uintptr_t >(x) % 16 == 0 and sys->n_dofs % 2 == 0;
+            for (int u = 0; u < info.n_unknowns; ++u)
+                contiguous = contiguous and use.dof_inds[u] == u;
+            a.contiguous_dofs = contiguous;
+            const bool full  = n_cols == sys->n_rhs;
+            const bool sf    = not info.is_boundary and use.opts.eval_strategy != 1;
+            cudaError_t err;
+            if (sf)
+            {
+                const auto& t = ctx->tables1d(sys->mesh->order, use.nq);
+                err           = (full ? use.inst->mf_sumfact_full : use.inst->mf_sumfact_one)(kernelRegistry()[use.kernel_id].object.get(), a, t,
+                                                                                    ctx->stream);
+            }
+            else
+            {
+                setDense(a, sys->mesh, use, info.is_boundary);
+                err = (full ? use.inst->local_apply_full : use.inst->local_apply_one)(kernelRegistry()[use.kernel_id].object.get(), a, ctx->stream);
+            }
+            cudaCheck(err, "operator apply launch");
+            if (a.n_work > 0)
+                ++launches;
+        }
+    if ((phases & L3B_APPLY_FINISH) and sys->has_bc and sys->n_dir > 0)
     {
         dirichletRowsListKernel<<< gridFor(sys->n_dir), 256, 0, ctx->stream >>>(sys->dir_list.ptr, sys->n_dir, x, y, sys->n_dofs, n_cols, alpha);
         ++launches;
     }
     cudaCheck(cudaGetLastError(), "operator apply");
-    sys->last_launches = launches;
+    sys->last_launches = launches; // of this call
+}
+void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta)
+{
+    mfApplyPhases(sys, x, y, n_cols, alpha, beta, L3B_APPLY_INIT | L3B_APPLY_ELEMENTS | L3B_APPLY_FINISH, 0, sys->mesh->n_elems);
 }
 
 // Preconditioned CG, Belos "Block CG" semantics for block size 1 (solve/BelosSolvers.hpp:76-89): left preconditioner,
@@ -1260,8 +1292,9 @@ int l3b_mf_create(l3b_context* ctx, l3b_mesh* mesh, int dpn, int n_rhs, const ui
             s->has_bc = true;
             s->dir_mask.alloc(s->n_dofs);
             s->dir_mask.upload(mask, s->n_dofs, ctx->stream);
+            // identity rows only for owned dofs: ghost rows are summed into their owner by the export (MatrixFreeSystem.hpp:1087-1103)
             std::vector< int32_t > list;
-            for (long long i = 0; i < s->n_dofs; ++i)
+            for (long long i = 0; i < mesh->n_owned_nodes * dpn; ++i)
                 if (mask[i])
                     list.push_back(static_cast< int32_t >(i));
             s->n_dir = static_cast< long long >(list.size());
@@ -1337,6 +1370,27 @@ int l3b_mf_download(l3b_mf* sys, double* diag, double* rhs)
 int l3b_mf_apply_device(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta)
 {
     return guardedCtx(sys->ctx, [&] { mfApplyDevice(sys, x, y, n_cols, alpha, beta); });
+}
+int l3b_mf_apply_phase_device(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta, int phases, int64_t elem_begin,
+                              int64_t elem_end)
+{
+    return guardedCtx(sys->ctx, [&] { mfApplyPhases(sys, x, y, n_cols, alpha, beta, phases, elem_begin, elem_end); });
+}
+int l3b_vec_gather(l3b_context* ctx, const double* src, int64_t ld, const int32_t* idx, int64_t n, int n_cols, double* dst)
+{
+    return guardedCtx(ctx, [&] {
+        if (n > 0)
+            vecGatherKernel<<< gridFor(n * n_cols), 256, 0, ctx->stream >>>(src, ld, idx, n, n_cols, dst);
+        cudaCheck(cudaGetLastError(), "gather");
+    });
+}
+int l3b_vec_scatter_add(l3b_context* ctx, double* dst, int64_t ld, const int32_t* idx, int64_t n, int n_cols, const double* src)
+{
+    return guardedCtx(ctx, [&] {
+        if (n > 0)
+            vecScatterAddKernel<<< gridFor(n * n_cols), 256, 0, ctx->stream >>>(dst, ld, idx, n, n_cols, src);
+        cudaCheck(cudaGetLastError(), "scatter-add");
+    });
 }
 int l3b_mf_apply(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta)
 {

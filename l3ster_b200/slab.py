@@ -1,0 +1,238 @@
+"""z-slab partition of the structured benchmark cube, one slab per rank.
+
+The reference partitions with Metis and renumbers so that every rank owns a contiguous global node range, local ids
+`[owned | ghost sorted by GID]` (mesh/PartitionMesh.hpp:411-440, dofs/NodeToDofMap.hpp:144-163). Metis is not available
+here, so the partition is the structured one the benchmarks would get from any sane partitioner: rank r takes the element
+layers z in [z0(r), z1(r)); the nodes of the plane shared with the slab below belong to the lower rank. Every rank builds
+its slab alone (no communication at set-up): both sides of an interface enumerate the shared plane in the same (y, x)
+lattice order, which is also the order of the ghost block — the stand-in for "sorted by GID".
+
+Halo pattern of the matrix-free apply (algsys/MatrixFreeSystem.hpp:1046-1122, comm/ImportExport.hpp):
+  Import  x: owner (rank r, top plane, packed) -> ghost block of rank r+1 (contiguous tail of its local vector)
+  Export  y: ghost block of rank r+1 (contiguous) -> rank r, added into its top-plane dofs
+Elements are numbered layer by layer, so the border elements (the ones that touch ghost nodes) are the first
+`n_border_elems` of the slab and the interior ones the contiguous rest.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+import l3ster_b200 as l3b
+
+
+def split_layers(n_layers, world):
+    """Element layers [z0, z1) of every rank; ranks may get zero layers when world > n_layers (tests/EmptyPartitionTest.cpp)."""
+    base, rem = divmod(n_layers, world)
+    out, z = [], 0
+    for r in range(world):
+        k = base + (1 if r < rem else 0)
+        out.append((z, z + k))
+        z += k
+    return out
+
+
+@dataclass
+class Slab:
+    rank: int
+    world: int
+    order: int
+    n_elems: int
+    n_local_nodes: int
+    n_owned_nodes: int
+    nodes: np.ndarray            # (n_elems, nodes_per_elem) local ids in the [owned | ghost] numbering
+    verts: np.ndarray            # (n_elems, 8, 3)
+    side_boundaries: np.ndarray  # (n_elems, 6), 0xFFFF = not on a physical boundary
+    lattice: np.ndarray          # (n_local_nodes, 3) global order-p lattice coordinates of the local nodes
+    n_border_elems: int          # elements [0, n_border_elems) touch ghost nodes
+    send_up_nodes: np.ndarray    # owned nodes of the top plane, (y, x) order: Import source / Export target
+    lower: int                   # rank that owns our ghosts, or -1
+    upper: int                   # rank whose ghosts we own, or -1
+
+    @property
+    def n_ghost_nodes(self):
+        return self.n_local_nodes - self.n_owned_nodes
+
+    def dirichlet_nodes(self, boundary_ids):
+        """local nodes (owned and ghost) on the physical sides carrying one of `boundary_ids`"""
+        nb = self.order + 1
+        sel = np.zeros(self.n_local_nodes, dtype=bool)
+        for side in range(6):
+            on = np.isin(self.side_boundaries[:, side], list(boundary_ids))
+            if on.any():
+                sel[self.nodes[on][:, l3b.side_node_inds(3, self.order, side)].ravel()] = True
+        return np.nonzero(sel)[0]
+
+
+def make_slab(x, y, z, order, rank, world) -> Slab:
+    """Slab `rank` of `world` of the cube mesh over the vertex coordinates x, y, z (benchmarks/Diffusion3D.hpp:8-24)."""
+    x, y, z = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z))
+    nz = len(z) - 1
+    layers = split_layers(nz, world)
+    z0, z1 = layers[rank]
+    p = order
+    if z1 == z0:
+        e = np.zeros
+        return Slab(rank, world, p, 0, 0, 0, e((0, (p + 1) ** 3), np.uint32), e((0, 8, 3)), e((0, 6), np.uint16), e((0, 3), np.int64), 0,
+                    e(0, np.int64), -1, -1)
+    # neighbours: nearest non-empty slabs
+    lower = next((r for r in range(rank - 1, -1, -1) if layers[r][1] > layers[r][0]), -1)
+    upper = next((r for r in range(rank + 1, world) if layers[r][1] > layers[r][0]), -1)
+    host = l3b.make_cube_mesh(x, y, z[z0:z1 + 1], order=p)
+    nodes0, verts = np.array(host.nodes, dtype=np.int64), np.array(host.verts)
+    sb = np.array(host.side_boundaries)
+    n_elems, n_nodes = host.n_elems, host.n_nodes
+    # lattice coordinates of every local node from the element's position and the node's place in it
+    ex = np.searchsorted(x, verts[:, 0, 0])
+    ey = np.searchsorted(y, verts[:, 0, 1])
+    ez = np.searchsorted(z, verts[:, 0, 2])
+    a = np.arange((p + 1) ** 3)
+    li, lj, lk = a % (p + 1), (a // (p + 1)) % (p + 1), a // (p + 1) ** 2
+    lat = np.zeros((n_nodes, 3), dtype=np.int64)
+    lat[nodes0.ravel(), 0] = (ex[:, None] * p + li[None, :]).ravel()
+    lat[nodes0.ravel(), 1] = (ey[:, None] * p + lj[None, :]).ravel()
+    lat[nodes0.ravel(), 2] = (ez[:, None] * p + lk[None, :]).ravel()
+    # ownership: the plane shared with the slab below belongs to the lower rank
+    ghost = (lat[:, 2] == z0 * p) if lower >= 0 else np.zeros(n_nodes, dtype=bool)
+    plane_key = lat[:, 1] * (len(x) * p + 1) + lat[:, 0]
+    owned_ids = np.nonzero(~ghost)[0]
+    ghost_ids = np.nonzero(ghost)[0]
+    ghost_ids = ghost_ids[np.argsort(plane_key[ghost_ids], kind="stable")]
+    perm = np.empty(n_nodes, dtype=np.int64)
+    perm[owned_ids] = np.arange(len(owned_ids))
+    perm[ghost_ids] = len(owned_ids) + np.arange(len(ghost_ids))
+    nodes = perm[nodes0].astype(np.uint32)
+    lat_new = np.empty_like(lat)
+    lat_new[perm] = lat
+    top = np.nonzero(lat_new[:, 2] == z1 * p)[0] if upper >= 0 else np.zeros(0, dtype=np.int64)
+    top = top[np.argsort((lat_new[top, 1] * (len(x) * p + 1) + lat_new[top, 0]), kind="stable")]
+    # the z faces between slabs are not physical boundaries (sides 0 = z-, 1 = z+, mesh/ElementTraits.hpp:88-93)
+    no_bnd = np.uint16(0xFFFF)
+    if lower >= 0:
+        sb[ez == z0, 0] = no_bnd
+    if upper >= 0:
+        sb[ez == z1 - 1, 1] = no_bnd
+    touches_ghost = (nodes >= len(owned_ids)).any(axis=1)
+    n_border = int(touches_ghost.sum())
+    assert not touches_ghost[n_border:].any(), "border elements are expected to be the first layer of the slab"
+    return Slab(rank, world, p, n_elems, n_nodes, len(owned_ids), nodes, verts, sb, lat_new, n_border, top, lower, upper)
+
+
+class Halo:
+    """Import / Export of the slab's interface dofs (comm/ImportExport.hpp:29-472) over torch.distributed point-to-point
+    calls: NCCL for device tensors, gloo for host tensors (the CPU tests). Vectors cover the local dofs [owned | ghost]."""
+
+    def __init__(self, slab: Slab, dofs_per_node, device="cpu", ctx=None):
+        import torch
+
+        self.torch, self.slab, self.ctx = torch, slab, ctx
+        self.n_owned_dofs = slab.n_owned_nodes * dofs_per_node
+        self.n_local_dofs = slab.n_local_nodes * dofs_per_node
+        self.n_ghost_dofs = self.n_local_dofs - self.n_owned_dofs
+        up = (slab.send_up_nodes[:, None] * dofs_per_node + np.arange(dofs_per_node)[None, :]).ravel().astype(np.int32)
+        self.n_up = len(up)
+        self.up_idx = torch.from_numpy(up).to(device)
+        self.send_up = torch.empty(self.n_up, dtype=torch.float64, device=device)
+        self.recv_up = torch.empty(self.n_up, dtype=torch.float64, device=device)
+
+    # pack / unpack: the library's kernels on the device (asynchronous on the context stream), torch indexing on the host
+    def pack(self, x):
+        if self.n_up == 0:
+            return 0
+        if x.is_cuda:
+            self.ctx.vec_gather(x.data_ptr(), self.n_local_dofs, self.up_idx.data_ptr(), self.n_up, self.send_up.data_ptr())
+            return 1
+        self.send_up.copy_(x[self.up_idx.long()])
+        return 0
+
+    def unpack_add(self, y):
+        if self.n_up == 0:
+            return 0
+        if y.is_cuda:
+            self.ctx.vec_scatter_add(y.data_ptr(), self.n_local_dofs, self.up_idx.data_ptr(), self.n_up, self.recv_up.data_ptr())
+            return 1
+        y.index_add_(0, self.up_idx.long(), self.recv_up)
+        return 0
+
+    def _p2p(self, send, dst, recv, src):
+        import torch.distributed as dist
+
+        ops = []
+        if dst >= 0 and send is not None and send.numel() > 0:
+            ops.append(dist.P2POp(dist.isend, send, dst))
+        if src >= 0 and recv is not None and recv.numel() > 0:
+            ops.append(dist.P2POp(dist.irecv, recv, src))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def import_x(self, x):
+        """owner -> ghost copies: the packed top plane goes up, the ghost block (contiguous tail of x) is filled from below"""
+        self._p2p(self.send_up, self.slab.upper, x[self.n_owned_dofs:] if self.n_ghost_dofs else None, self.slab.lower)
+
+    def export_y(self, y):
+        """ghost contributions -> owner: the ghost block goes down, the contributions from above land in recv_up"""
+        self._p2p(y[self.n_owned_dofs:] if self.n_ghost_dofs else None, self.slab.lower, self.recv_up, self.slab.upper)
+
+
+class SlabOperator:
+    """Matrix-free operator of one slab with the overlap of MatrixFreeSystem::applyImpl (:1046-1122): the first half of the
+    interior elements runs while the Import is in flight, then the border elements, then the second half of the interior
+    while the Export is in flight. Vectors are device tensors over the local dofs [owned | ghost]."""
+
+    def __init__(self, ctx, slab: Slab, dofs_per_node, kernel, dirichlet_boundary_ids=()):
+        import torch
+
+        self.torch, self.ctx, self.slab, self.dpn = torch, ctx, slab, dofs_per_node
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.halo = Halo(slab, dofs_per_node, dev, ctx)
+        self.n_local_dofs, self.n_owned_dofs = self.halo.n_local_dofs, self.halo.n_owned_dofs
+        self.mesh = self.sys = None
+        if slab.n_elems > 0:
+            self.mesh = l3b.Mesh(ctx, 3, slab.order, slab.verts, slab.nodes, slab.side_boundaries, slab.n_local_nodes, slab.n_owned_nodes)
+            mask = np.zeros(self.n_local_dofs, dtype=np.uint8)
+            if dirichlet_boundary_ids:
+                mask[slab.dirichlet_nodes(dirichlet_boundary_ids) * dofs_per_node] = 1  # dof 0 (T), benchmarks/Diffusion3D.hpp:102-104
+            self.sys = l3b.MatrixFreeSystem(ctx, self.mesh, dofs_per_node, 1, mask, None)
+            self.sys.assembleProblem(kernel)
+            self.sys.endAssembly()
+        self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+        self.comm = torch.cuda.Stream(device=dev)
+        self.launches = 0
+
+    def apply(self, x, y, alpha=1.0, beta=0.0):
+        """y[owned] = alpha (A x)[owned] + beta y[owned]; x[ghost] is overwritten by the Import. Asynchronous."""
+        torch, s, sys_, halo = self.torch, self.slab, self.sys, self.halo
+        if sys_ is None:
+            return
+        S, Cs = self.stream, self.comm
+        half = s.n_border_elems + (s.n_elems - s.n_border_elems) // 2
+        xp, yp = x.data_ptr(), y.data_ptr()
+        n = 0
+        with torch.cuda.stream(S):
+            n += halo.pack(x)
+            ev_packed = S.record_event()
+        with torch.cuda.stream(Cs):
+            Cs.wait_event(ev_packed)
+            halo.import_x(x)
+            ev_imported = Cs.record_event()
+        with torch.cuda.stream(S):
+            sys_.apply_phase_device(xp, yp, l3b.APPLY_INIT, 0, 0, alpha=alpha, beta=beta)
+            n += sys_.kernel_launches
+            sys_.apply_phase_device(xp, yp, l3b.APPLY_ELEMENTS, s.n_border_elems, half, alpha=alpha)
+            n += sys_.kernel_launches
+            S.wait_event(ev_imported)
+            sys_.apply_phase_device(xp, yp, l3b.APPLY_ELEMENTS, 0, s.n_border_elems, alpha=alpha)
+            n += sys_.kernel_launches
+            ev_border = S.record_event()
+        with torch.cuda.stream(Cs):
+            Cs.wait_event(ev_border)
+            halo.export_y(y)
+            ev_exported = Cs.record_event()
+        with torch.cuda.stream(S):
+            sys_.apply_phase_device(xp, yp, l3b.APPLY_ELEMENTS, half, s.n_elems, alpha=alpha)
+            n += sys_.kernel_launches
+            S.wait_event(ev_exported)
+            n += halo.unpack_add(y)
+            sys_.apply_phase_device(xp, yp, l3b.APPLY_FINISH, 0, 0, alpha=alpha)
+            n += sys_.kernel_launches
+        self.launches = n
