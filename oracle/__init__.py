@@ -26,7 +26,7 @@ def build(native: bool = False) -> str:
         objdir = os.path.join(_DIR, "_native")
         os.makedirs(objdir, exist_ok=True)
         srcs = ["math", "element", "sumfact", "kernels", "mesh", "system", "capi"]
-        cmd = ["g++", "-std=c++20", "-O3", "-march=native", "-fPIC", "-pthread", "-shared", "-o", os.path.join(objdir, out)]
+        cmd = ["g++", "-std=c++20", "-O3", "-march=native", "-fopenmp-simd", "-fPIC", "-pthread", "-shared", "-o", os.path.join(objdir, out)]
         cmd += [os.path.join(_DIR, s + ".cpp") for s in srcs]
         subprocess.run(cmd, check=True, cwd=_DIR)
         return os.path.join(objdir, out)

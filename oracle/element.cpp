@@ -380,29 +380,29 @@ void checkDims(const Kernel& kernel, ElementType et)
 void syrkLower(val_t* K, int L, const val_t* B, int ncols, val_t sign)
 {
     constexpr int        RT = 4, CT = 16;
-    std::vector< val_t > Bt(static_cast< std::size_t >(ncols) * L); // Bt[k][r]
+    const int            Lp = (L + CT - 1) / CT * CT; // rows padded with zeros: the micro-kernel has no edge conditionals
+    std::vector< val_t > Bt(static_cast< std::size_t >(ncols) * Lp, 0.); // Bt[k][r]
     for (int k = 0; k < ncols; ++k)
         for (int r = 0; r < L; ++r)
-            Bt[static_cast< std::size_t >(k) * L + r] = B[static_cast< std::size_t >(r) + static_cast< std::size_t >(k) * L];
+            Bt[static_cast< std::size_t >(k) * Lp + r] = B[static_cast< std::size_t >(r) + static_cast< std::size_t >(k) * L];
     for (int r0 = 0; r0 < L; r0 += RT)
     {
         const int rn = std::min(RT, L - r0);
         for (int c0 = 0; c0 <= r0 + rn - 1; c0 += CT)
         {
             const int cn = std::min(CT, L - c0);
-            val_t     acc[RT][CT];
-            for (auto& row : acc)
-                for (auto& v : row)
-                    v = 0.;
+            val_t     acc[RT][CT] = {};
             for (int k = 0; k < ncols; ++k)
             {
-                const val_t* bk = &Bt[static_cast< std::size_t >(k) * L];
+                const val_t* __restrict__ bk = &Bt[static_cast< std::size_t >(k) * Lp];
+                const val_t* __restrict__ bc = bk + c0;
+#pragma GCC unroll 4
                 for (int i = 0; i < RT; ++i)
                 {
-                    const val_t br = i < rn ? bk[r0 + i] : 0.;
-#pragma GCC ivdep
+                    const val_t br = bk[r0 + i];
+#pragma omp simd
                     for (int j = 0; j < CT; ++j)
-                        acc[i][j] += br * (j < cn ? bk[c0 + j] : 0.);
+                        acc[i][j] += br * bc[j];
                 }
             }
             for (int i = 0; i < rn; ++i)
