@@ -99,7 +99,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference(workload, n_threads, budget_s=15.0):
+def cpu_reference(workload, n_threads, budget_s=12.0):
     """The reference's CPU path (oracle restatement, -march=native build on this host), bounded sample."""
     from oracle import Oracle, build
 
@@ -114,24 +114,20 @@ def cpu_reference(workload, n_threads, budget_s=15.0):
         s = m.assembled_system(U)
         t = s.assemble("bench_diffusion3d", n_threads=n_threads)
         per_elem = t / 8
-        n = int(max(2, min(8, math.floor((budget_s / per_elem) ** (1 / 3)))))
+        n = int(max(2, min(16, math.floor((budget_s / per_elem) ** (1 / 3)))))
         m = make(n)
         s = m.assembled_system(U)
         t = s.assemble("bench_diffusion3d", n_threads=n_threads)
         return dict(value=n**3 / t, unit="elements/s", cores=n_threads, kind="port",
                     sample=f"oracle assembleGlobalSystem (local assembly + CRS scatter) of {n}^3 hex p=4 elements, {t:.2f} s")
-    m = make(4)
+    n = 16
+    m = make(n)
     s = m.matrix_free_system(U)
     s.add_kernel("bench_diffusion3d")
     x = np.random.default_rng(5489).uniform(-1, 1, size=(m.n_nodes * U, 1))
     s.apply(x, n_threads=n_threads)
     per_apply = s.last_secs
-    n = int(max(4, min(16, math.floor(4 * (budget_s / 5 / per_apply) ** (1 / 3)))))
-    m = make(n)
-    s = m.matrix_free_system(U)
-    s.add_kernel("bench_diffusion3d")
-    x = np.random.default_rng(5489).uniform(-1, 1, size=(m.n_nodes * U, 1))
-    reps = 5
+    reps = int(max(3, min(2000, math.ceil(budget_s / max(per_apply, 1e-6)))))
     s.apply(x, n_threads=n_threads, repeats=reps)
     t = s.last_secs
     return dict(value=m.n_nodes * U * reps / t, unit="DOFs/s", cores=n_threads, kind="port",
@@ -283,15 +279,16 @@ def main():
 
         ms, _, clocks = timed(step, args.steps, args.warmup)
         k_ms = float(np.mean(kernel_ms[-args.steps:]))
-        # e2e through the C ABI with host buffers: mesh geometry H2D each step, rhs D2H
-        verts, nodes = np.ascontiguousarray(host.verts), np.ascontiguousarray(host.nodes)
+        # e2e through the C ABI with host buffers: this step's element geometry H2D (pinned), assembly, rhs D2H (pinned)
+        verts_h = torch.from_numpy(np.ascontiguousarray(host.verts)).pin_memory()
+        rhs_h = torch.empty(sys_.n_dofs, dtype=torch.float64).pin_memory()
+        verts_np = verts_h.numpy()
 
         def step_e2e():
-            m2 = l3b.Mesh(ctx, 3, P, verts, nodes, None, host.n_nodes, host.n_nodes)  # H2D of this step's inputs (geometry)
+            mesh.update_verts(verts_np)            # H2D of this step's input
             sys_.beginAssembly()
             sys_.assembleProblem("bench_diffusion3d")
-            sys_.download(values=False)  # D2H of the assembled rhs
-            del m2
+            sys_.download_rhs_into(rhs_h.data_ptr())  # D2H of the step's result (synchronises)
 
         _, wall_ms, _ = timed(step_e2e, args.steps, 1)
         fp64_fma = ctx.microbench(0)
@@ -300,9 +297,9 @@ def main():
         executed = asm_executed_flops_per_elem() * n_elems / (k_ms * 1e-3) / 1e12
         return {
             "value": world * n_elems / (ms * 1e-3), "ms_per_step": ms,
-            "e2e": {"value": world * n_elems / (wall_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": int(verts.nbytes + nodes.nbytes),
+            "e2e": {"value": world * n_elems / (wall_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": int(verts_np.nbytes),
                     "d2h_bytes_per_step": int(sys_.n_dofs * 8),
-                    "what": "mesh geometry H2D + beginAssembly + assembleProblem + rhs D2H through the C ABI, wall clock"},
+                    "what": "element geometry H2D (pinned) + beginAssembly + assembleProblem + rhs D2H (pinned) through the C ABI, wall clock"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_dmma, "unit": "TFLOP/s", "frac": achieved / fp64_dmma,
                          "traffic": 3.46e6 * n_elems,
                          "kernel": "assembleDmmaKernel<bench_diffusion3d, hex p=4> (fp64 DMMA, mma.sync.m8n8k4.f64)", "kernel_ms": k_ms,

@@ -105,6 +105,8 @@ void l3b_free(void* p);
 /* ---- device mesh (mesh/LocalMeshView.hpp:13-57: vertices + local node ids + side → boundary id) ---------------------- */
 int  l3b_mesh_upload(l3b_context* ctx, int dim, int order, int64_t n_elems, const double* verts, const uint32_t* nodes,
                      const uint16_t* side_boundaries /* may be NULL */, int64_t n_local_nodes, int64_t n_owned_nodes, l3b_mesh** out);
+/* new vertex coordinates for the same connectivity (moving / re-read geometry): H2D copy + geometry records, no reallocation */
+int  l3b_mesh_update_verts(l3b_mesh* mesh, const double* verts);
 void l3b_mesh_destroy(l3b_mesh* mesh);
 
 /* ---- nodal fields (post/SolutionManager.hpp:54-101, post/FieldAccess.hpp:10-53): field-major [n_fields][n_local_nodes] */

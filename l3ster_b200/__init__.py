@@ -58,7 +58,7 @@ EXPORTED_SYMBOLS = [
     "l3b_tables_gll", "l3b_tables_gauss", "l3b_tables_1d", "l3b_tables_dense",
     "l3b_host_mesh_cube", "l3b_host_mesh_square", "l3b_host_mesh_destroy", "l3b_host_mesh_info", "l3b_host_mesh_nodes",
     "l3b_host_mesh_verts", "l3b_host_mesh_side_boundaries", "l3b_node_graph", "l3b_graph_expand", "l3b_free",
-    "l3b_mesh_upload", "l3b_mesh_destroy", "l3b_fields_upload", "l3b_fields_update", "l3b_fields_destroy",
+    "l3b_mesh_upload", "l3b_mesh_update_verts", "l3b_mesh_destroy", "l3b_fields_upload", "l3b_fields_update", "l3b_fields_destroy",
     "l3b_asm_create", "l3b_asm_destroy", "l3b_asm_nnz", "l3b_asm_begin_assembly", "l3b_asm_assemble", "l3b_asm_end_assembly",
     "l3b_asm_download", "l3b_asm_device_values", "l3b_asm_spmv", "l3b_asm_solve_cg", "l3b_asm_last_kernel_ms",
     "l3b_mf_create", "l3b_mf_destroy", "l3b_mf_assemble", "l3b_mf_end_assembly", "l3b_mf_download", "l3b_mf_apply_device", "l3b_mf_apply",
@@ -106,6 +106,7 @@ def lib():
     L.l3b_free.argtypes = [vp]
     L.l3b_free.restype = None
     L.l3b_mesh_upload.argtypes = [vp, i32, i32, i64, vp, vp, vp, i64, i64, C.POINTER(vp)]
+    L.l3b_mesh_update_verts.argtypes = [vp, vp]
     L.l3b_mesh_destroy.argtypes = [vp]
     L.l3b_mesh_destroy.restype = None
     L.l3b_fields_upload.argtypes = [vp, i64, i32, vp, C.POINTER(vp)]
@@ -361,6 +362,10 @@ class Context:
 
 
 class Mesh:
+    def update_verts(self, verts):
+        """new vertex coordinates, same connectivity (H2D copy, no reallocation)"""
+        self.ctx._chk(lib().l3b_mesh_update_verts(self._h, verts.ctypes.data))
+
     def __init__(self, ctx: Context, dim, order, verts, nodes, side_boundaries, n_local_nodes, n_owned_nodes):
         self.ctx, self.dim, self.order = ctx, dim, order
         verts = np.ascontiguousarray(verts, dtype=np.float64)
@@ -445,6 +450,10 @@ class AssembledSystem:
         rhs = np.zeros((self.n_rhs, self.n_dofs))
         self.ctx._chk(lib().l3b_asm_download(self._h, _p(vals), _p(rhs)))
         return vals, rhs.T.copy()
+
+    def download_rhs_into(self, host_ptr):
+        """rhs (n_rhs x n_dofs, C ABI layout) into a caller-owned (e.g. pinned) host buffer"""
+        self.ctx._chk(lib().l3b_asm_download(self._h, None, host_ptr))
 
     def getMatrix(self):
         import scipy.sparse as sp

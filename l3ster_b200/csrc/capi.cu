@@ -1090,6 +1090,19 @@ int l3b_mesh_upload(l3b_context* ctx, int dim, int order, int64_t n_elems, const
         *out = m.release();
     });
 }
+int l3b_mesh_update_verts(l3b_mesh* mesh, const double* verts)
+{
+    return guardedCtx(mesh->ctx, [&] {
+        auto* ctx = mesh->ctx;
+        mesh->verts.upload(verts, mesh->verts.n, ctx->stream);
+        if (mesh->dim == 3 and mesh->n_elems > 0)
+        {
+            hexGeometryKernel<<< gridFor(mesh->n_elems), 256, 0, ctx->stream >>>(mesh->verts.ptr, mesh->n_elems, mesh->hex_geo.ptr);
+            cudaCheck(cudaGetLastError(), "hex geometry");
+        }
+        cudaCheck(cudaStreamSynchronize(ctx->stream), "vertex upload"); // the host buffer may be reused on return
+    });
+}
 void l3b_mesh_destroy(l3b_mesh* mesh)
 {
     delete mesh;
