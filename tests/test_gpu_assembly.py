@@ -1,5 +1,7 @@
 """GPU parity: element-local least-squares assembly fused with the CRS scatter, algebraic Dirichlet BCs and the assembled
 solve, against the CPU oracle on identical inputs (through the C ABI). Sparsity is compared bit-exactly, values to 1e-12."""
+import os
+
 import numpy as np
 import pytest
 
@@ -145,3 +147,39 @@ def test_example02_diffusion2d(ctx):
     ref = spla.spsolve(A, r_o[:, 0])
     sol, tol, iters = s.solve(tol=1e-12, max_iters=20000)
     assert np.abs(sol - ref).max() < 1e-8 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("force_fma", [False, True], ids=["dmma", "dfma"])
+def test_single_element_fixtures(ctx, force_fma):
+    """tests/LocalAssemblyTests.cpp:3-43 + tests/LocalOperatorCommon.hpp:17-61 through the device path: K_e, F_e of the distorted quad
+    p=4 / hex p=3 fixtures (asm_opts{.value_order = 2}) against the oracle's assembleLocalSystem, entry by entry. The single-element
+    CRS is the dense row-major K_e. Runs in a subprocess for the DFMA kernel (the selection is read once per process)."""
+    if force_fma:
+        import subprocess
+        import sys
+
+        env = dict(os.environ, L3B_ASM_FMA="1")
+        # the whole module again with the register-tiled DFMA kernel (assemble.cuh) behind the same C ABI
+        out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", __file__, "-k", "not dfma"],
+                             env=env, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+        return
+    orc = oracle()
+    quad = dict(dim=2, p=4, verts=[[1, 1, 0], [2, 1, 0], [1, 3, 0], [3, 4, 0]], k="diffusion_kernel_2D", U=3, r=2)
+    hexa = dict(dim=3, p=3, verts=[[1, 1, 0], [2, 1, 0], [1, 3, 0], [3, 4, 0], [1, 1, 1], [2, 1, 1.5], [1, 3, 2], [3, 4, 3.5]],
+                k="diffusion_kernel_3D", U=4, r=3)
+    for fx in (quad, hexa):
+        dim, p, U = fx["dim"], fx["p"], fx["U"]
+        nn = (p + 1) ** dim
+        nodes = np.arange(nn, dtype=np.uint32)[None, :]
+        verts = np.array(fx["verts"], dtype=float)[None]
+        mesh = l3b.Mesh(ctx, dim, p, verts, nodes, None, nn, nn)
+        s = l3b.AssembledSystem(ctx, mesh, U, fx["r"])
+        s.beginAssembly()
+        s.assembleProblem(fx["k"], asm_opts=l3b.AssemblyOptions(value_order=2))
+        vals, rhs = s.download()
+        K, F = orc.assemble_local(fx["k"], dim, p, fx["verts"], n_rhs=fx["r"], value_order=2)
+        Kd = vals.reshape(nn * U, nn * U)
+        assert rel_err(Kd, K) < TOL
+        assert np.abs(Kd - Kd.T).max() <= 1e-13 * np.abs(K).max()
+        assert np.abs(rhs - F).max() <= TOL * max(np.abs(F).max(), 1.0)

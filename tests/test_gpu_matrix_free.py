@@ -211,3 +211,16 @@ def test_empty_partition(ctx):
     s.endAssembly()
     y = s.apply(np.zeros((0, 1)))
     assert y.shape == (0, 1)
+
+
+def test_line_per_thread_kernel_passes_the_same_suite():
+    """L3B_MF_LINES=1 routes hexahedra through mfSumFactApplyKernel (mf_sumfact.cuh) instead of the planes + columns kernel: the
+    whole module must pass with it too (the selection is read once per process, hence the subprocess)."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, L3B_MF_LINES="1")
+    out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", __file__, "-k", "not line_per_thread"],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
