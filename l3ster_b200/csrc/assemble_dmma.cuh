@@ -76,10 +76,12 @@ struct AsmDmmaCfg
     static constexpr int  LDA = TM + 4, LDB = TN + 4;                  // panel leading dimensions, ≡ 4 (mod 16)
     static constexpr int  KCMAX = cmax(32, 4 * E);                     // panel rows (quadrature points x equations) per chunk
     static constexpr int  QCMAX = 16;                                  // quadrature points per chunk, at most
-    // smem (doubles): panel A x 2 | panel B x 2 | coefficients A x 2 | coefficients B x 2 | rhs coefficients x 2 |
-    // node field values | vertices
-    static constexpr int off_b = 2 * KCMAX * LDA, off_ca = off_b + 2 * KCMAX * LDB, off_cb = off_ca + 2 * KCMAX * 4,
-                         off_cr = off_cb + 2 * KCMAX * 4, off_nv = off_cr + 2 * QCMAX * NRHS * 4, off_verts = off_nv + NN * NF,
+    // smem (doubles): panel A x 2 | panel B x 2 | coefficients A | coefficients B | rhs coefficients | node field values | vertices
+    // the per-point stage runs for a whole super-chunk of points at once, all threads, one point each: SROWS coefficient rows
+    // (points x equations of the pair) per panel — every point of a p <= 4 hexahedron in one go
+    static constexpr int  SROWS = cmax(512, 16 * E), SPTS = 128;
+    static constexpr int off_b = 2 * KCMAX * LDA, off_ca = off_b + 2 * KCMAX * LDB, off_cb = off_ca + SROWS * 4,
+                         off_cr = off_cb + SROWS * 4, off_nv = off_cr + SPTS * NRHS * 4, off_verts = off_nv + NN * NF,
                          total = off_verts + 8 * 3;
     static constexpr size_t smem_bytes = static_cast< size_t >(total) * sizeof(double);
     static constexpr int    min_blocks = smem_bytes <= 112 * 1024 and threads <= 256 ? 2 : 1;
@@ -188,21 +190,22 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
     int QC = (KCMAX / n_eq) & ~3;
     QC     = QC > QCMAX ? QCMAX : QC;
     const int  n_chunks = (args.n_qp + QC - 1) / QC;
+    // chunks per super-chunk of the per-point stage
+    int cps = Cfg::SROWS / (QC * n_eq);
+    cps     = cps * QC > Cfg::SPTS ? Cfg::SPTS / QC : cps;
     const int  n_k4     = QC * n_eq / 4;
     const bool rhs_duty = diag_pair and cb == 0; // this CTA also owns F_e[(a, u)] for the nodes a of row block rb
 
-    // ---- per-point stage of chunk c → coefficient tables [c & 1]. One warp (rotating with c), one lane per point:
-    // mapping, user kernel, then — through compile-time loops over the structurally non-zero operator entries only —
+    // ---- per-point stage of super-chunk sc → coefficient tables. All threads, one point each: mapping, user kernel, then —
+    // through compile-time loops over the structurally non-zero operator entries only —
     //     c0 = sqrt(w) A0(e,u),  c_d = sqrt(w) sum_s A_s(e,u) Jinv(s,d)        for the equations e of the pair and u, v.
-    const auto perPoint = [&](int c) {
-        if (warp != c % n_warps)
-            return;
-        double* const ca  = s_ca + (c & 1) * KCMAX * 4;
-        double* const cbp = s_cb + (c & 1) * KCMAX * 4;
-        double* const cr  = s_cr + (c & 1) * QCMAX * NRHS * 4;
-        for (int qc = lane; qc < QC; qc += 32)
+    const auto perPoint = [&](int sc) {
+        double* const ca  = s_ca;
+        double* const cbp = s_cb;
+        double* const cr  = s_cr;
+        for (int qc = tid; qc < cps * QC; qc += T) // qc: point within the super-chunk = row block qc * n_eq of the tables
         {
-            const int q = c * QC + qc;
+            const int q = sc * cps * QC + qc;
             if (q >= args.n_qp) // padding point: zero coefficients zero its panel rows
             {
                 for (int i = 0; i < n_eq * 4; ++i)
@@ -346,9 +349,10 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
     for (int r = 0; r < NRHS; ++r)
         f_acc[r] = 0.;
     const auto build = [&](int c) {
-        const double* const ca  = s_ca + (c & 1) * KCMAX * 4;
-        const double* const cbp = s_cb + (c & 1) * KCMAX * 4;
-        const double* const cr  = s_cr + (c & 1) * QCMAX * NRHS * 4;
+        const int           c_in = c % cps; // chunk within its super-chunk
+        const double* const ca   = s_ca + c_in * QC * n_eq * 4;
+        const double* const cbp  = s_cb + c_in * QC * n_eq * 4;
+        const double* const cr   = s_cr + c_in * QC * NRHS * 4;
         for (int pc = tid; pc < n_pcols * n_parts; pc += T)
         {
             const int  pcol = pc % n_pcols, part = pc / n_pcols;
@@ -401,10 +405,54 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
         }
     };
 
+    // ---- the build's table reads are L2 round trips (ncu r1 v3: 30 % of its samples on the long scoreboard): pull the slice of
+    // chunk c into L1 one iteration before it is built — same thread, same addresses, no registers held
+    const auto prefetchTables = [&](int c) {
+        for (int pc = tid; pc < n_pcols * n_parts; pc += T)
+        {
+            const int  pcol = pc % n_pcols, part = pc / n_pcols;
+            const bool is_b = pcol < TN;
+            const int  node = (is_b ? col0 : row0) + (is_b ? pcol : pcol - TN);
+            if (node >= NN or (not is_b and row0 == col0)) // same nodes as panel B: those lines are already on their way
+                continue;
+            for (int qc = part; qc < QC; qc += n_parts)
+            {
+                const int q = c * QC + qc;
+                if (q >= args.n_qp)
+                    break;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(tab_vals + q * NN + node));
+#pragma unroll
+                for (int d = 0; d < DIM; ++d)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(tab_ders + (q * DIM + d) * NN + node));
+            }
+        }
+    };
+
     // ---- accumulators: warp (wy, wx) owns rows wy*32 .. +32, columns wx*32 .. +32 of the tile as 4 x 4 DMMA tiles
-    const int  wy = warp / Cfg::WN, wx = warp % Cfg::WN;
-    const int  g = lane >> 2, tq = lane & 3;
-    const bool warp_live = not diag_pair or col0 + wx * 32 <= row0 + wy * 32 + 31; // not strictly above the diagonal
+    // For u == v the warp tiles strictly above the diagonal are dead. Warps sit on the scheduler `warp % 4`, so the live tiles are
+    // dealt to the warps in order (warp t takes the t-th live tile): every scheduler gets its share of the DMMA work.
+    int wy = warp / Cfg::WN, wx = warp % Cfg::WN;
+    bool warp_live = true;
+    if (diag_pair)
+    {
+        warp_live = false;
+        int n_live = 0;
+        for (int i = 0; i < Cfg::WM * Cfg::WN; ++i)
+        {
+            const int ty = i / Cfg::WN, tx = i % Cfg::WN;
+            if (col0 + tx * 32 <= row0 + ty * 32 + 31) // not strictly above the diagonal
+            {
+                if (n_live == warp)
+                {
+                    wy        = ty;
+                    wx        = tx;
+                    warp_live = true;
+                }
+                ++n_live;
+            }
+        }
+    }
+    const int g = lane >> 2, tq = lane & 3;
     double     acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -417,14 +465,20 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
     __syncthreads();
     build(0);
     if (n_chunks > 1)
-        perPoint(1);
+        prefetchTables(1);
     __syncthreads();
     for (int c = 0; c < n_chunks; ++c)
     {
+        if (c + 1 < n_chunks and (c + 1) % cps == 0)
+        {
+            // super-chunk boundary: the coefficients of the next chunks (nobody reads the old ones any more: build(c) is done)
+            perPoint((c + 1) / cps);
+            __syncthreads();
+        }
+        if (c + 2 < n_chunks)
+            prefetchTables(c + 2);
         if (c + 1 < n_chunks)
             build(c + 1);
-        if (c + 2 < n_chunks)
-            perPoint(c + 2);
         if (warp_live)
         {
             const double* const pb_c = s_pb + (c & 1) * KCMAX * LDB + wx * 32 + g;
@@ -476,18 +530,30 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
                 continue;
             double* const   rowp = args.crs_vals + args.row_ptr[static_cast< long long >(el_nodes[a]) * dpn + du] + dv;
             const uint16_t* pa_  = pos + a * NN;
+            // the slot positions of the whole row of tiles first (one memory round trip), then the atomics
+            int  p_ab[4][2], p_ba[4][2];
+            bool on[4][2];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
                 {
                     const int b = bcol[j][h];
-                    if (b >= NN or (diag_pair and b > a))
+                    on[j][h]    = b < NN and not(diag_pair and b > a);
+                    p_ab[j][h]  = on[j][h] ? pa_[b] : 0;
+                    p_ba[j][h]  = on[j][h] and (not diag_pair or b < a) ? pos[b * NN + a] : -1;
+                }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                {
+                    if (not on[j][h])
                         continue;
                     const double val = acc[i][j][h];
-                    atomicAdd(rowp + static_cast< int >(pa_[b]) * dpn, val);
-                    if (not diag_pair or b < a)
-                        atomicAdd(args.crs_vals + cbeg[j][h] + static_cast< int >(pos[b * NN + a]) * dpn, val);
+                    atomicAdd(rowp + p_ab[j][h] * dpn, val);
+                    if (p_ba[j][h] >= 0)
+                        atomicAdd(args.crs_vals + cbeg[j][h] + p_ba[j][h] * dpn, val);
                 }
         }
     }
