@@ -340,67 +340,83 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
     };
 
     // ---- panels of chunk c → s_pa/s_pb[c & 1]: rows k = qc * n_eq + ei, columns = the nodes of the row / column block.
-    // Work item ↔ (panel column, point of the chunk); with T a multiple of the column count a thread keeps its column.
     // A thread owns one panel column (several when T < n_pcols) and a share `part` of the chunk's points, so at most one
-    // A-side node — the one whose rhs entry it accumulates.
+    // A-side node — the one whose rhs entry it accumulates. Everything that does not depend on the chunk is hoisted here; the
+    // item loop is branch-free: columns of padding nodes are zeroed once and never written, padding points read the tables of
+    // the last real point against zero coefficients.
     const int n_pcols = a_in_b ? TN : TM + TN;
     const int n_parts = T >= n_pcols ? T / n_pcols : 1;
     double    f_acc[NRHS];
     for (int r = 0; r < NRHS; ++r)
         f_acc[r] = 0.;
-    const auto build = [&](int c) {
-        const int           c_in = c % cps; // chunk within its super-chunk
-        const double* const ca   = s_ca + c_in * QC * n_eq * 4;
-        const double* const cbp  = s_cb + c_in * QC * n_eq * 4;
-        const double* const cr   = s_cr + c_in * QC * NRHS * 4;
-        for (int pc = tid; pc < n_pcols * n_parts; pc += T)
-        {
-            const int  pcol = pc % n_pcols, part = pc / n_pcols;
-            const bool is_b = pcol < TN; // panel B columns first (they exist in both layouts)
-            const int  prow = is_b ? pcol : pcol - TN;
-            const int  node = (is_b ? col0 : row0) + prow;
-            double*    dst  = is_b ? s_pb + (c & 1) * KCMAX * LDB + prow : s_pa + (c & 1) * KCMAX * LDA + prow;
-            const int  ld   = is_b ? LDB : LDA;
-            // rhs rows: the A-side nodes (row block); with a_in_b they are the window [row0, row0 + TM) of panel B
-            const bool rhs_row = rhs_duty and (a_in_b ? (node >= row0 and node < row0 + TM) : not is_b);
+    for (int i = tid; i < 2 * KCMAX * LDA; i += T)
+        s_pa[i] = 0.;
+    for (int i = tid; i < 2 * KCMAX * LDB; i += T)
+        s_pb[i] = 0.;
+    const auto buildColumn = [&]< int NEQ >(std::integral_constant< int, NEQ >, int c, int pcol, int part) {
+        const bool is_b = pcol < TN; // panel B columns first (they exist in both layouts)
+        const int  prow = is_b ? pcol : pcol - TN;
+        const int  node = (is_b ? col0 : row0) + prow;
+        if (node >= NN)
+            return;
+        const int     ld    = is_b ? LDB : LDA;
+        const int     neq   = NEQ > 0 ? NEQ : n_eq;
+        const int     c_in  = c % cps; // chunk within its super-chunk
+        double*       dst   = (is_b ? s_pb + (c & 1) * KCMAX * LDB : s_pa + (c & 1) * KCMAX * LDA) + prow + part * neq * ld;
+        const double* cf    = (is_b ? s_cb : s_ca) + (c_in * QC + part) * neq * 4;
+        const double* cr    = s_cr + (c_in * QC + part) * NRHS * 4;
+        // rhs rows: the A-side nodes (row block); with a_in_b they are the window [row0, row0 + TM) of panel B
+        const bool    rhs_row = rhs_duty and (a_in_b ? (node >= row0 and node < row0 + TM) : not is_b);
+        const int     q_last  = args.n_qp - 1;
 #pragma unroll 4
-            for (int qc = part; qc < QC; qc += n_parts)
+        for (int qc = part; qc < QC; qc += n_parts)
+        {
+            const int q   = min(c * QC + qc, q_last);
+            double    bas[4] = {__ldg(tab_vals + q * NN + node), 0., 0., 0.};
+#pragma unroll
+            for (int d = 0; d < DIM; ++d)
+                bas[1 + d] = __ldg(tab_ders + (q * DIM + d) * NN + node);
+#pragma unroll
+            for (int ei = 0; ei < (NEQ > 0 ? NEQ : asm_max_equations); ++ei)
             {
-                const int q = c * QC + qc;
-                if (q < args.n_qp and node < NN)
+                if (NEQ == 0 and ei >= n_eq)
+                    break;
+                const double2 c01 = *reinterpret_cast< const double2* >(cf + ei * 4);
+                const double2 c23 = *reinterpret_cast< const double2* >(cf + ei * 4 + 2);
+                double        b   = c01.x * bas[0];
+                b                 = fma(c01.y, bas[1], b);
+                if constexpr (DIM >= 2)
+                    b = fma(c23.x, bas[2], b);
+                if constexpr (DIM >= 3)
+                    b = fma(c23.y, bas[3], b);
+                dst[ei * ld] = b;
+            }
+            if (rhs_row)
+#pragma unroll
+                for (int r = 0; r < NRHS; ++r)
                 {
-                    double bas[4] = {__ldg(tab_vals + q * NN + node), 0., 0., 0.};
+                    double acc = cr[r * 4] * bas[0];
 #pragma unroll
                     for (int d = 0; d < DIM; ++d)
-                        bas[1 + d] = __ldg(tab_ders + (q * DIM + d) * NN + node);
-                    const double* cf = (is_b ? cbp : ca) + qc * n_eq * 4;
-                    for (int ei = 0; ei < n_eq; ++ei)
-                    {
-                        const double2 c01 = *reinterpret_cast< const double2* >(cf + ei * 4);
-                        const double2 c23 = *reinterpret_cast< const double2* >(cf + ei * 4 + 2);
-                        double        b   = c01.x * bas[0];
-                        b                 = fma(c01.y, bas[1], b);
-                        if constexpr (DIM >= 2)
-                            b = fma(c23.x, bas[2], b);
-                        if constexpr (DIM >= 3)
-                            b = fma(c23.y, bas[3], b);
-                        dst[(qc * n_eq + ei) * ld] = b;
-                    }
-                    if (rhs_row)
-#pragma unroll
-                        for (int r = 0; r < NRHS; ++r)
-                        {
-                            const double* c4  = cr + (qc * NRHS + r) * 4;
-                            double        acc = c4[0] * bas[0];
-#pragma unroll
-                            for (int d = 0; d < DIM; ++d)
-                                acc = fma(c4[1 + d], bas[1 + d], acc);
-                            f_acc[r] += acc;
-                        }
+                        acc = fma(cr[r * 4 + 1 + d], bas[1 + d], acc);
+                    f_acc[r] += acc;
                 }
-                else
-                    for (int ei = 0; ei < n_eq; ++ei)
-                        dst[(qc * n_eq + ei) * ld] = 0.;
+            dst += n_parts * neq * ld;
+            cf += n_parts * neq * 4;
+            cr += n_parts * NRHS * 4;
+        }
+    };
+    const auto build = [&](int c) {
+        for (int pc = tid; pc < n_pcols * n_parts; pc += T)
+        {
+            const int pcol = pc % n_pcols, part = pc / n_pcols;
+            switch (n_eq)
+            {
+            case 1: buildColumn(std::integral_constant< int, 1 >{}, c, pcol, part); break;
+            case 2: buildColumn(std::integral_constant< int, 2 >{}, c, pcol, part); break;
+            case 3: buildColumn(std::integral_constant< int, 3 >{}, c, pcol, part); break;
+            case 4: buildColumn(std::integral_constant< int, 4 >{}, c, pcol, part); break;
+            default: buildColumn(std::integral_constant< int, 0 >{}, c, pcol, part); break;
             }
         }
     };
@@ -475,10 +491,18 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
             perPoint((c + 1) / cps);
             __syncthreads();
         }
-        if (c + 2 < n_chunks)
-            prefetchTables(c + 2);
-        if (c + 1 < n_chunks)
-            build(c + 1);
+        // Two of the four warps of every scheduler contract first and build afterwards, the other two the other way round:
+        // the DMMA pipe always has contracting warps while the builders wait on their table loads (both orders are legal:
+        // the contraction reads panel c & 1, the build writes panel (c + 1) & 1).
+        const bool build_first = ((warp >> 2) & 1) == 0 or not warp_live;
+        const auto buildNext   = [&] {
+            if (c + 2 < n_chunks)
+                prefetchTables(c + 2);
+            if (c + 1 < n_chunks)
+                build(c + 1);
+        };
+        if (build_first)
+            buildNext();
         if (warp_live)
         {
             const double* const pb_c = s_pb + (c & 1) * KCMAX * LDB + wx * 32 + g;
@@ -501,6 +525,8 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
                         dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
         }
+        if (not build_first)
+            buildNext();
         __syncthreads();
     }
 
