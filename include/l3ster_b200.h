@@ -148,6 +148,13 @@ int l3b_mf_assemble(l3b_mf* sys, int kernel_id, l3b_asm_opts opts, double time, 
                     const int* field_inds, const int* boundary_ids, int n_boundary_ids);
 /* MatrixFreeSystem::endAssembly → computeDiagAndRhs (:877-941) */
 int l3b_mf_end_assembly(l3b_mf* sys);
+/* the same in two steps for more than one rank: _begin accumulates the element contributions to diag and rhs over the local
+ * dofs [owned | ghost]; the caller export-adds the ghost parts to their owners (MatrixFreeSystem.hpp:925-938) through the
+ * device pointers below; _finish sets the owned Dirichlet dofs (diag = 1, rhs = g, :911-915) and closes the system. */
+int     l3b_mf_end_assembly_begin(l3b_mf* sys);
+int     l3b_mf_end_assembly_finish(l3b_mf* sys);
+double* l3b_mf_device_diag(l3b_mf* sys);
+double* l3b_mf_device_rhs(l3b_mf* sys);
 int l3b_mf_download(l3b_mf* sys, double* diag, double* rhs);
 /* Tpetra::Operator::apply → MatrixFreeSystem::applyImpl (:34-41, 1019-1140): y = alpha A x + beta y.
  * _device: x, y are device pointers (column-major, ld = n_local_dofs), asynchronous on the context stream.
@@ -175,6 +182,16 @@ int l3b_mf_apply_phase_device(l3b_mf* sys, const double* x, double* y, int n_col
  * gather: dst[i + c n] = src[idx[i] + c ld];  scatter_add: dst[idx[i] + c ld] += src[i + c n]. Asynchronous on the context stream. */
 int l3b_vec_gather(l3b_context* ctx, const double* src, int64_t ld, const int32_t* idx, int64_t n, int n_cols, double* dst);
 int l3b_vec_scatter_add(l3b_context* ctx, double* dst, int64_t ld, const int32_t* idx, int64_t n, int n_cols, const double* src);
+/* Preconditioned CG with callbacks, for operators and reductions the library does not own (the multi-rank apply with its halo
+ * exchange, MPI/NCCL all-reduce of the dot products): Belos Block-CG semantics as l3b_mf_solve_cg, native Jacobi from `diag`.
+ * Vectors are device pointers over n_local dofs of which the first n_owned are owned (dots and updates run over those).
+ * apply(user, x, y): y = A x, enqueued on the context stream. allreduce(user, s, n): in-place sum over the ranks of the n device
+ * scalars at s, ordered after the work already on the context stream (may be NULL on one rank). Both return 0 on success. */
+typedef int (*l3b_apply_callback)(void* user, const double* x, double* y);
+typedef int (*l3b_allreduce_callback)(void* user, double* scalars, int n);
+int l3b_pcg_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_apply_callback apply, l3b_allreduce_callback allreduce,
+                   void* user, const double* diag, const double* b, double* x, double tol, int max_iters, double* achieved_tol,
+                   int* iters);
 int64_t l3b_mf_num_dofs(const l3b_mf* sys);
 int     l3b_mf_kernel_launches(const l3b_mf* sys); /* device kernels launched by the last apply */
 

@@ -48,6 +48,9 @@ class AssemblyOptions:
         return _AsmOpts(self.value_order, self.derivative_order, self.eval_strategy)
 
 
+# callbacks of l3b_pcg_device
+APPLY_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
+ALLREDUCE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)
 _lib = None
 APPLY_INIT, APPLY_ELEMENTS, APPLY_FINISH = 1, 2, 4
 
@@ -64,6 +67,7 @@ EXPORTED_SYMBOLS = [
     "l3b_mf_create", "l3b_mf_destroy", "l3b_mf_assemble", "l3b_mf_end_assembly", "l3b_mf_download", "l3b_mf_apply_device", "l3b_mf_apply",
     "l3b_mf_solve_cg", "l3b_mf_num_dofs", "l3b_mf_kernel_launches", "l3b_microbench",
     "l3b_mf_apply_phase_device", "l3b_vec_gather", "l3b_vec_scatter_add",
+    "l3b_mf_end_assembly_begin", "l3b_mf_end_assembly_finish", "l3b_mf_device_diag", "l3b_mf_device_rhs", "l3b_pcg_device",
 ]
 
 
@@ -137,6 +141,13 @@ def lib():
     L.l3b_mf_apply_device.argtypes = [vp, vp, vp, i32, dbl, dbl]
     L.l3b_mf_apply_phase_device.argtypes = [vp, vp, vp, i32, dbl, dbl, i32, i64, i64]
     L.l3b_vec_gather.argtypes = [vp, vp, i64, vp, i64, i32, vp]
+    L.l3b_mf_end_assembly_begin.argtypes = [vp]
+    L.l3b_mf_end_assembly_finish.argtypes = [vp]
+    L.l3b_mf_device_diag.argtypes = [vp]
+    L.l3b_mf_device_diag.restype = vp
+    L.l3b_mf_device_rhs.argtypes = [vp]
+    L.l3b_mf_device_rhs.restype = vp
+    L.l3b_pcg_device.argtypes = [vp, i64, i64, APPLY_CB, ALLREDUCE_CB, vp, vp, vp, vp, dbl, i32, C.POINTER(dbl), C.POINTER(i32)]
     L.l3b_vec_scatter_add.argtypes = [vp, vp, i64, vp, i64, i32, vp]
     L.l3b_mf_apply.argtypes = [vp, vp, vp, i32, dbl, dbl]
     L.l3b_mf_solve_cg.argtypes = [vp, dbl, i32, vp, C.POINTER(dbl), C.POINTER(i32)]
@@ -346,6 +357,34 @@ class Context:
         self._chk(lib().l3b_microbench(self._h, mode, C.byref(out)))
         return out.value
 
+    def pcg(self, n_local, n_owned, apply, allreduce, diag_ptr, b_ptr, x_ptr, tol=1e-6, max_iters=10000):
+        """l3b_pcg_device: apply(x_ptr, y_ptr) and allreduce(scalars_ptr, n) are Python callables working on device pointers"""
+        err = []
+
+        def _apply(_, x, y):
+            try:
+                apply(x, y)
+                return 0
+            except Exception as exc:  # surfaces as an L3BError with the message kept
+                err.append(exc)
+                return 1
+
+        def _reduce(_, s, n):
+            try:
+                allreduce(s, n)
+                return 0
+            except Exception as exc:
+                err.append(exc)
+                return 1
+
+        a_cb = APPLY_CB(_apply)
+        r_cb = ALLREDUCE_CB(_reduce) if allreduce is not None else C.cast(None, ALLREDUCE_CB)
+        at, it = C.c_double(), C.c_int()
+        rc = lib().l3b_pcg_device(self._h, n_local, n_owned, a_cb, r_cb, None, diag_ptr, b_ptr, x_ptr, tol, max_iters, C.byref(at), C.byref(it))
+        if rc != 0:
+            raise L3BError(rc, lib().l3b_last_error(self._h).decode() + (f" ({err[0]!r})" if err else ""))
+        return at.value, it.value
+
     def vec_gather(self, src_ptr, ld, idx_ptr, n, dst_ptr, n_cols=1):
         self._chk(lib().l3b_vec_gather(self._h, src_ptr, ld, idx_ptr, n, n_cols, dst_ptr))
 
@@ -505,6 +544,21 @@ class MatrixFreeSystem:
 
     def endAssembly(self):
         self.ctx._chk(lib().l3b_mf_end_assembly(self._h))
+
+    def endAssemblyBegin(self):
+        """element contributions to diag / rhs over [owned | ghost]; export-add the ghost parts, then endAssemblyFinish()"""
+        self.ctx._chk(lib().l3b_mf_end_assembly_begin(self._h))
+
+    def endAssemblyFinish(self):
+        self.ctx._chk(lib().l3b_mf_end_assembly_finish(self._h))
+
+    @property
+    def device_diag(self):
+        return lib().l3b_mf_device_diag(self._h)
+
+    @property
+    def device_rhs(self):
+        return lib().l3b_mf_device_rhs(self._h)
 
     def download(self):
         diag = np.zeros(self.n_dofs)

@@ -791,23 +791,25 @@ void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double a
 // Preconditioned CG, Belos "Block CG" semantics for block size 1 (solve/BelosSolvers.hpp:76-89): left preconditioner,
 // absolute 2-norm of the (unpreconditioned) residual against `tol`, x0 = 0. One fused vector kernel and one 2-scalar
 // read-back per iteration.
-template < typename Apply >
-void pcg(l3b_context* ctx, long long n, Apply&& apply, const double* diag, const double* b, double* x /* device */, double tol,
-         int max_iters, double* achieved, int* iters)
+template < typename Apply, typename Reduce >
+void pcg(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Reduce&& reduce, const double* diag, const double* b,
+         double* x /* device */, double tol, int max_iters, double* achieved, int* iters)
 {
-    DevBuf< double > r(n), z(n), p(n), Ap(n), minv(n);
-    if (ctx->scalars.n < 8)
-        ctx->scalars.alloc(8);
-    double*    sc = ctx->scalars.ptr; // [0] rz, [1] pAp, [2] rr, [3] rz_new
+    // n = owned dofs: dots and updates run over those; p and Ap carry the ghost tail the operator needs
+    DevBuf< double > r(n), z(n), p(n_local), Ap(n_local), minv(n);
+    DevBuf< double > sc_buf(8);
+    double*    sc = sc_buf.ptr; // [0] rz, [1] pAp, [2] rr, [3] rz_new
     const auto s  = ctx->stream;
     const auto g  = gridFor(n);
     jacobiInvertKernel<<< g, 256, 0, s >>>(diag, minv.ptr, n, 1., 0.);
     cudaCheck(cudaMemsetAsync(x, 0, n * sizeof(double), s), "memset");
+    p.zero(s);
     cudaCheck(cudaMemcpyAsync(r.ptr, b, n * sizeof(double), cudaMemcpyDeviceToDevice, s), "copy");
     hadamardKernel<<< g, 256, 0, s >>>(z.ptr, minv.ptr, r.ptr, n);
     cudaCheck(cudaMemcpyAsync(p.ptr, z.ptr, n * sizeof(double), cudaMemcpyDeviceToDevice, s), "copy");
     cudaCheck(cudaMemsetAsync(sc, 0, 8 * sizeof(double), s), "memset");
     dot2Kernel<<< g, 256, 0, s >>>(r.ptr, r.ptr, r.ptr, z.ptr, n, sc + 2); // rr → sc[2], rz → sc[3]
+    reduce(sc + 2, 2);
     double h[2];
     cudaCheck(cudaMemcpyAsync(h, sc + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, s), "copy");
     cudaCheck(cudaStreamSynchronize(s), "sync");
@@ -821,7 +823,9 @@ void pcg(l3b_context* ctx, long long n, Apply&& apply, const double* diag, const
             apply(p.ptr, Ap.ptr);
             cudaCheck(cudaMemsetAsync(sc + 1, 0, 3 * sizeof(double), s), "memset");
             dot2Kernel<<< g, 256, 0, s >>>(p.ptr, Ap.ptr, nullptr, nullptr, n, sc + 1);
+            reduce(sc + 1, 1);
             cgUpdateKernel<<< g, 256, 0, s >>>(x, r.ptr, z.ptr, p.ptr, Ap.ptr, minv.ptr, n, sc, sc + 2);
+            reduce(sc + 2, 2);
             cudaCheck(cudaMemcpyAsync(h, sc + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, s), "copy");
             cudaCheck(cudaStreamSynchronize(s), "sync");
             ++it;
@@ -1273,12 +1277,12 @@ int l3b_asm_solve_cg(l3b_asm* sys, double tol, int max_iters, double* x, double*
             sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, diag.ptr);
         const long long threads = n * 32;
         pcg(
-            sys->ctx, n,
+            sys->ctx, n, n,
             [&](const double* in, double* out) {
                 spmvKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
                     sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, in, out);
             },
-            diag.ptr, sys->rhs.ptr, dx.ptr, tol, max_iters, achieved_tol, iters);
+            [](double*, int) {}, diag.ptr, sys->rhs.ptr, dx.ptr, tol, max_iters, achieved_tol, iters);
         dx.download(x, n, sys->ctx->stream);
         cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "solve");
     });
@@ -1343,7 +1347,7 @@ int l3b_mf_assemble(l3b_mf* sys, int kernel_id, l3b_asm_opts opts, double time, 
         sys->uses.push_back(makeUse(sys->mesh, sys->dpn, sys->n_rhs, kernel_id, opts, time, dof_inds, fields, field_inds, boundary_ids, n_boundary_ids));
     });
 }
-int l3b_mf_end_assembly(l3b_mf* sys)
+int l3b_mf_end_assembly_begin(l3b_mf* sys)
 {
     return guardedCtx(sys->ctx, [&] {
         if (sys->closed)
@@ -1362,12 +1366,54 @@ int l3b_mf_end_assembly(l3b_mf* sys)
             a.rhs      = sys->rhs.ptr;
             cudaCheck(use.inst->init(kernelRegistry()[use.kernel_id].object.get(), a, ctx->stream), "init launch");
         }
+        cudaCheck(cudaGetLastError(), "init");
+    });
+}
+int l3b_mf_end_assembly_finish(l3b_mf* sys)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (sys->closed)
+            fail(L3B_ERR_STATE, "`endAssembly()` was called more than once");
+        auto* ctx = sys->ctx;
         if (sys->has_bc)
             dirichletInitKernel<<< gridFor(sys->n_dofs), 256, 0, ctx->stream >>>(sys->dir_mask.ptr, sys->dir_vals.ptr, sys->diag.ptr, sys->rhs.ptr,
                                                                              sys->n_dofs, sys->n_dofs, sys->n_rhs);
         cudaCheck(cudaGetLastError(), "init");
         ctx->checkStatus();
         sys->closed = true;
+    });
+}
+int l3b_mf_end_assembly(l3b_mf* sys)
+{
+    const int rc = l3b_mf_end_assembly_begin(sys);
+    return rc != L3B_OK ? rc : l3b_mf_end_assembly_finish(sys);
+}
+double* l3b_mf_device_diag(l3b_mf* sys)
+{
+    return sys->diag.ptr;
+}
+double* l3b_mf_device_rhs(l3b_mf* sys)
+{
+    return sys->rhs.ptr;
+}
+int l3b_pcg_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_apply_callback apply, l3b_allreduce_callback allreduce,
+                   void* user, const double* diag, const double* b, double* x, double tol, int max_iters, double* achieved_tol,
+                   int* iters)
+{
+    return guardedCtx(ctx, [&] {
+        if (apply == nullptr or n_owned > n_local or n_owned < 0)
+            fail(L3B_ERR_INVALID_ARG, "l3b_pcg_device: invalid arguments");
+        pcg(
+            ctx, n_local, n_owned,
+            [&](const double* in, double* out) {
+                if (apply(user, in, out) != 0)
+                    fail(L3B_ERR_INVALID_ARG, "l3b_pcg_device: the apply callback failed");
+            },
+            [&](double* sc, int n) {
+                if (allreduce != nullptr and allreduce(user, sc, n) != 0)
+                    fail(L3B_ERR_INVALID_ARG, "l3b_pcg_device: the all-reduce callback failed");
+            },
+            diag, b, x, tol, max_iters, achieved_tol, iters);
     });
 }
 int l3b_mf_download(l3b_mf* sys, double* diag, double* rhs)
@@ -1432,8 +1478,8 @@ int l3b_mf_solve_cg(l3b_mf* sys, double tol, int max_iters, double* x, double* a
             fail(L3B_ERR_INVALID_ARG, "the CG driver handles one right-hand side");
         DevBuf< double > dx(sys->n_dofs);
         pcg(
-            sys->ctx, sys->n_dofs, [&](const double* in, double* out) { mfApplyDevice(sys, in, out, 1, 1., 0.); }, sys->diag.ptr, sys->rhs.ptr,
-            dx.ptr, tol, max_iters, achieved_tol, iters);
+            sys->ctx, sys->n_dofs, sys->n_dofs, [&](const double* in, double* out) { mfApplyDevice(sys, in, out, 1, 1., 0.); },
+            [](double*, int) {}, sys->diag.ptr, sys->rhs.ptr, dx.ptr, tol, max_iters, achieved_tol, iters);
         dx.download(x, sys->n_dofs, sys->ctx->stream);
         cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "solve");
     });

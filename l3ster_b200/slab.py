@@ -117,6 +117,18 @@ def make_slab(x, y, z, order, rank, world) -> Slab:
     return Slab(rank, world, p, n_elems, n_nodes, len(owned_ids), nodes, verts, sb, lat_new, n_border, top, lower, upper)
 
 
+class _DevicePtr:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def _device_view(ptr, n, device):
+    """zero-copy torch view of n doubles of device memory owned by the library"""
+    import torch
+
+    return torch.as_tensor(_DevicePtr(ptr, n), device=device)
+
+
 class Halo:
     """Import / Export of the slab's interface dofs (comm/ImportExport.hpp:29-472) over torch.distributed point-to-point
     calls: NCCL for device tensors, gloo for host tensors (the CPU tests). Vectors cover the local dofs [owned | ghost]."""
@@ -194,10 +206,48 @@ class SlabOperator:
                 mask[slab.dirichlet_nodes(dirichlet_boundary_ids) * dofs_per_node] = 1  # dof 0 (T), benchmarks/Diffusion3D.hpp:102-104
             self.sys = l3b.MatrixFreeSystem(ctx, self.mesh, dofs_per_node, 1, mask, None)
             self.sys.assembleProblem(kernel)
-            self.sys.endAssembly()
         self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
         self.comm = torch.cuda.Stream(device=dev)
         self.launches = 0
+        self.diag = self.rhs = None
+        if self.sys is not None:
+            # computeDiagAndRhs (MatrixFreeSystem.hpp:877-941): element contributions, Export-sum of the ghost parts, Dirichlet dofs
+            self.sys.endAssemblyBegin()
+            self.diag = _device_view(self.sys.device_diag, self.n_local_dofs, dev)
+            self.rhs = _device_view(self.sys.device_rhs, self.n_local_dofs, dev)
+            if slab.world > 1:
+                with torch.cuda.stream(self.stream):
+                    for v in (self.diag, self.rhs):
+                        self.halo.export_y(v)
+                        self.halo.unpack_add(v)
+            self.sys.endAssemblyFinish()
+        elif slab.world > 1:
+            pass  # an empty rank has no neighbours: nothing to exchange
+
+    def solve(self, tol=1e-6, max_iters=10000):
+        """CG + native Jacobi over all ranks (benchmarks/Diffusion3D.hpp:115-118): the library's PCG driver with this operator's
+        apply and an NCCL all-reduce for the dot products. Returns (x over the local dofs, achieved residual norm, iterations)."""
+        import torch.distributed as dist
+
+        torch = self.torch
+        dev = torch.device("cuda", torch.cuda.current_device())
+        x = torch.zeros(max(self.n_local_dofs, 1), dtype=torch.float64, device=dev)
+        multi = self.slab.world > 1 and dist.is_initialized()
+
+        def apply(xp, yp):
+            xv = _device_view(xp, self.n_local_dofs, dev)
+            yv = _device_view(yp, self.n_local_dofs, dev)
+            self.apply(xv, yv)
+
+        def allreduce(sp, n):
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(_device_view(sp, n, dev))
+
+        if self.sys is None:  # empty rank: take part in the reductions only
+            raise NotImplementedError("CG with empty ranks: give every rank at least one element layer")
+        res, it = self.ctx.pcg(self.n_local_dofs, self.n_owned_dofs, apply, allreduce if multi else None, self.sys.device_diag,
+                               self.sys.device_rhs, x.data_ptr(), tol, max_iters)
+        return x, res, it
 
     def apply(self, x, y, alpha=1.0, beta=0.0):
         """y[owned] = alpha (A x)[owned] + beta y[owned]; x[ghost] is overwritten by the Import. Asynchronous."""

@@ -65,6 +65,27 @@ def main():
         err = np.linalg.norm(y_all - y_ref) / np.linalg.norm(y_ref)
         ok = bool(np.isfinite(err) and err < 1e-12)
         print(f"slab apply over {world} ranks vs single GPU: rel err {err:.2e}, launches/apply {op.launches}")
+    # ---- distributed CG + Jacobi (all-reduced dots, export-summed diag / rhs) against the single-GPU solve
+    xs, res, its = op.solve(tol=1e-9, max_iters=2000)
+    ctx.synchronize()
+    mine = torch.cat([torch.from_numpy(key[:no].astype(np.float64)).cuda()[:, None], xs[: no * U].reshape(-1, U)], dim=1).contiguous()
+    padded = torch.full((n_max, U + 1), -1.0, dtype=torch.float64, device="cuda")
+    padded[:no] = mine
+    bufs = [torch.zeros_like(padded) for _ in range(world)]
+    dist.all_gather(bufs, padded)
+    bufs = [b[: int(s.item())] for b, s in zip(bufs, sizes)]
+    if rank == 0:
+        xw_sol, res_w, its_w = wop.solve(tol=1e-9, max_iters=2000)
+        ctx.synchronize()
+        x_ref = np.zeros_like(f)
+        x_ref[wkey] = xw_sol.cpu().numpy().reshape(-1, U)
+        x_all = np.full_like(f, np.nan)
+        for b in bufs:
+            b = b.cpu().numpy()
+            x_all[b[:, 0].astype(np.int64)] = b[:, 1:]
+        err = np.linalg.norm(x_all - x_ref) / np.linalg.norm(x_ref)
+        print(f"distributed CG: {its} iterations, residual {res:.2e}; single GPU: {its_w} iterations, residual {res_w:.2e}; solution rel diff {err:.2e}")
+        ok = ok and bool(np.isfinite(err) and err < 1e-6 and abs(its - its_w) <= 2 and res <= 1e-9)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
