@@ -65,6 +65,10 @@ struct MfHexCfg
     static constexpr int  PSZ = CT % 2 == 0 ? CT + 1 : CT;  // plane stride
     // elements per batch: fill ~128 threads, but keep the batch's tensors within ~100 KB of shared memory
     static constexpr int  EPB = [] {
+#ifdef L3B_HEX_EPB
+        if (CT == 25)
+            return L3B_HEX_EPB; // experiment override for the nq = 5 instances
+#endif
         int epb = cmax(1, 128 / CT);
         while (epb > 1 and 3 * F * NQ * epb * PSZ * 8 > 100 * 1024)
             --epb;

@@ -13,6 +13,7 @@ Halo pattern of the matrix-free apply (algsys/MatrixFreeSystem.hpp:1046-1122, co
 Elements are numbered layer by layer, so the border elements (the ones that touch ghost nodes) are the first
 `n_border_elems` of the slab and the interior ones the contiguous rest.
 """
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -187,9 +188,9 @@ class Halo:
 
 
 class SlabOperator:
-    """Matrix-free operator of one slab with the overlap of MatrixFreeSystem::applyImpl (:1046-1122): the first half of the
-    interior elements runs while the Import is in flight, then the border elements, then the second half of the interior
-    while the Export is in flight. Vectors are device tensors over the local dofs [owned | ghost]."""
+    """Matrix-free operator of one slab with the overlap of MatrixFreeSystem::applyImpl (:1046-1122): the interior elements run
+    while the Import is in flight, then the border elements, then the Export-sum. Vectors are device tensors over the local
+    dofs [owned | ghost]."""
 
     def __init__(self, ctx, slab: Slab, dofs_per_node, kernel, dirichlet_boundary_ids=()):
         import torch
@@ -209,6 +210,7 @@ class SlabOperator:
         self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
         self.comm = torch.cuda.Stream(device=dev)
         self.launches = 0
+        self.split_interior = os.environ.get("L3B_SLAB_SPLIT", "0") == "1"  # measured on 2 B200: 1.70 ms unsplit, 2.03 ms split
         self.diag = self.rhs = None
         if self.sys is not None:
             # computeDiagAndRhs (MatrixFreeSystem.hpp:877-941): element contributions, Export-sum of the ghost parts, Dirichlet dofs
@@ -255,7 +257,14 @@ class SlabOperator:
         if sys_ is None:
             return
         S, Cs = self.stream, self.comm
-        half = s.n_border_elems + (s.n_elems - s.n_border_elems) // 2
+        if s.world == 1 or (s.lower < 0 and s.upper < 0):  # no neighbours: one launch over all elements
+            with torch.cuda.stream(S):
+                sys_.apply_device(x.data_ptr(), y.data_ptr(), 1, alpha, beta)
+            self.launches = sys_.kernel_launches
+            return
+        # all interior elements run while the Import is in flight; the 2 MB Export is left exposed — splitting the interior in two
+        # (L3B_SLAB_SPLIT=1: one half hides the Import, one the Export) costs a third launch and measured slower
+        half = s.n_border_elems + (s.n_elems - s.n_border_elems) // 2 if self.split_interior else s.n_elems
         xp, yp = x.data_ptr(), y.data_ptr()
         n = 0
         with torch.cuda.stream(S):
@@ -279,8 +288,9 @@ class SlabOperator:
             halo.export_y(y)
             ev_exported = Cs.record_event()
         with torch.cuda.stream(S):
-            sys_.apply_phase_device(xp, yp, l3b.APPLY_ELEMENTS, half, s.n_elems, alpha=alpha)
-            n += sys_.kernel_launches
+            if half < s.n_elems:
+                sys_.apply_phase_device(xp, yp, l3b.APPLY_ELEMENTS, half, s.n_elems, alpha=alpha)
+                n += sys_.kernel_launches
             S.wait_event(ev_exported)
             n += halo.unpack_add(y)
             sys_.apply_phase_device(xp, yp, l3b.APPLY_FINISH, 0, 0, alpha=alpha)
