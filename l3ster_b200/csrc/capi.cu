@@ -677,6 +677,8 @@ struct l3b_mf
     DevBuf< uint32_t >       elem_dir;
     DevBuf< int32_t >        dir_list; // the Dirichlet dofs, ascending
     long long                n_dir = 0;
+    DevBuf< double >         dir_g;            // prescribed values, zero off the Dirichlet dofs: operand of the lifting apply
+    bool                     lift_needed = false; // some prescribed value is non-zero
     DevBuf< double >         dir_vals, diag, rhs;
     bool                     has_bc = false, closed = false;
     std::vector< KernelUse > uses;
@@ -710,6 +712,52 @@ int guardedCtx(const l3b_context* ctx, F&& f)
     }
 }
 
+// y[dofs(e)] += alpha K_e x[dofs(e)] for one registered kernel over the domain elements [elem_begin, elem_end) (boundary kernels:
+// their whole side list, with the range that contains element 0). `masked`: honour the Dirichlet mask (the operator apply) or not
+// (the Dirichlet lifting of the initialisation). Returns the number of kernels launched.
+int applyUse(l3b_mf* sys, const KernelUse& use, const double* x, double* y, int n_cols, double alpha, bool masked, long long elem_begin,
+             long long elem_end)
+{
+    auto*       ctx  = sys->ctx;
+    const auto& info = kernelRegistry()[use.kernel_id].info;
+    ElemArgs    a    = baseArgs(sys->mesh, use, sys->dpn, sys->n_dofs);
+    if (info.is_boundary)
+    {
+        if (elem_begin != 0) // the side work list is not split: it runs with the range that contains element 0
+            return 0;
+    }
+    else
+    {
+        a.first_elem = elem_begin;
+        a.n_work     = elem_end - elem_begin;
+    }
+    a.x              = x;
+    a.y              = y;
+    a.n_cols         = n_cols;
+    a.alpha          = alpha;
+    a.dir_mask       = sys->has_bc and masked ? sys->dir_mask.ptr : nullptr;
+    a.elem_dir       = sys->has_bc and masked ? sys->elem_dir.ptr : nullptr;
+    bool contiguous  = info.n_unknowns == sys->dpn and reinterpret_cast< uintptr_t >(x) % 16 == 0 and sys->n_dofs % 2 == 0;
+    for (int u = 0; u < info.n_unknowns; ++u)
+        contiguous = contiguous and use.dof_inds[u] == u;
+    a.contiguous_dofs = contiguous;
+    const bool full  = n_cols == sys->n_rhs;
+    const bool sf    = not info.is_boundary and use.opts.eval_strategy != 1;
+    cudaError_t err;
+    if (sf)
+    {
+        const auto& t = ctx->tables1d(sys->mesh->order, use.nq);
+        err           = (full ? use.inst->mf_sumfact_full : use.inst->mf_sumfact_one)(kernelRegistry()[use.kernel_id].object.get(), a, t, ctx->stream);
+    }
+    else
+    {
+        setDense(a, sys->mesh, use, info.is_boundary);
+        err = (full ? use.inst->local_apply_full : use.inst->local_apply_one)(kernelRegistry()[use.kernel_id].object.get(), a, ctx->stream);
+    }
+    cudaCheck(err, "operator apply launch");
+    return a.n_work > 0 ? 1 : 0;
+}
+
 // y = alpha A x + beta y on device pointers, in the phases of l3b_mf_apply_phase_device
 void mfApplyPhases(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta, int phases, long long elem_begin,
                    long long elem_end)
@@ -734,47 +782,7 @@ void mfApplyPhases(l3b_mf* sys, const double* x, double* y, int n_cols, double a
     }
     if (phases & L3B_APPLY_ELEMENTS)
         for (const auto& use : sys->uses)
-        {
-            const auto& info = kernelRegistry()[use.kernel_id].info;
-            ElemArgs    a    = baseArgs(sys->mesh, use, sys->dpn, sys->n_dofs);
-            if (info.is_boundary)
-            {
-                if (elem_begin != 0) // the side work list is not split: it runs with the range that contains element 0
-                    continue;
-            }
-            else
-            {
-                a.first_elem = elem_begin;
-                a.n_work     = elem_end - elem_begin;
-            }
-            a.x              = x;
-            a.y              = y;
-            a.n_cols         = n_cols;
-            a.alpha          = alpha;
-            a.dir_mask       = sys->has_bc ? sys->dir_mask.ptr : nullptr;
-            a.elem_dir       = sys->has_bc ? sys->elem_dir.ptr : nullptr;
-            bool contiguous  = info.n_unknowns == sys->dpn and reinterpret_cast< uintptr_t >(x) % 16 == 0 and sys->n_dofs % 2 == 0;
-            for (int u = 0; u < info.n_unknowns; ++u)
-                contiguous = contiguous and use.dof_inds[u] == u;
-            a.contiguous_dofs = contiguous;
-            const bool full  = n_cols == sys->n_rhs;
-            const bool sf    = not info.is_boundary and use.opts.eval_strategy != 1;
-            cudaError_t err;
-            if (sf)
-            {
-                const auto& t = ctx->tables1d(sys->mesh->order, use.nq);
-                err           = (full ? use.inst->mf_sumfact_full : use.inst->mf_sumfact_one)(kernelRegistry()[use.kernel_id].object.get(), a, t,
-                                                                                    ctx->stream);
-            }
-            else
-            {
-                setDense(a, sys->mesh, use, info.is_boundary);
-                err = (full ? use.inst->local_apply_full : use.inst->local_apply_one)(kernelRegistry()[use.kernel_id].object.get(), a, ctx->stream);
-            }
-            cudaCheck(err, "operator apply launch");
-            if (a.n_work > 0)
-                ++launches;
-        }
+            launches += applyUse(sys, use, x, y, n_cols, alpha, true, elem_begin, elem_end);
     if ((phases & L3B_APPLY_FINISH) and sys->has_bc and sys->n_dir > 0)
     {
         dirichletRowsListKernel<<< gridFor(sys->n_dir), 256, 0, ctx->stream >>>(sys->dir_list.ptr, sys->n_dir, x, y, sys->n_dofs, n_cols, alpha);
@@ -1322,6 +1330,21 @@ int l3b_mf_create(l3b_context* ctx, l3b_mesh* mesh, int dpn, int n_rhs, const ui
                 s->dir_vals.upload(vals, s->dir_vals.n, ctx->stream);
             else
                 s->dir_vals.zero(ctx->stream);
+            std::vector< double > g(static_cast< size_t >(s->n_dofs) * n_rhs, 0.);
+            if (vals)
+                for (int c = 0; c < n_rhs; ++c)
+                    for (long long i = 0; i < s->n_dofs; ++i)
+                        if (mask[i] and vals[i + c * s->n_dofs] != 0.)
+                        {
+                            g[i + c * s->n_dofs] = vals[i + c * s->n_dofs];
+                            s->lift_needed       = true;
+                        }
+            if (s->lift_needed)
+            {
+                s->dir_g.alloc(g.size());
+                s->dir_g.upload(g.data(), g.size(), ctx->stream);
+                cudaCheck(cudaStreamSynchronize(ctx->stream), "Dirichlet values upload");
+            }
             if (mesh->n_elems > 0)
             {
                 s->elem_dir.alloc(mesh->n_elems);
@@ -1355,6 +1378,12 @@ int l3b_mf_end_assembly_begin(l3b_mf* sys)
         auto* ctx = sys->ctx;
         sys->diag.zero(ctx->stream);
         sys->rhs.zero(ctx->stream);
+        // domain kernels: diag + F_e by the coefficient-form kernel (mf_init.cuh), then the Dirichlet lifting rhs -= A_unmasked g as
+        // one operator apply; boundary kernels (and everything under L3B_MF_INIT_DENSE=1): the dense H_q formulation
+        static const bool force_dense = [] {
+            const char* e = std::getenv("L3B_MF_INIT_DENSE");
+            return e != nullptr and e[0] == '1';
+        }();
         for (const auto& use : sys->uses)
         {
             const auto& info = kernelRegistry()[use.kernel_id].info;
@@ -1364,7 +1393,10 @@ int l3b_mf_end_assembly_begin(l3b_mf* sys)
             a.dir_vals = sys->has_bc ? sys->dir_vals.ptr : nullptr;
             a.diag     = sys->diag.ptr;
             a.rhs      = sys->rhs.ptr;
-            cudaCheck(use.inst->init(kernelRegistry()[use.kernel_id].object.get(), a, ctx->stream), "init launch");
+            const bool fast = use.inst->init_fast != nullptr and not force_dense;
+            cudaCheck((fast ? use.inst->init_fast : use.inst->init)(kernelRegistry()[use.kernel_id].object.get(), a, ctx->stream), "init launch");
+            if (fast and sys->lift_needed)
+                applyUse(sys, use, sys->dir_g.ptr, sys->rhs.ptr, sys->n_rhs, -1., false, 0, sys->mesh->n_elems);
         }
         cudaCheck(cudaGetLastError(), "init");
     });

@@ -14,6 +14,7 @@
 #include "assemble_dmma.cuh"
 #include "local_element.cuh"
 #include "mf_hex_planes.cuh"
+#include "mf_init.cuh"
 #include "mf_sumfact.cuh"
 #include "registry.hpp"
 
@@ -128,6 +129,19 @@ inline bool forceFmaAssembly()
     return force;
 }
 template < typename KernelT, int DIM, int P >
+cudaError_t launchMfInitFast(const void* obj, const ElemArgs& args, cudaStream_t stream)
+{
+    using Cfg = MfInitCfg< KernelT, DIM, P >;
+    if (args.n_work == 0)
+        return cudaSuccess;
+    constexpr auto fn = mfInitDiagRhsKernel< KernelT, DIM, P >;
+    if (const auto err = raiseSmemLimit< fn >(Cfg::smem_bytes); err != cudaSuccess)
+        return err;
+    fn<<< static_cast< unsigned >(args.n_work), Cfg::threads, Cfg::smem_bytes, stream >>>(*static_cast< const KernelT* >(obj), args);
+    return cudaGetLastError();
+}
+
+template < typename KernelT, int DIM, int P >
 cudaError_t launchAssemble(const void* obj, const ElemArgs& args, cudaStream_t stream)
 {
     using Cfg = AsmCfg< KernelT, DIM, P >;
@@ -186,6 +200,8 @@ KernelInstance makeInstance()
     inst.local_apply_full    = launchLocal< KernelT, DIM, P, NRHS, MODE_APPLY >;
     inst.local_apply_one     = launchLocal< KernelT, DIM, P, 1, MODE_APPLY >;
     inst.init                = launchLocal< KernelT, DIM, P, NRHS, MODE_INIT >;
+    if constexpr (not KernelT::is_boundary)
+        inst.init_fast = launchMfInitFast< KernelT, DIM, P >; // diag + F_e only: the caller applies the Dirichlet lifting
     inst.assemble            = launchAssemble< KernelT, DIM, P >;
     inst.asm_blocks_per_elem = AsmCfg< KernelT, DIM, P >::n_pairs;
     return inst;

@@ -31,6 +31,7 @@ struct KernelInstance
     MfLaunch   mf_sumfact_one  = nullptr; // n_cols == 1
     ElemLaunch local_apply_full = nullptr, local_apply_one = nullptr;
     ElemLaunch init     = nullptr;
+    ElemLaunch init_fast = nullptr; // domain kernels: diag + F_e without the Dirichlet lifting (mf_init.cuh)
     ElemLaunch assemble = nullptr;
     // work per launch unit, for occupancy/grid decisions and reporting
     int mf_elems_per_block = 1, asm_blocks_per_elem = 1;

@@ -36,7 +36,12 @@ def main():
         mask[host.boundary_nodes([1, 2, 3, 4, 5, 6]) * 4] = 1
         m = l3b.MatrixFreeSystem(ctx, mesh, 4, 1, mask, None)
         m.assembleProblem("bench_diffusion3d")
+        import time
+        ctx.synchronize()
+        t0 = time.perf_counter()
         m.endAssembly()
+        ctx.synchronize()
+        print("mf endAssembly (diag + rhs) ms", 1e3 * (time.perf_counter() - t0))
         x = np.random.default_rng(0).uniform(-1, 1, size=(m.n_dofs, 1))
         for _ in range(4):
             y = m.apply(x)
