@@ -344,9 +344,11 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
     // A-side node — the one whose rhs entry it accumulates. Everything that does not depend on the chunk is hoisted here; the
     // item loop is branch-free: columns of padding nodes are zeroed once and never written, padding points read the tables of
     // the last real point against zero coefficients.
-    const int n_pcols = a_in_b ? TN : TM + TN;
-    const int n_parts = T >= n_pcols ? T / n_pcols : 1;
-    double    f_acc[NRHS];
+    // u != v over the same node block: both panels are functions of the same table values — one item builds both (`dual`)
+    const bool dual    = not a_in_b and row0 == col0 and TM == TN;
+    const int  n_pcols = a_in_b or dual ? TN : TM + TN;
+    const int  n_parts = T >= n_pcols ? T / n_pcols : 1;
+    double     f_acc[NRHS];
     for (int r = 0; r < NRHS; ++r)
         f_acc[r] = 0.;
     for (int i = tid; i < 2 * KCMAX * LDA; i += T)
@@ -364,6 +366,8 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
         const int     c_in  = c % cps; // chunk within its super-chunk
         double*       dst   = (is_b ? s_pb + (c & 1) * KCMAX * LDB : s_pa + (c & 1) * KCMAX * LDA) + prow + part * neq * ld;
         const double* cf    = (is_b ? s_cb : s_ca) + (c_in * QC + part) * neq * 4;
+        double*       dst2  = s_pa + (c & 1) * KCMAX * LDA + prow + part * neq * LDA; // dual: the A panel of the same node
+        const double* cf2   = s_ca + (c_in * QC + part) * neq * 4;
         const double* cr    = s_cr + (c_in * QC + part) * NRHS * 4;
         // rhs rows: the A-side nodes (row block); with a_in_b they are the window [row0, row0 + TM) of panel B
         const bool    rhs_row = rhs_duty and (a_in_b ? (node >= row0 and node < row0 + TM) : not is_b);
@@ -390,6 +394,26 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
                 if constexpr (DIM >= 3)
                     b = fma(c23.y, bas[3], b);
                 dst[ei * ld] = b;
+            }
+            if (dual)
+            {
+#pragma unroll
+                for (int ei = 0; ei < (NEQ > 0 ? NEQ : asm_max_equations); ++ei)
+                {
+                    if (NEQ == 0 and ei >= n_eq)
+                        break;
+                    const double2 c01 = *reinterpret_cast< const double2* >(cf2 + ei * 4);
+                    const double2 c23 = *reinterpret_cast< const double2* >(cf2 + ei * 4 + 2);
+                    double        b   = c01.x * bas[0];
+                    b                 = fma(c01.y, bas[1], b);
+                    if constexpr (DIM >= 2)
+                        b = fma(c23.x, bas[2], b);
+                    if constexpr (DIM >= 3)
+                        b = fma(c23.y, bas[3], b);
+                    dst2[ei * LDA] = b;
+                }
+                dst2 += n_parts * neq * LDA;
+                cf2 += n_parts * neq * 4;
             }
             if (rhs_row)
 #pragma unroll
