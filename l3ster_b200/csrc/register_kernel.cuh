@@ -119,12 +119,14 @@ cudaError_t launchLocal(const void* obj, const ElemArgs& args, cudaStream_t stre
     return cudaGetLastError();
 }
 
-// L3B_ASM_FMA=1 in the environment selects the register-tiled DFMA kernel (assemble.cuh) instead of the DMMA kernel
-inline bool forceFmaAssembly()
+// Which assembly kernel: the DMMA kernel (assemble_dmma.cuh) from 32 nodes per element up, the register-tiled DFMA kernel
+// (assemble.cuh) below — the measured crossover (profiles/r1_order_sweep.jsonl, hex U=4 E=7: p=1 DFMA 5x faster, p=2 equal, p>=3 DMMA
+// 2.8-3.7x faster; small elements waste the 32 x 32 DMMA warp tiles). L3B_ASM_FMA=1 / L3B_ASM_FMA=0 force one or the other.
+inline int forcedAssemblyKernel() // -1 auto, 0 DMMA, 1 DFMA
 {
-    static const bool force = [] {
+    static const int force = [] {
         const char* e = std::getenv("L3B_ASM_FMA");
-        return e != nullptr and e[0] == '1';
+        return e == nullptr ? -1 : e[0] == '1' ? 1 : 0;
     }();
     return force;
 }
@@ -147,7 +149,7 @@ cudaError_t launchAssemble(const void* obj, const ElemArgs& args, cudaStream_t s
     using Cfg = AsmCfg< KernelT, DIM, P >;
     if (args.n_work == 0)
         return cudaSuccess;
-    if (not forceFmaAssembly())
+    if (forcedAssemblyKernel() == 0 or (forcedAssemblyKernel() < 0 and AsmDmmaCfg< KernelT, DIM, P >::NN >= 32))
     {
         using DCfg                  = AsmDmmaCfg< KernelT, DIM, P >;
         static const AsmPairs pairs = DCfg::makePairs();

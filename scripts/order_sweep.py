@@ -1,0 +1,87 @@
+"""BASELINE configs[4]: local-assembly order sweep on 3-D hexahedra (benchmarks/LocalAssemblyBenchmarks.cpp:41-87), CUDA-core (DFMA,
+assemble.cuh) against tensor-core (DMMA, assemble_dmma.cuh) kernel, and the matrix-free apply, per element order.
+
+    python scripts/order_sweep.py            # both assembly kernels (the DFMA one in a subprocess: the selection is per process)
+
+Flops are the reference's own DPFlops count (LocalAssemblyBenchmarks.cpp:71-75). One JSON line per (order, kernel)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import l3ster_b200 as l3b  # noqa: E402
+
+U, E = 4, 7
+
+
+def node_dist(n):
+    dx, x, out = 1.0 / n, 0.0, []
+    for _ in range(n + 1):
+        out.append(x)
+        x += dx
+    return np.array(out)
+
+
+def ref_flops(p):
+    nn, q = (p + 1) ** 3, (p + 1) ** 3
+    L = nn * U
+    return q * (18 * nn + 7 * L * E + (L + 1) ** 2 / 2 * (2 * E + 1))
+
+
+def run(kind):
+    import torch
+
+    ctx = l3b.Context(0)
+    for p in (1, 2, 3, 4, 5, 6):
+        # elements so that the CRS stays below ~6 GB
+        n = {1: 40, 2: 28, 3: 20, 4: 14, 5: 10, 6: 8}[p]
+        host = l3b.make_cube_mesh(node_dist(n), order=p)
+        mesh = ctx.upload_mesh(host)
+        a = l3b.AssembledSystem(ctx, mesh, U, 1, host.node_graph())
+        ms = []
+        for it in range(5):
+            a.beginAssembly()
+            a.assembleProblem("bench_diffusion3d")
+            ms.append(a.last_kernel_ms)
+        k_ms = float(np.mean(ms[2:]))
+        line = {"order": p, "kernel": kind, "elements": host.n_elems, "kernel_ms": k_ms, "elements_per_s": host.n_elems / (k_ms * 1e-3),
+                "tflops_reference_count": ref_flops(p) * host.n_elems / (k_ms * 1e-3) / 1e12}
+        if kind == "dmma":  # the matrix-free apply of the same order, once
+            del a
+            nm = {1: 128, 2: 96, 3: 80, 4: 64, 5: 48, 6: 40}[p]
+            hm = l3b.make_cube_mesh(node_dist(nm), order=p)
+            mm = ctx.upload_mesh(hm)
+            mask = np.zeros(hm.n_nodes * U, dtype=np.uint8)
+            mask[hm.boundary_nodes([1, 2, 3, 4, 5, 6]) * U] = 1
+            s = l3b.MatrixFreeSystem(ctx, mm, U, 1, mask, None)
+            s.assembleProblem("bench_diffusion3d")
+            s.endAssembly()
+            x = torch.rand(s.n_dofs, dtype=torch.float64, device="cuda")
+            y = torch.zeros_like(x)
+            stream = torch.cuda.ExternalStream(ctx.stream)
+            for _ in range(3):
+                s.apply_device(x.data_ptr(), y.data_ptr())
+            ctx.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(10):
+                s.apply_device(x.data_ptr(), y.data_ptr())
+            e1.record(stream)
+            ctx.synchronize()
+            t = e0.elapsed_time(e1) / 10
+            line.update({"mf_elements": hm.n_elems, "mf_dofs": s.n_dofs, "mf_ms_per_apply": t, "mf_gdofs_per_s": s.n_dofs / (t * 1e-3) / 1e9,
+                         "mf_bytes_per_dof": (16 * s.n_dofs + hm.n_elems * (192 + 4 * ((p + 1) ** 3 - (p - 1) ** 3 + 1))) / s.n_dofs})
+            del s, mm, hm
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        run(sys.argv[1])
+    else:
+        run("dmma")
+        subprocess.run([sys.executable, os.path.abspath(__file__), "dfma"], env=dict(os.environ, L3B_ASM_FMA="1"), check=True)

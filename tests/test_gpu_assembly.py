@@ -149,7 +149,7 @@ def test_example02_diffusion2d(ctx):
     assert np.abs(sol - ref).max() < 1e-8 * max(1.0, np.abs(ref).max())
 
 
-@pytest.mark.parametrize("force_fma", [False, True], ids=["dmma", "dfma"])
+@pytest.mark.parametrize("force_fma", [False, True], ids=["auto", "dfma"])
 def test_single_element_fixtures(ctx, force_fma):
     """tests/LocalAssemblyTests.cpp:3-43 + tests/LocalOperatorCommon.hpp:17-61 through the device path: K_e, F_e of the distorted quad
     p=4 / hex p=3 fixtures (asm_opts{.value_order = 2}) against the oracle's assembleLocalSystem, entry by entry. The single-element
@@ -158,11 +158,12 @@ def test_single_element_fixtures(ctx, force_fma):
         import subprocess
         import sys
 
-        env = dict(os.environ, L3B_ASM_FMA="1")
-        # the whole module again with the register-tiled DFMA kernel (assemble.cuh) behind the same C ABI
-        out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", __file__, "-k", "not dfma"],
-                             env=env, capture_output=True, text=True, timeout=900)
-        assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+        # the whole module again with each kernel forced for every element size (the default picks by nodes per element)
+        for forced in ("1", "0"):
+            env = dict(os.environ, L3B_ASM_FMA=forced)
+            out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", __file__, "-k", "not dfma"],
+                                 env=env, capture_output=True, text=True, timeout=900)
+            assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
         return
     orc = oracle()
     quad = dict(dim=2, p=4, verts=[[1, 1, 0], [2, 1, 0], [1, 3, 0], [3, 4, 0]], k="diffusion_kernel_2D", U=3, r=2)
