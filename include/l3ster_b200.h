@@ -130,6 +130,8 @@ int l3b_asm_assemble(l3b_asm* sys, int kernel_id, l3b_asm_opts opts, double time
  * columns eliminated into the rhs. vals: n_dirichlet x n_rhs column-major. */
 int l3b_asm_end_assembly(l3b_asm* sys, int64_t n_dirichlet, const int32_t* dirichlet_dofs, const double* dirichlet_vals);
 int l3b_asm_download(l3b_asm* sys, double* values /* nnz, may be NULL */, double* rhs /* n_dofs x n_rhs, may be NULL */);
+/* device values in the library's own row layout (row (n, d): column-dof-major, entry (neighbour k, dof v) at v * deg(n) + k);
+ * l3b_asm_download converts to the reference's node-major Tpetra layout */
 double* l3b_asm_device_values(l3b_asm* sys);
 /* y = A x on the device CRS (Tpetra::CrsMatrix::apply), host buffers */
 int l3b_asm_spmv(l3b_asm* sys, const double* x, double* y);

@@ -242,8 +242,10 @@ __global__ void __launch_bounds__(asm_threads) assembleKernel(const KernelT kern
         __syncthreads();
     }
 
-    // ---- scatter into the CRS values: slot(row (a,u), col (b,v)) = row_ptr[dof(a,u)] + pos[e][a][b] * dofs_per_node + dof_inds[v]
+    // ---- scatter into the CRS values: slot(row (a,u), col (b,v)) = row_ptr[dof(a,u)] + dof_inds[v] * deg(node a) + pos[e][a][b]
+    // (device layout of the values: device_common.cuh, ElemArgs)
     const uint16_t* pos = args.slot_pos + e * static_cast< long long >(NN) * NN;
+    const int       dpn = args.dofs_per_node;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
     {
@@ -251,8 +253,8 @@ __global__ void __launch_bounds__(asm_threads) assembleKernel(const KernelT kern
         if (r >= L)
             continue;
         const int       ra = r / U, ru = r % U;
-        const long long grow = static_cast< long long >(el_nodes[ra]) * args.dofs_per_node + args.dof_inds[ru];
-        const long long rbeg = args.row_ptr[grow];
+        const long long na = el_nodes[ra], np_a = args.node_ptr[na], deg_a = args.node_ptr[na + 1] - np_a;
+        const long long rbeg = dpn * (dpn * np_a + args.dof_inds[ru] * deg_a);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
         {
@@ -260,12 +262,11 @@ __global__ void __launch_bounds__(asm_threads) assembleKernel(const KernelT kern
             if (c >= L)
                 continue;
             const int ca = c / U, cu = c % U;
-            atomicAdd(args.crs_vals + rbeg + static_cast< long long >(pos[ra * NN + ca]) * args.dofs_per_node + args.dof_inds[cu], acc[i][j]);
+            atomicAdd(args.crs_vals + rbeg + args.dof_inds[cu] * deg_a + pos[ra * NN + ca], acc[i][j]);
             if (bi != bj) // mirrored entry K_e[c][r]
             {
-                const long long gcol = static_cast< long long >(el_nodes[ca]) * args.dofs_per_node + args.dof_inds[cu];
-                atomicAdd(args.crs_vals + args.row_ptr[gcol] + static_cast< long long >(pos[ca * NN + ra]) * args.dofs_per_node +
-                              args.dof_inds[ru],
+                const long long nb = el_nodes[ca], np_b = args.node_ptr[nb], deg_b = args.node_ptr[nb + 1] - np_b;
+                atomicAdd(args.crs_vals + dpn * (dpn * np_b + args.dof_inds[cu] * deg_b) + args.dof_inds[ru] * deg_b + pos[ca * NN + ra],
                           acc[i][j]);
             }
         }

@@ -554,7 +554,8 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
         __syncthreads();
     }
 
-    // ---- scatter into the CRS values: slot(row (a,u), col (b,v)) = row_ptr[dof(a,u)] + pos[e][a][b] * dofs_per_node + dof_inds[v]
+    // ---- scatter into the CRS values: slot(row (a,u), col (b,v)) = row_ptr[dof(a,u)] + dof_inds[v] * deg(node a) + pos[e][a][b]
+    // (column-dof-major rows, device_common.cuh: consecutive nodes b are consecutive doubles, so the REDs of a warp share sectors)
     // DMMA accumulator layout: acc[i][j][h] = tile(row i*8 + g, column j*8 + 2*tq + h). For u == v only b <= a is
     // scattered, with its mirror image when b < a; for u != v every entry and its mirror K_e[(b,v)][(a,u)].
     if (warp_live)
@@ -570,7 +571,13 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
             {
                 const int b = col0 + wx * 32 + j * 8 + 2 * tq + h;
                 bcol[j][h]  = b;
-                cbeg[j][h]  = b < NN ? args.row_ptr[static_cast< long long >(el_nodes[b]) * dpn + dv] + du : 0;
+                if (b < NN)
+                {
+                    const long long nb = el_nodes[b], np_b = args.node_ptr[nb], deg_b = args.node_ptr[nb + 1] - np_b;
+                    cbeg[j][h]         = dpn * (dpn * np_b + dv * deg_b) + du * deg_b; // row (b, v), column dof u
+                }
+                else
+                    cbeg[j][h] = 0;
             }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -578,7 +585,8 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
             const int a = row0 + wy * 32 + i * 8 + g;
             if (a >= NN)
                 continue;
-            double* const   rowp = args.crs_vals + args.row_ptr[static_cast< long long >(el_nodes[a]) * dpn + du] + dv;
+            const long long na = el_nodes[a], np_a = args.node_ptr[na], deg_a = args.node_ptr[na + 1] - np_a;
+            double* const   rowp = args.crs_vals + dpn * (dpn * np_a + du * deg_a) + dv * deg_a; // row (a, u), column dof v
             const uint16_t* pa_  = pos + a * NN;
             // the slot positions of the whole row of tiles first (one memory round trip), then the atomics
             int  p_ab[4][2], p_ba[4][2];
@@ -601,9 +609,9 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
                     if (not on[j][h])
                         continue;
                     const double val = acc[i][j][h];
-                    atomicAdd(rowp + p_ab[j][h] * dpn, val);
+                    atomicAdd(rowp + p_ab[j][h], val);
                     if (p_ba[j][h] >= 0)
-                        atomicAdd(args.crs_vals + cbeg[j][h] + p_ba[j][h] * dpn, val);
+                        atomicAdd(args.crs_vals + cbeg[j][h] + p_ba[j][h], val);
                 }
         }
     }

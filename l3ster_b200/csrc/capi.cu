@@ -324,8 +324,8 @@ __global__ void spmvKernel(const long long* node_ptr, const uint32_t* node_nbr, 
     const long long n = row / dpn, d = row % dpn, deg = node_ptr[n + 1] - node_ptr[n];
     const long long beg = dpn * (dpn * node_ptr[n] + d * deg);
     double          acc = 0.;
-    for (long long k = lane; k < deg * dpn; k += 32)
-        acc = fma(vals[beg + k], x[static_cast< long long >(node_nbr[node_ptr[n] + k / dpn]) * dpn + k % dpn], acc);
+    for (long long k = lane; k < deg * dpn; k += 32) // entry k of the row = (neighbour k % deg, column dof k / deg)
+        acc = fma(vals[beg + k], x[static_cast< long long >(node_nbr[node_ptr[n] + k % deg]) * dpn + k / deg], acc);
     for (int off = 16; off > 0; off >>= 1)
         acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (lane == 0)
@@ -345,7 +345,7 @@ __global__ void dirichletAlgebraicKernel(const long long* node_ptr, const uint32
     {
         for (long long k = lane; k < deg * dpn; k += 32)
         {
-            const long long col = static_cast< long long >(node_nbr[node_ptr[n] + k / dpn]) * dpn + k % dpn;
+            const long long col = static_cast< long long >(node_nbr[node_ptr[n] + k % deg]) * dpn + k / deg;
             vals[beg + k]       = col == row ? 1. : 0.;
         }
         if (lane == 0)
@@ -358,7 +358,7 @@ __global__ void dirichletAlgebraicKernel(const long long* node_ptr, const uint32
         double acc = 0.;
         for (long long k = lane; k < deg * dpn; k += 32)
         {
-            const long long col = static_cast< long long >(node_nbr[node_ptr[n] + k / dpn]) * dpn + k % dpn;
+            const long long col = static_cast< long long >(node_nbr[node_ptr[n] + k % deg]) * dpn + k / deg;
             if (is_bc[col])
                 acc = fma(vals[beg + k], bc_vals[col + c * ld], acc);
         }
@@ -369,7 +369,7 @@ __global__ void dirichletAlgebraicKernel(const long long* node_ptr, const uint32
     }
     for (long long k = lane; k < deg * dpn; k += 32)
     {
-        const long long col = static_cast< long long >(node_nbr[node_ptr[n] + k / dpn]) * dpn + k % dpn;
+        const long long col = static_cast< long long >(node_nbr[node_ptr[n] + k % deg]) * dpn + k / deg;
         if (is_bc[col])
             vals[beg + k] = 0.;
     }
@@ -391,7 +391,7 @@ __global__ void extractDiagKernel(const long long* node_ptr, const uint32_t* nod
         else
             hi = mid;
     }
-    diag[row] = vals[beg + lo * dpn + d];
+    diag[row] = vals[beg + d * deg + lo];
 }
 
 unsigned gridFor(long long n, int block = 256)
@@ -652,6 +652,7 @@ struct l3b_asm
     int                 dpn = 0, n_rhs = 1;
     long long           n_dofs = 0, nnz = 0;
     DevBuf< long long > node_ptr, row_ptr;
+    std::vector< long long > node_ptr_host; // for the layout conversion of l3b_asm_download
     DevBuf< uint32_t >  node_nbr;
     DevBuf< uint16_t >  slot_pos;
     DevBuf< double >    values, rhs;
@@ -1162,6 +1163,7 @@ int l3b_asm_create(l3b_context* ctx, l3b_mesh* mesh, int dpn, int n_rhs, const i
         s->node_nbr.alloc(node_ptr[N]);
         static_assert(sizeof(long long) == sizeof(int64_t));
         s->node_ptr.upload(reinterpret_cast< const long long* >(node_ptr), N + 1, ctx->stream);
+        s->node_ptr_host.assign(node_ptr, node_ptr + N + 1);
         s->node_nbr.upload(node_nbr, node_ptr[N], ctx->stream);
         s->row_ptr.alloc(s->n_dofs + 1);
         rowPtrKernel<<< static_cast< unsigned >((s->n_dofs + 1 + 255) / 256), 256, 0, ctx->stream >>>(s->node_ptr.ptr, N, dpn, s->row_ptr.ptr);
@@ -1206,6 +1208,7 @@ int l3b_asm_assemble(l3b_asm* sys, int kernel_id, l3b_asm_opts opts, double time
         ElemArgs    a    = baseArgs(sys->mesh, use, sys->dpn, sys->n_dofs);
         setDense(a, sys->mesh, use, info.is_boundary);
         a.row_ptr  = sys->row_ptr.ptr;
+        a.node_ptr = sys->node_ptr.ptr;
         a.slot_pos = sys->slot_pos.ptr;
         a.crs_vals = sys->values.ptr;
         a.rhs      = sys->rhs.ptr;
@@ -1256,6 +1259,25 @@ int l3b_asm_download(l3b_asm* sys, double* values, double* rhs)
         if (rhs)
             sys->rhs.download(rhs, sys->rhs.n, sys->ctx->stream);
         cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "download");
+        if (values)
+        {
+            // device rows are column-dof-major (v * deg + k); the reference's Tpetra rows are node-major (k * dpn + v)
+            const int             dpn = sys->dpn;
+            std::vector< double > row;
+            long long             beg = 0;
+            for (long long n = 0; n < sys->mesh->n_local_nodes; ++n)
+            {
+                const long long deg = sys->node_ptr_host[n + 1] - sys->node_ptr_host[n];
+                row.resize(static_cast< size_t >(deg) * dpn);
+                for (int d = 0; d < dpn; ++d, beg += deg * dpn)
+                {
+                    std::copy(values + beg, values + beg + deg * dpn, row.begin());
+                    for (long long k = 0; k < deg; ++k)
+                        for (int v = 0; v < dpn; ++v)
+                            values[beg + k * dpn + v] = row[v * deg + k];
+                }
+            }
+        }
     });
 }
 double* l3b_asm_device_values(l3b_asm* sys)

@@ -75,7 +75,10 @@ struct ElemArgs
     const double* tab_pts;
     const double* tab_wts;
     int           n_qp;
-    // CRS (assembly)
+    // CRS (assembly). Device layout of the values: row (n, d) starts at row_ptr = dpn * (dpn * node_ptr[n] + d * deg(n)) and holds its
+    // entries column-dof-major: (neighbour k, column dof v) sits at v * deg(n) + k, so that consecutive neighbour nodes are consecutive
+    // doubles (the scatter's atomics then share 32-byte sectors). l3b_asm_download returns the reference's node-major row layout.
+    const long long* node_ptr;
     const long long* row_ptr;
     const uint16_t*  slot_pos; // [elem][a][b]: position (in node units) of node b's block in the rows of node a
     double*          crs_vals;
