@@ -174,6 +174,99 @@ struct Example02BC
     }
 };
 
+// examples/07-karman-2D/source.cpp:21-155 (BASELINE configs[3]): unknowns (u, v, vorticity, p), nu = 1 / Re with Re = 100, dt = 0.05
+namespace karman
+{
+inline constexpr double nu = 1. / 100., dt = .05;
+inline constexpr int    IU = 0, IV = 1, IO = 2, IP = 3;
+template < typename Op, typename Rhs >
+L3B_HD constexpr void fillSteady(Op& A0, Op& A1, Op& A2, Rhs& rhs, double u, double v, double du_dx, double dv_dx, double du_dy, double dv_dy)
+{
+    // momentum equations
+    A0(0, IU) = du_dx;
+    A0(0, IV) = du_dy;
+    A1(0, IU) = u;
+    A1(0, IP) = 1.;
+    A2(0, IU) = v;
+    A2(0, IO) = nu;
+    rhs(0, 0) = u * du_dx + v * du_dy;
+    A0(1, IU) = dv_dx;
+    A0(1, IV) = dv_dy;
+    A1(1, IV) = u;
+    A1(1, IO) = -nu;
+    A2(1, IV) = v;
+    A2(1, IP) = 1.;
+    rhs(1, 0) = u * dv_dx + v * dv_dy;
+    // incompressibility
+    A1(2, IU) = 1.;
+    A2(2, IV) = 1.;
+    // vorticity definition
+    A0(3, IO) = 1.;
+    A1(3, IV) = -1.;
+    A2(3, IU) = 1.;
+}
+} // namespace karman
+struct KarmanSteady
+{
+    template < typename In, typename Out >
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
+    {
+        const auto& [field_vals, field_ders, point] = in;
+        const auto& [u, v]                          = field_vals; // velocity of the previous iteration
+        const auto& [x_ders, y_ders]                = field_ders;
+        const auto& [du_dx, dv_dx]                  = x_ders;
+        const auto& [du_dy, dv_dy]                  = y_ders;
+        auto& [operators, rhs] = out;
+        auto& [A0, A1, A2]     = operators;
+        karman::fillSteady(A0, A1, A2, rhs, u, v, du_dx, dv_dx, du_dy, dv_dy);
+    }
+};
+struct KarmanTransient
+{
+    template < typename In, typename Out >
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
+    {
+        const auto& [field_vals, field_ders, point]  = in;
+        const auto& [u1, v1, u2, v2]                 = field_vals; // velocities of the 2 previous time steps
+        const auto& [x_ders, y_ders]                 = field_ders;
+        const auto& [du1_dx, dv1_dx, du2_dx, dv2_dx] = x_ders;
+        const auto& [du1_dy, dv1_dy, du2_dy, dv2_dy] = y_ders;
+        auto& [operators, rhs] = out;
+        auto& [A0, A1, A2]     = operators;
+        const double u = 2 * u1 - u2, v = 2 * v1 - v2; // extrapolated in time
+        const double du_dx = 2 * du1_dx - du2_dx, dv_dx = 2 * dv1_dx - dv2_dx;
+        const double du_dy = 2 * du1_dy - du2_dy, dv_dy = 2 * dv1_dy - dv2_dy;
+        karman::fillSteady(A0, A1, A2, rhs, u, v, du_dx, dv_dx, du_dy, dv_dy);
+        A0(0, karman::IU) += 1.5 / karman::dt;
+        A0(1, karman::IV) += 1.5 / karman::dt;
+        rhs(0, 0) += (2 * u1 - .5 * u2) / karman::dt;
+        rhs(1, 0) += (2 * v1 - .5 * v2) / karman::dt;
+        for (size_t op = 0; op < 3; ++op) // scale the momentum equations by dt
+            for (size_t unknown = 0; unknown != 4; ++unknown)
+                for (size_t eq = 0; eq != 2; ++eq)
+                    operators[op](eq, unknown) *= karman::dt;
+        for (size_t eq = 0; eq != 2; ++eq)
+            rhs(eq, 0) *= karman::dt;
+    }
+};
+struct KarmanOutlet // on the dofs (u, v, p)
+{
+    template < typename In, typename Out >
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
+    {
+        const double nx        = in.normal[0];
+        const double ny        = in.normal[1];
+        auto& [operators, rhs] = out;
+        auto& [A0, A1, A2]     = operators;
+        A0(0, 2) = -nx;
+        A1(0, 0) = karman::nu * nx;
+        A2(0, 0) = karman::nu * ny;
+        A0(1, 2) = -ny;
+        A1(1, 1) = karman::nu * nx;
+        A2(1, 1) = karman::nu * ny;
+    }
+};
+
 // benchmarks/Kernels.hpp:3-65
 struct NS3D
 {

@@ -332,6 +332,15 @@ class OracleAssembled:
                                                      len(boundary_ids), _ptr(b), C.byref(secs)))
         return secs.value
 
+    def assemble_ex(self, kernel, value_order=1, der_order=0, time=0.0, fields=None, n_threads=1, boundary_ids=(), dof_inds=None, field_inds=None):
+        """assemble with the kernel's unknowns mapped to system dofs / its fields to storage columns"""
+        f = None if fields is None else np.ascontiguousarray(fields, dtype=np.float64)
+        b = np.ascontiguousarray(list(boundary_ids) or [0], dtype=np.int32)
+        di = None if dof_inds is None else np.ascontiguousarray(dof_inds, dtype=np.int32)
+        fi = None if field_inds is None else np.ascontiguousarray(field_inds, dtype=np.int32)
+        self.mesh.orc._chk(self.lib.orc_asm_assemble_ex(self.h, kernel.encode(), value_order, der_order, C.c_double(time), _ptr(f), n_threads,
+                                                        len(boundary_ids), _ptr(b), _ptr(di), _ptr(fi)))
+
     def apply_dirichlet(self, dofs, vals):
         dofs = np.ascontiguousarray(dofs, dtype=np.int32)
         vals = np.ascontiguousarray(np.asarray(vals, dtype=np.float64).reshape(len(dofs), -1).T)

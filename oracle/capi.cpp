@@ -431,6 +431,21 @@ int orc_asm_assemble(void* h, const char* kernel, int value_order, int der_order
             *secs = std::chrono::duration< double >(std::chrono::steady_clock::now() - t0).count();
     });
 }
+// the same with the kernel's unknowns mapped to system dofs and its fields to storage columns (either may be null = identity)
+int orc_asm_assemble_ex(void* h, const char* kernel, int value_order, int der_order, double time, const double* fields, int n_threads,
+                        int n_bnd_ids, const int* bnd_ids, const int* dof_inds, const int* field_inds)
+{
+    return guarded([&] {
+        auto&              s = static_cast< AsmHandle* >(h)->sys;
+        const auto         k = kernelWithRhs(kernel, s.n_rhs);
+        std::vector< int > di, fi;
+        if (dof_inds)
+            di.assign(dof_inds, dof_inds + k.params.n_unknowns);
+        if (field_inds)
+            fi.assign(field_inds, field_inds + k.params.n_fields);
+        assembleGlobalSystem(s, k, mkOpts(value_order, der_order, 0), time, fields, n_threads, {bnd_ids, bnd_ids + n_bnd_ids}, di, fi);
+    });
+}
 int orc_asm_dirichlet(void* h, int n, const int* dofs, const double* vals)
 {
     return guarded([&] {

@@ -143,6 +143,73 @@ void example02_bc(In in, Out out)
     A0(0, 2) = in.normal[1];
 }
 
+// examples/07-karman-2D/source.cpp:21-78: unknowns (u, v, vorticity, p), nu = 1 / Re, Re = 100
+constexpr double karman_nu = 1. / 100., karman_dt = .05;
+void karmanFillSteady(Out out, double u, double v, double du_dx, double dv_dx, double du_dy, double dv_dy)
+{
+    constexpr int IU = 0, IV = 1, IO = 2, IP = 3;
+    auto&         A0 = out.operators[0];
+    auto&         A1 = out.operators[1];
+    auto&         A2 = out.operators[2];
+    A0(0, IU) = du_dx;
+    A0(0, IV) = du_dy;
+    A1(0, IU) = u;
+    A1(0, IP) = 1.;
+    A2(0, IU) = v;
+    A2(0, IO) = karman_nu;
+    out.rhs(0, 0) = u * du_dx + v * du_dy;
+    A0(1, IU) = dv_dx;
+    A0(1, IV) = dv_dy;
+    A1(1, IV) = u;
+    A1(1, IO) = -karman_nu;
+    A2(1, IV) = v;
+    A2(1, IP) = 1.;
+    out.rhs(1, 0) = u * dv_dx + v * dv_dy;
+    A1(2, IU) = 1.;
+    A2(2, IV) = 1.;
+    A0(3, IO) = 1.;
+    A1(3, IV) = -1.;
+    A2(3, IU) = 1.;
+}
+// examples/07-karman-2D/source.cpp:84-98
+void karman_steady(In in, Out out)
+{
+    karmanFillSteady(out, in.field_vals[0], in.field_vals[1], in.field_ders[0][0], in.field_ders[0][1], in.field_ders[1][0], in.field_ders[1][1]);
+}
+// examples/07-karman-2D/source.cpp:101-136 (BDF2)
+void karman_transient(In in, Out out)
+{
+    const double u1 = in.field_vals[0], v1 = in.field_vals[1], u2 = in.field_vals[2], v2 = in.field_vals[3];
+    const double u = 2 * u1 - u2, v = 2 * v1 - v2;
+    const double du_dx = 2 * in.field_ders[0][0] - in.field_ders[0][2], dv_dx = 2 * in.field_ders[0][1] - in.field_ders[0][3];
+    const double du_dy = 2 * in.field_ders[1][0] - in.field_ders[1][2], dv_dy = 2 * in.field_ders[1][1] - in.field_ders[1][3];
+    karmanFillSteady(out, u, v, du_dx, dv_dx, du_dy, dv_dy);
+    out.operators[0](0, 0) += 1.5 / karman_dt;
+    out.operators[0](1, 1) += 1.5 / karman_dt;
+    out.rhs(0, 0) += (2 * u1 - .5 * u2) / karman_dt;
+    out.rhs(1, 0) += (2 * v1 - .5 * v2) / karman_dt;
+    for (int op = 0; op < 3; ++op)
+        for (int unknown = 0; unknown < 4; ++unknown)
+            for (int eq = 0; eq < 2; ++eq)
+                out.operators[op](eq, unknown) *= karman_dt;
+    for (int eq = 0; eq < 2; ++eq)
+        out.rhs(eq, 0) *= karman_dt;
+}
+// examples/07-karman-2D/source.cpp:139-155: outlet condition on the dofs (u, v, p)
+void karman_outlet(In in, Out out)
+{
+    const double nx = in.normal[0], ny = in.normal[1];
+    auto&        A0 = out.operators[0];
+    auto&        A1 = out.operators[1];
+    auto&        A2 = out.operators[2];
+    A0(0, 2) = -nx;
+    A1(0, 0) = karman_nu * nx;
+    A2(0, 0) = karman_nu * ny;
+    A0(1, 2) = -ny;
+    A1(1, 1) = karman_nu * nx;
+    A2(1, 1) = karman_nu * ny;
+}
+
 // benchmarks/Kernels.hpp:3-65
 void ns3d_kernel(In in, Out out)
 {
@@ -243,6 +310,9 @@ std::map< std::string, Kernel > makeRegistry()
     r["example02_domain"]        = Kernel{{2, 4, 3, 0, 1}, false, example02_domain};
     r["example02_bc"]            = Kernel{{2, 1, 3, 0, 1}, true, example02_bc};
     r["ns3d_kernel"]             = Kernel{{3, 8, 7, 7, 1}, false, ns3d_kernel};
+    r["karman_steady"]           = Kernel{{2, 4, 4, 2, 1}, false, karman_steady};
+    r["karman_transient"]        = Kernel{{2, 4, 4, 4, 1}, false, karman_transient};
+    r["karman_outlet"]           = Kernel{{2, 2, 3, 0, 1}, true, karman_outlet};
     r["dense_probe_3D"]          = Kernel{{3, 5, 3, 2, 1}, false, dense_probe_3D};
     r["dense_probe_2D"]          = Kernel{{2, 4, 2, 2, 1}, false, dense_probe_2D};
     return r;

@@ -297,7 +297,8 @@ struct AssembledSystem
 // algsys/AssembleGlobalSystem.hpp:13-96 + ScatterLocalSystem.hpp:25-54 (CondensationPolicy::None)
 void assembleGlobalSystem(AssembledSystem& sys, const Kernel& kernel, const AssemblyOptions& opts, val_t time,
                           const val_t* fields /*field-major [n_fields][n_nodes] or null*/, int n_threads,
-                          const std::vector< int >& boundary_ids /*for boundary kernels*/);
+                          const std::vector< int >& boundary_ids /*for boundary kernels*/,
+                          const std::vector< int >& dof_inds = {}, const std::vector< int >& field_inds = {});
 // bcs/DirichletBC.hpp:82-150 — algebraic Dirichlet application (row/col zeroing, rhs lifting)
 void applyDirichletAlgebraic(AssembledSystem& sys, const std::vector< local_dof_t >& dofs, const std::vector< val_t >& vals);
 

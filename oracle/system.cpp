@@ -146,12 +146,15 @@ void sumIntoLocalValues(AssembledSystem& sys, local_dof_t row, const local_dof_t
 
 // algsys/AssembleGlobalSystem.hpp:13-96 → assembleLocalSystem → StaticCondensationManager<None>::condenseSystem
 // (StaticCondensationManager.hpp:110-121) → getDofsFromNodes (dofs/DofsFromNodes.hpp:72-87) → scatterLocalSystem
+// dof_inds: kernel unknown u -> system dof (getDofsFromNodes(nodes, map, dof_inds), dofs/DofsFromNodes.hpp:72-87); field_inds: kernel
+// field f -> column of the field storage (post/FieldAccess.hpp:10-53). Empty = identity.
 void assembleGlobalSystem(AssembledSystem& sys, const Kernel& kernel, const AssemblyOptions& opts, val_t time, const val_t* fields,
-                          int n_threads, const std::vector< int >& boundary_ids)
+                          int n_threads, const std::vector< int >& boundary_ids, const std::vector< int >& dof_inds,
+                          const std::vector< int >& field_inds)
 {
     const Mesh& mesh = *sys.mesh;
     const int   nn = mesh.nodesPerElem(), kU = kernel.params.n_unknowns, NF = kernel.params.n_fields, NRHS = kernel.params.n_rhs;
-    if (kU != sys.U or NRHS != sys.n_rhs)
+    if ((dof_inds.empty() ? kU != sys.U : static_cast< int >(dof_inds.size()) != kU) or NRHS != sys.n_rhs)
         throw std::invalid_argument{"oracle assembled system: kernel unknowns / rhs must match the system"};
     const int         L      = nn * kU;
     const std::size_t n_dofs = mesh.n_nodes * sys.U;
@@ -201,13 +204,20 @@ void assembleGlobalSystem(AssembledSystem& sys, const Kernel& kernel, const Asse
         const auto    [e, side] = work[wi];
         const n_id_t* el_nodes = &mesh.elem_nodes[e * nn];
         if (NF > 0)
-            gatherFields(fields, mesh.n_nodes, el_nodes, nn, NF, s.node_vals.data());
+        {
+            if (field_inds.empty())
+                gatherFields(fields, mesh.n_nodes, el_nodes, nn, NF, s.node_vals.data());
+            else
+                for (int a = 0; a < nn; ++a)
+                    for (int f = 0; f < NF; ++f)
+                        s.node_vals[static_cast< std::size_t >(a) * NF + f] = fields[el_nodes[a] + static_cast< std::size_t >(field_inds[f]) * mesh.n_nodes];
+        }
         const auto& rbq = tables[side < 0 ? 0 : 1 + side];
         assembleLocalSystem(kernel, mesh.et, mesh.order, &mesh.elem_verts[e * (1u << nativeDim(mesh.et)) * 3], s.node_vals.data(), rbq,
                             time, side, s.K.data(), s.F.data());
         for (int a = 0; a < nn; ++a)
             for (int u = 0; u < kU; ++u)
-                s.dofs[a * kU + u] = static_cast< local_dof_t >(el_nodes[a] * sys.U + u);
+                s.dofs[a * kU + u] = static_cast< local_dof_t >(el_nodes[a] * sys.U + (dof_inds.empty() ? u : dof_inds[u]));
         for (int r = 0; r < L; ++r)
         {
             sumIntoLocalValues(sys, s.dofs[r], s.dofs.data(), &s.K[static_cast< std::size_t >(r) * L], L);

@@ -184,3 +184,36 @@ def test_single_element_fixtures(ctx, force_fma):
         assert rel_err(Kd, K) < TOL
         assert np.abs(Kd - Kd.T).max() <= 1e-13 * np.abs(K).max()
         assert np.abs(rhs - F).max() <= TOL * max(np.abs(F).max(), 1.0)
+
+
+def test_karman_kernels_assembled(ctx):
+    """BASELINE configs[3] (examples/07-karman-2D/source.cpp:21-155): the steady and the BDF2 Navier-Stokes kernels (U=4, previous-field
+    values and gradients, AssemblyOptions{1, 1} -> nq = 8) plus the outlet boundary kernel on the dof subset (u, v, p), quad p=4,
+    distorted structured mesh instead of the Gmsh file; matrix, rhs and the assembled solve's operator against the oracle."""
+    U = 4
+    pm = PairedMesh(2, default_dists(2, 4), 4)
+    mesh = pm.upload(ctx)
+    fdata = np.random.default_rng(11).uniform(-1, 1, size=(6, pm.n_nodes))  # SolutionManager with 6 stored fields
+    fields = ctx.upload_fields(fdata)
+    opts = l3b.AssemblyOptions(value_order=1, derivative_order=1)
+    for kname, finds in (("karman_steady", [4, 1]), ("karman_transient", [0, 1, 2, 3])):
+        sys_g = l3b.AssembledSystem(ctx, mesh, U)
+        sys_o = pm.orc.assembled_system(U)
+        sys_g.beginAssembly()
+        sys_g.assembleProblem(kname, fields=fields, field_inds=finds, asm_opts=opts, time=0.3)
+        sys_g.assembleProblem("karman_outlet", boundary_ids=[2], dof_inds=[0, 1, 3], asm_opts=opts)
+        sys_o.assemble_ex(kname, 1, 1, 0.3, fdata, n_threads=4, field_inds=finds)
+        sys_o.assemble_ex("karman_outlet", 1, 1, 0.0, None, n_threads=1, boundary_ids=[2], dof_inds=[0, 1, 3])
+        vals_o, rhs_o = sys_o.get()
+        vals_g, rhs_g = sys_g.download()
+        assert rel_err(vals_g, vals_o) < TOL, kname
+        assert rel_err(rhs_g, rhs_o) < TOL, kname
+        # Dirichlet u, v on the inlet and the walls (source.cpp:158-180), then the operator of the closed system
+        nodes = pm.host.boundary_nodes([1, 3, 4])
+        dofs = np.sort(np.concatenate([nodes * U, nodes * U + 1])).astype(np.int32)
+        dvals = np.random.default_rng(5).uniform(-1, 1, size=(len(dofs), 1))
+        sys_g.endAssembly(dofs, dvals)
+        sys_o.apply_dirichlet(dofs, dvals)
+        vals_o, rhs_o = sys_o.get()
+        vals_g, rhs_g = sys_g.download()
+        assert rel_err(vals_g, vals_o) < TOL and rel_err(rhs_g, rhs_o) < TOL, kname

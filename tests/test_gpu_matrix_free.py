@@ -224,3 +224,29 @@ def test_line_per_thread_kernel_passes_the_same_suite():
     out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", __file__, "-k", "not line_per_thread"],
                          env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+
+
+def test_karman_kernels_matrix_free(ctx):
+    """examples/07-karman-2D kernels through the matrix-free system: sum-factorised apply with previous-field access (quad p=4,
+    nq = 8 > nb = 5) + the outlet boundary kernel on the dofs (u, v, p), against the assembled oracle matrix."""
+    import scipy.sparse as sp
+
+    U = 4
+    pm = PairedMesh(2, default_dists(2, 3), 4)
+    mesh = pm.upload(ctx)
+    fdata = np.random.default_rng(11).uniform(-1, 1, size=(4, pm.n_nodes))
+    fields = ctx.upload_fields(fdata)
+    opts = l3b.AssemblyOptions(value_order=1, derivative_order=1)
+    s = l3b.MatrixFreeSystem(ctx, mesh, U, 1)
+    s.assembleProblem("karman_transient", fields=fields, asm_opts=opts, time=0.1)
+    s.assembleProblem("karman_outlet", boundary_ids=[2], dof_inds=[0, 1, 3], asm_opts=opts)
+    s.endAssembly()
+    so = pm.orc.assembled_system(U)
+    so.assemble_ex("karman_transient", 1, 1, 0.1, fdata, n_threads=4)
+    so.assemble_ex("karman_outlet", 1, 1, 0.0, None, boundary_ids=[2], dof_inds=[0, 1, 3])
+    vals_o, rhs_o = so.get()
+    A = sp.csr_matrix((vals_o, so.col_ind, so.row_ptr), shape=(so.n_dofs,) * 2)
+    x = np.random.default_rng(3).uniform(-1, 1, size=(so.n_dofs, 1))
+    assert rel_err(s.apply(x), A @ x) < TOL
+    diag, rhs = s.download()
+    assert rel_err(diag, A.diagonal()) < TOL and rel_err(rhs, rhs_o) < TOL
