@@ -115,9 +115,13 @@ def cpu_reference(workload, n_threads, budget_s=12.0):
         t = s.assemble("bench_diffusion3d", n_threads=n_threads)
         per_elem = t / 8
         n = int(max(2, min(16, math.floor((budget_s / per_elem) ** (1 / 3)))))
-        m = make(n)
-        s = m.assembled_system(U)
-        t = s.assemble("bench_diffusion3d", n_threads=n_threads)
+        for _ in range(3):  # the 2^3 probe overestimates the cost per element (thread start-up): grow until the sample is long enough
+            m = make(n)
+            s = m.assembled_system(U)
+            t = s.assemble("bench_diffusion3d", n_threads=n_threads)
+            if t > 0.4 * budget_s or n >= 16:
+                break
+            n = int(min(16, max(n + 1, math.floor(n * (0.8 * budget_s / t) ** (1 / 3)))))
         return dict(value=n**3 / t, unit="elements/s", cores=n_threads, kind="port",
                     sample=f"oracle assembleGlobalSystem (local assembly + CRS scatter) of {n}^3 hex p=4 elements, {t:.2f} s")
     n = 16
