@@ -135,6 +135,18 @@ int l3b_asm_download(l3b_asm* sys, double* values /* nnz, may be NULL */, double
 double* l3b_asm_device_values(l3b_asm* sys);
 /* y = A x on the device CRS (Tpetra::CrsMatrix::apply), host buffers */
 int l3b_asm_spmv(l3b_asm* sys, const double* x, double* y);
+/* the same on device vectors over the local dofs, asynchronous on the context stream; and the diagonal of the local matrix.
+ * More than one rank: every rank keeps the rows of its local nodes [owned | ghost] as its elements assembled them (the reference
+ * instead export-adds the shared rows to their owners at endAssembly, AssembledSystem.hpp:384-389); the global operator is then
+ * Import x, local product, Export-sum of the ghost rows of y (l3ster_b200/slab.py: SlabAssembledOperator), the same halo as the
+ * matrix-free apply, and the global diagonal the Export-sum of the local ones. */
+int l3b_asm_spmv_device(l3b_asm* sys, const double* x, double* y);
+int l3b_asm_diag_device(l3b_asm* sys, double* diag);
+double* l3b_asm_device_rhs(l3b_asm* sys);
+/* l3b_asm_end_assembly for a rank that also holds ghost rows: Dirichlet rows become identity rows for the first n_owned_dofs dofs
+ * and zero rows for the ghost dofs (their owner holds the identity row; the Export-sum must add nothing to it) */
+int l3b_asm_end_assembly_ranked(l3b_asm* sys, int64_t n_dirichlet, const int32_t* dirichlet_dofs, const double* dirichlet_vals,
+                                int64_t n_owned_dofs);
 /* CG + native Jacobi on the assembled matrix (solve/BelosSolvers.hpp:116-123, NativePreconditioners.hpp:36-100) */
 int l3b_asm_solve_cg(l3b_asm* sys, double tol, int max_iters, double* x /* host, n_dofs */, double* achieved_tol, int* iters);
 /* timing of the last l3b_asm_assemble kernel launches (ms, CUDA events on the context stream) */

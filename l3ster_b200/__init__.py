@@ -68,6 +68,7 @@ EXPORTED_SYMBOLS = [
     "l3b_mf_solve_cg", "l3b_mf_num_dofs", "l3b_mf_kernel_launches", "l3b_microbench",
     "l3b_mf_apply_phase_device", "l3b_vec_gather", "l3b_vec_scatter_add",
     "l3b_mf_end_assembly_begin", "l3b_mf_end_assembly_finish", "l3b_mf_device_diag", "l3b_mf_device_rhs", "l3b_pcg_device",
+    "l3b_asm_spmv_device", "l3b_asm_diag_device", "l3b_asm_device_rhs", "l3b_asm_end_assembly_ranked",
 ]
 
 
@@ -142,6 +143,11 @@ def lib():
     L.l3b_mf_apply_phase_device.argtypes = [vp, vp, vp, i32, dbl, dbl, i32, i64, i64]
     L.l3b_vec_gather.argtypes = [vp, vp, i64, vp, i64, i32, vp]
     L.l3b_mf_end_assembly_begin.argtypes = [vp]
+    L.l3b_asm_spmv_device.argtypes = [vp, vp, vp]
+    L.l3b_asm_diag_device.argtypes = [vp, vp]
+    L.l3b_asm_device_rhs.argtypes = [vp]
+    L.l3b_asm_device_rhs.restype = vp
+    L.l3b_asm_end_assembly_ranked.argtypes = [vp, i64, vp, vp, i64]
     L.l3b_mf_end_assembly_finish.argtypes = [vp]
     L.l3b_mf_device_diag.argtypes = [vp]
     L.l3b_mf_device_diag.restype = vp
@@ -480,6 +486,23 @@ class AssembledSystem:
         d = None if n == 0 else np.ascontiguousarray(dirichlet_dofs, dtype=np.int32)
         v = None if n == 0 else np.ascontiguousarray(np.asarray(dirichlet_vals, dtype=np.float64).reshape(n, -1).T)
         self.ctx._chk(lib().l3b_asm_end_assembly(self._h, n, _p(d), _p(v)))
+
+    def endAssemblyRanked(self, dirichlet_dofs, dirichlet_vals, n_owned_dofs):
+        """endAssembly on a rank that also holds ghost rows: ghost copies of Dirichlet rows become zero rows"""
+        n = 0 if dirichlet_dofs is None else len(dirichlet_dofs)
+        d = None if n == 0 else np.ascontiguousarray(dirichlet_dofs, dtype=np.int32)
+        v = None if n == 0 else np.ascontiguousarray(np.asarray(dirichlet_vals, dtype=np.float64).reshape(n, -1).T)
+        self.ctx._chk(lib().l3b_asm_end_assembly_ranked(self._h, n, _p(d), _p(v), n_owned_dofs))
+
+    def spmv_device(self, x_ptr, y_ptr):
+        self.ctx._chk(lib().l3b_asm_spmv_device(self._h, x_ptr, y_ptr))
+
+    def diag_device(self, diag_ptr):
+        self.ctx._chk(lib().l3b_asm_diag_device(self._h, diag_ptr))
+
+    @property
+    def device_rhs(self):
+        return lib().l3b_asm_device_rhs(self._h)
 
     def graph(self):
         return expand_graph(self.node_ptr, self.node_nbr, self.dofs_per_node)

@@ -333,7 +333,8 @@ __global__ void spmvKernel(const long long* node_ptr, const uint32_t* node_nbr, 
 }
 // algebraic Dirichlet BCs (bcs/DirichletBC.hpp:82-150), one warp per row
 __global__ void dirichletAlgebraicKernel(const long long* node_ptr, const uint32_t* node_nbr, double* vals, long long n_nodes, int dpn,
-                                         const uint8_t* is_bc, const double* bc_vals, double* rhs, long long ld, int n_rhs)
+                                         const uint8_t* is_bc, const double* bc_vals, double* rhs, long long ld, int n_rhs,
+                                         long long n_owned_dofs)
 {
     const long long row  = (blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x) / 32;
     const int       lane = threadIdx.x & 31;
@@ -346,11 +347,11 @@ __global__ void dirichletAlgebraicKernel(const long long* node_ptr, const uint32
         for (long long k = lane; k < deg * dpn; k += 32)
         {
             const long long col = static_cast< long long >(node_nbr[node_ptr[n] + k % deg]) * dpn + k / deg;
-            vals[beg + k]       = col == row ? 1. : 0.;
+            vals[beg + k]       = col == row and row < n_owned_dofs ? 1. : 0.; // ghost copies of a Dirichlet row stay empty
         }
         if (lane == 0)
             for (int c = 0; c < n_rhs; ++c)
-                rhs[row + c * ld] = bc_vals[row + c * ld];
+                rhs[row + c * ld] = row < n_owned_dofs ? bc_vals[row + c * ld] : 0.;
         return;
     }
     for (int c = 0; c < n_rhs; ++c)
@@ -1223,6 +1224,10 @@ int l3b_asm_assemble(l3b_asm* sys, int kernel_id, l3b_asm_opts opts, double time
 }
 int l3b_asm_end_assembly(l3b_asm* sys, int64_t n_dir, const int32_t* dofs, const double* vals)
 {
+    return l3b_asm_end_assembly_ranked(sys, n_dir, dofs, vals, sys->n_dofs);
+}
+int l3b_asm_end_assembly_ranked(l3b_asm* sys, int64_t n_dir, const int32_t* dofs, const double* vals, int64_t n_owned_dofs)
+{
     return guardedCtx(sys->ctx, [&] {
         if (not sys->open)
             fail(L3B_ERR_STATE, "`endAssembly()` was called more than once");
@@ -1245,7 +1250,7 @@ int l3b_asm_end_assembly(l3b_asm* sys, int64_t n_dir, const int32_t* dofs, const
             const long long threads = sys->n_dofs * 32;
             dirichletAlgebraicKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
                 sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, d_mask.ptr, d_bc.ptr, sys->rhs.ptr,
-                sys->n_dofs, sys->n_rhs);
+                sys->n_dofs, sys->n_rhs, n_owned_dofs);
             cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "Dirichlet BC application");
         }
         sys->open = false;
@@ -1295,6 +1300,27 @@ int l3b_asm_spmv(l3b_asm* sys, const double* x, double* y)
         dy.download(y, sys->n_dofs, sys->ctx->stream);
         cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "spmv");
     });
+}
+int l3b_asm_spmv_device(l3b_asm* sys, const double* x, double* y)
+{
+    return guardedCtx(sys->ctx, [&] {
+        const long long threads = sys->n_dofs * 32;
+        spmvKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
+            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, x, y);
+        cudaCheck(cudaGetLastError(), "spmv");
+    });
+}
+int l3b_asm_diag_device(l3b_asm* sys, double* diag)
+{
+    return guardedCtx(sys->ctx, [&] {
+        extractDiagKernel<<< static_cast< unsigned >((sys->n_dofs + 255) / 256), 256, 0, sys->ctx->stream >>>(
+            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, diag);
+        cudaCheck(cudaGetLastError(), "diagonal");
+    });
+}
+double* l3b_asm_device_rhs(l3b_asm* sys)
+{
+    return sys->rhs.ptr;
 }
 int l3b_asm_solve_cg(l3b_asm* sys, double tol, int max_iters, double* x, double* achieved_tol, int* iters)
 {

@@ -296,3 +296,66 @@ class SlabOperator:
             sys_.apply_phase_device(xp, yp, l3b.APPLY_FINISH, 0, 0, alpha=alpha)
             n += sys_.kernel_launches
         self.launches = n
+
+
+class SlabAssembledOperator:
+    """Assembled system of one slab (BASELINE configs[1] on more than one GPU): every rank assembles its elements into the rows of
+    its local nodes [owned | ghost] (`assembleProblem`, no exchange — as in the reference); the global operator is Import x, local
+    sparse product, Export-sum of the ghost rows, the global diagonal and rhs the Export-sums of the local ones. The reference
+    export-adds the shared ROWS to their owners at endAssembly instead (AssembledSystem.hpp:384-389): same operator, same halo."""
+
+    def __init__(self, ctx, slab: Slab, dofs_per_node, kernel, dirichlet_boundary_ids=(), dirichlet_value=0.0):
+        import torch
+
+        self.torch, self.ctx, self.slab, self.dpn = torch, ctx, slab, dofs_per_node
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.halo = Halo(slab, dofs_per_node, dev, ctx)
+        self.n_local_dofs, self.n_owned_dofs = self.halo.n_local_dofs, self.halo.n_owned_dofs
+        self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+        self.mesh = l3b.Mesh(ctx, 3, slab.order, slab.verts, slab.nodes, slab.side_boundaries, slab.n_local_nodes, slab.n_owned_nodes)
+        self.sys = l3b.AssembledSystem(ctx, self.mesh, dofs_per_node, 1)
+        self.sys.beginAssembly()
+        self.sys.assembleProblem(kernel)
+        dofs = slab.dirichlet_nodes(dirichlet_boundary_ids) * dofs_per_node if dirichlet_boundary_ids else np.zeros(0, dtype=np.int64)
+        self.sys.endAssemblyRanked(dofs.astype(np.int32), np.full((len(dofs), 1), dirichlet_value), self.n_owned_dofs)
+        self.rhs = _device_view(self.sys.device_rhs, self.n_local_dofs, dev)
+        self.diag = torch.zeros(self.n_local_dofs, dtype=torch.float64, device=dev)
+        with torch.cuda.stream(self.stream):
+            self.sys.diag_device(self.diag.data_ptr())
+            if slab.world > 1:
+                for v in (self.diag, self.rhs):
+                    self.halo.export_y(v)
+                    self.halo.unpack_add(v)
+        ctx.synchronize()
+
+    def apply(self, x, y):
+        """y[owned] = (A x)[owned]; x[ghost] is overwritten by the Import. Asynchronous on the context stream."""
+        torch, halo = self.torch, self.halo
+        with torch.cuda.stream(self.stream):
+            if self.slab.world > 1:
+                halo.pack(x)
+                halo.import_x(x)
+            self.sys.spmv_device(x.data_ptr(), y.data_ptr())
+            if self.slab.world > 1:
+                halo.export_y(y)
+                halo.unpack_add(y)
+
+    def solve(self, tol=1e-6, max_iters=10000):
+        """CG + Jacobi over all ranks on the assembled matrix (solve/BelosSolvers.hpp:116-123)"""
+        import torch.distributed as dist
+
+        torch = self.torch
+        dev = torch.device("cuda", torch.cuda.current_device())
+        x = torch.zeros(self.n_local_dofs, dtype=torch.float64, device=dev)
+        multi = self.slab.world > 1 and dist.is_initialized()
+
+        def apply(xp, yp):
+            self.apply(_device_view(xp, self.n_local_dofs, dev), _device_view(yp, self.n_local_dofs, dev))
+
+        def allreduce(sp, n):
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(_device_view(sp, n, dev))
+
+        res, it = self.ctx.pcg(self.n_local_dofs, self.n_owned_dofs, apply, allreduce if multi else None, self.diag.data_ptr(),
+                               self.rhs.data_ptr(), x.data_ptr(), tol, max_iters)
+        return x, res, it

@@ -10,7 +10,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import l3ster_b200 as l3b  # noqa: E402
-from l3ster_b200.slab import SlabOperator, make_slab  # noqa: E402
+from l3ster_b200.slab import SlabAssembledOperator, SlabOperator, make_slab  # noqa: E402
 
 U, P = 4, 4
 BND = [1, 2, 3, 4, 5, 6]
@@ -86,6 +86,44 @@ def main():
         err = np.linalg.norm(x_all - x_ref) / np.linalg.norm(x_ref)
         print(f"distributed CG: {its} iterations, residual {res:.2e}; single GPU: {its_w} iterations, residual {res_w:.2e}; solution rel diff {err:.2e}")
         ok = ok and bool(np.isfinite(err) and err < 1e-6 and abs(its - its_w) <= 2 and res <= 1e-9)
+    # ---- the assembled system over the same slabs (p = 2 keeps the CRS small): distributed CG against the single-GPU solve
+    P2 = 2
+    slab2 = make_slab(x1, y1, z1, P2, rank, world)
+    aop = SlabAssembledOperator(ctx, slab2, U, "bench_diffusion3d", BND)
+    xa, res_a, its_a = aop.solve(tol=1e-10, max_iters=4000)
+    ctx.synchronize()
+    n_lat2 = n * P2 + 1, n * P2 + 1
+    key2 = slab2.lattice[:, 0] + n_lat2[0] * (slab2.lattice[:, 1] + n_lat2[1] * slab2.lattice[:, 2])
+    no2 = slab2.n_owned_nodes
+    sizes2 = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    dist.all_gather(sizes2, torch.tensor([no2], dtype=torch.int64, device="cuda"))
+    n_max2 = max(int(s.item()) for s in sizes2)
+    padded = torch.full((n_max2, U + 1), -1.0, dtype=torch.float64, device="cuda")
+    padded[:no2] = torch.cat([torch.from_numpy(key2[:no2].astype(np.float64)).cuda()[:, None], xa[: no2 * U].reshape(-1, U)], dim=1)
+    bufs2 = [torch.zeros_like(padded) for _ in range(world)]
+    dist.all_gather(bufs2, padded)
+    bufs2 = [b[: int(s.item())] for b, s in zip(bufs2, sizes2)]
+    if rank == 0:
+        whole2 = make_slab(x1, y1, z1, P2, 0, 1)
+        wa = SlabAssembledOperator(ctx, whole2, U, "bench_diffusion3d", BND)
+        xw2, res_w2, its_w2 = wa.solve(tol=1e-10, max_iters=4000)
+        # and the matrix-free operator of the same mesh must give the same solution
+        wm = SlabOperator(ctx, whole2, U, "bench_diffusion3d", BND)
+        xm2, _, its_m2 = wm.solve(tol=1e-10, max_iters=4000)
+        ctx.synchronize()
+        wkey2 = whole2.lattice[:, 0] + n_lat2[0] * (whole2.lattice[:, 1] + n_lat2[1] * whole2.lattice[:, 2])
+        n_all = n_lat2[0] * n_lat2[1] * (nz * P2 + 1)
+        x_ref2 = np.zeros((n_all, U))
+        x_ref2[wkey2] = xw2.cpu().numpy().reshape(-1, U)
+        x_all2 = np.full((n_all, U), np.nan)
+        for b in bufs2:
+            b = b.cpu().numpy()
+            x_all2[b[:, 0].astype(np.int64)] = b[:, 1:]
+        err2 = np.linalg.norm(x_all2 - x_ref2) / np.linalg.norm(x_ref2)
+        err_mf = float(torch.linalg.norm(xm2 - xw2) / torch.linalg.norm(xw2))
+        print(f"assembled distributed CG: {its_a} iterations (single GPU {its_w2}, matrix-free {its_m2}); solution rel diff {err2:.2e}, "
+              f"assembled vs matrix-free {err_mf:.2e}")
+        ok = ok and bool(np.isfinite(err2) and err2 < 1e-7 and abs(its_a - its_w2) <= 2 and err_mf < 1e-7)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
