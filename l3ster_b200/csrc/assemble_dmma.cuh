@@ -32,6 +32,9 @@
 
 namespace l3b
 {
+#ifndef L3B_ASM_KCMAX
+#define L3B_ASM_KCMAX 32
+#endif
 constexpr int asm_max_equations = 16;
 constexpr int asm_max_pairs     = max_unknowns * (max_unknowns + 1) / 2;
 
@@ -74,15 +77,16 @@ struct AsmDmmaCfg
     static constexpr int  threads = WM * WN * 32;
     static constexpr int  n_rb = (NN + TM - 1) / TM, n_cb = (NN + TN - 1) / TN; // row / column blocks
     static constexpr int  LDA = TM + 4, LDB = TN + 4;                  // panel leading dimensions, ≡ 4 (mod 16)
-    static constexpr int  KCMAX = cmax(32, 4 * E);                     // panel rows (quadrature points x equations) per chunk
+    static constexpr int  KCMAX = cmax(L3B_ASM_KCMAX, 4 * E);                     // panel rows (quadrature points x equations) per chunk
     static constexpr int  QCMAX = 32;                                  // quadrature points per chunk, at most (fewer chunk barriers: 61 k -> 52 k cycles per n_eq = 1 tile)
     // smem (doubles): panel A x 2 | panel B x 2 | coefficients A | coefficients B | rhs coefficients | node field values | vertices
     // the per-point stage runs for a whole super-chunk of points at once, all threads, one point each: SROWS coefficient rows
     // (points x equations of the pair) per panel — every point of a p <= 4 hexahedron in one go
     static constexpr int  SROWS = cmax(512, 16 * E), SPTS = 128;
+    static constexpr int NQ1MAX = 16; // 1-D quadrature points the shared-memory copy of the 1-D tables has room for
     static constexpr int off_b = 2 * KCMAX * LDA, off_ca = off_b + 2 * KCMAX * LDB, off_cb = off_ca + SROWS * 4,
                          off_cr = off_cb + SROWS * 4, off_nv = off_cr + SPTS * NRHS * 4, off_verts = off_nv + NN * NF,
-                         total = off_verts + 8 * 3;
+                         off_t1d = off_verts + 8 * 3, off_qidx = off_t1d + 2 * (P + 1) * NQ1MAX, total = off_qidx + SPTS / 2;
     static constexpr size_t smem_bytes = static_cast< size_t >(total) * sizeof(double);
     static constexpr int    min_blocks = smem_bytes <= 112 * 1024 and threads <= 256 ? 2 : 1;
     static_assert(E <= asm_max_equations and U <= max_unknowns);
@@ -123,6 +127,10 @@ struct AsmDmmaCfg
     }
 };
 
+#ifdef L3B_ASM_TIMING
+// experiment: per-warp phase clocks inside the chunk loop [cta][warp][build, mma, barrier, n_eq]
+static __device__ long long g_asm_timing[4096][16][4];
+#endif
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
@@ -147,6 +155,8 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
     double* const s_cr    = smem + Cfg::off_cr; // [buf][qc][r][4]
     double* const s_nv    = smem + Cfg::off_nv;
     double* const s_verts = smem + Cfg::off_verts;
+    double* const s_t1d   = smem + Cfg::off_t1d;                                      // [interp | der][b][q]
+    uint32_t* const s_qidx = reinterpret_cast< uint32_t* >(smem + Cfg::off_qidx);      // per point of the super-chunk: qx | qy << 8 | qz << 16
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // ---- which (element, unknown pair, node tile) is this?
@@ -176,6 +186,12 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
 
     for (int i = tid; i < nv * 3; i += T)
         s_verts[i] = args.verts[e * nv * 3 + i];
+    // tensor-product evaluation of the basis in the panel build (no table traffic in the chunk loop) when the 1-D tables are given
+    const int  nq1    = args.nq1d;
+    const bool tensor = not is_bnd and args.tab1d != nullptr and nq1 <= Cfg::NQ1MAX;
+    if (tensor)
+        for (int i = tid; i < 2 * (P + 1) * nq1; i += T)
+            s_t1d[i] = args.tab1d[i];
     if constexpr (NF > 0)
         for (int i = tid; i < NN * NF; i += T)
             s_nv[i] = args.fields[el_nodes[i / NF] + args.field_inds[i % NF] * args.field_stride];
@@ -206,6 +222,12 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
         for (int qc = tid; qc < cps * QC; qc += T) // qc: point within the super-chunk = row block qc * n_eq of the tables
         {
             const int q = sc * cps * QC + qc;
+            if (tensor)
+            {
+                const int qq = min(q, args.n_qp - 1);
+                s_qidx[qc]   = static_cast< uint32_t >(qq % nq1) | static_cast< uint32_t >((qq / nq1) % nq1) << 8 |
+                             static_cast< uint32_t >(qq / (nq1 * nq1)) << 16;
+            }
             if (q >= args.n_qp) // padding point: zero coefficients zero its panel rows
             {
                 for (int i = 0; i < n_eq * 4; ++i)
@@ -372,62 +394,133 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
         // rhs rows: the A-side nodes (row block); with a_in_b they are the window [row0, row0 + TM) of panel B
         const bool    rhs_row = rhs_duty and (a_in_b ? (node >= row0 and node < row0 + TM) : not is_b);
         const int     q_last  = args.n_qp - 1;
-#pragma unroll 4
-        for (int qc = part; qc < QC; qc += n_parts)
-        {
-            const int q   = min(c * QC + qc, q_last);
-            double    bas[4] = {__ldg(tab_vals + q * NN + node), 0., 0., 0.};
-#pragma unroll
-            for (int d = 0; d < DIM; ++d)
-                bas[1 + d] = __ldg(tab_ders + (q * DIM + d) * NN + node);
-#pragma unroll
-            for (int ei = 0; ei < (NEQ > 0 ? NEQ : asm_max_equations); ++ei)
+        // the basis of `node` at a point: products of the 1-D tables in shared memory, or the dense tables (L2)
+        constexpr int NB1     = P + 1;
+        const double* const tI = s_t1d, * const tD = s_t1d + NB1 * nq1;
+        const int     ix = node % NB1, iy = (node / NB1) % NB1, iz = DIM == 3 ? node / (NB1 * NB1) : 0;
+        const auto    basisAt = [&](int qc_in_chunk, double (&bas)[4]) {
+            if (tensor)
             {
-                if (NEQ == 0 and ei >= n_eq)
-                    break;
-                const double2 c01 = *reinterpret_cast< const double2* >(cf + ei * 4);
-                const double2 c23 = *reinterpret_cast< const double2* >(cf + ei * 4 + 2);
-                double        b   = c01.x * bas[0];
-                b                 = fma(c01.y, bas[1], b);
-                if constexpr (DIM >= 2)
-                    b = fma(c23.x, bas[2], b);
-                if constexpr (DIM >= 3)
-                    b = fma(c23.y, bas[3], b);
-                dst[ei * ld] = b;
-            }
-            if (dual)
-            {
-#pragma unroll
-                for (int ei = 0; ei < (NEQ > 0 ? NEQ : asm_max_equations); ++ei)
+                const uint32_t qi = s_qidx[c_in * QC + qc_in_chunk];
+                const int      qx = qi & 0xff, qy = (qi >> 8) & 0xff, qz = qi >> 16;
+                const double   bx = tI[ix * nq1 + qx], dx = tD[ix * nq1 + qx], by = tI[iy * nq1 + qy], dy = tD[iy * nq1 + qy];
+                if constexpr (DIM == 2)
                 {
-                    if (NEQ == 0 and ei >= n_eq)
-                        break;
-                    const double2 c01 = *reinterpret_cast< const double2* >(cf2 + ei * 4);
-                    const double2 c23 = *reinterpret_cast< const double2* >(cf2 + ei * 4 + 2);
-                    double        b   = c01.x * bas[0];
-                    b                 = fma(c01.y, bas[1], b);
-                    if constexpr (DIM >= 2)
-                        b = fma(c23.x, bas[2], b);
-                    if constexpr (DIM >= 3)
-                        b = fma(c23.y, bas[3], b);
-                    dst2[ei * LDA] = b;
+                    bas[0] = bx * by;
+                    bas[1] = dx * by;
+                    bas[2] = bx * dy;
+                    bas[3] = 0.;
                 }
+                else
+                {
+                    const double bz = tI[iz * nq1 + qz], dz = tD[iz * nq1 + qz];
+                    const double xy = bx * by, yz = by * bz;
+                    bas[0] = xy * bz;
+                    bas[1] = dx * yz;
+                    bas[2] = bx * dy * bz;
+                    bas[3] = xy * dz;
+                }
+            }
+            else
+            {
+                const int q = min(c * QC + qc_in_chunk, q_last);
+                bas[0]      = __ldg(tab_vals + q * NN + node);
+                bas[3]      = 0.;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d)
+                    bas[1 + d] = __ldg(tab_ders + (q * DIM + d) * NN + node);
+            }
+        };
+        // one panel entry: c . (N, dN/dxi) as two independent half sums — the fp64 pipe's dependent-issue latency, not its
+        // throughput, is what a chain of four DFMAs would pay here
+        const auto entry = [](const double* cf4, const double (&bas)[4]) {
+            const double2 c01 = *reinterpret_cast< const double2* >(cf4);
+            const double2 c23 = *reinterpret_cast< const double2* >(cf4 + 2);
+            double        t0  = c01.x * bas[0];
+            t0                = fma(c01.y, bas[1], t0);
+            if constexpr (DIM == 2)
+                return fma(c23.x, bas[2], t0);
+            else
+            {
+                double t1 = c23.x * bas[2];
+                t1        = fma(c23.y, bas[3], t1);
+                return t0 + t1;
+            }
+        };
+        if constexpr (NEQ > 0)
+        {
+            // two points per trip, every entry of both an independent chain (explicit ILP: the compiler keeps the loop rolled)
+            constexpr int G = 2;
+            for (int qc = part; qc < QC; qc += G * n_parts)
+            {
+                double bas[G][4];
+                bool   on[G];
+#pragma unroll
+                for (int gi = 0; gi < G; ++gi)
+                {
+                    on[gi] = qc + gi * n_parts < QC;
+                    basisAt(on[gi] ? qc + gi * n_parts : qc, bas[gi]);
+                }
+#pragma unroll
+                for (int ei = 0; ei < NEQ; ++ei)
+#pragma unroll
+                    for (int gi = 0; gi < G; ++gi)
+                    {
+                        // (a padding trip writes rows of the next chunk's share that this same thread rewrites later)
+                        if (on[gi])
+                            dst[(gi * n_parts * NEQ + ei) * ld] = entry(cf + (gi * n_parts * NEQ + ei) * 4, bas[gi]);
+                        if (dual and on[gi])
+                            dst2[(gi * n_parts * NEQ + ei) * LDA] = entry(cf2 + (gi * n_parts * NEQ + ei) * 4, bas[gi]);
+                    }
+                if (rhs_row)
+#pragma unroll
+                    for (int gi = 0; gi < G; ++gi)
+                        if (on[gi])
+#pragma unroll
+                            for (int r = 0; r < NRHS; ++r)
+                            {
+                                const double* c4  = cr + (gi * n_parts * NRHS + r) * 4;
+                                double        acc = c4[0] * bas[gi][0];
+#pragma unroll
+                                for (int d = 0; d < DIM; ++d)
+                                    acc = fma(c4[1 + d], bas[gi][1 + d], acc);
+                                f_acc[r] += acc;
+                            }
+                dst += G * n_parts * NEQ * ld;
+                cf += G * n_parts * NEQ * 4;
+                dst2 += G * n_parts * NEQ * LDA;
+                cf2 += G * n_parts * NEQ * 4;
+                cr += G * n_parts * NRHS * 4;
+            }
+        }
+        else
+        {
+            for (int qc = part; qc < QC; qc += n_parts)
+            {
+                double bas[4];
+                basisAt(qc, bas);
+                for (int ei = 0; ei < n_eq; ++ei)
+                {
+                    dst[ei * ld] = entry(cf + ei * 4, bas);
+                    if (dual)
+                        dst2[ei * LDA] = entry(cf2 + ei * 4, bas);
+                }
+                if (rhs_row)
+#pragma unroll
+                    for (int r = 0; r < NRHS; ++r)
+                    {
+                        double acc = cr[r * 4] * bas[0];
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d)
+                            acc = fma(cr[r * 4 + 1 + d], bas[1 + d], acc);
+                        f_acc[r] += acc;
+                    }
+                dst += n_parts * neq * ld;
+                cf += n_parts * neq * 4;
                 dst2 += n_parts * neq * LDA;
                 cf2 += n_parts * neq * 4;
+                cr += n_parts * NRHS * 4;
             }
-            if (rhs_row)
-#pragma unroll
-                for (int r = 0; r < NRHS; ++r)
-                {
-                    double acc = cr[r * 4] * bas[0];
-#pragma unroll
-                    for (int d = 0; d < DIM; ++d)
-                        acc = fma(cr[r * 4 + 1 + d], bas[1 + d], acc);
-                    f_acc[r] += acc;
-                }
-            dst += n_parts * neq * ld;
-            cf += n_parts * neq * 4;
-            cr += n_parts * NRHS * 4;
         }
     };
     const auto build = [&](int c) {
@@ -448,6 +541,8 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
     // ---- the build's table reads are L2 round trips (ncu r1 v3: 30 % of its samples on the long scoreboard): pull the slice of
     // chunk c into L1 one iteration before it is built — same thread, same addresses, no registers held
     const auto prefetchTables = [&](int c) {
+        if (tensor)
+            return;
         for (int pc = tid; pc < n_pcols * n_parts; pc += T)
         {
             const int  pcol = pc % n_pcols, part = pc / n_pcols;
@@ -469,27 +564,41 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
     };
 
     // ---- accumulators: warp (wy, wx) owns rows wy*32 .. +32, columns wx*32 .. +32 of the tile as 4 x 4 DMMA tiles
-    // For u == v the warp tiles strictly above the diagonal are dead. Warps sit on the scheduler `warp % 4`, so the live tiles are
-    // dealt to the warps in order (warp t takes the t-th live tile): every scheduler gets its share of the DMMA work.
-    int wy = warp / Cfg::WN, wx = warp % Cfg::WN;
-    bool warp_live = true;
+    // For u == v the warp tiles strictly above the diagonal are dead, and a warp tile ON the diagonal only needs its 8 x 8 DMMA
+    // tiles on or below it (10 of 16). Warps sit on the scheduler `warp % 4`, so the live tiles are dealt to the warps by cost:
+    // warp t takes the t-th tile of the order [diagonal, diagonal, full, full, diagonal, diagonal, full, ...] — for the 4 x 4 case
+    // the schedulers get 2 diagonal + 1 full, 2 diagonal + 1 full, 2 full, 2 full tiles (2.25 / 2.25 / 2 / 2 tile units).
+    int  wy = warp / Cfg::WN, wx = warp % Cfg::WN;
+    bool warp_live = true, warp_on_diag = false;
     if (diag_pair)
     {
         warp_live = false;
-        int n_live = 0;
+        int n_d = 0, n_f = 0; // diagonal / full live tiles met so far
+        // position of the k-th diagonal (full) tile in the dealing order: two diagonals, two fulls, two diagonals, two fulls, rest
+        const auto slotOfDiag = [](int k) { return k < 2 ? k : k < 4 ? k + 2 : -1; };
+        const auto slotOfFull = [](int k) { return k < 2 ? k + 2 : k + 4; };
+        int n_diag_total = 0;
+        for (int i = 0; i < Cfg::WM * Cfg::WN; ++i)
+            n_diag_total += col0 + (i % Cfg::WN) * 32 == row0 + (i / Cfg::WN) * 32;
+        const bool pattern = n_diag_total == 4 and Cfg::WM * Cfg::WN == 16; // otherwise: diagonals first, then the full tiles
+        int n_full_before = 0;
         for (int i = 0; i < Cfg::WM * Cfg::WN; ++i)
         {
             const int ty = i / Cfg::WN, tx = i % Cfg::WN;
-            if (col0 + tx * 32 <= row0 + ty * 32 + 31) // not strictly above the diagonal
+            if (col0 + tx * 32 > row0 + ty * 32 + 31) // strictly above the diagonal
+                continue;
+            const bool on_diag = col0 + tx * 32 == row0 + ty * 32;
+            const int  slot    = pattern ? (on_diag ? slotOfDiag(n_d) : slotOfFull(n_f)) : (on_diag ? n_d : n_diag_total + n_f);
+            if (slot == warp)
             {
-                if (n_live == warp)
-                {
-                    wy        = ty;
-                    wx        = tx;
-                    warp_live = true;
-                }
-                ++n_live;
+                wy           = ty;
+                wx           = tx;
+                warp_live    = true;
+                warp_on_diag = on_diag;
             }
+            n_d += on_diag;
+            n_f += not on_diag;
+            (void)n_full_before;
         }
     }
     const int g = lane >> 2, tq = lane & 3;
@@ -507,6 +616,9 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
     if (n_chunks > 1)
         prefetchTables(1);
     __syncthreads();
+#ifdef L3B_ASM_TIMING
+    long long tm_build = 0, tm_mma = 0, tm_bar = 0;
+#endif
     for (int c = 0; c < n_chunks; ++c)
     {
         if (c + 1 < n_chunks and (c + 1) % cps == 0)
@@ -515,10 +627,12 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
             perPoint((c + 1) / cps);
             __syncthreads();
         }
-        // Two of the four warps of every scheduler contract first and build afterwards, the other two the other way round:
-        // the DMMA pipe always has contracting warps while the builders wait on their table loads (both orders are legal:
-        // the contraction reads panel c & 1, the build writes panel (c + 1) & 1).
-        const bool build_first = ((warp >> 2) & 1) == 0 or not warp_live;
+        // every warp builds its share of the next panel, then contracts the current one (building in some warps while others
+        // contract was measured slower: the build's short fp64 chains starve behind the DMMA stream)
+        const bool build_first = true;
+#ifdef L3B_ASM_TIMING
+        long long t0 = clock64();
+#endif
         const auto buildNext   = [&] {
             if (c + 2 < n_chunks)
                 prefetchTables(c + 2);
@@ -527,6 +641,10 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
         };
         if (build_first)
             buildNext();
+#ifdef L3B_ASM_TIMING
+        long long t1 = clock64();
+        if (build_first) tm_build += t1 - t0;
+#endif
         if (warp_live)
         {
             const double* const pb_c = s_pb + (c & 1) * KCMAX * LDB + wx * 32 + g;
@@ -546,13 +664,34 @@ __global__ void __launch_bounds__(AsmDmmaCfg< KernelT, DIM, P >::threads, AsmDmm
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                        if (j <= i or not warp_on_diag) // a diagonal warp tile: nothing above its own diagonal is scattered
+                            dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
         }
+#ifdef L3B_ASM_TIMING
+        long long t2 = clock64();
+        tm_mma += t2 - t1;
+#endif
         if (not build_first)
             buildNext();
+#ifdef L3B_ASM_TIMING
+        long long t3 = clock64();
+        if (not build_first) tm_build += t3 - t2;
+#endif
         __syncthreads();
+#ifdef L3B_ASM_TIMING
+        tm_bar += clock64() - t3;
+#endif
     }
+#ifdef L3B_ASM_TIMING
+    if (lane == 0 and blockIdx.x < 4096 and warp < 16)
+    {
+        g_asm_timing[blockIdx.x][warp][0] = tm_build;
+        g_asm_timing[blockIdx.x][warp][1] = tm_mma;
+        g_asm_timing[blockIdx.x][warp][2] = tm_bar;
+        g_asm_timing[blockIdx.x][warp][3] = n_eq * 16 + (diag_pair ? 1 : 0);
+    }
+#endif
 
     // ---- scatter into the CRS values: slot(row (a,u), col (b,v)) = row_ptr[dof(a,u)] + dof_inds[v] * deg(node a) + pos[e][a][b]
     // (column-dof-major rows, device_common.cuh: consecutive nodes b are consecutive doubles, so the REDs of a warp share sectors)

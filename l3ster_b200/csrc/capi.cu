@@ -416,6 +416,8 @@ struct l3b_context
     {
         int              n_qp = 0;
         DevBuf< double > vals, ders, pts, wts; // domain: one table; boundary: n_sides tables back to back
+        DevBuf< double > t1d;                  // domain only: 1-D interpolation and derivative tables [2][nb][nq]
+        int              nq1d = 0;
     };
     std::map< std::tuple< int, int, int, bool >, std::unique_ptr< DenseDev > > dense;
 
@@ -448,6 +450,16 @@ struct l3b_context
             ders.insert(ders.end(), t.derivatives.begin(), t.derivatives.end());
             pts.insert(pts.end(), t.points.begin(), t.points.end());
             wts.insert(wts.end(), t.weights.begin(), t.weights.end());
+        }
+        if (not boundary)
+        {
+            const auto&           t = tables1d(order, nq);
+            std::vector< double > both(t.interp);
+            both.insert(both.end(), t.der.begin(), t.der.end());
+            d->t1d.alloc(both.size());
+            d->t1d.upload(both.data(), both.size(), stream);
+            d->nq1d = nq;
+            cudaCheck(cudaStreamSynchronize(stream), "1-D table upload"); // `both` dies at the end of this block
         }
         d->vals.alloc(vals.size());
         d->ders.alloc(ders.size());
@@ -643,6 +655,8 @@ void setDense(ElemArgs& a, l3b_mesh* mesh, const KernelUse& use, bool boundary)
     a.tab_pts     = d.pts.ptr;
     a.tab_wts     = d.wts.ptr;
     a.n_qp        = d.n_qp;
+    a.tab1d       = boundary ? nullptr : d.t1d.ptr;
+    a.nq1d        = d.nq1d;
 }
 } // namespace
 

@@ -75,6 +75,10 @@ struct ElemArgs
     const double* tab_pts;
     const double* tab_wts;
     int           n_qp;
+    // domain quadrature of tensor elements: the 1-D tables behind the dense ones, [interp (nb x nq) | der (nb x nq)], b-major, and
+    // nq; point q = qx + nq (qy + nq qz), node a = ix + nb (iy + nb iz). Null for side quadratures.
+    const double* tab1d;
+    int           nq1d;
     // CRS (assembly). Device layout of the values: row (n, d) starts at row_ptr = dpn * (dpn * node_ptr[n] + d * deg(n)) and holds its
     // entries column-dof-major: (neighbour k, column dof v) sits at v * deg(n) + k, so that consecutive neighbour nodes are consecutive
     // doubles (the scatter's atomics then share 32-byte sectors). l3b_asm_download returns the reference's node-major row layout.
