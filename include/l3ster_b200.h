@@ -149,6 +149,9 @@ int l3b_asm_end_assembly_ranked(l3b_asm* sys, int64_t n_dirichlet, const int32_t
                                 int64_t n_owned_dofs);
 /* CG + native Jacobi on the assembled matrix (solve/BelosSolvers.hpp:116-123, NativePreconditioners.hpp:36-100) */
 int l3b_asm_solve_cg(l3b_asm* sys, double tol, int max_iters, double* x /* host, n_dofs */, double* achieved_tol, int* iters);
+/* GMRES + native Jacobi on the assembled matrix (solve/BelosSolvers.hpp:125-131) */
+int l3b_asm_solve_gmres(l3b_asm* sys, double tol, int restart_length, int max_restarts, int max_iters, double* x, double* achieved_tol,
+                        int* iters);
 /* timing of the last l3b_asm_assemble kernel launches (ms, CUDA events on the context stream) */
 double l3b_asm_last_kernel_ms(const l3b_asm* sys);
 
@@ -177,6 +180,8 @@ int l3b_mf_apply_device(l3b_mf* sys, const double* x, double* y, int n_cols, dou
 int l3b_mf_apply(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta);
 /* CG + native Jacobi, x0 = 0, rhs = system rhs column 0 (benchmarks/Diffusion3D.hpp:115-118) */
 int l3b_mf_solve_cg(l3b_mf* sys, double tol, int max_iters, double* x /* host */, double* achieved_tol, int* iters);
+int l3b_mf_solve_gmres(l3b_mf* sys, double tol, int restart_length, int max_restarts, int max_iters, double* x /* host */,
+                       double* achieved_tol, int* iters);
 /* The same apply split into the phases MatrixFreeSystem::applyImpl overlaps with its halo exchange (:1046-1122):
  *   L3B_APPLY_INIT     y <- beta y                                   (:1038)
  *   L3B_APPLY_ELEMENTS y[dofs(e)] += alpha K_e x[dofs(e)] for the domain elements e in [elem_begin, elem_end) — the caller passes
@@ -203,6 +208,12 @@ int l3b_vec_scatter_add(l3b_context* ctx, double* dst, int64_t ld, const int32_t
  * scalars at s, ordered after the work already on the context stream (may be NULL on one rank). Both return 0 on success. */
 typedef int (*l3b_apply_callback)(void* user, const double* x, double* y);
 typedef int (*l3b_allreduce_callback)(void* user, double* scalars, int n);
+/* Restarted GMRES with the same callbacks: Belos "Pseudoblock GMRES" as solve/BelosSolvers.hpp:42-131 configures it ("Num Blocks" =
+ * restart_length 250, "Maximum Restarts" 39 by default, solve/SolverInterface.hpp:26-37), left Jacobi preconditioner, x0 = 0,
+ * convergence on the preconditioned residual norm of the Givens recurrence (Belos' implicit test, absolute). */
+int l3b_gmres_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_apply_callback apply, l3b_allreduce_callback allreduce,
+                     void* user, const double* diag, const double* b, double* x, double tol, int restart_length, int max_restarts,
+                     int max_iters, double* achieved_tol, int* iters);
 int l3b_pcg_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_apply_callback apply, l3b_allreduce_callback allreduce,
                    void* user, const double* diag, const double* b, double* x, double tol, int max_iters, double* achieved_tol,
                    int* iters);

@@ -69,6 +69,7 @@ EXPORTED_SYMBOLS = [
     "l3b_mf_apply_phase_device", "l3b_vec_gather", "l3b_vec_scatter_add",
     "l3b_mf_end_assembly_begin", "l3b_mf_end_assembly_finish", "l3b_mf_device_diag", "l3b_mf_device_rhs", "l3b_pcg_device",
     "l3b_asm_spmv_device", "l3b_asm_diag_device", "l3b_asm_device_rhs", "l3b_asm_end_assembly_ranked",
+    "l3b_gmres_device", "l3b_asm_solve_gmres", "l3b_mf_solve_gmres",
 ]
 
 
@@ -143,6 +144,9 @@ def lib():
     L.l3b_mf_apply_phase_device.argtypes = [vp, vp, vp, i32, dbl, dbl, i32, i64, i64]
     L.l3b_vec_gather.argtypes = [vp, vp, i64, vp, i64, i32, vp]
     L.l3b_mf_end_assembly_begin.argtypes = [vp]
+    L.l3b_asm_solve_gmres.argtypes = [vp, dbl, i32, i32, i32, vp, C.POINTER(dbl), C.POINTER(i32)]
+    L.l3b_mf_solve_gmres.argtypes = [vp, dbl, i32, i32, i32, vp, C.POINTER(dbl), C.POINTER(i32)]
+    L.l3b_gmres_device.argtypes = [vp, i64, i64, APPLY_CB, ALLREDUCE_CB, vp, vp, vp, vp, dbl, i32, i32, i32, C.POINTER(dbl), C.POINTER(i32)]
     L.l3b_asm_spmv_device.argtypes = [vp, vp, vp]
     L.l3b_asm_diag_device.argtypes = [vp, vp]
     L.l3b_asm_device_rhs.argtypes = [vp]
@@ -535,6 +539,13 @@ class AssembledSystem:
         self.ctx._chk(lib().l3b_asm_solve_cg(self._h, tol, max_iters, _p(x), C.byref(at), C.byref(it)))
         return x, at.value, it.value
 
+    def solve_gmres(self, tol=1e-6, restart_length=250, max_restarts=39, max_iters=10000):
+        """lstr::Gmres with the native Jacobi preconditioner (solve/BelosSolvers.hpp:125-131, SolverInterface.hpp:26-37 defaults)"""
+        x = np.zeros(self.n_dofs)
+        at, it = C.c_double(), C.c_int()
+        self.ctx._chk(lib().l3b_asm_solve_gmres(self._h, tol, restart_length, max_restarts, max_iters, _p(x), C.byref(at), C.byref(it)))
+        return x, at.value, it.value
+
     @property
     def last_kernel_ms(self):
         return lib().l3b_asm_last_kernel_ms(self._h)
@@ -615,6 +626,12 @@ class MatrixFreeSystem:
         x = np.zeros(self.n_dofs)
         at, it = C.c_double(), C.c_int()
         self.ctx._chk(lib().l3b_mf_solve_cg(self._h, tol, max_iters, _p(x), C.byref(at), C.byref(it)))
+        return x, at.value, it.value
+
+    def solve_gmres(self, tol=1e-6, restart_length=250, max_restarts=39, max_iters=10000):
+        x = np.zeros(self.n_dofs)
+        at, it = C.c_double(), C.c_int()
+        self.ctx._chk(lib().l3b_mf_solve_gmres(self._h, tol, restart_length, max_restarts, max_iters, _p(x), C.byref(at), C.byref(it)))
         return x, at.value, it.value
 
     @property

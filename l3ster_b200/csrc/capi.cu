@@ -271,6 +271,43 @@ __global__ void hadamardKernel(double* z, const double* minv, const double* r, l
     for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
         z[i] = minv[i] * r[i];
 }
+// classical Gram-Schmidt pass of GMRES: out[i] += V_i . w for i < m (V: m vectors of leading dimension ld)
+__global__ void gsDotsKernel(const double* V, long long ld, int m, const double* w, long long n, double* out)
+{
+    for (int i = 0; i < m; ++i)
+    {
+        const double* v = V + i * ld;
+        double        s = 0.;
+        for (long long k = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; k < n; k += static_cast< long long >(gridDim.x) * blockDim.x)
+            s = fma(v[k], w[k], s);
+        s = blockSum(s);
+        if (threadIdx.x == 0)
+            atomicAdd(out + i, s);
+    }
+}
+// w += sign * sum_{i < m} h[i] V_i
+__global__ void gsAxpyKernel(const double* V, long long ld, int m, const double* h, double sign, double* w, long long n)
+{
+    for (long long k = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; k < n; k += static_cast< long long >(gridDim.x) * blockDim.x)
+    {
+        double acc = 0.;
+        for (int i = 0; i < m; ++i)
+            acc = fma(h[i], V[i * ld + k], acc);
+        w[k] = fma(sign, acc, w[k]);
+    }
+}
+// w = minv * (b - w)
+__global__ void precResidualKernel(double* w, const double* b, const double* minv, long long n)
+{
+    for (long long k = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; k < n; k += static_cast< long long >(gridDim.x) * blockDim.x)
+        w[k] = minv[k] * (b[k] - w[k]);
+}
+// v = a * w
+__global__ void scaledCopyKernel(double* v, const double* w, double a, long long n)
+{
+    for (long long k = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; k < n; k += static_cast< long long >(gridDim.x) * blockDim.x)
+        v[k] = a * w[k];
+}
 // dof-level CRS helpers on the node-block layout: row (n, d) = for each neighbour m (ascending): dofs_per_node entries
 __global__ void rowPtrKernel(const long long* node_ptr, long long n_nodes, int dpn, long long* row_ptr)
 {
@@ -864,6 +901,122 @@ void pcg(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Reduce
     *achieved = rnorm;
     *iters    = it;
 }
+// Restarted GMRES, left-preconditioned with native Jacobi — Belos "Pseudoblock GMRES" as the reference configures it
+// (solve/BelosSolvers.hpp:42-131: "Num Blocks" = restart_length, "Maximum Restarts", left preconditioner, absolute residual by
+// default), x0 = 0. Orthogonalisation: classical Gram-Schmidt applied twice (two fused dot/update kernel pairs per iteration — the
+// all-reduce friendly form; Belos' default DGKS is the same idea). The convergence test is Belos' implicit one: the norm of the
+// preconditioned residual from the Givens recurrence, against `tol`.
+template < typename Apply, typename Reduce >
+void gmres(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Reduce&& reduce, const double* diag, const double* b,
+           double* x /* device */, double tol, int restart, int max_restarts, int max_iters, double* achieved, int* iters)
+{
+    const int        m = std::max(1, restart);
+    DevBuf< double > V(static_cast< size_t >(m + 1) * n), w(n_local), xin(n_local), minv(n), hd(m + 2);
+    const auto       s = ctx->stream;
+    const auto       g = gridFor(n);
+    std::vector< double > H(static_cast< size_t >(m + 1) * m, 0.), cs(m), sn(m), gvec(m + 1), hcol(m + 2), y(m);
+    jacobiInvertKernel<<< g, 256, 0, s >>>(diag, minv.ptr, n, 1., 0.);
+    cudaCheck(cudaMemsetAsync(x, 0, n * sizeof(double), s), "memset");
+    xin.zero(s);
+    w.zero(s);
+    int    it = 0, restarts = 0;
+    double res = 0.;
+    const auto dotsTo = [&](int cnt, const double* vec) { // hd[0..cnt) = V_i . vec, all-reduced, copied to hcol
+        cudaCheck(cudaMemsetAsync(hd.ptr, 0, (m + 2) * sizeof(double), s), "memset");
+        gsDotsKernel<<< g, 256, 0, s >>>(V.ptr, n, cnt, vec, n, hd.ptr);
+        reduce(hd.ptr, cnt);
+    };
+    while (true)
+    {
+        // r = M^-1 (b - A x)
+        cudaCheck(cudaMemcpyAsync(xin.ptr, x, n * sizeof(double), cudaMemcpyDeviceToDevice, s), "copy");
+        apply(xin.ptr, w.ptr);
+        precResidualKernel<<< g, 256, 0, s >>>(w.ptr, b, minv.ptr, n); // w = M^-1 (b - A x)
+        cudaCheck(cudaMemsetAsync(hd.ptr, 0, (m + 2) * sizeof(double), s), "memset");
+        dot2Kernel<<< g, 256, 0, s >>>(w.ptr, w.ptr, nullptr, nullptr, n, hd.ptr);
+        reduce(hd.ptr, 1);
+        double beta2 = 0.;
+        cudaCheck(cudaMemcpyAsync(&beta2, hd.ptr, sizeof(double), cudaMemcpyDeviceToHost, s), "copy");
+        cudaCheck(cudaStreamSynchronize(s), "sync");
+        const double beta = std::sqrt(beta2);
+        res               = beta;
+        if (not(beta > tol) or it >= max_iters or restarts > max_restarts)
+            break;
+        scaledCopyKernel<<< g, 256, 0, s >>>(V.ptr, w.ptr, 1. / beta, n);
+        std::fill(gvec.begin(), gvec.end(), 0.);
+        gvec[0] = beta;
+        int j   = 0;
+        for (; j < m and it < max_iters; ++j)
+        {
+            // w = M^-1 A v_j
+            cudaCheck(cudaMemcpyAsync(xin.ptr, V.ptr + static_cast< size_t >(j) * n, n * sizeof(double), cudaMemcpyDeviceToDevice, s), "copy");
+            apply(xin.ptr, w.ptr);
+            hadamardKernel<<< g, 256, 0, s >>>(w.ptr, minv.ptr, w.ptr, n);
+            std::fill(hcol.begin(), hcol.end(), 0.);
+            for (int pass = 0; pass < 2; ++pass) // classical Gram-Schmidt, twice
+            {
+                dotsTo(j + 1, w.ptr);
+                gsAxpyKernel<<< g, 256, 0, s >>>(V.ptr, n, j + 1, hd.ptr, -1., w.ptr, n);
+                std::vector< double > part(j + 1);
+                cudaCheck(cudaMemcpyAsync(part.data(), hd.ptr, (j + 1) * sizeof(double), cudaMemcpyDeviceToHost, s), "copy");
+                cudaCheck(cudaStreamSynchronize(s), "sync");
+                for (int i = 0; i <= j; ++i)
+                    hcol[i] += part[i];
+            }
+            cudaCheck(cudaMemsetAsync(hd.ptr, 0, (m + 2) * sizeof(double), s), "memset");
+            dot2Kernel<<< g, 256, 0, s >>>(w.ptr, w.ptr, nullptr, nullptr, n, hd.ptr);
+            reduce(hd.ptr, 1);
+            double nw2 = 0.;
+            cudaCheck(cudaMemcpyAsync(&nw2, hd.ptr, sizeof(double), cudaMemcpyDeviceToHost, s), "copy");
+            cudaCheck(cudaStreamSynchronize(s), "sync");
+            hcol[j + 1] = std::sqrt(nw2);
+            if (hcol[j + 1] > 0.)
+                scaledCopyKernel<<< g, 256, 0, s >>>(V.ptr + static_cast< size_t >(j + 1) * n, w.ptr, 1. / hcol[j + 1], n);
+            // Givens rotations on the new column
+            for (int i = 0; i < j; ++i)
+            {
+                const double t = cs[i] * hcol[i] + sn[i] * hcol[i + 1];
+                hcol[i + 1]    = -sn[i] * hcol[i] + cs[i] * hcol[i + 1];
+                hcol[i]        = t;
+            }
+            const double d = std::hypot(hcol[j], hcol[j + 1]);
+            cs[j]          = d > 0. ? hcol[j] / d : 1.;
+            sn[j]          = d > 0. ? hcol[j + 1] / d : 0.;
+            hcol[j]        = d;
+            hcol[j + 1]    = 0.;
+            gvec[j + 1]    = -sn[j] * gvec[j];
+            gvec[j]        = cs[j] * gvec[j];
+            for (int i = 0; i <= j; ++i)
+                H[static_cast< size_t >(i) * m + j] = hcol[i];
+            ++it;
+            res = std::fabs(gvec[j + 1]);
+            if (not(res > tol))
+            {
+                ++j;
+                break;
+            }
+        }
+        // x += V_j y, R y = g
+        for (int i = j - 1; i >= 0; --i)
+        {
+            double acc = gvec[i];
+            for (int k = i + 1; k < j; ++k)
+                acc -= H[static_cast< size_t >(i) * m + k] * y[k];
+            y[i] = acc / H[static_cast< size_t >(i) * m + i];
+        }
+        hd.upload(y.data(), j, s);
+        gsAxpyKernel<<< g, 256, 0, s >>>(V.ptr, n, j, hd.ptr, 1., x, n);
+        cudaCheck(cudaStreamSynchronize(s), "sync");
+        if (not(res > tol) or it >= max_iters)
+            break;
+        ++restarts;
+        if (restarts > max_restarts)
+            break;
+    }
+    cudaCheck(cudaGetLastError(), "gmres");
+    *achieved = res;
+    *iters    = it;
+}
 } // namespace
 
 extern "C"
@@ -1315,6 +1468,28 @@ int l3b_asm_spmv(l3b_asm* sys, const double* x, double* y)
         cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "spmv");
     });
 }
+int l3b_asm_solve_gmres(l3b_asm* sys, double tol, int restart_length, int max_restarts, int max_iters, double* x, double* achieved_tol,
+                        int* iters)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (sys->open)
+            fail(L3B_ERR_STATE, "`solve()` was called before `endAssembly()`");
+        const auto       n = sys->n_dofs;
+        DevBuf< double > diag(n), dx(n);
+        extractDiagKernel<<< static_cast< unsigned >((n + 255) / 256), 256, 0, sys->ctx->stream >>>(
+            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, diag.ptr);
+        const long long threads = n * 32;
+        gmres(
+            sys->ctx, n, n,
+            [&](const double* in, double* out) {
+                spmvKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
+                    sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, in, out);
+            },
+            [](double*, int) {}, diag.ptr, sys->rhs.ptr, dx.ptr, tol, restart_length, max_restarts, max_iters, achieved_tol, iters);
+        dx.download(x, n, sys->ctx->stream);
+        cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "solve");
+    });
+}
 int l3b_asm_spmv_device(l3b_asm* sys, const double* x, double* y)
 {
     return guardedCtx(sys->ctx, [&] {
@@ -1489,6 +1664,41 @@ double* l3b_mf_device_diag(l3b_mf* sys)
 double* l3b_mf_device_rhs(l3b_mf* sys)
 {
     return sys->rhs.ptr;
+}
+int l3b_gmres_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_apply_callback apply, l3b_allreduce_callback allreduce,
+                     void* user, const double* diag, const double* b, double* x, double tol, int restart_length, int max_restarts,
+                     int max_iters, double* achieved_tol, int* iters)
+{
+    return guardedCtx(ctx, [&] {
+        if (apply == nullptr or n_owned > n_local or n_owned < 0 or restart_length < 1)
+            fail(L3B_ERR_INVALID_ARG, "l3b_gmres_device: invalid arguments");
+        gmres(
+            ctx, n_local, n_owned,
+            [&](const double* in, double* out) {
+                if (apply(user, in, out) != 0)
+                    fail(L3B_ERR_INVALID_ARG, "l3b_gmres_device: the apply callback failed");
+            },
+            [&](double* sc, int n) {
+                if (allreduce != nullptr and allreduce(user, sc, n) != 0)
+                    fail(L3B_ERR_INVALID_ARG, "l3b_gmres_device: the all-reduce callback failed");
+            },
+            diag, b, x, tol, restart_length, max_restarts, max_iters, achieved_tol, iters);
+    });
+}
+int l3b_mf_solve_gmres(l3b_mf* sys, double tol, int restart_length, int max_restarts, int max_iters, double* x, double* achieved_tol, int* iters)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (not sys->closed)
+            fail(L3B_ERR_STATE, "`solve()` was called before `endAssembly()`");
+        if (sys->n_rhs != 1)
+            fail(L3B_ERR_INVALID_ARG, "the GMRES driver handles one right-hand side");
+        DevBuf< double > dx(sys->n_dofs);
+        gmres(
+            sys->ctx, sys->n_dofs, sys->n_dofs, [&](const double* in, double* out) { mfApplyDevice(sys, in, out, 1, 1., 0.); },
+            [](double*, int) {}, sys->diag.ptr, sys->rhs.ptr, dx.ptr, tol, restart_length, max_restarts, max_iters, achieved_tol, iters);
+        dx.download(x, sys->n_dofs, sys->ctx->stream);
+        cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "solve");
+    });
 }
 int l3b_pcg_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_apply_callback apply, l3b_allreduce_callback allreduce,
                    void* user, const double* diag, const double* b, double* x, double tol, int max_iters, double* achieved_tol,

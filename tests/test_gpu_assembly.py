@@ -217,3 +217,46 @@ def test_karman_kernels_assembled(ctx):
         vals_o, rhs_o = sys_o.get()
         vals_g, rhs_g = sys_g.download()
         assert rel_err(vals_g, vals_o) < TOL and rel_err(rhs_g, rhs_o) < TOL, kname
+
+
+def test_gmres_matches_cg_and_direct_solve(ctx):
+    """lstr::Gmres (Belos Pseudoblock GMRES, left Jacobi, restart) on the assembled and on the matrix-free diffusion system: same
+    solution as CG and as a direct solve of the oracle matrix (tests/SolverTests.cpp:172-238 check convergence only); a short
+    restart length exercises the restart path."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    pm = PairedMesh(2, default_dists(2, 4), 4)  # example02_domain is registered for quad p=4, nq=5
+    mesh = pm.upload(ctx)
+    U = 3
+    nodes = pm.host.boundary_nodes([1, 2, 3, 4])
+    dofs = (nodes * U).astype(np.int32)
+    dvals = np.random.default_rng(2).uniform(-1, 1, size=(len(dofs), 1))
+    s = l3b.AssembledSystem(ctx, mesh, U)
+    s.beginAssembly()
+    s.assembleProblem("example02_domain")
+    s.endAssembly(dofs, dvals)
+    so = pm.orc.assembled_system(U)
+    so.assemble("example02_domain")
+    so.apply_dirichlet(dofs, dvals)
+    v_o, r_o = so.get()
+    A = sp.csr_matrix((v_o, so.col_ind, so.row_ptr), shape=(so.n_dofs,) * 2).tocsc()
+    ref = spla.spsolve(A, r_o[:, 0])
+    x_cg, _, it_cg = s.solve(tol=1e-11, max_iters=20000)
+    for restart in (250, 30):
+        x_g, res, it_g = s.solve_gmres(tol=1e-11, restart_length=restart, max_restarts=400, max_iters=20000)
+        assert res <= 1e-11 and it_g > 0
+        assert np.abs(x_g - ref).max() < 1e-8 * max(1.0, np.abs(ref).max()), restart
+        assert np.abs(x_g - x_cg).max() < 1e-8 * max(1.0, np.abs(ref).max())
+    # full GMRES on an SPD matrix needs no more iterations than CG needs for the same (preconditioned) residual
+    assert s.solve_gmres(tol=1e-11, restart_length=2000)[2] <= it_cg + 5
+    # matrix-free operator, same system
+    mask = np.zeros(pm.n_nodes * U, dtype=np.uint8)
+    mask[dofs] = 1
+    vals = np.zeros((pm.n_nodes * U, 1))
+    vals[dofs] = dvals
+    mf = l3b.MatrixFreeSystem(ctx, mesh, U, 1, mask, vals)
+    mf.assembleProblem("example02_domain")
+    mf.endAssembly()
+    x_m, res_m, it_m = mf.solve_gmres(tol=1e-11, restart_length=250)
+    assert np.abs(x_m - ref).max() < 1e-8 * max(1.0, np.abs(ref).max())
