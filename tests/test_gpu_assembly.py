@@ -260,3 +260,37 @@ def test_gmres_matches_cg_and_direct_solve(ctx):
     mf.endAssembly()
     x_m, res_m, it_m = mf.solve_gmres(tol=1e-11, restart_length=250)
     assert np.abs(x_m - ref).max() < 1e-8 * max(1.0, np.abs(ref).max())
+
+
+def test_assembly_state_machine_and_argument_errors(ctx):
+    """The OpenForAssembly <-> Closed state machine of AssembledSystem (AssembledSystem.hpp:455-461) and the argument checks of the
+    C ABI surface as errors with the reference's wording, never as silent wrong results."""
+    pm = PairedMesh(2, default_dists(2, 2), 4)
+    mesh = pm.upload(ctx)
+    s = l3b.AssembledSystem(ctx, mesh, 3)
+    with pytest.raises(l3b.L3BError):  # assembleProblem before beginAssembly
+        s.assembleProblem("example02_domain")
+    s.beginAssembly()
+    with pytest.raises(l3b.L3BError):  # solve while open
+        s.solve()
+    with pytest.raises(l3b.L3BError):  # a 3-D kernel on a 2-D mesh
+        s.assembleProblem("bench_diffusion3d")
+    with pytest.raises(l3b.L3BError):  # dof index out of range
+        s.assembleProblem("example02_domain", dof_inds=[0, 1, 7])
+    with pytest.raises(l3b.L3BError):  # boundary kernel without boundary ids on a mesh without side table
+        m2 = l3b.Mesh(ctx, 2, 4, pm.verts, pm.host.nodes, None, pm.n_nodes, pm.n_nodes)
+        l3b.AssembledSystem(ctx, m2, 3).assembleProblem("example02_bc", boundary_ids=[1])
+    s.assembleProblem("example02_domain")
+    s.endAssembly()
+    with pytest.raises(l3b.L3BError):  # endAssembly twice
+        s.endAssembly()
+    # the matrix-free system has the same gate
+    mf = l3b.MatrixFreeSystem(ctx, mesh, 3, 1)
+    mf.assembleProblem("example02_domain")
+    with pytest.raises(l3b.L3BError):  # apply before endAssembly
+        mf.apply(np.zeros((pm.n_nodes * 3, 1)))
+    mf.endAssembly()
+    with pytest.raises(l3b.L3BError):  # assembleProblem after endAssembly
+        mf.assembleProblem("example02_domain")
+    with pytest.raises(l3b.L3BError):  # 2 columns into a 1-rhs system
+        mf.apply(np.zeros((pm.n_nodes * 3, 2)))
