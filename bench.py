@@ -344,6 +344,7 @@ def main():
         yh = torch.empty(n_local, dtype=torch.float64).pin_memory()
         xd = xh.to("cuda")
         yd = torch.zeros_like(xd)
+        torch.cuda.synchronize()  # filled on torch's stream; the library works on its own non-blocking stream
 
         def step():
             op.apply(xd, yd, 1.0, 0.0)

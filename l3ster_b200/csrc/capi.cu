@@ -154,9 +154,15 @@ __global__ void hexGeometryKernel(const double* verts, long long n_elems, double
                 for (int s = 0; s < 3; ++s)
                     Jt[d][s] = g[(1 << d) * 3 + s];
             g[hex_geo_det] = invert< 3 >(Jt, Jti);
+            bool diagonal = true;
             for (int s = 0; s < 3; ++s)
                 for (int d = 0; d < 3; ++d)
+                {
                     g[hex_geo_jti + s * 3 + d] = Jti[s][d];
+                    diagonal                   = diagonal and (s == d or Jti[s][d] == 0.);
+                }
+            if (diagonal)
+                g[hex_geo_affine] = 2.; // axis-aligned box
         }
     }
 }

@@ -477,6 +477,10 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
                         fval[f][q] = s_V[((F0 + f) * NQ + q) * (EPB * PSZ) + col_off];
             }
             bool violated = false;
+            // DIAGJ: the element is an axis-aligned box (J^-1 diagonal, flagged in the geometry record): physical gradients and the
+            // pull-back of the fluxes are three multiplies per unknown instead of 3 x 3 multiply-adds
+            const auto pointStage = [&](auto diag_tag) {
+                constexpr bool DIAGJ = decltype(diag_tag)::value;
 #pragma unroll
             for (int r = 0; r < NRHS; ++r)
             {
@@ -517,7 +521,7 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
                         in.field_vals[f] = fval[f][qz];
 #pragma unroll
                         for (int s = 0; s < 3; ++s)
-                            in.field_ders[s][f] = fma(Jti[s][2], dzf, fma(Jti[s][1], dyf, Jti[s][0] * dxf));
+                            in.field_ders[s][f] = DIAGJ ? Jti[s][s] * (s == 0 ? dxf : s == 1 ? dyf : dzf) : fma(Jti[s][2], dzf, fma(Jti[s][1], dyf, Jti[s][0] * dxf));
                     }
                     const auto   res = kernel(in);
                     const double wgt = wxy * tab.w[qz] * detJ;
@@ -547,7 +551,7 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
                     staticFor< U >([&](auto u) {
                         staticFor< 3 >([&](auto s) {
                             if constexpr (gradNeeded< KernelT >(s, u))
-                                g_phys[s][u] = fma(Jti[s][2], dref[2][u], fma(Jti[s][1], dref[1][u], Jti[s][0] * dref[0][u]));
+                                g_phys[s][u] = DIAGJ ? Jti[s][s] * dref[s][u] : fma(Jti[s][2], dref[2][u], fma(Jti[s][1], dref[1][u], Jti[s][0] * dref[0][u]));
                         });
                     });
                     double tv[E];
@@ -578,9 +582,14 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
                         staticFor< 3 >([&](auto s) {
                             if constexpr (gradNeeded< KernelT >(s, u))
                             {
+                                if constexpr (DIAGJ)
+                                    rd[s] = Jti[s][s] * ps[s];
+                                else
+                                {
 #pragma unroll
-                                for (int d = 0; d < 3; ++d)
-                                    rd[d] = fma(Jti[s][d], ps[s], rd[d]);
+                                    for (int d = 0; d < 3; ++d)
+                                        rd[d] = fma(Jti[s][d], ps[s], rd[d]);
+                                }
                             }
                         });
                         const int off = ((r * U + u) * NQ + qz) * (EPB * PSZ) + col_off;
@@ -598,6 +607,11 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
                     for (int q = 0; q < NQ; ++q)
                         s_V[((r * U + u) * NQ + q) * (EPB * PSZ) + col_off] = wacc[u][q];
             }
+            };
+            if (geo[hex_geo_affine] == 2.)
+                pointStage(std::true_type{});
+            else
+                pointStage(std::false_type{});
             if (violated)
                 atomicOr(args.status, status_sparsity_violation);
         }

@@ -234,6 +234,7 @@ class SlabOperator:
         torch = self.torch
         dev = torch.device("cuda", torch.cuda.current_device())
         x = torch.zeros(max(self.n_local_dofs, 1), dtype=torch.float64, device=dev)
+        torch.cuda.current_stream().synchronize()  # torch filled x on its own stream; the library's stream does not wait for it
         multi = self.slab.world > 1 and dist.is_initialized()
 
         def apply(xp, yp):
@@ -320,6 +321,7 @@ class SlabAssembledOperator:
         self.sys.endAssemblyRanked(dofs.astype(np.int32), np.full((len(dofs), 1), dirichlet_value), self.n_owned_dofs)
         self.rhs = _device_view(self.sys.device_rhs, self.n_local_dofs, dev)
         self.diag = torch.zeros(self.n_local_dofs, dtype=torch.float64, device=dev)
+        torch.cuda.current_stream().synchronize()
         with torch.cuda.stream(self.stream):
             self.sys.diag_device(self.diag.data_ptr())
             if slab.world > 1:
@@ -347,6 +349,7 @@ class SlabAssembledOperator:
         torch = self.torch
         dev = torch.device("cuda", torch.cuda.current_device())
         x = torch.zeros(self.n_local_dofs, dtype=torch.float64, device=dev)
+        torch.cuda.current_stream().synchronize()  # torch filled x on its own stream; the library's stream does not wait for it
         multi = self.slab.world > 1 and dist.is_initialized()
 
         def apply(xp, yp):

@@ -62,6 +62,7 @@ def run(kind):
             s.endAssembly()
             x = torch.rand(s.n_dofs, dtype=torch.float64, device="cuda")
             y = torch.zeros_like(x)
+            torch.cuda.synchronize()
             stream = torch.cuda.ExternalStream(ctx.stream)
             for _ in range(3):
                 s.apply_device(x.data_ptr(), y.data_ptr())

@@ -32,6 +32,7 @@ def main():
     xl[slab.n_owned_nodes:] = np.nan
     x = torch.from_numpy(xl.ravel()).cuda()
     y = torch.zeros_like(x)
+    torch.cuda.synchronize()  # tensors are filled on torch's stream, the library runs on its own
     for _ in range(3):  # repeated applies: the halo buffers and events are reused
         op.apply(x, y)
     ctx.synchronize()
@@ -54,6 +55,7 @@ def main():
         wkey = whole.lattice[:, 0] + n_lat[0] * (whole.lattice[:, 1] + n_lat[1] * whole.lattice[:, 2])
         xw = torch.from_numpy(f[wkey].ravel().copy()).cuda()
         yw = torch.zeros_like(xw)
+        torch.cuda.synchronize()
         wop.apply(xw, yw)
         ctx.synchronize()
         y_ref = np.zeros_like(f)

@@ -41,9 +41,10 @@ def test_matrix_free_apply_properties_at_64_cubed(ctx):
     x = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
     y = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
     Ax, Ay, Axy = (torch.empty_like(x) for _ in range(3))
+    z = 0.3 * x - 1.7 * y
+    torch.cuda.synchronize()  # the tensors were filled on torch's stream, the library works on its own (non-blocking) stream
     s.apply_device(x.data_ptr(), Ax.data_ptr())
     s.apply_device(y.data_ptr(), Ay.data_ptr())
-    z = 0.3 * x - 1.7 * y
     s.apply_device(z.data_ptr(), Axy.data_ptr())
     ctx.synchronize()
     scale = float(torch.linalg.norm(Ax) * torch.linalg.norm(y))
@@ -54,6 +55,7 @@ def test_matrix_free_apply_properties_at_64_cubed(ctx):
     assert torch.equal(Ax[d], x[d])                                                  # Dirichlet rows are identity rows
     # y = alpha A x + beta y
     y0 = y.clone()
+    torch.cuda.synchronize()
     s.apply_device(x.data_ptr(), y.data_ptr(), 1, -0.5, 2.0)
     ctx.synchronize()
     assert float(torch.linalg.norm(y - (2.0 * y0 - 0.5 * Ax)) / torch.linalg.norm(y)) < 1e-12
