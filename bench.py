@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--n-asm", type=int, default=16, help="elements per edge, assembly workload (per GPU)")
     ap.add_argument("--n-mf", type=int, default=64, help="elements per edge, matrix-free workload (per GPU)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workload")
+    ap.add_argument("--cg-max-iters", type=int, default=10000, help="matrix-free workload: iteration cap of the CG solve timed after the applies (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -362,6 +363,18 @@ def main():
 
         _, wall_ms, _ = timed(step_e2e, args.steps, 1)
         owned_total = sum_over_ranks(float(n_owned))
+        cg = None
+        if args.cg_max_iters > 0:
+            # the benchmark's solve (benchmarks/Diffusion3D.hpp:115-118): CG + native Jacobi, tol 1e-6 (absolute), x0 = 0, rhs of the source f = 1
+            del yd
+            barrier()
+            t0 = time.perf_counter()
+            _, res, iters = op.solve(1e-6, args.cg_max_iters)
+            ctx.synchronize()
+            cg_s = max_over_ranks(time.perf_counter() - t0)
+            cg = {"iters": int(iters), "achieved_residual": float(res), "seconds": cg_s, "ms_per_iteration": cg_s * 1e3 / max(iters, 1),
+                  "dofs_per_s": owned_total * iters / cg_s, "tol": 1e-6, "max_iters": args.cg_max_iters,
+                  "what": "full CG + Jacobi solve on the device, one operator apply + 12 vector passes per iteration, wall clock, max over ranks"}
         gbs = mf_bytes_per_apply(n_owned, n_elems) / (ms * 1e-3) / 1e9
         fp64_fma = ctx.microbench(0)
         return {
@@ -380,7 +393,7 @@ def main():
                                  "roofline is the ceiling of this formulation",
                          "traffic_source": "dram__bytes_read + write of profiles/r1_mf_v7 (6.05 kB per element incl. the y read-modify-write), "
                                            "scaled to this launch"},
-            "gpu_launches": launches * args.steps, "clocks": clocks,
+            "gpu_launches": launches * args.steps, "clocks": clocks, "cg_solve": cg,
             "config": {"workload": f"Diffusion3DBenchmarkMatrixFree operator apply: {n} x {n} x {n * world} hex p=4 on [0,1]^2 x [0,{world}], "
                                    f"U=4, E=7, nq=5, Dirichlet T=0 on the six faces, one z-slab of {n}^3 elements per GPU",
                        "elements_per_gpu": n_elems, "owned_dofs_per_gpu": n_owned, "ghost_dofs_per_gpu": n_local - n_owned,
@@ -401,6 +414,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": main_res["config"],
             "e2e": main_res["e2e"], "roofline": main_res["roofline"], "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"]}
+    if main_res.get("cg_solve"):
+        line["cg_solve"] = main_res["cg_solve"]
     if also:
         line["also"] = also
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -64,7 +64,8 @@ typedef struct l3b_kernel_info
 {
     char name[64];
     int  dimension, n_equations, n_unknowns, n_fields, n_rhs, is_boundary;
-    int  n_instances; /* compiled (order, nq) pairs */
+    int  n_instances; /* compiled (order, nq) pairs; residual kernels: one per order with nq = 0 (any quadrature size) */
+    int  is_residual; /* an integrand for l3b_compute_integral / l3b_compute_norm_l2, not an equation kernel */
 } l3b_kernel_info;
 int l3b_kernel_count(void);
 int l3b_kernel_find(const char* name); /* id or -1 */
@@ -217,6 +218,17 @@ int l3b_gmres_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_app
 int l3b_pcg_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_apply_callback apply, l3b_allreduce_callback allreduce,
                    void* user, const double* diag, const double* b, double* x, double tol, int max_iters, double* achieved_tol,
                    int* iters);
+/* ---- integrals and norms of residual kernels (post/Integral.hpp:102-121 computeIntegral, post/NormL2.hpp:31-60 computeNormL2) ----
+ * The kernel is a registered residual kernel `(const Input&, Rhs&) -> void` (common/KernelInterface.hpp:140-176); a domain kernel is
+ * integrated over all elements of the mesh, a boundary kernel over the sides carrying one of `boundary_ids`. The integrand is
+ * jacobian * kernel(input) on the Gauss-Legendre rule of order opts.order(element order) (Integral.hpp:66-69 — not doubled as in the
+ * assembly); the norm squares each component, doubles value_order and derivative_order and returns the square roots
+ * (NormL2.hpp:10-28, 44). out: n_equations * n_rhs doubles on the host, this rank's share (the caller all-reduces the integral, resp.
+ * the squares of the norm, over the ranks: Integral.hpp:116-119). */
+int l3b_compute_integral(l3b_context* ctx, l3b_mesh* mesh, int kernel_id, l3b_asm_opts opts, double time, const l3b_fields* fields,
+                         const int* field_inds, const int* boundary_ids, int n_boundary_ids, double* out);
+int l3b_compute_norm_l2(l3b_context* ctx, l3b_mesh* mesh, int kernel_id, l3b_asm_opts opts, double time, const l3b_fields* fields,
+                        const int* field_inds, const int* boundary_ids, int n_boundary_ids, double* out);
 int64_t l3b_mf_num_dofs(const l3b_mf* sys);
 int     l3b_mf_kernel_launches(const l3b_mf* sys); /* device kernels launched by the last apply */
 

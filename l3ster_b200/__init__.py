@@ -30,7 +30,7 @@ class L3BError(RuntimeError):
 
 class _KernelInfo(C.Structure):
     _fields_ = [("name", C.c_char * 64), ("dimension", C.c_int), ("n_equations", C.c_int), ("n_unknowns", C.c_int), ("n_fields", C.c_int),
-                ("n_rhs", C.c_int), ("is_boundary", C.c_int), ("n_instances", C.c_int)]
+                ("n_rhs", C.c_int), ("is_boundary", C.c_int), ("n_instances", C.c_int), ("is_residual", C.c_int)]
 
 
 class _AsmOpts(C.Structure):
@@ -70,6 +70,7 @@ EXPORTED_SYMBOLS = [
     "l3b_mf_end_assembly_begin", "l3b_mf_end_assembly_finish", "l3b_mf_device_diag", "l3b_mf_device_rhs", "l3b_pcg_device",
     "l3b_asm_spmv_device", "l3b_asm_diag_device", "l3b_asm_device_rhs", "l3b_asm_end_assembly_ranked",
     "l3b_gmres_device", "l3b_asm_solve_gmres", "l3b_mf_solve_gmres",
+    "l3b_compute_integral", "l3b_compute_norm_l2",
 ]
 
 
@@ -138,6 +139,8 @@ def lib():
     L.l3b_mf_destroy.argtypes = [vp]
     L.l3b_mf_destroy.restype = None
     L.l3b_mf_assemble.argtypes = [vp, i32, _AsmOpts, dbl, vp, vp, vp, vp, i32]
+    for f in ("l3b_compute_integral", "l3b_compute_norm_l2"):
+        getattr(L, f).argtypes = [vp, vp, i32, _AsmOpts, dbl, vp, vp, vp, i32, vp]
     L.l3b_mf_end_assembly.argtypes = [vp]
     L.l3b_mf_download.argtypes = [vp, vp, vp]
     L.l3b_mf_apply_device.argtypes = [vp, vp, vp, i32, dbl, dbl]
@@ -201,7 +204,8 @@ def kernel_info(name_or_id):
         lib().l3b_kernel_get_instance(kid, i, C.byref(o), C.byref(q))
         inst.append((o.value, q.value))
     return dict(id=kid, name=info.name.decode(), dimension=info.dimension, n_equations=info.n_equations, n_unknowns=info.n_unknowns,
-                n_fields=info.n_fields, n_rhs=info.n_rhs, is_boundary=bool(info.is_boundary), instances=inst)
+                n_fields=info.n_fields, n_rhs=info.n_rhs, is_boundary=bool(info.is_boundary), is_residual=bool(info.is_residual),
+                instances=inst)
 
 
 def list_kernels():
@@ -411,6 +415,22 @@ class Context:
 
 
 class Mesh:
+    def _integrate(self, fn, kernel, boundary_ids, fields, field_inds, asm_opts, time):
+        kid, _, fh, fi, bi, nb = _kernel_args(kernel, None, fields, field_inds, boundary_ids)
+        info = kernel_info(kid)
+        out = np.zeros(info["n_equations"] * info["n_rhs"])
+        self.ctx._chk(fn(self.ctx._h, self._h, kid, asm_opts._c(), time, fh, _p(fi), _p(bi), nb, _p(out)))
+        return out
+
+    def computeIntegral(self, kernel, boundary_ids=(), fields=None, field_inds=None, asm_opts=AssemblyOptions(), time=0.0):
+        """computeIntegral (post/Integral.hpp:102-121) of a residual kernel over this rank's elements (domain kernel) or over the sides
+        carrying `boundary_ids` (boundary kernel); the caller sums over ranks"""
+        return self._integrate(lib().l3b_compute_integral, kernel, boundary_ids, fields, field_inds, asm_opts, time)
+
+    def computeNormL2(self, kernel, boundary_ids=(), fields=None, field_inds=None, asm_opts=AssemblyOptions(), time=0.0):
+        """computeNormL2 (post/NormL2.hpp:31-60); on more than one rank sum the squares over the ranks"""
+        return self._integrate(lib().l3b_compute_norm_l2, kernel, boundary_ids, fields, field_inds, asm_opts, time)
+
     def update_verts(self, verts):
         """new vertex coordinates, same connectivity (H2D copy, no reallocation)"""
         self.ctx._chk(lib().l3b_mesh_update_verts(self._h, verts.ctypes.data))

@@ -579,6 +579,37 @@ struct KernelUse
     std::shared_ptr< WorkList > boundary_work; // boundary kernels only
 };
 
+// the (element, side) pairs lying on the given boundary ids (the reference's BoundaryView, mesh/BoundaryView.hpp)
+std::shared_ptr< WorkList > makeBoundaryWork(l3b_mesh* mesh, const int* boundary_ids, int n_boundary_ids)
+{
+    if (mesh->side_bnd.empty())
+        fail(L3B_ERR_INVALID_ARG, "boundary kernel on a mesh without side boundary ids");
+    std::vector< int32_t > el;
+    std::vector< uint8_t > sd;
+    for (long long e = 0; e < mesh->n_elems; ++e)
+        for (int s = 0; s < mesh->n_sides; ++s)
+        {
+            const auto id = mesh->side_bnd[e * mesh->n_sides + s];
+            if (id == host::no_boundary)
+                continue;
+            for (int k = 0; k < n_boundary_ids; ++k)
+                if (boundary_ids[k] == id)
+                {
+                    el.push_back(static_cast< int32_t >(e));
+                    sd.push_back(static_cast< uint8_t >(s));
+                    break;
+                }
+        }
+    auto wl = std::make_shared< WorkList >();
+    wl->n   = static_cast< long long >(el.size());
+    wl->elems.alloc(el.size());
+    wl->sides.alloc(sd.size());
+    wl->elems.upload(el.data(), el.size(), mesh->ctx->stream);
+    wl->sides.upload(sd.data(), sd.size(), mesh->ctx->stream);
+    cudaCheck(cudaStreamSynchronize(mesh->ctx->stream), "work list upload");
+    return wl;
+}
+
 KernelUse makeUse(l3b_mesh* mesh, int dofs_per_node, int n_rhs, int kernel_id, l3b_asm_opts opts, double time, const int* dof_inds,
                   const l3b_fields* fields, const int* field_inds, const int* boundary_ids, int n_boundary_ids)
 {
@@ -587,6 +618,8 @@ KernelUse makeUse(l3b_mesh* mesh, int dofs_per_node, int n_rhs, int kernel_id, l
         fail(L3B_ERR_INVALID_ARG, "invalid kernel id");
     const auto& entry = reg[kernel_id];
     const auto& info  = entry.info;
+    if (info.is_residual)
+        fail(L3B_ERR_INVALID_ARG, "kernel '" + info.name + "' is a residual kernel (an integrand), not an equation kernel");
     if (info.dim != mesh->dim)
         fail(L3B_ERR_INVALID_ARG, "The dimensions of the kernel do not match the dimensions of the domain");
     if (info.n_rhs != n_rhs)
@@ -629,34 +662,7 @@ KernelUse makeUse(l3b_mesh* mesh, int dofs_per_node, int n_rhs, int kernel_id, l
         use.fields = fields;
     }
     if (info.is_boundary)
-    {
-        if (mesh->side_bnd.empty())
-            fail(L3B_ERR_INVALID_ARG, "boundary kernel on a mesh without side boundary ids");
-        std::vector< int32_t > el;
-        std::vector< uint8_t > sd;
-        for (long long e = 0; e < mesh->n_elems; ++e)
-            for (int s = 0; s < mesh->n_sides; ++s)
-            {
-                const auto id = mesh->side_bnd[e * mesh->n_sides + s];
-                if (id == host::no_boundary)
-                    continue;
-                for (int k = 0; k < n_boundary_ids; ++k)
-                    if (boundary_ids[k] == id)
-                    {
-                        el.push_back(static_cast< int32_t >(e));
-                        sd.push_back(static_cast< uint8_t >(s));
-                        break;
-                    }
-            }
-        auto wl = std::make_shared< WorkList >();
-        wl->n   = static_cast< long long >(el.size());
-        wl->elems.alloc(el.size());
-        wl->sides.alloc(sd.size());
-        wl->elems.upload(el.data(), el.size(), mesh->ctx->stream);
-        wl->sides.upload(sd.data(), sd.size(), mesh->ctx->stream);
-        cudaCheck(cudaStreamSynchronize(mesh->ctx->stream), "work list upload");
-        use.boundary_work = std::move(wl);
-    }
+        use.boundary_work = makeBoundaryWork(mesh, boundary_ids, n_boundary_ids);
     return use;
 }
 
@@ -857,7 +863,25 @@ void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double a
 
 // Preconditioned CG, Belos "Block CG" semantics for block size 1 (solve/BelosSolvers.hpp:76-89): left preconditioner,
 // absolute 2-norm of the (unpreconditioned) residual against `tol`, x0 = 0. One fused vector kernel and one 2-scalar
-// read-back per iteration.
+// read-back per iteration. The read-back goes to pinned memory behind an event, and the host waits for it only after it has
+// queued the next direction update and operator apply: the device never idles on the convergence test (the speculative work
+// touches p and Ap only, so x is final when the test succeeds).
+struct PinnedScalars
+{
+    double* h = nullptr;
+    PinnedScalars() { cudaCheck(cudaMallocHost(&h, 8 * sizeof(double)), "cudaMallocHost"); }
+    ~PinnedScalars() { cudaFreeHost(h); }
+    PinnedScalars(const PinnedScalars&)            = delete;
+    PinnedScalars& operator=(const PinnedScalars&) = delete;
+};
+struct Event
+{
+    cudaEvent_t ev = nullptr;
+    Event() { cudaCheck(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate"); }
+    ~Event() { cudaEventDestroy(ev); }
+    Event(const Event&)            = delete;
+    Event& operator=(const Event&) = delete;
+};
 template < typename Apply, typename Reduce >
 void pcg(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Reduce&& reduce, const double* diag, const double* b,
          double* x /* device */, double tol, int max_iters, double* achieved, int* iters)
@@ -865,7 +889,10 @@ void pcg(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Reduce
     // n = owned dofs: dots and updates run over those; p and Ap carry the ghost tail the operator needs
     DevBuf< double > r(n), z(n), p(n_local), Ap(n_local), minv(n);
     DevBuf< double > sc_buf(8);
+    PinnedScalars    pinned;
+    Event            read_back;
     double*    sc = sc_buf.ptr; // [0] rz, [1] pAp, [2] rr, [3] rz_new
+    double*    h  = pinned.h;
     const auto s  = ctx->stream;
     const auto g  = gridFor(n);
     jacobiInvertKernel<<< g, 256, 0, s >>>(diag, minv.ptr, n, 1., 0.);
@@ -877,31 +904,37 @@ void pcg(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Reduce
     cudaCheck(cudaMemsetAsync(sc, 0, 8 * sizeof(double), s), "memset");
     dot2Kernel<<< g, 256, 0, s >>>(r.ptr, r.ptr, r.ptr, z.ptr, n, sc + 2); // rr → sc[2], rz → sc[3]
     reduce(sc + 2, 2);
-    double h[2];
     cudaCheck(cudaMemcpyAsync(h, sc + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, s), "copy");
     cudaCheck(cudaStreamSynchronize(s), "sync");
     double rnorm = std::sqrt(h[0]);
     int    it    = 0;
-    if (rnorm > tol)
+    if (rnorm > tol and max_iters > 0)
     {
         cudaCheck(cudaMemcpyAsync(sc, sc + 3, sizeof(double), cudaMemcpyDeviceToDevice, s), "copy"); // rz
-        while (it < max_iters)
+        apply(p.ptr, Ap.ptr);
+        while (true)
         {
-            apply(p.ptr, Ap.ptr);
             cudaCheck(cudaMemsetAsync(sc + 1, 0, 3 * sizeof(double), s), "memset");
             dot2Kernel<<< g, 256, 0, s >>>(p.ptr, Ap.ptr, nullptr, nullptr, n, sc + 1);
             reduce(sc + 1, 1);
             cgUpdateKernel<<< g, 256, 0, s >>>(x, r.ptr, z.ptr, p.ptr, Ap.ptr, minv.ptr, n, sc, sc + 2);
             reduce(sc + 2, 2);
             cudaCheck(cudaMemcpyAsync(h, sc + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, s), "copy");
-            cudaCheck(cudaStreamSynchronize(s), "sync");
+            cudaCheck(cudaEventRecord(read_back.ev, s), "event");
             ++it;
+            const bool last = it >= max_iters;
+            if (not last) // queued before the convergence test is known: next direction and its operator apply
+            {
+                cgDirectionKernel<<< g, 256, 0, s >>>(p.ptr, z.ptr, n, sc + 3, sc);
+                cudaCheck(cudaMemcpyAsync(sc, sc + 3, sizeof(double), cudaMemcpyDeviceToDevice, s), "copy");
+                apply(p.ptr, Ap.ptr);
+            }
+            cudaCheck(cudaEventSynchronize(read_back.ev), "sync");
             rnorm = std::sqrt(h[0]);
-            if (not(rnorm > tol))
+            if (last or not(rnorm > tol))
                 break;
-            cgDirectionKernel<<< g, 256, 0, s >>>(p.ptr, z.ptr, n, sc + 3, sc);
-            cudaCheck(cudaMemcpyAsync(sc, sc + 3, sizeof(double), cudaMemcpyDeviceToDevice, s), "copy");
         }
+        cudaCheck(cudaStreamSynchronize(s), "sync"); // the speculative tail reads buffers this function owns
     }
     cudaCheck(cudaGetLastError(), "pcg");
     *achieved = rnorm;
@@ -1100,6 +1133,7 @@ int l3b_kernel_get_info(int id, l3b_kernel_info* out)
     out->n_fields    = i.n_fields;
     out->n_rhs       = i.n_rhs;
     out->is_boundary = i.is_boundary;
+    out->is_residual = i.is_residual;
     out->n_instances = static_cast< int >(r[id].instances.size());
     return L3B_OK;
 }
@@ -1803,3 +1837,76 @@ int l3b_mf_kernel_launches(const l3b_mf* sys)
     return sys->last_launches;
 }
 } // extern "C"
+
+namespace
+{
+// computeIntegral / computeNormL2 (post/Integral.hpp:55-121, post/NormL2.hpp:10-60), this rank's elements
+void integrate(l3b_context* ctx, l3b_mesh* mesh, int kernel_id, l3b_asm_opts opts, double time, const l3b_fields* fields,
+               const int* field_inds, const int* boundary_ids, int n_boundary_ids, bool norm, double* out)
+{
+    auto& reg = kernelRegistry();
+    if (kernel_id < 0 or kernel_id >= static_cast< int >(reg.size()))
+        fail(L3B_ERR_INVALID_ARG, "invalid kernel id");
+    const auto& entry = reg[kernel_id];
+    const auto& info  = entry.info;
+    if (not info.is_residual)
+        fail(L3B_ERR_INVALID_ARG, "kernel '" + info.name + "' is an equation kernel, integrals take residual kernels");
+    if (info.dim != mesh->dim)
+        fail(L3B_ERR_INVALID_ARG, "The dimensions of the kernel do not match the dimensions of the domain");
+    if (opts.value_order < 1)
+        fail(L3B_ERR_INVALID_ARG, "value_order must be >= 1");
+    KernelUse use;
+    use.kernel_id = kernel_id;
+    use.opts      = opts;
+    AssemblyOptions ao;
+    ao.value_order      = opts.value_order * (norm ? 2 : 1); // NormL2.hpp:10-19
+    ao.derivative_order = opts.derivative_order * (norm ? 2 : 1);
+    use.nq              = ao.order(mesh->order) / 2 + 1; // QO = options.order(EO) (Integral.hpp:66-69), size QO / 2 + 1
+    use.inst            = entry.find(mesh->order, 0);
+    if (not use.inst or not use.inst->integrate)
+        fail(L3B_ERR_NO_INSTANCE, "residual kernel '" + info.name + "' is not compiled for order " + std::to_string(mesh->order));
+    use.time = time;
+    if (info.n_fields > 0)
+    {
+        if (not fields)
+            fail(L3B_ERR_INVALID_ARG, "kernel needs external fields but none were passed");
+        if (fields->n_nodes != mesh->n_local_nodes)
+            fail(L3B_ERR_INVALID_ARG, "field storage does not match the mesh's local node count");
+        for (int f = 0; f < info.n_fields; ++f)
+        {
+            use.field_inds[f] = field_inds ? field_inds[f] : f;
+            if (use.field_inds[f] < 0 or use.field_inds[f] >= fields->n_fields)
+                fail(L3B_ERR_INVALID_ARG, "field index out of range");
+        }
+        use.fields = fields;
+    }
+    if (info.is_boundary)
+        use.boundary_work = makeBoundaryWork(mesh, boundary_ids, n_boundary_ids);
+    const int        nv = info.n_equations * info.n_rhs;
+    DevBuf< double > sums(nv);
+    sums.zero(ctx->stream);
+    ElemArgs a = baseArgs(mesh, use, 1, 0);
+    setDense(a, mesh, use, info.is_boundary);
+    a.y      = sums.ptr;
+    a.n_cols = norm ? 1 : 0;
+    cudaCheck(use.inst->integrate(entry.object.get(), a, ctx->stream), "integrate");
+    sums.download(out, nv, ctx->stream);
+    cudaCheck(cudaStreamSynchronize(ctx->stream), "integrate");
+    if (norm)
+        for (int i = 0; i < nv; ++i)
+            out[i] = std::sqrt(out[i]);
+}
+} // namespace
+
+extern "C" {
+int l3b_compute_integral(l3b_context* ctx, l3b_mesh* mesh, int kernel_id, l3b_asm_opts opts, double time, const l3b_fields* fields,
+                         const int* field_inds, const int* boundary_ids, int n_boundary_ids, double* out)
+{
+    return guardedCtx(ctx, [&] { integrate(ctx, mesh, kernel_id, opts, time, fields, field_inds, boundary_ids, n_boundary_ids, false, out); });
+}
+int l3b_compute_norm_l2(l3b_context* ctx, l3b_mesh* mesh, int kernel_id, l3b_asm_opts opts, double time, const l3b_fields* fields,
+                        const int* field_inds, const int* boundary_ids, int n_boundary_ids, double* out)
+{
+    return guardedCtx(ctx, [&] { integrate(ctx, mesh, kernel_id, opts, time, fields, field_inds, boundary_ids, n_boundary_ids, true, out); });
+}
+}

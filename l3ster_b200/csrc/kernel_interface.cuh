@@ -187,6 +187,56 @@ constexpr auto wrapBoundaryEquationKernel(Kernel kernel)
     return BoundaryEquationKernel< Kernel, params >{kernel};
 }
 
+// common/KernelInterface.hpp:140-176, 192-204: residual kernels `(const Input&, Rhs&) -> void`, the integrands of
+// computeIntegral / computeNormL2 (post/Integral.hpp, post/NormL2.hpp). The reference leaves the result uninitialised before the call;
+// here it starts from zero.
+template < typename Kernel, KernelParams params >
+struct ResidualDomainKernel
+{
+    static constexpr auto parameters  = params;
+    static constexpr bool is_boundary = false;
+    using Input                       = typename KernelInterface< params >::DomainInput;
+    using Rhs                         = typename KernelInterface< params >::Rhs;
+    using functor_type                = Kernel;
+    constexpr ResidualDomainKernel(Kernel kernel) : m_kernel{kernel} {}
+    L3B_HD constexpr Rhs operator()(const Input& input) const
+    {
+        Rhs retval{};
+        retval.setZero();
+        m_kernel(input, retval);
+        return retval;
+    }
+    Kernel m_kernel;
+};
+template < typename Kernel, KernelParams params >
+struct ResidualBoundaryKernel
+{
+    static constexpr auto parameters  = params;
+    static constexpr bool is_boundary = true;
+    using Input                       = typename KernelInterface< params >::BoundaryInput;
+    using Rhs                         = typename KernelInterface< params >::Rhs;
+    using functor_type                = Kernel;
+    constexpr ResidualBoundaryKernel(Kernel kernel) : m_kernel{kernel} {}
+    L3B_HD constexpr Rhs operator()(const Input& input) const
+    {
+        Rhs retval{};
+        retval.setZero();
+        m_kernel(input, retval);
+        return retval;
+    }
+    Kernel m_kernel;
+};
+template < KernelParams params, typename Kernel >
+constexpr auto wrapDomainResidualKernel(Kernel kernel)
+{
+    return ResidualDomainKernel< Kernel, params >{kernel};
+}
+template < KernelParams params, typename Kernel >
+constexpr auto wrapBoundaryResidualKernel(Kernel kernel)
+{
+    return ResidualBoundaryKernel< Kernel, params >{kernel};
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Structural sparsity of a kernel's operators, discovered at compile time.
 //

@@ -364,5 +364,74 @@ struct DenseProbe2D
             out.rhs[e] = 1. + 0.5 * e + in.point.space[1] * in.field_vals[1];
     }
 };
+
+// ---- residual kernels: integrands of computeIntegral / computeNormL2 (post/Integral.hpp, post/NormL2.hpp)
+// tests/Diffusion2D.hpp:82-91 (node_dist.back() == 1), used as domain and as boundary residual kernel
+struct Diffusion2DError
+{
+    template < typename In, typename Out >
+    L3B_HD constexpr void operator()(const In& in, Out& error) const
+    {
+        const auto& point             = in.point;
+        const auto& vals              = in.field_vals;
+        const auto& [T, dT_dx, dT_dy] = vals;
+        error[0]                      = T - point.space.x() / 1.;
+        error[1]                      = dT_dx - 1. / 1.;
+        error[2]                      = dT_dy;
+    }
+};
+// examples/07-karman-2D/source.cpp:158-166
+struct KarmanFlowRate
+{
+    template < typename In, typename Out >
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
+    {
+        const auto& [field_vals, field_ders, point, normal] = in;
+        const auto& [u, v]                                  = field_vals;
+        const double nx = normal[0], ny = normal[1];
+        out[0] = u * nx + v * ny;
+    }
+};
+// not in the reference: polynomial / field probes with closed-form integrals on boxes (same bodies as oracle/kernels.cpp)
+struct IntegrandProbe2D
+{
+    template < typename In, typename Out >
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
+    {
+        out[0] = 1.;
+        out[1] = in.point.space[0] * in.point.space[0] * in.point.space[1] + in.point.time;
+        out[2] = in.field_vals[0] + 0.5 * in.field_ders[0][1] - in.field_ders[1][0] * in.point.space[1];
+    }
+};
+struct IntegrandProbe3D
+{
+    template < typename In, typename Out >
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
+    {
+        out[0] = 1.;
+        out[1] = in.point.space[0] * in.point.space[1] * in.point.space[1] * in.point.space[2] + in.point.time;
+        out[2] = in.field_vals[0] + 0.5 * in.field_ders[0][1] - in.field_ders[2][0] * in.point.space[1];
+    }
+};
+struct BoundaryProbe2D
+{
+    template < typename In, typename Out >
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
+    {
+        out[0] = 1.;
+        out[1] = in.point.space[0] * in.normal[0] + in.point.space[1] * in.normal[1];
+        out[2] = in.field_vals[0] * in.normal[0] + in.field_ders[1][1];
+    }
+};
+struct BoundaryProbe3D
+{
+    template < typename In, typename Out >
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
+    {
+        out[0] = 1.;
+        out[1] = in.point.space[0] * in.normal[0] + in.point.space[1] * in.normal[1] + in.point.space[2] * in.normal[2];
+        out[2] = in.field_vals[0] * in.normal[2] + in.field_ders[1][1];
+    }
+};
 } // namespace l3b::kernels
 #endif

@@ -12,6 +12,7 @@
 
 #include "assemble.cuh"
 #include "assemble_dmma.cuh"
+#include "integrate.cuh"
 #include "local_element.cuh"
 #include "mf_hex_planes.cuh"
 #include "mf_init.cuh"
@@ -169,6 +170,19 @@ cudaError_t launchAssemble(const void* obj, const ElemArgs& args, cudaStream_t s
     return cudaGetLastError();
 }
 
+template < typename KernelT, int DIM, int P >
+cudaError_t launchIntegrate(const void* obj, const ElemArgs& args, cudaStream_t stream)
+{
+    using Cfg = IntegrateCfg< KernelT, DIM, P >;
+    if (args.n_work == 0)
+        return cudaSuccess;
+    constexpr auto fn = integrateKernel< KernelT, DIM, P >;
+    if (const auto err = raiseSmemLimit< fn >(Cfg::smem_bytes); err != cudaSuccess)
+        return err;
+    fn<<< static_cast< unsigned >(args.n_work), local_threads, Cfg::smem_bytes, stream >>>(*static_cast< const KernelT* >(obj), args);
+    return cudaGetLastError();
+}
+
 template < int P_, int NQ_ >
 struct PQ
 {
@@ -209,6 +223,33 @@ KernelInstance makeInstance()
     return inst;
 }
 
+// residual kernels: one instance per element order, any quadrature size
+template < typename KernelT, int... orders >
+int registerResidualKernel(const char* name, const KernelT& kernel)
+{
+    constexpr auto params = KernelT::parameters;
+    KernelEntry    entry;
+    entry.info.name        = name;
+    entry.info.dim         = params.dimension;
+    entry.info.n_equations = static_cast< int >(params.n_equations);
+    entry.info.n_unknowns  = 0;
+    entry.info.n_fields    = static_cast< int >(params.n_fields);
+    entry.info.n_rhs       = static_cast< int >(params.n_rhs);
+    entry.info.is_boundary = KernelT::is_boundary;
+    entry.info.is_residual = true;
+    entry.object           = std::make_shared< KernelT >(kernel);
+    const auto add         = [&]< int P >(std::integral_constant< int, P >) {
+        KernelInstance inst;
+        inst.order     = P;
+        inst.nq        = 0;
+        inst.integrate = launchIntegrate< KernelT, params.dimension, P >;
+        entry.instances.push_back(inst);
+    };
+    (add(std::integral_constant< int, orders >{}), ...);
+    kernelRegistry().push_back(std::move(entry));
+    return static_cast< int >(kernelRegistry().size()) - 1;
+}
+
 template < typename KernelT, typename... pqs >
 int registerKernel(const char* name, const KernelT& kernel)
 {
@@ -235,4 +276,11 @@ int registerKernel(const char* name, const KernelT& kernel)
 #define L3B_REGISTER_BOUNDARY_KERNEL(NAME, FUNCTOR, PARAMS, ...)                                                                \
     static const int l3b_registered_##NAME =                                                                                   \
         ::l3b::registerKernel< ::l3b::BoundaryEquationKernel< FUNCTOR, PARAMS >, __VA_ARGS__ >(#NAME, ::l3b::wrapBoundaryEquationKernel< PARAMS >(FUNCTOR{}))
+// residual kernels (wrapDomainResidualKernel / wrapBoundaryResidualKernel, common/KernelInterface.hpp:192-204): list the element orders
+#define L3B_REGISTER_DOMAIN_RESIDUAL_KERNEL(NAME, FUNCTOR, PARAMS, ...)                                                         \
+    static const int l3b_registered_##NAME =                                                                                   \
+        ::l3b::registerResidualKernel< ::l3b::ResidualDomainKernel< FUNCTOR, PARAMS >, __VA_ARGS__ >(#NAME, ::l3b::wrapDomainResidualKernel< PARAMS >(FUNCTOR{}))
+#define L3B_REGISTER_BOUNDARY_RESIDUAL_KERNEL(NAME, FUNCTOR, PARAMS, ...)                                                       \
+    static const int l3b_registered_##NAME =                                                                                   \
+        ::l3b::registerResidualKernel< ::l3b::ResidualBoundaryKernel< FUNCTOR, PARAMS >, __VA_ARGS__ >(#NAME, ::l3b::wrapBoundaryResidualKernel< PARAMS >(FUNCTOR{}))
 #endif

@@ -18,6 +18,7 @@ struct KernelInfo
     std::string name;
     int         dim = 0, n_equations = 0, n_unknowns = 0, n_fields = 0, n_rhs = 1;
     bool        is_boundary = false;
+    bool        is_residual = false; // integrand of computeIntegral / computeNormL2, not an equation kernel
 };
 
 // launchers return the CUDA error of the launch; `kernel_obj` points at the registered functor instance
@@ -33,6 +34,7 @@ struct KernelInstance
     ElemLaunch init     = nullptr;
     ElemLaunch init_fast = nullptr; // domain kernels: diag + F_e without the Dirichlet lifting (mf_init.cuh)
     ElemLaunch assemble = nullptr;
+    ElemLaunch integrate = nullptr; // residual kernels only; nq == 0: any quadrature size (dense tables at run time)
     // work per launch unit, for occupancy/grid decisions and reporting
     int mf_elems_per_block = 1, asm_blocks_per_elem = 1;
 };
@@ -45,7 +47,7 @@ struct KernelEntry
     const KernelInstance*         find(int order, int nq) const
     {
         for (const auto& i : instances)
-            if (i.order == order and i.nq == nq)
+            if (i.order == order and (i.nq == nq or i.nq == 0))
                 return &i;
         return nullptr;
     }

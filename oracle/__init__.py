@@ -297,6 +297,17 @@ class OracleMesh:
     def assembled_system(self, U, n_rhs=1):
         return OracleAssembled(self, U, n_rhs)
 
+    def compute_integral(self, kernel, boundary_ids=(), fields=None, field_inds=None, value_order=1, der_order=0, time=0.0, norm_l2=False):
+        """computeIntegral / computeNormL2 (post/Integral.hpp:102-121, post/NormL2.hpp:31-60) of a residual kernel"""
+        f = None if fields is None else np.ascontiguousarray(fields, dtype=np.float64)
+        b = np.ascontiguousarray(list(boundary_ids) or [0], dtype=np.int32)
+        fi = None if field_inds is None else np.ascontiguousarray(field_inds, dtype=np.int32)
+        out = np.zeros(64)
+        n = C.c_int(0)
+        self.orc._chk(self.orc.lib.orc_compute_integral(self.h, kernel.encode(), value_order, der_order, C.c_double(time), _ptr(f), _ptr(fi),
+                                                        len(boundary_ids), _ptr(b), int(norm_l2), _ptr(out), C.byref(n)))
+        return out[: n.value].copy()
+
     def matrix_free_system(self, U, n_rhs=1, is_dirichlet=None, dirichlet_vals=None):
         return OracleMatrixFree(self, U, n_rhs, is_dirichlet, dirichlet_vals)
 

@@ -462,6 +462,22 @@ void orc_asm_get(void* h, double* values, double* rhs)
         std::copy(s.rhs.begin(), s.rhs.end(), rhs);
 }
 
+// computeIntegral / computeNormL2 of a residual kernel on the mesh (one rank); out: n_equations * n_rhs doubles
+int orc_compute_integral(void* mesh_h, const char* kernel, int value_order, int der_order, double time, const double* fields,
+                         const int* field_inds, int n_bnd_ids, const int* bnd_ids, int norm_l2, double* out, int* n_out)
+{
+    return guarded([&] {
+        const auto&        mesh = static_cast< MeshHandle* >(mesh_h)->mesh;
+        const auto&        k    = getKernel(kernel);
+        std::vector< int > fi;
+        if (field_inds)
+            fi.assign(field_inds, field_inds + k.params.n_fields);
+        const auto r = computeIntegral(mesh, k, mkOpts(value_order, der_order, 0), time, fields, {bnd_ids, bnd_ids + n_bnd_ids}, fi, norm_l2 != 0);
+        std::copy(r.begin(), r.end(), out);
+        *n_out = static_cast< int >(r.size());
+    });
+}
+
 // ---- matrix-free system
 void* orc_mf_create(void* mesh_h, int U, int n_rhs, const unsigned char* is_dirichlet, const double* dirichlet_vals)
 {

@@ -479,6 +479,33 @@ void assembleLocalSystem(const Kernel&         kernel,
             K[static_cast< std::size_t >(r) * L + c] = K[static_cast< std::size_t >(c) * L + r];
 }
 
+// post/Integral.hpp:11-53: sum_q weight_q * jacobian_q * kernel(input_q); the residual kernel writes its Rhs (E x n_rhs)
+void evalElementIntegral(const Kernel&         kernel,
+                         ElementType           et,
+                         int                   order,
+                         const val_t*          verts,
+                         const val_t*          node_vals,
+                         const RefBasisAtQuad& rbq,
+                         val_t                 time,
+                         int                   side,
+                         bool                  squared,
+                         val_t*                out)
+{
+    checkDims(kernel, et);
+    const int nv = kernel.params.n_equations * kernel.params.n_rhs;
+    std::fill_n(out, nv, 0.);
+    QpEval qp{kernel, numNodes(et, order)};
+    for (int q = 0; q < rbq.quad.size; ++q)
+    {
+        qp.eval(kernel, et, verts, node_vals, rbq, q, time, side);
+        for (int i = 0; i < nv; ++i)
+        {
+            const val_t r = squared ? qp.F[i] * qp.F[i] : qp.F[i]; // post/NormL2.hpp:21-28
+            out[i] += qp.jacobian * r * rbq.quad.weights[q];
+        }
+    }
+}
+
 // algsys/EvaluateLocalOperator.hpp:94-146, 211-263
 void evaluateLocalOperator(const Kernel&         kernel,
                            ElementType           et,

@@ -298,9 +298,56 @@ void dense_probe_2D(In in, Out out)
         out.rhs[e] = 1. + 0.5 * e + in.space[1] * in.field_vals[1];
 }
 
+// ---- residual kernels (integrands of computeIntegral / computeNormL2): they fill `rhs` only
+// tests/Diffusion2D.hpp:82-91 (node_dist.back() == 1), used as domain and as boundary residual kernel
+void diffusion2d_error(In in, Out out)
+{
+    const auto T = in.field_vals[0], dT_dx = in.field_vals[1], dT_dy = in.field_vals[2];
+    out.rhs[0] = T - in.space[0] / 1.;
+    out.rhs[1] = dT_dx - 1. / 1.;
+    out.rhs[2] = dT_dy;
+}
+// examples/07-karman-2D/source.cpp:158-166
+void karman_flowrate(In in, Out out)
+{
+    out.rhs[0] = in.field_vals[0] * in.normal[0] + in.field_vals[1] * in.normal[1];
+}
+// not in the reference: polynomial / field probes with closed-form integrals on boxes
+void integrand_probe_2D(In in, Out out)
+{
+    out.rhs[0] = 1.;
+    out.rhs[1] = in.space[0] * in.space[0] * in.space[1] + in.time;
+    out.rhs[2] = in.field_vals[0] + 0.5 * in.field_ders[0][1] - in.field_ders[1][0] * in.space[1];
+}
+void integrand_probe_3D(In in, Out out)
+{
+    out.rhs[0] = 1.;
+    out.rhs[1] = in.space[0] * in.space[1] * in.space[1] * in.space[2] + in.time;
+    out.rhs[2] = in.field_vals[0] + 0.5 * in.field_ders[0][1] - in.field_ders[2][0] * in.space[1];
+}
+void boundary_probe_2D(In in, Out out)
+{
+    out.rhs[0] = 1.;
+    out.rhs[1] = in.space[0] * in.normal[0] + in.space[1] * in.normal[1]; // closed boundary: 2 x area
+    out.rhs[2] = in.field_vals[0] * in.normal[0] + in.field_ders[1][1];
+}
+void boundary_probe_3D(In in, Out out)
+{
+    out.rhs[0] = 1.;
+    out.rhs[1] = in.space[0] * in.normal[0] + in.space[1] * in.normal[1] + in.space[2] * in.normal[2]; // closed boundary: 3 x volume
+    out.rhs[2] = in.field_vals[0] * in.normal[2] + in.field_ders[1][1];
+}
+
 std::map< std::string, Kernel > makeRegistry()
 {
     std::map< std::string, Kernel > r;
+    r["diffusion2d_error_dom"]   = Kernel{{2, 3, 0, 3, 1}, false, diffusion2d_error};
+    r["diffusion2d_error_bnd"]   = Kernel{{2, 3, 0, 3, 1}, true, diffusion2d_error};
+    r["karman_flowrate"]         = Kernel{{2, 1, 0, 2, 1}, true, karman_flowrate};
+    r["integrand_probe_2D"]      = Kernel{{2, 3, 0, 2, 1}, false, integrand_probe_2D};
+    r["integrand_probe_3D"]      = Kernel{{3, 3, 0, 2, 1}, false, integrand_probe_3D};
+    r["boundary_probe_2D"]       = Kernel{{2, 3, 0, 2, 1}, true, boundary_probe_2D};
+    r["boundary_probe_3D"]       = Kernel{{3, 3, 0, 2, 1}, true, boundary_probe_3D};
     r["diffusion_kernel_2D"]     = Kernel{{2, 4, 3, 0, 1}, false, diffusion_kernel_2D};
     r["diffusion_kernel_2D_var"] = Kernel{{2, 4, 3, 1, 1}, false, diffusion_kernel_2D_var};
     r["diffusion_kernel_3D"]     = Kernel{{3, 7, 4, 0, 1}, false, diffusion_kernel_3D< false >};

@@ -187,6 +187,19 @@ void assembleLocalSystem(const Kernel&         kernel,
                          val_t*                K_out,
                          val_t*                F_out);
 
+// post/Integral.hpp:11-53 evalElementIntegral / evalElementBoundaryIntegral: out[E * n_rhs] = sum_q w_q jac_q kernel(input_q), the kernel
+// being a residual kernel (it fills `rhs` only); squared: every component is squared first (post/NormL2.hpp:21-28)
+void evalElementIntegral(const Kernel&         kernel,
+                         ElementType           et,
+                         int                   order,
+                         const val_t*          verts,
+                         const val_t*          node_vals,
+                         const RefBasisAtQuad& rbq,
+                         val_t                 time,
+                         int                   side,
+                         bool                  squared,
+                         val_t*                out);
+
 // algsys/EvaluateLocalOperator.hpp:211-263 — y = K_e x without forming K_e; x, y column-major L x n_cols
 void evaluateLocalOperator(const Kernel&         kernel,
                            ElementType           et,
@@ -299,6 +312,10 @@ void assembleGlobalSystem(AssembledSystem& sys, const Kernel& kernel, const Asse
                           const val_t* fields /*field-major [n_fields][n_nodes] or null*/, int n_threads,
                           const std::vector< int >& boundary_ids /*for boundary kernels*/,
                           const std::vector< int >& dof_inds = {}, const std::vector< int >& field_inds = {});
+// post/Integral.hpp:55-121 computeIntegral and post/NormL2.hpp:31-60 computeNormL2 on one rank: quadrature order opts.order(EO) — not
+// doubled as in the assembly (Integral.hpp:66-69); the norm doubles both option orders, squares the components and takes square roots
+std::vector< val_t > computeIntegral(const Mesh& mesh, const Kernel& kernel, const AssemblyOptions& opts, val_t time, const val_t* fields,
+                                     const std::vector< int >& boundary_ids, const std::vector< int >& field_inds, bool norm_l2);
 // bcs/DirichletBC.hpp:82-150 — algebraic Dirichlet application (row/col zeroing, rhs lifting)
 void applyDirichletAlgebraic(AssembledSystem& sys, const std::vector< local_dof_t >& dofs, const std::vector< val_t >& vals);
 

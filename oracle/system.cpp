@@ -76,6 +76,51 @@ int quadOrder(const AssemblyOptions& o, int EO)
 }
 } // namespace
 
+// post/Integral.hpp:55-121, post/NormL2.hpp:10-60
+std::vector< val_t > computeIntegral(const Mesh& mesh, const Kernel& kernel, const AssemblyOptions& opts_in, val_t time, const val_t* fields,
+                                     const std::vector< int >& boundary_ids, const std::vector< int >& field_inds, bool norm_l2)
+{
+    AssemblyOptions opts = opts_in;
+    if (norm_l2)
+    {
+        opts.value_order *= 2;
+        opts.derivative_order *= 2;
+    }
+    const int qo = opts.order(mesh.order);
+    const int nn = mesh.nodesPerElem(), NF = kernel.params.n_fields, nv = kernel.params.n_equations * kernel.params.n_rhs;
+    std::vector< val_t > total(nv, 0.), part(nv), node_vals(static_cast< std::size_t >(nn) * std::max(NF, 1));
+    const auto one = [&](std::size_t e, int side, const RefBasisAtQuad& rbq) {
+        const n_id_t* el_nodes = &mesh.elem_nodes[e * nn];
+        for (int a = 0; a < nn; ++a)
+            for (int f = 0; f < NF; ++f)
+                node_vals[static_cast< std::size_t >(a) * NF + f] =
+                    fields[el_nodes[a] + static_cast< std::size_t >(field_inds.empty() ? f : field_inds[f]) * mesh.n_nodes];
+        evalElementIntegral(kernel, mesh.et, mesh.order, &mesh.elem_verts[e * (1u << nativeDim(mesh.et)) * 3], node_vals.data(), rbq, time,
+                            side, norm_l2, part.data());
+        for (int i = 0; i < nv; ++i)
+            total[i] += part[i];
+    };
+    if (not kernel.is_boundary)
+    {
+        const auto rbq = makeRefBasisAtDomainQuad(mesh.et, mesh.order, qo);
+        for (std::size_t e = 0; e < mesh.n_elems; ++e)
+            one(e, -1, rbq);
+    }
+    else
+    {
+        std::vector< RefBasisAtQuad > tables;
+        for (int s = 0; s < numSides(mesh.et); ++s)
+            tables.push_back(makeRefBasisAtBoundaryQuad(mesh.et, mesh.order, qo, s));
+        for (const auto& b : mesh.boundary)
+            if (std::find(boundary_ids.begin(), boundary_ids.end(), b.domain_id) != boundary_ids.end())
+                one(b.parent, b.side, tables[b.side]);
+    }
+    if (norm_l2)
+        for (auto& v : total)
+            v = std::sqrt(v);
+    return total;
+}
+
 // algsys/SparsityGraph.hpp:25-81 (count with over-allocation → fill with duplicates → sort + unique per row) and
 // :254-278 (rows inserted with sorted local column ids). Single rank, all U unknowns active on every node:
 // global dof of (node, u) = node*U + u   (dofs/NodeToDofMap.hpp:249-264), local id == global id.

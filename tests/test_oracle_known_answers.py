@@ -362,3 +362,28 @@ def test_degenerate_element_throws(orc):
     verts = [[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0], [0, 0, -1], [1, 0, -1], [0, 1, -1], [1, 1, -1]]
     with pytest.raises(RuntimeError, match="degenerate element"):
         orc.assemble_local("diffusion_kernel_3D", HEX, 2, verts)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_integrals_of_residual_kernels(orc, dim):
+    """post/Integral.hpp / post/NormL2.hpp restatement against closed forms: measure, a polynomial moment, the perimeter / surface and
+    the divergence theorem on a box [0, 2]^D; then the divergence theorem again on a distorted mesh (both sides polynomial)."""
+    d = np.linspace(0.0, 2.0, 4)
+    m = orc.mesh_square(d, d, order=2) if dim == 2 else orc.mesh_cube(d, d, d, order=2)
+    f = np.zeros((2, m.n_nodes))
+    vol = 2.0**dim
+    got = m.compute_integral(f"integrand_probe_{dim}D", fields=f, time=0.5, value_order=2)
+    moment = (8 / 3) * 2 if dim == 2 else 2 * (8 / 3) * 2  # int x^2 y over [0,2]^2; int x y^2 z over [0,2]^3
+    assert np.allclose(got, [vol, moment + 0.5 * vol, 0.0], rtol=1e-13, atol=1e-13)
+    sides = list(range(1, 2 * dim + 1))
+    got = m.compute_integral(f"boundary_probe_{dim}D", boundary_ids=sides, fields=f)
+    assert np.allclose(got, [2 * dim * 2.0 ** (dim - 1), dim * vol, 0.0], rtol=1e-13, atol=1e-13)
+    # a nodal field equal to x: its integral, its x-derivative and the L2 norm of (1, ., .)
+    got = m.compute_integral(f"integrand_probe_{dim}D", fields=f, norm_l2=True)
+    assert abs(got[0] - np.sqrt(vol)) < 1e-13
+    from common import distort
+
+    m.set_verts(distort(m.elem_verts))
+    v = m.compute_integral(f"integrand_probe_{dim}D", fields=f, value_order=3)[0]
+    s = m.compute_integral(f"boundary_probe_{dim}D", boundary_ids=sides, fields=f, value_order=3)[1]
+    assert abs(s / dim - v) < 1e-12 * v
