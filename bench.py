@@ -367,14 +367,17 @@ def main():
         if args.cg_max_iters > 0:
             # the benchmark's solve (benchmarks/Diffusion3D.hpp:115-118): CG + native Jacobi, tol 1e-6 (absolute), x0 = 0, rhs of the source f = 1
             del yd
-            barrier()
-            t0 = time.perf_counter()
-            _, res, iters = op.solve(1e-6, args.cg_max_iters)
-            ctx.synchronize()
-            cg_s = max_over_ranks(time.perf_counter() - t0)
+            op.solve(1e-6, 2)  # loads the solver's kernels
+            cg_s = float("inf")
+            for _ in range(2):  # two solves, the faster one is reported (run-to-run spread of the whole solve: ~5 %)
+                barrier()
+                t0 = time.perf_counter()
+                _, res, iters = op.solve(1e-6, args.cg_max_iters)
+                ctx.synchronize()
+                cg_s = min(cg_s, max_over_ranks(time.perf_counter() - t0))
             cg = {"iters": int(iters), "achieved_residual": float(res), "seconds": cg_s, "ms_per_iteration": cg_s * 1e3 / max(iters, 1),
                   "dofs_per_s": owned_total * iters / cg_s, "tol": 1e-6, "max_iters": args.cg_max_iters,
-                  "what": "full CG + Jacobi solve on the device, one operator apply + 12 vector passes per iteration, wall clock, max over ranks"}
+                  "what": "full CG + Jacobi solve on the device, one operator apply (p.Ap fused) + 10 vector passes per iteration, wall clock, max over ranks, faster of two solves"}
         gbs = mf_bytes_per_apply(n_owned, n_elems) / (ms * 1e-3) / 1e9
         fp64_fma = ctx.microbench(0)
         return {

@@ -196,8 +196,11 @@ enum
     L3B_APPLY_ELEMENTS = 2,
     L3B_APPLY_FINISH   = 4
 };
+/* energy: NULL, or a device scalar to which the ELEMENTS and FINISH phases add x^T A x of column 0 — this rank's elements and owned
+ * Dirichlet dofs, so that the sum over the phases and over the ranks is the global x^T A x (alpha and beta do not enter). CG uses it for
+ * p.Ap: the quadrature-point stage has w |B x_e|^2 at hand, which saves the dot-product pass over both vectors. */
 int l3b_mf_apply_phase_device(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta, int phases,
-                              int64_t elem_begin, int64_t elem_end);
+                              int64_t elem_begin, int64_t elem_end, double* energy);
 /* halo packing for comm::Import / comm::Export (comm/ImportExport.hpp:29-472) with device index lists:
  * gather: dst[i + c n] = src[idx[i] + c ld];  scatter_add: dst[idx[i] + c ld] += src[i + c n]. Asynchronous on the context stream. */
 int l3b_vec_gather(l3b_context* ctx, const double* src, int64_t ld, const int32_t* idx, int64_t n, int n_cols, double* dst);
@@ -205,9 +208,11 @@ int l3b_vec_scatter_add(l3b_context* ctx, double* dst, int64_t ld, const int32_t
 /* Preconditioned CG with callbacks, for operators and reductions the library does not own (the multi-rank apply with its halo
  * exchange, MPI/NCCL all-reduce of the dot products): Belos Block-CG semantics as l3b_mf_solve_cg, native Jacobi from `diag`.
  * Vectors are device pointers over n_local dofs of which the first n_owned are owned (dots and updates run over those).
- * apply(user, x, y): y = A x, enqueued on the context stream. allreduce(user, s, n): in-place sum over the ranks of the n device
- * scalars at s, ordered after the work already on the context stream (may be NULL on one rank). Both return 0 on success. */
-typedef int (*l3b_apply_callback)(void* user, const double* x, double* y);
+ * apply(user, x, y, energy): y = A x, enqueued on the context stream; energy is NULL or a zeroed device scalar: an operator that can
+ * add this rank's share of x^T A x to it while applying (l3b_mf_apply_phase_device) returns 1, otherwise it leaves it alone and returns 0
+ * (the solver then runs its own dot product); any other return value is a failure. allreduce(user, s, n): in-place sum over the ranks of
+ * the n device scalars at s, ordered after the work already on the context stream (may be NULL on one rank); returns 0 on success. */
+typedef int (*l3b_apply_callback)(void* user, const double* x, double* y, double* energy);
 typedef int (*l3b_allreduce_callback)(void* user, double* scalars, int n);
 /* Restarted GMRES with the same callbacks: Belos "Pseudoblock GMRES" as solve/BelosSolvers.hpp:42-131 configures it ("Num Blocks" =
  * restart_length 250, "Maximum Restarts" 39 by default, solve/SolverInterface.hpp:26-37), left Jacobi preconditioner, x0 = 0,

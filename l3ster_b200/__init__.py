@@ -49,7 +49,7 @@ class AssemblyOptions:
 
 
 # callbacks of l3b_pcg_device
-APPLY_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
+APPLY_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
 ALLREDUCE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)
 _lib = None
 APPLY_INIT, APPLY_ELEMENTS, APPLY_FINISH = 1, 2, 4
@@ -144,7 +144,7 @@ def lib():
     L.l3b_mf_end_assembly.argtypes = [vp]
     L.l3b_mf_download.argtypes = [vp, vp, vp]
     L.l3b_mf_apply_device.argtypes = [vp, vp, vp, i32, dbl, dbl]
-    L.l3b_mf_apply_phase_device.argtypes = [vp, vp, vp, i32, dbl, dbl, i32, i64, i64]
+    L.l3b_mf_apply_phase_device.argtypes = [vp, vp, vp, i32, dbl, dbl, i32, i64, i64, vp]
     L.l3b_vec_gather.argtypes = [vp, vp, i64, vp, i64, i32, vp]
     L.l3b_mf_end_assembly_begin.argtypes = [vp]
     L.l3b_asm_solve_gmres.argtypes = [vp, dbl, i32, i32, i32, vp, C.POINTER(dbl), C.POINTER(i32)]
@@ -372,16 +372,16 @@ class Context:
         return out.value
 
     def pcg(self, n_local, n_owned, apply, allreduce, diag_ptr, b_ptr, x_ptr, tol=1e-6, max_iters=10000):
-        """l3b_pcg_device: apply(x_ptr, y_ptr) and allreduce(scalars_ptr, n) are Python callables working on device pointers"""
+        """l3b_pcg_device: apply(x_ptr, y_ptr, energy_ptr) and allreduce(scalars_ptr, n) are Python callables working on device pointers;
+        apply returns True when it added this rank's share of x^T A x to the device scalar at energy_ptr (see l3b_apply_callback)"""
         err = []
 
-        def _apply(_, x, y):
+        def _apply(_, x, y, e):
             try:
-                apply(x, y)
-                return 0
+                return 1 if apply(x, y, e) is True else 0
             except Exception as exc:  # surfaces as an L3BError with the message kept
                 err.append(exc)
-                return 1
+                return 2
 
         def _reduce(_, s, n):
             try:
@@ -634,13 +634,17 @@ class MatrixFreeSystem:
         """host buffers already in the C ABI layout (column-major, contiguous): no numpy copies in the timed region"""
         self.ctx._chk(lib().l3b_mf_apply(self._h, xf.ctypes.data, yf.ctypes.data, n_cols, alpha, beta))
 
-    def apply_device(self, x_ptr, y_ptr, n_cols=1, alpha=1.0, beta=0.0):
-        self.ctx._chk(lib().l3b_mf_apply_device(self._h, x_ptr, y_ptr, n_cols, alpha, beta))
+    def apply_device(self, x_ptr, y_ptr, n_cols=1, alpha=1.0, beta=0.0, energy_ptr=None):
+        if energy_ptr is None:
+            self.ctx._chk(lib().l3b_mf_apply_device(self._h, x_ptr, y_ptr, n_cols, alpha, beta))
+        else:
+            self.apply_phase_device(x_ptr, y_ptr, APPLY_INIT | APPLY_ELEMENTS | APPLY_FINISH, n_cols=n_cols, alpha=alpha, beta=beta, energy_ptr=energy_ptr)
 
-    def apply_phase_device(self, x_ptr, y_ptr, phases, elem_begin=0, elem_end=None, n_cols=1, alpha=1.0, beta=0.0):
-        """One phase of the apply (APPLY_INIT | APPLY_ELEMENTS | APPLY_FINISH) on device pointers over [owned | ghost] dofs."""
+    def apply_phase_device(self, x_ptr, y_ptr, phases, elem_begin=0, elem_end=None, n_cols=1, alpha=1.0, beta=0.0, energy_ptr=None):
+        """One phase of the apply (APPLY_INIT | APPLY_ELEMENTS | APPLY_FINISH) on device pointers over [owned | ghost] dofs; energy_ptr:
+        device scalar that collects x^T A x of column 0 (elements of this call, owned Dirichlet dofs in the FINISH phase)."""
         end = self.mesh.n_elems if elem_end is None else elem_end
-        self.ctx._chk(lib().l3b_mf_apply_phase_device(self._h, x_ptr, y_ptr, n_cols, alpha, beta, phases, elem_begin, end))
+        self.ctx._chk(lib().l3b_mf_apply_phase_device(self._h, x_ptr, y_ptr, n_cols, alpha, beta, phases, elem_begin, end, energy_ptr))
 
     def solve(self, tol=1e-6, max_iters=10000):
         x = np.zeros(self.n_dofs)

@@ -167,13 +167,25 @@ __global__ void hexGeometryKernel(const double* verts, long long n_elems, double
     }
 }
 // the same over a compact list of the Dirichlet dofs (O(surface) instead of a pass over the whole vector)
-__global__ void dirichletRowsListKernel(const int32_t* dofs, long long n_dir, const double* x, double* y, long long ld, int n_cols, double alpha)
+// energy (may be null): x^T A x picks up x_d^2 per owned Dirichlet dof d of column 0 (the identity rows)
+__global__ void dirichletRowsListKernel(const int32_t* dofs, long long n_dir, const double* x, double* y, long long ld, int n_cols, double alpha,
+                                        double* energy, long long n_owned_dofs)
 {
+    double e = 0.;
     for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n_dir; i += static_cast< long long >(gridDim.x) * blockDim.x)
     {
         const long long d = dofs[i];
         for (int c = 0; c < n_cols; ++c)
             y[d + c * ld] += alpha * x[d + c * ld];
+        if (d < n_owned_dofs)
+            e = fma(x[d], x[d], e);
+    }
+    if (energy != nullptr)
+    {
+        for (int off = 16; off > 0; off >>= 1)
+            e += __shfl_xor_sync(0xffffffffu, e, off);
+        if ((threadIdx.x & 31) == 0 and e != 0.)
+            atomicAdd(energy, e);
     }
 }
 // halo packing (comm/ImportExport.hpp): gather / scatter-add through a device index list
@@ -241,15 +253,14 @@ __global__ void dot2Kernel(const double* a, const double* b, const double* c, co
             atomicAdd(out + 1, s1);
     }
 }
-// x += a p ; r -= a Ap ; z = minv r ; out[0] += r.r ; out[1] += r.z     (a = rz / pAp read from device scalars)
-__global__ void cgUpdateKernel(double* x, double* r, double* z, const double* p, const double* Ap, const double* minv, long long n,
-                               const double* scal /* [rz, pAp] */, double* out)
+// r -= a Ap ; z = minv r ; out[0] += r.r ; out[1] += r.z     (a = rz / pAp read from device scalars)
+__global__ void cgUpdateKernel(double* r, double* z, const double* Ap, const double* minv, long long n, const double* scal /* [rz, pAp] */,
+                               double* out)
 {
     const double a  = scal[0] / scal[1];
     double       s0 = 0., s1 = 0.;
     for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
     {
-        x[i] = fma(a, p[i], x[i]);
         const double ri = fma(-a, Ap[i], r[i]);
         r[i]            = ri;
         const double zi = minv[i] * ri;
@@ -265,12 +276,23 @@ __global__ void cgUpdateKernel(double* x, double* r, double* z, const double* p,
         atomicAdd(out + 1, s1);
     }
 }
-// p = z + (rz_new / rz_old) p
-__global__ void cgDirectionKernel(double* p, const double* z, long long n, const double* rz_new, const double* rz_old)
+// x += a p ; p = z + (rz_new / rz_old) p     (the x update rides on the pass that reads p anyway; scal = [rz_old, pAp, rr, rz_new])
+__global__ void cgDirectionKernel(double* x, double* p, const double* z, long long n, const double* scal)
 {
-    const double b = rz_new[0] / rz_old[0];
+    const double a = scal[0] / scal[1], b = scal[3] / scal[0];
     for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
-        p[i] = fma(b, p[i], z[i]);
+    {
+        const double pi = p[i];
+        x[i]            = fma(a, pi, x[i]);
+        p[i]            = fma(b, pi, z[i]);
+    }
+}
+// x += a p     (last iteration: no next direction)
+__global__ void cgFinalKernel(double* x, const double* p, long long n, const double* scal)
+{
+    const double a = scal[0] / scal[1];
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
+        x[i] = fma(a, p[i], x[i]);
 }
 __global__ void hadamardKernel(double* z, const double* minv, const double* r, long long n)
 {
@@ -780,7 +802,7 @@ int guardedCtx(const l3b_context* ctx, F&& f)
 // y[dofs(e)] += alpha K_e x[dofs(e)] for one registered kernel over the domain elements [elem_begin, elem_end) (boundary kernels:
 // their whole side list, with the range that contains element 0). `masked`: honour the Dirichlet mask (the operator apply) or not
 // (the Dirichlet lifting of the initialisation). Returns the number of kernels launched.
-int applyUse(l3b_mf* sys, const KernelUse& use, const double* x, double* y, int n_cols, double alpha, bool masked, long long elem_begin,
+int applyUse(l3b_mf* sys, const KernelUse& use, const double* x, double* y, int n_cols, double alpha, bool masked, double* energy, long long elem_begin,
              long long elem_end)
 {
     auto*       ctx  = sys->ctx;
@@ -800,6 +822,7 @@ int applyUse(l3b_mf* sys, const KernelUse& use, const double* x, double* y, int 
     a.y              = y;
     a.n_cols         = n_cols;
     a.alpha          = alpha;
+    a.energy         = energy;
     a.dir_mask       = sys->has_bc and masked ? sys->dir_mask.ptr : nullptr;
     a.elem_dir       = sys->has_bc and masked ? sys->elem_dir.ptr : nullptr;
     bool contiguous  = info.n_unknowns == sys->dpn and reinterpret_cast< uintptr_t >(x) % 16 == 0 and sys->n_dofs % 2 == 0;
@@ -824,8 +847,10 @@ int applyUse(l3b_mf* sys, const KernelUse& use, const double* x, double* y, int 
 }
 
 // y = alpha A x + beta y on device pointers, in the phases of l3b_mf_apply_phase_device
+// energy (may be null): the ELEMENTS and FINISH phases add x^T A x of column 0, restricted to this rank's elements and owned Dirichlet
+// dofs, to this device scalar
 void mfApplyPhases(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta, int phases, long long elem_begin,
-                   long long elem_end)
+                   long long elem_end, double* energy = nullptr)
 {
     auto* ctx = sys->ctx;
     if (not sys->closed)
@@ -834,6 +859,8 @@ void mfApplyPhases(l3b_mf* sys, const double* x, double* y, int n_cols, double a
         fail(L3B_ERR_INVALID_ARG, "n_cols must equal the system's n_rhs or 1");
     if (elem_begin < 0 or elem_end > sys->mesh->n_elems or elem_begin > elem_end)
         fail(L3B_ERR_INVALID_ARG, "element range out of bounds");
+    if (energy != nullptr and n_cols != 1)
+        fail(L3B_ERR_INVALID_ARG, "the energy x^T A x is collected for single-column applies only");
     int launches = 0;
     if (phases & L3B_APPLY_INIT)
     {
@@ -847,23 +874,24 @@ void mfApplyPhases(l3b_mf* sys, const double* x, double* y, int n_cols, double a
     }
     if (phases & L3B_APPLY_ELEMENTS)
         for (const auto& use : sys->uses)
-            launches += applyUse(sys, use, x, y, n_cols, alpha, true, elem_begin, elem_end);
+            launches += applyUse(sys, use, x, y, n_cols, alpha, true, energy, elem_begin, elem_end);
     if ((phases & L3B_APPLY_FINISH) and sys->has_bc and sys->n_dir > 0)
     {
-        dirichletRowsListKernel<<< gridFor(sys->n_dir), 256, 0, ctx->stream >>>(sys->dir_list.ptr, sys->n_dir, x, y, sys->n_dofs, n_cols, alpha);
+        dirichletRowsListKernel<<< gridFor(sys->n_dir), 256, 0, ctx->stream >>>(sys->dir_list.ptr, sys->n_dir, x, y, sys->n_dofs, n_cols, alpha, energy,
+                                                                                static_cast< long long >(sys->mesh->n_owned_nodes) * sys->dpn);
         ++launches;
     }
     cudaCheck(cudaGetLastError(), "operator apply");
     sys->last_launches = launches; // of this call
 }
-void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta)
+void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta, double* energy = nullptr)
 {
-    mfApplyPhases(sys, x, y, n_cols, alpha, beta, L3B_APPLY_INIT | L3B_APPLY_ELEMENTS | L3B_APPLY_FINISH, 0, sys->mesh->n_elems);
+    mfApplyPhases(sys, x, y, n_cols, alpha, beta, L3B_APPLY_INIT | L3B_APPLY_ELEMENTS | L3B_APPLY_FINISH, 0, sys->mesh->n_elems, energy);
 }
 
 // Preconditioned CG, Belos "Block CG" semantics for block size 1 (solve/BelosSolvers.hpp:76-89): left preconditioner,
-// absolute 2-norm of the (unpreconditioned) residual against `tol`, x0 = 0. One fused vector kernel and one 2-scalar
-// read-back per iteration. The read-back goes to pinned memory behind an event, and the host waits for it only after it has
+// absolute 2-norm of the (unpreconditioned) residual against `tol`, x0 = 0. Two fused vector kernels (10 vector passes) and one
+// 2-scalar read-back per iteration. The read-back goes to pinned memory behind an event, and the host waits for it only after it has
 // queued the next direction update and operator apply: the device never idles on the convergence test (the speculative work
 // touches p and Ap only, so x is final when the test succeeds).
 struct PinnedScalars
@@ -911,23 +939,29 @@ void pcg(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Reduce
     if (rnorm > tol and max_iters > 0)
     {
         cudaCheck(cudaMemcpyAsync(sc, sc + 3, sizeof(double), cudaMemcpyDeviceToDevice, s), "copy"); // rz
-        apply(p.ptr, Ap.ptr);
+        // the operator may add p.Ap to sc[1] itself (matrix-free apply: the energy falls out of its quadrature-point stage)
+        const auto applyAndDot = [&] {
+            cudaCheck(cudaMemsetAsync(sc + 1, 0, 3 * sizeof(double), s), "memset");
+            if (not apply(p.ptr, Ap.ptr, sc + 1))
+                dot2Kernel<<< g, 256, 0, s >>>(p.ptr, Ap.ptr, nullptr, nullptr, n, sc + 1);
+        };
+        applyAndDot();
         while (true)
         {
-            cudaCheck(cudaMemsetAsync(sc + 1, 0, 3 * sizeof(double), s), "memset");
-            dot2Kernel<<< g, 256, 0, s >>>(p.ptr, Ap.ptr, nullptr, nullptr, n, sc + 1);
             reduce(sc + 1, 1);
-            cgUpdateKernel<<< g, 256, 0, s >>>(x, r.ptr, z.ptr, p.ptr, Ap.ptr, minv.ptr, n, sc, sc + 2);
+            cgUpdateKernel<<< g, 256, 0, s >>>(r.ptr, z.ptr, Ap.ptr, minv.ptr, n, sc, sc + 2);
             reduce(sc + 2, 2);
             cudaCheck(cudaMemcpyAsync(h, sc + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, s), "copy");
             cudaCheck(cudaEventRecord(read_back.ev, s), "event");
             ++it;
             const bool last = it >= max_iters;
-            if (not last) // queued before the convergence test is known: next direction and its operator apply
+            if (last)
+                cgFinalKernel<<< g, 256, 0, s >>>(x, p.ptr, n, sc);
+            else // queued before the convergence test is known: x update + next direction, and its operator apply
             {
-                cgDirectionKernel<<< g, 256, 0, s >>>(p.ptr, z.ptr, n, sc + 3, sc);
+                cgDirectionKernel<<< g, 256, 0, s >>>(x, p.ptr, z.ptr, n, sc);
                 cudaCheck(cudaMemcpyAsync(sc, sc + 3, sizeof(double), cudaMemcpyDeviceToDevice, s), "copy");
-                apply(p.ptr, Ap.ptr);
+                applyAndDot();
             }
             cudaCheck(cudaEventSynchronize(read_back.ev), "sync");
             rnorm = std::sqrt(h[0]);
@@ -1563,9 +1597,10 @@ int l3b_asm_solve_cg(l3b_asm* sys, double tol, int max_iters, double* x, double*
         const long long threads = n * 32;
         pcg(
             sys->ctx, n, n,
-            [&](const double* in, double* out) {
+            [&](const double* in, double* out, double*) {
                 spmvKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
                     sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, in, out);
+                return false; // p.Ap by a dot-product pass
             },
             [](double*, int) {}, diag.ptr, sys->rhs.ptr, dx.ptr, tol, max_iters, achieved_tol, iters);
         dx.download(x, n, sys->ctx->stream);
@@ -1673,7 +1708,7 @@ int l3b_mf_end_assembly_begin(l3b_mf* sys)
             const bool fast = use.inst->init_fast != nullptr and not force_dense;
             cudaCheck((fast ? use.inst->init_fast : use.inst->init)(kernelRegistry()[use.kernel_id].object.get(), a, ctx->stream), "init launch");
             if (fast and sys->lift_needed)
-                applyUse(sys, use, sys->dir_g.ptr, sys->rhs.ptr, sys->n_rhs, -1., false, 0, sys->mesh->n_elems);
+                applyUse(sys, use, sys->dir_g.ptr, sys->rhs.ptr, sys->n_rhs, -1., false, nullptr, 0, sys->mesh->n_elems);
         }
         cudaCheck(cudaGetLastError(), "init");
     });
@@ -1715,7 +1750,8 @@ int l3b_gmres_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_app
         gmres(
             ctx, n_local, n_owned,
             [&](const double* in, double* out) {
-                if (apply(user, in, out) != 0)
+                const int rc = apply(user, in, out, nullptr);
+                if (rc != 0 and rc != 1)
                     fail(L3B_ERR_INVALID_ARG, "l3b_gmres_device: the apply callback failed");
             },
             [&](double* sc, int n) {
@@ -1749,9 +1785,11 @@ int l3b_pcg_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_apply
             fail(L3B_ERR_INVALID_ARG, "l3b_pcg_device: invalid arguments");
         pcg(
             ctx, n_local, n_owned,
-            [&](const double* in, double* out) {
-                if (apply(user, in, out) != 0)
+            [&](const double* in, double* out, double* energy) {
+                const int rc = apply(user, in, out, energy);
+                if (rc != 0 and rc != 1)
                     fail(L3B_ERR_INVALID_ARG, "l3b_pcg_device: the apply callback failed");
+                return rc == 1;
             },
             [&](double* sc, int n) {
                 if (allreduce != nullptr and allreduce(user, sc, n) != 0)
@@ -1775,9 +1813,9 @@ int l3b_mf_apply_device(l3b_mf* sys, const double* x, double* y, int n_cols, dou
     return guardedCtx(sys->ctx, [&] { mfApplyDevice(sys, x, y, n_cols, alpha, beta); });
 }
 int l3b_mf_apply_phase_device(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta, int phases, int64_t elem_begin,
-                              int64_t elem_end)
+                              int64_t elem_end, double* energy)
 {
-    return guardedCtx(sys->ctx, [&] { mfApplyPhases(sys, x, y, n_cols, alpha, beta, phases, elem_begin, elem_end); });
+    return guardedCtx(sys->ctx, [&] { mfApplyPhases(sys, x, y, n_cols, alpha, beta, phases, elem_begin, elem_end, energy); });
 }
 int l3b_vec_gather(l3b_context* ctx, const double* src, int64_t ld, const int32_t* idx, int64_t n, int n_cols, double* dst)
 {
@@ -1822,7 +1860,11 @@ int l3b_mf_solve_cg(l3b_mf* sys, double tol, int max_iters, double* x, double* a
             fail(L3B_ERR_INVALID_ARG, "the CG driver handles one right-hand side");
         DevBuf< double > dx(sys->n_dofs);
         pcg(
-            sys->ctx, sys->n_dofs, sys->n_dofs, [&](const double* in, double* out) { mfApplyDevice(sys, in, out, 1, 1., 0.); },
+            sys->ctx, sys->n_dofs, sys->n_dofs,
+            [&](const double* in, double* out, double* energy) {
+                mfApplyDevice(sys, in, out, 1, 1., 0., energy);
+                return true; // p.Ap comes out of the apply
+            },
             [](double*, int) {}, sys->diag.ptr, sys->rhs.ptr, dx.ptr, tol, max_iters, achieved_tol, iters);
         dx.download(x, sys->n_dofs, sys->ctx->stream);
         cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "solve");

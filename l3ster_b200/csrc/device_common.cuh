@@ -53,6 +53,9 @@ struct ElemArgs
     long long     ld;
     int           n_cols;
     double        alpha;
+    // operator apply only, may be null: x^T A x of operand column 0 over the elements of this launch is added here (for CG's p.Ap:
+    // sum_q w |B_q x_e|^2 falls out of the point stage, which saves the separate dot-product pass over both vectors)
+    double* energy;
     // Dirichlet mask per local dof (may be null) and prescribed values (ld-strided, may be null)
     const uint8_t* dir_mask;
     const double*  dir_vals;

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(local_threads) localElementKernel(const Kernel
     const double*   tab_pts  = args.tab_pts + tab_off * DIM;
     const double*   tab_wts  = args.tab_wts + tab_off;
 
+    double energy = 0.;
     for (int q = 0; q < args.n_qp; ++q)
     {
         // mapping (MapReferenceToPhysical.hpp:28-89) — every thread redundantly, it is a handful of FMAs
@@ -231,6 +232,10 @@ __global__ void __launch_bounds__(local_threads) localElementKernel(const Kernel
                 }
         }
         blockReduce< E * NCOL >(tv, s_red);
+        if constexpr (MODE == MODE_APPLY)
+            if (tid == 0 and args.energy != nullptr) // x^T A x of column 0: sum_q w |H_q^T x_e|^2
+                for (int eq = 0; eq < E; ++eq)
+                    energy = fma(tv[eq] * weight, tv[eq], energy);
         // y += H (w t)
         for (int a = tid; a < NN; a += local_threads)
         {
@@ -256,6 +261,9 @@ __global__ void __launch_bounds__(local_threads) localElementKernel(const Kernel
         __syncthreads();
     }
 
+    if constexpr (MODE == MODE_APPLY)
+        if (tid == 0 and args.energy != nullptr)
+            atomicAdd(args.energy, energy);
     // scatter
     for (int a = tid; a < NN; a += local_threads)
     {

@@ -91,6 +91,14 @@ struct MfHexCfg
     static constexpr int  min_blocks  = smem_bytes <= 112 * 1024 ? 2 : 1;
 #endif
     static constexpr bool supported   = CT <= 49 and smem_bytes <= 220 * 1024;
+    // second copy of the point stage for axis-aligned elements: measured per order (ms per apply with / without, profiles/r1_final_summary.md):
+    // p=4 1.50 / 1.63, but p=3 1.52 / 1.44, p=2 1.21 / 1.19, p=5 2.09 / 1.75 (at the 255-register limit the extra code costs more than
+    // the saved multiply-adds) — so only the nq = 5 instances carry it
+#ifdef L3B_HEX_DIAG_FAST_MAX_NQ
+    static constexpr bool diag_fast_path = NQ <= L3B_HEX_DIAG_FAST_MAX_NQ; // experiment override
+#else
+    static constexpr bool diag_fast_path = NQ == 5;
+#endif
     static constexpr bool mask_bits_fit = NB * U <= 64;
     static_assert(params.dimension == 3);
     static_assert(NQ >= NB, "collocation differentiation at the Gauss points needs nq >= nb (value_order >= 1)");
@@ -144,7 +152,9 @@ __device__ __forceinline__ void cpAsyncWaitAll()
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-template < typename KernelT, int P, int NQ, int NRHS >
+// ENERGY: also accumulate x^T A x (ElemArgs::energy). A separate instantiation: the plain apply keeps its registers (240 at p = 4;
+// one more live double costs 6 registers and 3 % of the apply).
+template < typename KernelT, int P, int NQ, int NRHS, bool ENERGY = false >
 __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfHexCfg< KernelT, P, NQ, NRHS >::min_blocks)
     mfHexPlanesKernel(const KernelT kernel, const __grid_constant__ ElemArgs args, const __grid_constant__ SumFactTables< P + 1, NQ > tab)
 {
@@ -281,6 +291,8 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
         prefetchIds(1);
     cpAsyncCommit();
 
+    constexpr bool want_energy = ENERGY;
+    double         energy      = 0.; // this thread's share of x^T A x = sum_q w |B_q x_e|^2 (operand column 0)
     for (int it = 0; it < n_it; ++it)
     {
         const int       n_active = activeIn(it);
@@ -566,6 +578,9 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
                             });
                         });
                         tv[eq] = acc * wgt;
+                        if constexpr (want_energy)
+                            if (r == 0)
+                                energy = fma(acc, tv[eq], energy);
                     });
                     staticFor< U >([&](auto u) {
                         double a0 = 0., ps[3] = {0., 0., 0.};
@@ -608,8 +623,13 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
                         s_V[((r * U + u) * NQ + q) * (EPB * PSZ) + col_off] = wacc[u][q];
             }
             };
-            if (geo[hex_geo_affine] == 2.)
-                pointStage(std::true_type{});
+            if constexpr (Cfg::diag_fast_path)
+            {
+                if (geo[hex_geo_affine] == 2.)
+                    pointStage(std::true_type{});
+                else
+                    pointStage(std::false_type{});
+            }
             else
                 pointStage(std::false_type{});
             if (violated)
@@ -764,6 +784,14 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
             }
         }
 #endif
+    }
+    if constexpr (want_energy)
+    {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+            energy += __shfl_xor_sync(0xffffffffu, energy, off);
+        if ((tid & 31) == 0)
+            atomicAdd(args.energy, energy);
     }
 }
 } // namespace l3b

@@ -227,6 +227,12 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
 
     if (active)
         buildGeometryCoefs< DIM >(args.verts + e * nv * 3, s_geo, t, TPE);
+    // x^T A x of operand column 0 (ElemArgs::energy): per-thread share of sum_q w |B_q x_e|^2, summed through shared memory
+    __shared__ double s_energy;
+    const bool        want_energy = args.energy != nullptr;
+    double            energy      = 0.;
+    if (threadIdx.x == 0)
+        s_energy = 0.;
 
     // ---- gather (MatrixFreeSystem.hpp:421-467) into s_val[f], f = rhs*U + u, then the NF external fields.
     // One lane per (node, unknown): the U dofs of a node are adjacent in x, so a warp touches ~32/U sectors per load
@@ -464,6 +470,8 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
                     });
                 });
                 tv[eq] = acc * wgt;
+                if (want_energy and r == 0)
+                    energy = fma(acc, tv[eq], energy);
             });
             staticFor< U >([&](auto u) {
                 double a0 = 0., ps[DIM];
@@ -491,8 +499,12 @@ __global__ void __launch_bounds__(MfSumFactCfg< KernelT, DIM, P, NQ, NRHS >::thr
                 }
             });
         }
+        if (want_energy)
+            atomicAdd(&s_energy, energy);
     }
     __syncthreads();
+    if (want_energy and threadIdx.x == 0)
+        atomicAdd(args.energy, s_energy);
 
     // ---- transposed stage: v = r0 + sum_d D_d^T r_d, then Gauss points → nodes; all in place on s_val[f < F0]
     {

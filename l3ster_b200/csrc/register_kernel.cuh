@@ -72,21 +72,11 @@ inline bool forceLineKernel()
     }();
     return force;
 }
-template < typename KernelT, int P, int NQ, int NC >
-cudaError_t launchMfHex(const void* obj, const ElemArgs& args, const tables::Tables1D& t, cudaStream_t stream)
+template < typename KernelT, int P, int NQ, int NC, bool ENERGY >
+cudaError_t launchMfHexImpl(const void* obj, const ElemArgs& args, const SumFactTables< P + 1, NQ >& tab, cudaStream_t stream)
 {
-    using Cfg = MfHexCfg< KernelT, P, NQ, NC >;
-    if (forceLineKernel())
-        return launchMfSumFact< KernelT, 3, P, NQ, NC >(obj, args, t, stream);
-    if (args.n_work == 0)
-        return cudaSuccess;
-    SumFactTables< P + 1, NQ > tab;
-    std::copy(t.interp.begin(), t.interp.end(), tab.interp);
-    std::copy(t.der.begin(), t.der.end(), tab.der);
-    std::copy(t.colloc.begin(), t.colloc.end(), tab.colloc);
-    std::copy(t.w.begin(), t.w.end(), tab.w);
-    std::copy(t.pts.begin(), t.pts.end(), tab.pts);
-    constexpr auto fn = mfHexPlanesKernel< KernelT, P, NQ, NC >;
+    using Cfg         = MfHexCfg< KernelT, P, NQ, NC >;
+    constexpr auto fn = mfHexPlanesKernel< KernelT, P, NQ, NC, ENERGY >;
     if (const auto err = raiseSmemLimit< fn >(Cfg::smem_bytes); err != cudaSuccess)
         return err;
     static const cudaError_t carveout =
@@ -105,6 +95,27 @@ cudaError_t launchMfHex(const void* obj, const ElemArgs& args, const tables::Tab
     const auto      grid      = static_cast< unsigned >(std::min< long long >(n_batches, resident));
     fn<<< grid, Cfg::threads, Cfg::smem_bytes, stream >>>(*static_cast< const KernelT* >(obj), args, tab);
     return cudaGetLastError();
+}
+template < typename KernelT, int P, int NQ, int NC >
+cudaError_t launchMfHex(const void* obj, const ElemArgs& args, const tables::Tables1D& t, cudaStream_t stream)
+{
+    if (forceLineKernel())
+        return launchMfSumFact< KernelT, 3, P, NQ, NC >(obj, args, t, stream);
+    if (args.n_work == 0)
+        return cudaSuccess;
+    SumFactTables< P + 1, NQ > tab;
+    std::copy(t.interp.begin(), t.interp.end(), tab.interp);
+    std::copy(t.der.begin(), t.der.end(), tab.der);
+    std::copy(t.colloc.begin(), t.colloc.end(), tab.colloc);
+    std::copy(t.w.begin(), t.w.end(), tab.w);
+    std::copy(t.pts.begin(), t.pts.end(), tab.pts);
+    // the energy variant only for single-column applies (CG): the full-n_rhs instantiations stay single
+    if constexpr (NC == 1)
+        if (args.energy != nullptr)
+            return launchMfHexImpl< KernelT, P, NQ, NC, true >(obj, args, tab, stream);
+    if (args.energy != nullptr)
+        return cudaErrorNotSupported;
+    return launchMfHexImpl< KernelT, P, NQ, NC, false >(obj, args, tab, stream);
 }
 
 template < typename KernelT, int DIM, int P, int NC, int MODE >

@@ -237,10 +237,11 @@ class SlabOperator:
         torch.cuda.current_stream().synchronize()  # torch filled x on its own stream; the library's stream does not wait for it
         multi = self.slab.world > 1 and dist.is_initialized()
 
-        def apply(xp, yp):
+        def apply(xp, yp, energy_ptr):
             xv = _device_view(xp, self.n_local_dofs, dev)
             yv = _device_view(yp, self.n_local_dofs, dev)
-            self.apply(xv, yv)
+            self.apply(xv, yv, energy_ptr=energy_ptr)
+            return True  # p.Ap comes out of the element kernels: no dot-product pass
 
         def allreduce(sp, n):
             with torch.cuda.stream(self.stream):
@@ -252,15 +253,16 @@ class SlabOperator:
                                self.sys.device_rhs, x.data_ptr(), tol, max_iters)
         return x, res, it
 
-    def apply(self, x, y, alpha=1.0, beta=0.0):
-        """y[owned] = alpha (A x)[owned] + beta y[owned]; x[ghost] is overwritten by the Import. Asynchronous."""
+    def apply(self, x, y, alpha=1.0, beta=0.0, energy_ptr=None):
+        """y[owned] = alpha (A x)[owned] + beta y[owned]; x[ghost] is overwritten by the Import. Asynchronous. energy_ptr: device scalar
+        that receives this rank's share of x^T A x (l3b_mf_apply_phase_device)."""
         torch, s, sys_, halo = self.torch, self.slab, self.sys, self.halo
         if sys_ is None:
             return
         S, Cs = self.stream, self.comm
         if s.world == 1 or (s.lower < 0 and s.upper < 0):  # no neighbours: one launch over all elements
             with torch.cuda.stream(S):
-                sys_.apply_device(x.data_ptr(), y.data_ptr(), 1, alpha, beta)
+                sys_.apply_device(x.data_ptr(), y.data_ptr(), 1, alpha, beta, energy_ptr=energy_ptr)
             self.launches = sys_.kernel_launches
             return
         # all interior elements run while the Import is in flight; the 2 MB Export is left exposed — splitting the interior in two
@@ -278,10 +280,10 @@ class SlabOperator:
         with torch.cuda.stream(S):
             sys_.apply_phase_device(xp, yp, l3b.APPLY_INIT, 0, 0, alpha=alpha, beta=beta)
             n += sys_.kernel_launches
-            sys_.apply_phase_device(xp, yp, l3b.APPLY_ELEMENTS, s.n_border_elems, half, alpha=alpha)
+            sys_.apply_phase_device(xp, yp, l3b.APPLY_ELEMENTS, s.n_border_elems, half, alpha=alpha, energy_ptr=energy_ptr)
             n += sys_.kernel_launches
             S.wait_event(ev_imported)
-            sys_.apply_phase_device(xp, yp, l3b.APPLY_ELEMENTS, 0, s.n_border_elems, alpha=alpha)
+            sys_.apply_phase_device(xp, yp, l3b.APPLY_ELEMENTS, 0, s.n_border_elems, alpha=alpha, energy_ptr=energy_ptr)
             n += sys_.kernel_launches
             ev_border = S.record_event()
         with torch.cuda.stream(Cs):
@@ -290,11 +292,11 @@ class SlabOperator:
             ev_exported = Cs.record_event()
         with torch.cuda.stream(S):
             if half < s.n_elems:
-                sys_.apply_phase_device(xp, yp, l3b.APPLY_ELEMENTS, half, s.n_elems, alpha=alpha)
+                sys_.apply_phase_device(xp, yp, l3b.APPLY_ELEMENTS, half, s.n_elems, alpha=alpha, energy_ptr=energy_ptr)
                 n += sys_.kernel_launches
             S.wait_event(ev_exported)
             n += halo.unpack_add(y)
-            sys_.apply_phase_device(xp, yp, l3b.APPLY_FINISH, 0, 0, alpha=alpha)
+            sys_.apply_phase_device(xp, yp, l3b.APPLY_FINISH, 0, 0, alpha=alpha, energy_ptr=energy_ptr)
             n += sys_.kernel_launches
         self.launches = n
 
@@ -352,8 +354,9 @@ class SlabAssembledOperator:
         torch.cuda.current_stream().synchronize()  # torch filled x on its own stream; the library's stream does not wait for it
         multi = self.slab.world > 1 and dist.is_initialized()
 
-        def apply(xp, yp):
+        def apply(xp, yp, _energy_ptr):
             self.apply(_device_view(xp, self.n_local_dofs, dev), _device_view(yp, self.n_local_dofs, dev))
+            return False
 
         def allreduce(sp, n):
             with torch.cuda.stream(self.stream):

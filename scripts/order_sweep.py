@@ -32,26 +32,28 @@ def ref_flops(p):
     return q * (18 * nn + 7 * L * E + (L + 1) ** 2 / 2 * (2 * E + 1))
 
 
-def run(kind):
+def run(kind, orders=(1, 2, 3, 4, 5, 6)):
     import torch
 
     ctx = l3b.Context(0)
-    for p in (1, 2, 3, 4, 5, 6):
-        # elements so that the CRS stays below ~6 GB
-        n = {1: 40, 2: 28, 3: 20, 4: 14, 5: 10, 6: 8}[p]
-        host = l3b.make_cube_mesh(node_dist(n), order=p)
-        mesh = ctx.upload_mesh(host)
-        a = l3b.AssembledSystem(ctx, mesh, U, 1, host.node_graph())
-        ms = []
-        for it in range(5):
-            a.beginAssembly()
-            a.assembleProblem("bench_diffusion3d")
-            ms.append(a.last_kernel_ms)
-        k_ms = float(np.mean(ms[2:]))
-        line = {"order": p, "kernel": kind, "elements": host.n_elems, "kernel_ms": k_ms, "elements_per_s": host.n_elems / (k_ms * 1e-3),
-                "tflops_reference_count": ref_flops(p) * host.n_elems / (k_ms * 1e-3) / 1e12}
-        if kind == "dmma":  # the matrix-free apply of the same order, once
+    for p in orders:
+        line = {"order": p, "kernel": kind}
+        if kind != "mf":
+            # elements so that the CRS stays below ~6 GB
+            n = {1: 40, 2: 28, 3: 20, 4: 14, 5: 10, 6: 8}[p]
+            host = l3b.make_cube_mesh(node_dist(n), order=p)
+            mesh = ctx.upload_mesh(host)
+            a = l3b.AssembledSystem(ctx, mesh, U, 1, host.node_graph())
+            ms = []
+            for it in range(5):
+                a.beginAssembly()
+                a.assembleProblem("bench_diffusion3d")
+                ms.append(a.last_kernel_ms)
+            k_ms = float(np.mean(ms[2:]))
+            line.update({"elements": host.n_elems, "kernel_ms": k_ms, "elements_per_s": host.n_elems / (k_ms * 1e-3),
+                         "tflops_reference_count": ref_flops(p) * host.n_elems / (k_ms * 1e-3) / 1e12})
             del a
+        if kind in ("dmma", "mf"):  # the matrix-free apply of the same order, once
             nm = {1: 128, 2: 96, 3: 80, 4: 64, 5: 48, 6: 40}[p]
             hm = l3b.make_cube_mesh(node_dist(nm), order=p)
             mm = ctx.upload_mesh(hm)
@@ -81,7 +83,9 @@ def run(kind):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 2:  # e.g. `order_sweep.py mf 4 5 6`: the matrix-free apply only, these orders
+        run(sys.argv[1], tuple(int(a) for a in sys.argv[2:]))
+    elif len(sys.argv) > 1:
         run(sys.argv[1])
     else:
         run("dmma")

@@ -250,3 +250,44 @@ def test_karman_kernels_matrix_free(ctx):
     assert rel_err(s.apply(x), A @ x) < TOL
     diag, rhs = s.download()
     assert rel_err(diag, A.diagonal()) < TOL and rel_err(rhs, rhs_o) < TOL
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[3], CASES[6], CASES[9], CASES[11]], ids=lambda c: f"{c[0]}-d{c[2]}-p{c[4]}")
+@pytest.mark.parametrize("strategy", [0, 1], ids=["sumfact", "local_element"])
+def test_apply_energy_is_x_dot_Ax(ctx, case, strategy):
+    """The device scalar of l3b_mf_apply_phase_device collects x^T A x (CG's p.Ap) inside the element kernels — planes + columns, line per
+    thread and dense local-element kernels, with Dirichlet identity rows — and must equal the dot product of x with the applied y."""
+    import torch
+
+    kname, _, dim, n, p, opts, n_rhs = case
+    opts = l3b.AssemblyOptions(opts.value_order, opts.derivative_order, strategy)
+    info = l3b.kernel_info(kname)
+    U, NF = info["n_unknowns"], info["n_fields"]
+    pm = PairedMesh(dim, default_dists(dim, n), p)
+    mesh = pm.upload(ctx)
+    fdata = _fields(NF, pm.n_nodes, 7) if NF else None
+    mask, dvals = _dirichlet(pm, U, [1, 2 * dim], [0, U - 1], n_rhs, 3)
+    s = l3b.MatrixFreeSystem(ctx, mesh, U, n_rhs, mask, dvals)
+    fields = ctx.upload_fields(fdata) if NF else None
+    s.assembleProblem(kname, fields=fields, asm_opts=opts, time=0.37)
+    if dim == 2 and kname == "example02_domain":
+        s.assembleProblem("example02_bc", boundary_ids=[2, 3])  # a boundary kernel in the same operator
+    s.endAssembly()
+    x = torch.from_numpy(np.random.default_rng(5).uniform(-1, 1, size=s.n_dofs)).cuda()
+    y = torch.zeros_like(x)
+    e = torch.zeros(1, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    s.apply_device(x.data_ptr(), y.data_ptr(), 1, -0.7, 0.0, energy_ptr=e.data_ptr())  # alpha must not enter the energy
+    ctx.synchronize()
+    xAx = float(torch.dot(x, y).item()) / -0.7
+    assert abs(e.item() - xAx) <= 1e-12 * abs(xAx)
+    # the same in phases over two element ranges (the multi-rank apply): the shares add up
+    e.zero_()
+    torch.cuda.synchronize()
+    half = pm.host.n_elems // 2
+    s.apply_phase_device(x.data_ptr(), y.data_ptr(), l3b.APPLY_INIT, 0, 0)
+    s.apply_phase_device(x.data_ptr(), y.data_ptr(), l3b.APPLY_ELEMENTS, half, pm.host.n_elems, energy_ptr=e.data_ptr())
+    s.apply_phase_device(x.data_ptr(), y.data_ptr(), l3b.APPLY_ELEMENTS, 0, half, energy_ptr=e.data_ptr())
+    s.apply_phase_device(x.data_ptr(), y.data_ptr(), l3b.APPLY_FINISH, 0, 0, energy_ptr=e.data_ptr())
+    ctx.synchronize()
+    assert abs(e.item() - xAx) <= 1e-12 * abs(xAx)
