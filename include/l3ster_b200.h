@@ -234,6 +234,26 @@ int l3b_compute_integral(l3b_context* ctx, l3b_mesh* mesh, int kernel_id, l3b_as
                          const int* field_inds, const int* boundary_ids, int n_boundary_ids, double* out);
 int l3b_compute_norm_l2(l3b_context* ctx, l3b_mesh* mesh, int kernel_id, l3b_asm_opts opts, double time, const l3b_fields* fields,
                         const int* field_inds, const int* boundary_ids, int n_boundary_ids, double* out);
+/* ---- static condensation, CondensationPolicy::ElementBoundary (algsys/StaticCondensationManager.hpp:135-535) ---------------------
+ * The element matrices are assembled, with the ordinary l3b_asm_* calls, into an element-local system: an l3b_asm over the same
+ * elements with node ids e * nodes_per_elem + a (every element its own nodes: the CRS is then the dense K_e, block by block). The
+ * condensed system lives on the primary (element-boundary) nodes: l3b_crs_create makes its storage from the node graph of the
+ * elements' boundary-node lists (no mesh: it only receives l3b_cond_condense's contributions, then takes l3b_asm_end_assembly — the
+ * algebraic Dirichlet conditions in primary dof numbering — and the solvers like any l3b_asm).
+ *   l3b_cond_create: bnd_idx / int_idx = local node indices of the boundary / interior nodes of an element; elem_prim[e][ib] = primary
+ *     id of boundary node ib; elem_nodes[e][a] = node id in the original mesh (for the recovered solution).
+ *   l3b_cond_condense (StaticCondensationManager::endAssemblyImpl :330-353, with condenseSystemImpl's K_pp scatter :355-418 folded in):
+ *     adds K_pp - K_pi K_ii^-1 K_ip and f_p - K_pi K_ii^-1 f_i of every element to the condensed system; closes the element-local one.
+ *   l3b_cond_recover (recoverSolutionImpl :420-535): x_i = K_ii^-1 (f_i - K_ip x_p); out[node * dofs_per_node + d + r * n_nodes * dpn]. */
+typedef struct l3b_cond l3b_cond;
+int  l3b_crs_create(l3b_context* ctx, int64_t n_nodes, int dofs_per_node, int n_rhs, const int64_t* node_ptr, const uint32_t* node_nbr,
+                    l3b_asm** out);
+int  l3b_cond_create(l3b_context* ctx, l3b_asm* elem_sys, l3b_asm* cond_sys, int64_t n_elems, int nodes_per_elem, int n_bnd,
+                     const int* bnd_idx, int n_int, const int* int_idx, const uint32_t* elem_prim, const uint32_t* elem_nodes,
+                     l3b_cond** out);
+void l3b_cond_destroy(l3b_cond* cond);
+int  l3b_cond_condense(l3b_cond* cond);
+int  l3b_cond_recover(l3b_cond* cond, const double* x_condensed, int64_t n_nodes, double* out);
 int64_t l3b_mf_num_dofs(const l3b_mf* sys);
 int     l3b_mf_kernel_launches(const l3b_mf* sys); /* device kernels launched by the last apply */
 

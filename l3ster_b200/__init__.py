@@ -71,6 +71,7 @@ EXPORTED_SYMBOLS = [
     "l3b_asm_spmv_device", "l3b_asm_diag_device", "l3b_asm_device_rhs", "l3b_asm_end_assembly_ranked",
     "l3b_gmres_device", "l3b_asm_solve_gmres", "l3b_mf_solve_gmres",
     "l3b_compute_integral", "l3b_compute_norm_l2",
+    "l3b_crs_create", "l3b_cond_create", "l3b_cond_destroy", "l3b_cond_condense", "l3b_cond_recover",
 ]
 
 
@@ -139,6 +140,11 @@ def lib():
     L.l3b_mf_destroy.argtypes = [vp]
     L.l3b_mf_destroy.restype = None
     L.l3b_mf_assemble.argtypes = [vp, i32, _AsmOpts, dbl, vp, vp, vp, vp, i32]
+    L.l3b_crs_create.argtypes = [vp, i64, i32, i32, vp, vp, C.POINTER(vp)]
+    L.l3b_cond_create.argtypes = [vp, vp, vp, i64, i32, i32, vp, i32, vp, vp, vp, C.POINTER(vp)]
+    L.l3b_cond_destroy.argtypes = [vp]
+    L.l3b_cond_condense.argtypes = [vp]
+    L.l3b_cond_recover.argtypes = [vp, vp, i64, vp]
     for f in ("l3b_compute_integral", "l3b_compute_norm_l2"):
         getattr(L, f).argtypes = [vp, vp, i32, _AsmOpts, dbl, vp, vp, vp, i32, vp]
     L.l3b_mf_end_assembly.argtypes = [vp]
@@ -490,6 +496,18 @@ class AssembledSystem:
         self._h = C.c_void_p()
         ctx._chk(lib().l3b_asm_create(ctx._h, mesh._h, dofs_per_node, n_rhs, _p(self.node_ptr), _p(self.node_nbr), C.byref(self._h)))
         self.nnz = int(lib().l3b_asm_nnz(self._h))
+
+    @classmethod
+    def from_graph(cls, ctx: Context, n_nodes, dofs_per_node, n_rhs, graph):
+        """Storage over a node graph without a mesh (l3b_crs_create): the condensed system of static condensation"""
+        self = cls.__new__(cls)
+        self.ctx, self.mesh, self.dofs_per_node, self.n_rhs = ctx, None, dofs_per_node, n_rhs
+        self.node_ptr, self.node_nbr = graph
+        self.n_dofs = n_nodes * dofs_per_node
+        self._h = C.c_void_p()
+        ctx._chk(lib().l3b_crs_create(ctx._h, n_nodes, dofs_per_node, n_rhs, _p(self.node_ptr), _p(self.node_nbr), C.byref(self._h)))
+        self.nnz = int(lib().l3b_asm_nnz(self._h))
+        return self
 
     def __del__(self):
         try:

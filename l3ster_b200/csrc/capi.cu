@@ -4,6 +4,7 @@
 
 #include "mesh_host.hpp"
 #include "mf_hex_planes.cuh"
+#include "condense.cuh"
 #include "registry.hpp"
 #include "tables.hpp"
 
@@ -736,6 +737,7 @@ struct l3b_asm
     l3b_context*        ctx  = nullptr;
     l3b_mesh*           mesh = nullptr;
     int                 dpn = 0, n_rhs = 1;
+    long long           n_nodes = 0; // rows / dpn; == mesh->n_local_nodes when there is a mesh (l3b_crs_create: none)
     long long           n_dofs = 0, nnz = 0;
     DevBuf< long long > node_ptr, row_ptr;
     std::vector< long long > node_ptr_host; // for the layout conversion of l3b_asm_download
@@ -1399,6 +1401,7 @@ int l3b_asm_create(l3b_context* ctx, l3b_mesh* mesh, int dpn, int n_rhs, const i
         s->dpn       = dpn;
         s->n_rhs     = n_rhs;
         const auto N = mesh->n_local_nodes;
+        s->n_nodes   = N;
         s->n_dofs    = N * dpn;
         s->nnz       = node_ptr[N] * dpn * dpn;
         s->node_ptr.alloc(N + 1);
@@ -1418,6 +1421,32 @@ int l3b_asm_create(l3b_context* ctx, l3b_mesh* mesh, int dpn, int n_rhs, const i
                                                                                            s->slot_pos.ptr, ctx->status.ptr);
         cudaCheck(cudaGetLastError(), "slot map");
         ctx->checkStatus();
+        cudaCheck(cudaEventCreate(&s->ev0), "event");
+        cudaCheck(cudaEventCreate(&s->ev1), "event");
+        *out = s.release();
+    });
+}
+// the same storage without a mesh: rows of `n_nodes` nodes, filled by l3b_condense (the condensed system of static condensation)
+int l3b_crs_create(l3b_context* ctx, int64_t n_nodes, int dpn, int n_rhs, const int64_t* node_ptr, const uint32_t* node_nbr, l3b_asm** out)
+{
+    return guardedCtx(ctx, [&] {
+        auto s     = std::make_unique< l3b_asm >();
+        s->ctx     = ctx;
+        s->dpn     = dpn;
+        s->n_rhs   = n_rhs;
+        s->n_nodes = n_nodes;
+        s->n_dofs  = n_nodes * dpn;
+        s->nnz     = node_ptr[n_nodes] * dpn * dpn;
+        s->node_ptr.alloc(n_nodes + 1);
+        s->node_nbr.alloc(node_ptr[n_nodes]);
+        s->node_ptr.upload(reinterpret_cast< const long long* >(node_ptr), n_nodes + 1, ctx->stream);
+        s->node_ptr_host.assign(node_ptr, node_ptr + n_nodes + 1);
+        s->node_nbr.upload(node_nbr, node_ptr[n_nodes], ctx->stream);
+        s->row_ptr.alloc(s->n_dofs + 1);
+        rowPtrKernel<<< static_cast< unsigned >((s->n_dofs + 1 + 255) / 256), 256, 0, ctx->stream >>>(s->node_ptr.ptr, n_nodes, dpn, s->row_ptr.ptr);
+        s->values.alloc(s->nnz);
+        s->rhs.alloc(s->n_dofs * n_rhs);
+        cudaCheck(cudaGetLastError(), "crs create");
         cudaCheck(cudaEventCreate(&s->ev0), "event");
         cudaCheck(cudaEventCreate(&s->ev1), "event");
         *out = s.release();
@@ -1445,6 +1474,8 @@ int l3b_asm_assemble(l3b_asm* sys, int kernel_id, l3b_asm_opts opts, double time
     return guardedCtx(sys->ctx, [&] {
         if (not sys->open)
             fail(L3B_ERR_STATE, "`assembleProblem()` was called before `beginAssembly()`");
+        if (sys->mesh == nullptr)
+            fail(L3B_ERR_STATE, "this system has no mesh (l3b_crs_create): it takes contributions from l3b_condense only");
         const auto  use  = makeUse(sys->mesh, sys->dpn, sys->n_rhs, kernel_id, opts, time, dof_inds, fields, field_inds, boundary_ids, n_boundary_ids);
         const auto& info = kernelRegistry()[kernel_id].info;
         ElemArgs    a    = baseArgs(sys->mesh, use, sys->dpn, sys->n_dofs);
@@ -1490,7 +1521,7 @@ int l3b_asm_end_assembly_ranked(l3b_asm* sys, int64_t n_dir, const int32_t* dofs
             d_bc.upload(bc.data(), bc.size(), sys->ctx->stream);
             const long long threads = sys->n_dofs * 32;
             dirichletAlgebraicKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
-                sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, d_mask.ptr, d_bc.ptr, sys->rhs.ptr,
+                sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, d_mask.ptr, d_bc.ptr, sys->rhs.ptr,
                 sys->n_dofs, sys->n_rhs, n_owned_dofs);
             cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "Dirichlet BC application");
         }
@@ -1511,7 +1542,7 @@ int l3b_asm_download(l3b_asm* sys, double* values, double* rhs)
             const int             dpn = sys->dpn;
             std::vector< double > row;
             long long             beg = 0;
-            for (long long n = 0; n < sys->mesh->n_local_nodes; ++n)
+            for (long long n = 0; n < sys->n_nodes; ++n)
             {
                 const long long deg = sys->node_ptr_host[n + 1] - sys->node_ptr_host[n];
                 row.resize(static_cast< size_t >(deg) * dpn);
@@ -1537,7 +1568,7 @@ int l3b_asm_spmv(l3b_asm* sys, const double* x, double* y)
         dx.upload(x, sys->n_dofs, sys->ctx->stream);
         const long long threads = sys->n_dofs * 32;
         spmvKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
-            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, dx.ptr, dy.ptr);
+            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, dx.ptr, dy.ptr);
         dy.download(y, sys->n_dofs, sys->ctx->stream);
         cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "spmv");
     });
@@ -1551,13 +1582,13 @@ int l3b_asm_solve_gmres(l3b_asm* sys, double tol, int restart_length, int max_re
         const auto       n = sys->n_dofs;
         DevBuf< double > diag(n), dx(n);
         extractDiagKernel<<< static_cast< unsigned >((n + 255) / 256), 256, 0, sys->ctx->stream >>>(
-            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, diag.ptr);
+            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, diag.ptr);
         const long long threads = n * 32;
         gmres(
             sys->ctx, n, n,
             [&](const double* in, double* out) {
                 spmvKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
-                    sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, in, out);
+                    sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, in, out);
             },
             [](double*, int) {}, diag.ptr, sys->rhs.ptr, dx.ptr, tol, restart_length, max_restarts, max_iters, achieved_tol, iters);
         dx.download(x, n, sys->ctx->stream);
@@ -1569,7 +1600,7 @@ int l3b_asm_spmv_device(l3b_asm* sys, const double* x, double* y)
     return guardedCtx(sys->ctx, [&] {
         const long long threads = sys->n_dofs * 32;
         spmvKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
-            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, x, y);
+            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, x, y);
         cudaCheck(cudaGetLastError(), "spmv");
     });
 }
@@ -1577,7 +1608,7 @@ int l3b_asm_diag_device(l3b_asm* sys, double* diag)
 {
     return guardedCtx(sys->ctx, [&] {
         extractDiagKernel<<< static_cast< unsigned >((sys->n_dofs + 255) / 256), 256, 0, sys->ctx->stream >>>(
-            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, diag);
+            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, diag);
         cudaCheck(cudaGetLastError(), "diagonal");
     });
 }
@@ -1593,13 +1624,13 @@ int l3b_asm_solve_cg(l3b_asm* sys, double tol, int max_iters, double* x, double*
         const auto       n = sys->n_dofs;
         DevBuf< double > diag(n), dx(n);
         extractDiagKernel<<< static_cast< unsigned >((n + 255) / 256), 256, 0, sys->ctx->stream >>>(
-            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, diag.ptr);
+            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, diag.ptr);
         const long long threads = n * 32;
         pcg(
             sys->ctx, n, n,
             [&](const double* in, double* out, double*) {
                 spmvKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
-                    sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->mesh->n_local_nodes, sys->dpn, in, out);
+                    sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, in, out);
                 return false; // p.Ap by a dot-product pass
             },
             [](double*, int) {}, diag.ptr, sys->rhs.ptr, dx.ptr, tol, max_iters, achieved_tol, iters);
@@ -1950,5 +1981,144 @@ int l3b_compute_norm_l2(l3b_context* ctx, l3b_mesh* mesh, int kernel_id, l3b_asm
                         const int* field_inds, const int* boundary_ids, int n_boundary_ids, double* out)
 {
     return guardedCtx(ctx, [&] { integrate(ctx, mesh, kernel_id, opts, time, fields, field_inds, boundary_ids, n_boundary_ids, true, out); });
+}
+}
+
+// ---- static condensation (algsys/StaticCondensationManager.hpp:135-535), see condense.cuh
+struct l3b_cond
+{
+    l3b_context*       ctx = nullptr;
+    l3b_asm *          elem_sys = nullptr, *cond_sys = nullptr;
+    long long          n_elems = 0;
+    int                NN = 0, nB = 0, nI = 0;
+    DevBuf< int >      bnd_idx, int_idx;
+    DevBuf< uint32_t > elem_prim, elem_nodes;
+    DevBuf< uint16_t > pos;
+    DevBuf< double >   work;
+    size_t             smem_condense = 0;
+    bool               condensed = false;
+};
+extern "C" {
+int l3b_cond_create(l3b_context* ctx, l3b_asm* elem_sys, l3b_asm* cond_sys, int64_t n_elems, int nodes_per_elem, int n_bnd, const int* bnd_idx,
+                    int n_int, const int* int_idx, const uint32_t* elem_prim, const uint32_t* elem_nodes, l3b_cond** out)
+{
+    return guardedCtx(ctx, [&] {
+        if (elem_sys->dpn != cond_sys->dpn or elem_sys->n_rhs != cond_sys->n_rhs or n_bnd + n_int != nodes_per_elem or
+            elem_sys->n_nodes != n_elems * nodes_per_elem)
+            fail(L3B_ERR_INVALID_ARG, "l3b_cond_create: the element-local and the condensed system do not fit together");
+        auto c      = std::make_unique< l3b_cond >();
+        c->ctx      = ctx;
+        c->elem_sys = elem_sys;
+        c->cond_sys = cond_sys;
+        c->n_elems  = n_elems;
+        c->NN       = nodes_per_elem;
+        c->nB       = n_bnd;
+        c->nI       = n_int;
+        c->bnd_idx.alloc(std::max(n_bnd, 1));
+        c->int_idx.alloc(std::max(n_int, 1));
+        c->bnd_idx.upload(bnd_idx, n_bnd, ctx->stream);
+        c->int_idx.upload(int_idx, n_int, ctx->stream);
+        c->elem_prim.alloc(std::max< long long >(n_elems * n_bnd, 1));
+        c->elem_nodes.alloc(std::max< long long >(n_elems * nodes_per_elem, 1));
+        c->elem_prim.upload(elem_prim, n_elems * n_bnd, ctx->stream);
+        c->elem_nodes.upload(elem_nodes, n_elems * nodes_per_elem, ctx->stream);
+        const long long n_pos = n_elems * n_bnd * n_bnd;
+        c->pos.alloc(std::max< long long >(n_pos, 1));
+        if (n_pos > 0)
+            slotMapKernel<<< static_cast< unsigned >((n_pos + 255) / 256), 256, 0, ctx->stream >>>(
+                c->elem_prim.ptr, n_elems, n_bnd, cond_sys->node_ptr.ptr, cond_sys->node_nbr.ptr, c->pos.ptr, ctx->status.ptr);
+        cudaCheck(cudaGetLastError(), "slot map");
+        ctx->checkStatus();
+        const long long nId  = static_cast< long long >(n_int) * elem_sys->dpn;
+        const size_t    rest = static_cast< size_t >(2 * nId + cond_rows * nId + nId * elem_sys->n_rhs) * sizeof(double);
+        c->smem_condense     = rest + static_cast< size_t >(nId * nId) * sizeof(double);
+        if (c->smem_condense > 200 * 1024) // K_ii does not fit shared memory: invert it in a global work buffer
+        {
+            c->work.alloc(n_elems * nId * nId);
+            c->smem_condense = rest;
+        }
+        if (c->smem_condense > 48 * 1024)
+            cudaCheck(cudaFuncSetAttribute(condenseKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(c->smem_condense)), "smem");
+        cudaCheck(cudaStreamSynchronize(ctx->stream), "cond create");
+        *out = c.release();
+    });
+}
+void l3b_cond_destroy(l3b_cond* c)
+{
+    delete c;
+}
+/* endAssembly of the condensation manager (:330-353): Schur complements and condensed right-hand sides of all elements are added to
+ * the (zeroed by its beginAssembly) condensed system; K_ii^-1 replaces K_ii in the element-local storage */
+int l3b_cond_condense(l3b_cond* c)
+{
+    return guardedCtx(c->ctx, [&] {
+        if (not c->elem_sys->open or not c->cond_sys->open)
+            fail(L3B_ERR_STATE, "l3b_cond_condense: both systems must be open for assembly");
+        if (c->n_elems > 0)
+        {
+            CondArgs a{};
+            a.ke        = c->elem_sys->values.ptr;
+            a.fe        = c->elem_sys->rhs.ptr;
+            a.ld_e      = c->elem_sys->n_dofs;
+            a.NN        = c->NN;
+            a.U         = c->elem_sys->dpn;
+            a.n_rhs     = c->elem_sys->n_rhs;
+            a.nB        = c->nB;
+            a.nI        = c->nI;
+            a.bnd_idx   = c->bnd_idx.ptr;
+            a.int_idx   = c->int_idx.ptr;
+            a.elem_prim = c->elem_prim.ptr;
+            a.pos       = c->pos.ptr;
+            a.node_ptr  = c->cond_sys->node_ptr.ptr;
+            a.vals      = c->cond_sys->values.ptr;
+            a.rhs       = c->cond_sys->rhs.ptr;
+            a.ld_c      = c->cond_sys->n_dofs;
+            a.work      = c->work.ptr;
+            a.status    = c->ctx->status.ptr;
+            condenseKernel<<< static_cast< unsigned >(c->n_elems), cond_threads, c->smem_condense, c->ctx->stream >>>(a);
+            cudaCheck(cudaGetLastError(), "condense");
+        }
+        c->ctx->checkStatus();
+        c->elem_sys->open = false; // its K_ii blocks now hold inverses: no further assembly into them
+        c->condensed      = true;
+    });
+}
+/* recoverSolution (:420-535): x_c = solution of the condensed system (host, n_primary_dofs x n_rhs column-major); out = nodal values
+ * over the mesh's nodes (host, n_nodes x dofs_per_node row-major per rhs: out[node * U + u + r * n_nodes * U]) */
+int l3b_cond_recover(l3b_cond* c, const double* x_c, int64_t n_nodes, double* out)
+{
+    return guardedCtx(c->ctx, [&] {
+        if (not c->condensed)
+            fail(L3B_ERR_STATE, "l3b_cond_recover before l3b_cond_condense");
+        const int        U = c->elem_sys->dpn, R = c->elem_sys->n_rhs;
+        DevBuf< double > dx(c->cond_sys->n_dofs * R), dout(n_nodes * U * R);
+        dx.upload(x_c, c->cond_sys->n_dofs * R, c->ctx->stream);
+        dout.zero(c->ctx->stream);
+        if (c->n_elems > 0)
+        {
+            RecoverArgs a{};
+            a.ke         = c->elem_sys->values.ptr;
+            a.fe         = c->elem_sys->rhs.ptr;
+            a.ld_e       = c->elem_sys->n_dofs;
+            a.NN         = c->NN;
+            a.U          = U;
+            a.n_rhs      = R;
+            a.nB         = c->nB;
+            a.nI         = c->nI;
+            a.bnd_idx    = c->bnd_idx.ptr;
+            a.int_idx    = c->int_idx.ptr;
+            a.elem_prim  = c->elem_prim.ptr;
+            a.elem_nodes = c->elem_nodes.ptr;
+            a.x_c        = dx.ptr;
+            a.ld_c       = c->cond_sys->n_dofs;
+            a.out        = dout.ptr;
+            a.ld_out     = n_nodes * U;
+            const size_t smem = static_cast< size_t >(c->nB + c->nI) * U * sizeof(double);
+            recoverKernel<<< static_cast< unsigned >(c->n_elems), cond_threads, smem, c->ctx->stream >>>(a);
+            cudaCheck(cudaGetLastError(), "recover");
+        }
+        dout.download(out, n_nodes * U * R, c->ctx->stream);
+        cudaCheck(cudaStreamSynchronize(c->ctx->stream), "recover");
+    });
 }
 }

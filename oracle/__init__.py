@@ -412,3 +412,37 @@ class OracleMatrixFree:
         at, it = C.c_double(), C.c_int()
         self.mesh.orc._chk(self.lib.orc_mf_cg(self.h, C.c_double(tol), max_iters, n_threads, _ptr(x), C.byref(at), C.byref(it)))
         return x, at.value, it.value
+
+
+def condense_element_boundary(K, F, elem_nodes, bnd_idx, int_idx, U):
+    """CondensationPolicy::ElementBoundary restated on an assembled system (algsys/StaticCondensationManager.hpp:330-418): K dense
+    (n_dofs x n_dofs, all nodes, dof = node * U + u), F (n_dofs x n_rhs). Per element: K_ii = rows/cols of its interior nodes (only
+    this element contributes there, :391-403), K_pi = its boundary rows x interior cols (:405-416), and the primary block receives
+    -K_pi K_ii^-1 K_ip, the primary rhs -K_pi K_ii^-1 f_i (:340-347; Eigen's dynamic-size inverse() is a partially pivoted LU, as
+    numpy.linalg.inv). Returns (primary nodes, S, F_c, recover) with recover(x_c) -> nodal solution over all dofs (:420-535)."""
+    import numpy as np
+
+    K = np.array(K, dtype=np.float64)
+    F = np.array(F, dtype=np.float64).reshape(K.shape[0], -1)
+    elem_nodes = np.asarray(elem_nodes, dtype=np.int64)
+    prim_nodes = np.unique(elem_nodes[:, bnd_idx])
+    dofs = lambda nodes: (np.asarray(nodes)[:, None] * U + np.arange(U)[None, :]).ravel()
+    P = dofs(prim_nodes)
+    S, Fc = K.copy(), F.copy()
+    saved = []
+    for en in elem_nodes:
+        p, i = dofs(en[bnd_idx]), dofs(en[int_idx])
+        Kii_inv = np.linalg.inv(K[np.ix_(i, i)])
+        Kpi = K[np.ix_(p, i)]
+        S[np.ix_(p, p)] -= Kpi @ Kii_inv @ Kpi.T
+        Fc[p] -= Kpi @ Kii_inv @ F[i]
+        saved.append((p, i, Kii_inv, Kpi))
+
+    def recover(x_c):
+        x = np.zeros_like(F)
+        x[P] = np.asarray(x_c).reshape(len(P), -1)
+        for p, i, Kii_inv, Kpi in saved:
+            x[i] = Kii_inv @ (F[i] - Kpi.T @ x[p])
+        return x
+
+    return prim_nodes, S[np.ix_(P, P)], Fc[P], recover

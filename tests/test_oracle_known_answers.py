@@ -387,3 +387,33 @@ def test_integrals_of_residual_kernels(orc, dim):
     v = m.compute_integral(f"integrand_probe_{dim}D", fields=f, value_order=3)[0]
     s = m.compute_integral(f"boundary_probe_{dim}D", boundary_ids=sides, fields=f, value_order=3)[1]
     assert abs(s / dim - v) < 1e-12 * v
+
+
+def test_static_condensation_is_exact(orc):
+    """The restated ElementBoundary condensation (StaticCondensationManager.hpp:330-535): solving the condensed system and recovering
+    the interior values gives the solution of the full system (2-D diffusion, p=3, a penalty on T along the boundary makes K regular)."""
+    from oracle import condense_element_boundary
+
+    d = np.linspace(0.0, 1.0, 3)
+    m = orc.mesh_square(d, d, order=3)
+    U = 3
+    s = m.assembled_system(U)
+    s.assemble("example02_domain")
+    vals, rhs = s.get()
+    import l3ster_b200 as l3b
+    import scipy.sparse as sp
+
+    ptr, nbr = l3b.node_graph(m.n_nodes, m.elem_nodes.astype(np.uint32))
+    row_ptr, col_ind = l3b.expand_graph(ptr, nbr, U)
+    K = sp.csr_matrix((vals, col_ind, row_ptr), shape=(len(rhs), len(rhs))).toarray()
+    nb = 4
+    idx = np.arange(nb * nb)
+    on_bnd = ((idx % nb) % 3 == 0) | ((idx // nb) % 3 == 0)
+    bnd_idx, int_idx = np.flatnonzero(on_bnd), np.flatnonzero(~on_bnd)
+    for n in np.unique(m.bnd_nodes):
+        K[int(n) * U, int(n) * U] += 1e3
+    prim, S, Fc, recover = condense_element_boundary(K, rhs, m.elem_nodes, bnd_idx, int_idx, U)
+    assert len(prim) == m.n_nodes - m.n_elems * len(int_idx)
+    x_full = np.linalg.solve(K, rhs)
+    x_cond = recover(np.linalg.solve(S, Fc))
+    assert np.abs(x_cond - x_full).max() < 1e-10 * np.abs(x_full).max()
