@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--n-mf", type=int, default=64, help="elements per edge, matrix-free workload (per GPU)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workload")
     ap.add_argument("--cg-max-iters", type=int, default=10000, help="matrix-free workload: iteration cap of the CG solve timed after the applies (0 = skip)")
+    ap.add_argument("--condensed", action="store_true", help="assembly workload: also time CondensationPolicy::ElementBoundary")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -275,6 +276,7 @@ def main():
         graph = host.node_graph()
         sys_ = l3b.AssembledSystem(ctx, mesh, U, 1, graph)
         n_elems = host.n_elems
+        crs_nnz, n_dofs_asm = sys_.nnz, sys_.n_dofs
         kernel_ms = []
 
         def step():
@@ -296,6 +298,32 @@ def main():
             sys_.download_rhs_into(rhs_h.data_ptr())  # D2H of the step's result (synchronises)
 
         _, wall_ms, _ = timed(step_e2e, args.steps, 1)
+        condensed = None
+        if args.condensed:
+            # the policy benchmarks/Diffusion3DBenchmark.cpp:6 itself runs: CondensationPolicy::ElementBoundary. Same elements; a step is
+            # beginAssembly + assembleProblem into the element-local storage + the Schur complements into the primary-node CRS.
+            from l3ster_b200.condensation import CondensedAssembledSystem
+
+            del sys_
+            cs = CondensedAssembledSystem(ctx, host, U)
+
+            def step_c():
+                cs.beginAssembly()
+                cs.assembleProblem("bench_diffusion3d")
+                cs.endAssembly()
+
+            def step_a():
+                cs.beginAssembly()
+                cs.assembleProblem("bench_diffusion3d")
+
+            ms_a, _, _ = timed(step_a, 3, 2)
+            cs.endAssembly()
+            ms_c, _, _ = timed(step_c, 3, 2)
+            condensed = {"value": world * n_elems / (ms_c * 1e-3), "unit": "elements/s", "ms_per_step": ms_c, "assemble_ms": ms_a,
+                         "condense_ms": ms_c - ms_a, "primary_dofs_per_gpu": cs.n_primary_dofs, "crs_nnz_per_gpu": cs.condensed.nnz,
+                         "steps": 3, "what": "beginAssembly + assembleProblem (element-local, block-diagonal storage) + endAssembly "
+                                             "(K_pp - K_pi K_ii^-1 K_ip of every element into the CRS of the primary dofs), CUDA events"}
+            del cs
         fp64_fma = ctx.microbench(0)
         fp64_dmma = ctx.microbench(1)
         achieved = ASM_FLOPS_PER_ELEM * n_elems / (k_ms * 1e-3) / 1e12
@@ -303,7 +331,7 @@ def main():
         return {
             "value": world * n_elems / (ms * 1e-3), "ms_per_step": ms,
             "e2e": {"value": world * n_elems / (wall_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": int(verts_np.nbytes),
-                    "d2h_bytes_per_step": int(sys_.n_dofs * 8),
+                    "d2h_bytes_per_step": int(n_dofs_asm * 8),
                     "what": "element geometry H2D (pinned) + beginAssembly + assembleProblem + rhs D2H (pinned) through the C ABI, wall clock"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_dmma, "unit": "TFLOP/s", "frac": achieved / fp64_dmma,
                          "traffic": 3.46e6 * n_elems,
@@ -319,10 +347,10 @@ def main():
                                  "operator entries (33 of 112 equation x unknown-pair products survive), hence achieved > executed and "
                                  "frac may exceed 1; frac_executed is the DMMA pipe share of the flops really issued",
                          "traffic_source": "dram__bytes_read + write of profiles/r1_asm_dmma_v3 (3.46 MB per element), scaled to this launch"},
-            "gpu_launches": args.steps, "clocks": clocks,
+            "gpu_launches": args.steps, "clocks": clocks, "condensed": condensed,
             "config": {"workload": f"Diffusion3DBenchmark assembly + CRS scatter: cube [0,1]^3, {n}^3 hex p=4 per GPU, U=4, E=7, nq=5, "
                                    f"CondensationPolicy::None", "elements_per_gpu": n_elems, "dofs_per_gpu": host.n_nodes * U,
-                       "crs_nnz_per_gpu": sys_.nnz, "l2": "CRS values (%.1f GB) larger than L2" % (sys_.nnz * 8 / 1e9),
+                       "crs_nnz_per_gpu": crs_nnz, "l2": "CRS values (%.1f GB) larger than L2" % (crs_nnz * 8 / 1e9),
                        "step": "beginAssembly (zero values + rhs) + assembleProblem",
                        "multi_gpu": "one n^3 block per rank; assembleProblem has no exchange step in the reference either (shared rows are "
                                     "exported at endAssembly, outside the timed region)"},
@@ -417,8 +445,9 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": main_res["config"],
             "e2e": main_res["e2e"], "roofline": main_res["roofline"], "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"]}
-    if main_res.get("cg_solve"):
-        line["cg_solve"] = main_res["cg_solve"]
+    for extra in ("cg_solve", "condensed"):
+        if main_res.get(extra):
+            line[extra] = main_res[extra]
     if also:
         line["also"] = also
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -2029,13 +2029,15 @@ int l3b_cond_create(l3b_context* ctx, l3b_asm* elem_sys, l3b_asm* cond_sys, int6
                 c->elem_prim.ptr, n_elems, n_bnd, cond_sys->node_ptr.ptr, cond_sys->node_nbr.ptr, c->pos.ptr, ctx->status.ptr);
         cudaCheck(cudaGetLastError(), "slot map");
         ctx->checkStatus();
-        const long long nId  = static_cast< long long >(n_int) * elem_sys->dpn;
-        const size_t    rest = static_cast< size_t >(2 * nId + cond_rows * nId + nId * elem_sys->n_rhs) * sizeof(double);
-        c->smem_condense     = rest + static_cast< size_t >(nId * nId) * sizeof(double);
-        if (c->smem_condense > 200 * 1024) // K_ii does not fit shared memory: invert it in a global work buffer
+        const int nId = n_int * elem_sys->dpn;
+        const int nPd    = n_bnd * elem_sys->dpn;
+        c->smem_condense = condSmemBytes(nId, nPd, elem_sys->n_rhs, true);
+        if (c->smem_condense > 113 * 1024) // K_ii does not fit shared memory (two CTAs per SM): invert it in a global work buffer
         {
-            c->work.alloc(n_elems * nId * nId);
-            c->smem_condense = rest;
+            c->work.alloc(n_elems * static_cast< long long >(nId) * condLdM(nId));
+            c->smem_condense = condSmemBytes(nId, nPd, elem_sys->n_rhs, false);
+            if (c->smem_condense > 220 * 1024)
+                fail(L3B_ERR_INVALID_ARG, "static condensation: the element's interior block is too large for this kernel");
         }
         if (c->smem_condense > 48 * 1024)
             cudaCheck(cudaFuncSetAttribute(condenseKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(c->smem_condense)), "smem");
@@ -2079,7 +2081,7 @@ int l3b_cond_condense(l3b_cond* c)
             cudaCheck(cudaGetLastError(), "condense");
         }
         c->ctx->checkStatus();
-        c->elem_sys->open = false; // its K_ii blocks now hold inverses: no further assembly into them
+        c->elem_sys->open = false; // K_ip and f_i are now W and g: no further assembly into this storage
         c->condensed      = true;
     });
 }
@@ -2113,7 +2115,7 @@ int l3b_cond_recover(l3b_cond* c, const double* x_c, int64_t n_nodes, double* ou
             a.ld_c       = c->cond_sys->n_dofs;
             a.out        = dout.ptr;
             a.ld_out     = n_nodes * U;
-            const size_t smem = static_cast< size_t >(c->nB + c->nI) * U * sizeof(double);
+            const size_t smem = static_cast< size_t >(c->nB) * U * sizeof(double);
             recoverKernel<<< static_cast< unsigned >(c->n_elems), cond_threads, smem, c->ctx->stream >>>(a);
             cudaCheck(cudaGetLastError(), "recover");
         }
