@@ -334,7 +334,7 @@ def main():
                     "d2h_bytes_per_step": int(n_dofs_asm * 8),
                     "what": "element geometry H2D (pinned) + beginAssembly + assembleProblem + rhs D2H (pinned) through the C ABI, wall clock"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_dmma, "unit": "TFLOP/s", "frac": achieved / fp64_dmma,
-                         "traffic": 3.46e6 * n_elems,
+                         "traffic": 3.57e6 * n_elems,
                          "kernel": "assembleDmmaKernel<bench_diffusion3d, hex p=4> (fp64 DMMA, mma.sync.m8n8k4.f64)", "kernel_ms": k_ms,
                          "algorithmic_flops_per_element": ASM_FLOPS_PER_ELEM,
                          "peak_source": "fp64 DMMA microkernel measured in this run (MEASURED_PEAKS.json carries bf16 and HBM figures only); "
@@ -346,7 +346,7 @@ def main():
                                  "benchmarks/LocalAssemblyBenchmarks.cpp:71-75); the kernel skips the products with structurally zero "
                                  "operator entries (33 of 112 equation x unknown-pair products survive), hence achieved > executed and "
                                  "frac may exceed 1; frac_executed is the DMMA pipe share of the flops really issued",
-                         "traffic_source": "dram__bytes_read + write of profiles/r1_asm_dmma_v3 (3.46 MB per element), scaled to this launch"},
+                         "traffic_source": "dram__bytes_read + write of profiles/r1b_ncu_raw.txt (3.57 MB per element), scaled to this launch"},
             "gpu_launches": args.steps, "clocks": clocks, "condensed": condensed,
             "config": {"workload": f"Diffusion3DBenchmark assembly + CRS scatter: cube [0,1]^3, {n}^3 hex p=4 per GPU, U=4, E=7, nq=5, "
                                    f"CondensationPolicy::None", "elements_per_gpu": n_elems, "dofs_per_gpu": host.n_nodes * U,
@@ -414,7 +414,7 @@ def main():
                     "d2h_bytes_per_step": int(n_local * 8),
                     "what": "pinned host x -> device, phased apply with halo exchange, device y -> pinned host, wall clock"},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                         "traffic": 6.05e3 * n_elems,
+                         "traffic": 5.99e3 * n_elems,
                          "kernel": "mfHexPlanesKernel<bench_diffusion3d, hex p=4, nq=5> (+ memset of y, Dirichlet-row and halo pack/unpack kernels)",
                          "algorithmic_bytes_per_dof": mf_bytes_per_apply(n_owned, n_elems) / max(n_owned, 1), "peak_source": hbm_src,
                          "fp64_tflops_reference_formulation": MF_FLOPS_PER_ELEM * n_elems / (ms * 1e-3) / 1e12,
@@ -422,7 +422,7 @@ def main():
                          "note": "the p=4, U=4, E=7 apply is bound by the fp64 pipe, not HBM (SURVEY §7): ~46 k DFMA per element after "
                                  "structural-zero elimination = 0.72 ms per 64^3 apply at the measured DFMA peak, i.e. 26 % of the HBM "
                                  "roofline is the ceiling of this formulation",
-                         "traffic_source": "dram__bytes_read + write of profiles/r1_mf_v7 (6.05 kB per element incl. the y read-modify-write), "
+                         "traffic_source": "dram__bytes_read + write of profiles/r1b_ncu_raw.txt (5.99 kB per element incl. the y read-modify-write), "
                                            "scaled to this launch"},
             "gpu_launches": launches * args.steps, "clocks": clocks, "cg_solve": cg,
             "config": {"workload": f"Diffusion3DBenchmarkMatrixFree operator apply: {n} x {n} x {n * world} hex p=4 on [0,1]^2 x [0,{world}], "
