@@ -69,6 +69,15 @@ struct MfHexCfg
         if (CT == 25)
             return L3B_HEX_EPB; // experiment override for the nq = 5 instances
 #endif
+        // nq >= 6: one 256-thread CTA per SM wastes fewer lanes than two of 128 (49 columns: 5 x 49 = 245 of 256 against 98 of 128);
+        // measured per 48^3 / 40^3 apply: p=5 1.73 -> 1.60 ms, p=6 2.39 -> 1.95 ms
+        if (CT >= 36)
+        {
+            int wide = 256 / CT;
+            while (wide > 1 and 3 * F * NQ * wide * PSZ * 8 > 200 * 1024)
+                --wide;
+            return wide;
+        }
         int epb = cmax(1, 128 / CT);
         while (epb > 1 and 3 * F * NQ * epb * PSZ * 8 > 100 * 1024)
             --epb;
