@@ -48,7 +48,7 @@ class Oracle:
         lib.orc_ref_basis_value.restype = C.c_double
         lib.orc_ref_basis_der.restype = C.c_double
         lib.orc_boundary_jacobian.restype = C.c_double
-        for name in ("orc_mesh_cube", "orc_mesh_square", "orc_mesh_single", "orc_asm_create", "orc_mf_create"):
+        for name in ("orc_mesh_cube", "orc_mesh_square", "orc_mesh_single", "orc_mesh_from_arrays", "orc_asm_create", "orc_mf_create"):
             getattr(lib, name).restype = C.c_void_p
         lib.orc_asm_nnz.restype = C.c_longlong
 
@@ -230,6 +230,18 @@ class Oracle:
         dx = np.ascontiguousarray(dx, dtype=np.float64)
         dy = dx if dy is None else np.ascontiguousarray(dy, dtype=np.float64)
         h = self.lib.orc_mesh_square(len(dx), _ptr(dx), len(dy), _ptr(dy), order)
+        if not h:
+            raise RuntimeError(self.lib.orc_last_error().decode())
+        return OracleMesh(self, h)
+
+    def mesh_from_arrays(self, et, coords, elems, bnd_elems, bnd_domains, bnd_ids, order):
+        """order-1 mesh by arrays -> convertMeshToOrder(order) + matchBoundaries (the general, geometric-matching path)"""
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        elems = np.ascontiguousarray(elems, dtype=np.int64)
+        be = np.ascontiguousarray(bnd_elems, dtype=np.int64)
+        bd = np.ascontiguousarray(bnd_domains, dtype=np.int32)
+        bi = np.ascontiguousarray(bnd_ids, dtype=np.int64)
+        h = self.lib.orc_mesh_from_arrays(et, len(coords), _ptr(coords), len(elems), _ptr(elems), len(be), _ptr(be), _ptr(bd), _ptr(bi), order)
         if not h:
             raise RuntimeError(self.lib.orc_last_error().decode())
         return OracleMesh(self, h)

@@ -324,6 +324,51 @@ void* orc_mesh_single(int et, int order, const double* verts)
     });
     return ret;
 }
+// an order-1 mesh given by arrays (what mesh::readMesh produces: node coordinates, volume elements with vertex lists in lexicographic
+// order, boundary elements with their domain ids; ids: volume elements 0.., boundary elements as given), converted to `order` and
+// boundary-matched — the general path of mesh/ConvertMeshToOrder.hpp, for unstructured parity tests
+void* orc_mesh_from_arrays(int et, long long n_nodes, const double* coords, long long n_elems, const long long* elems, long long n_bnd,
+                           const long long* bnd_elems, const int* bnd_domains, const long long* bnd_ids, int order)
+{
+    void* ret = nullptr;
+    guarded([&] {
+        Mesh       m;
+        const auto t  = static_cast< ElementType >(et);
+        const int  nv = 1 << et, nbv = 1 << (et - 1);
+        m.et          = t;
+        m.order       = 1;
+        m.n_nodes     = static_cast< std::size_t >(n_nodes);
+        m.n_elems     = static_cast< std::size_t >(n_elems);
+        for (long long e = 0; e < n_elems; ++e)
+        {
+            m.elem_ids.push_back(static_cast< n_id_t >(e));
+            for (int v = 0; v < nv; ++v)
+            {
+                const auto n = elems[e * nv + v];
+                m.elem_nodes.push_back(static_cast< n_id_t >(n));
+                m.elem_verts.insert(m.elem_verts.end(), coords + 3 * n, coords + 3 * n + 3);
+            }
+        }
+        for (long long b = 0; b < n_bnd; ++b)
+        {
+            Mesh::BoundaryElem be;
+            be.domain_id = bnd_domains[b];
+            be.id        = static_cast< n_id_t >(bnd_ids[b]);
+            for (int v = 0; v < nbv; ++v)
+            {
+                const auto n = bnd_elems[b * nbv + v];
+                be.nodes.push_back(static_cast< n_id_t >(n));
+                be.verts.insert(be.verts.end(), coords + 3 * n, coords + 3 * n + 3);
+            }
+            m.boundary.push_back(std::move(be));
+        }
+        if (order > 1)
+            m = convertMeshToOrder(m, order);
+        matchBoundaries(m);
+        ret = new MeshHandle{std::move(m)};
+    });
+    return ret;
+}
 void orc_mesh_free(void* h)
 {
     delete static_cast< MeshHandle* >(h);
