@@ -377,9 +377,7 @@ class Context:
         self._chk(lib().l3b_microbench(self._h, mode, C.byref(out)))
         return out.value
 
-    def pcg(self, n_local, n_owned, apply, allreduce, diag_ptr, b_ptr, x_ptr, tol=1e-6, max_iters=10000):
-        """l3b_pcg_device: apply(x_ptr, y_ptr, energy_ptr) and allreduce(scalars_ptr, n) are Python callables working on device pointers;
-        apply returns True when it added this rank's share of x^T A x to the device scalar at energy_ptr (see l3b_apply_callback)"""
+    def _krylov_callbacks(self, apply, allreduce):
         err = []
 
         def _apply(_, x, y, e):
@@ -397,10 +395,24 @@ class Context:
                 err.append(exc)
                 return 1
 
-        a_cb = APPLY_CB(_apply)
-        r_cb = ALLREDUCE_CB(_reduce) if allreduce is not None else C.cast(None, ALLREDUCE_CB)
+        return APPLY_CB(_apply), (ALLREDUCE_CB(_reduce) if allreduce is not None else C.cast(None, ALLREDUCE_CB)), err
+
+    def pcg(self, n_local, n_owned, apply, allreduce, diag_ptr, b_ptr, x_ptr, tol=1e-6, max_iters=10000):
+        """l3b_pcg_device: apply(x_ptr, y_ptr, energy_ptr) and allreduce(scalars_ptr, n) are Python callables working on device pointers;
+        apply returns True when it added this rank's share of x^T A x to the device scalar at energy_ptr (see l3b_apply_callback)"""
+        a_cb, r_cb, err = self._krylov_callbacks(apply, allreduce)
         at, it = C.c_double(), C.c_int()
         rc = lib().l3b_pcg_device(self._h, n_local, n_owned, a_cb, r_cb, None, diag_ptr, b_ptr, x_ptr, tol, max_iters, C.byref(at), C.byref(it))
+        if rc != 0:
+            raise L3BError(rc, lib().l3b_last_error(self._h).decode() + (f" ({err[0]!r})" if err else ""))
+        return at.value, it.value
+
+    def gmres(self, n_local, n_owned, apply, allreduce, diag_ptr, b_ptr, x_ptr, tol=1e-6, restart_length=250, max_restarts=39, max_iters=10000):
+        """l3b_gmres_device with the same callbacks as pcg (the energy pointer is always null here)"""
+        a_cb, r_cb, err = self._krylov_callbacks(apply, allreduce)
+        at, it = C.c_double(), C.c_int()
+        rc = lib().l3b_gmres_device(self._h, n_local, n_owned, a_cb, r_cb, None, diag_ptr, b_ptr, x_ptr, tol, restart_length, max_restarts,
+                                    max_iters, C.byref(at), C.byref(it))
         if rc != 0:
             raise L3BError(rc, lib().l3b_last_error(self._h).decode() + (f" ({err[0]!r})" if err else ""))
         return at.value, it.value

@@ -37,6 +37,7 @@ class Slab:
     rank: int
     world: int
     order: int
+    dim: int
     n_elems: int
     n_local_nodes: int
     n_owned_nodes: int
@@ -55,46 +56,49 @@ class Slab:
 
     def dirichlet_nodes(self, boundary_ids):
         """local nodes (owned and ghost) on the physical sides carrying one of `boundary_ids`"""
-        nb = self.order + 1
         sel = np.zeros(self.n_local_nodes, dtype=bool)
-        for side in range(6):
+        for side in range(2 * self.dim):
             on = np.isin(self.side_boundaries[:, side], list(boundary_ids))
             if on.any():
-                sel[self.nodes[on][:, l3b.side_node_inds(3, self.order, side)].ravel()] = True
+                sel[self.nodes[on][:, l3b.side_node_inds(self.dim, self.order, side)].ravel()] = True
         return np.nonzero(sel)[0]
 
 
 def make_slab(x, y, z, order, rank, world) -> Slab:
-    """Slab `rank` of `world` of the cube mesh over the vertex coordinates x, y, z (benchmarks/Diffusion3D.hpp:8-24)."""
-    x, y, z = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z))
-    nz = len(z) - 1
-    layers = split_layers(nz, world)
+    """Slab `rank` of `world` of the cube mesh over the vertex coordinates x, y, z (benchmarks/Diffusion3D.hpp:8-24), cut into layers
+    along z; with z = None: strip `rank` of the square mesh over x, y, cut along y (the 2-D configurations)."""
+    dim = 2 if z is None else 3
+    axes = [np.ascontiguousarray(a, dtype=np.float64) for a in ((x, y) if dim == 2 else (x, y, z))]
+    cut = axes[-1]
+    layers = split_layers(len(cut) - 1, world)
     z0, z1 = layers[rank]
     p = order
+    nn, nv, ns = (p + 1) ** dim, 2**dim, 2 * dim
     if z1 == z0:
         e = np.zeros
-        return Slab(rank, world, p, 0, 0, 0, e((0, (p + 1) ** 3), np.uint32), e((0, 8, 3)), e((0, 6), np.uint16), e((0, 3), np.int64), 0,
+        return Slab(rank, world, p, dim, 0, 0, 0, e((0, nn), np.uint32), e((0, nv, 3)), e((0, ns), np.uint16), e((0, dim), np.int64), 0,
                     e(0, np.int64), -1, -1)
     # neighbours: nearest non-empty slabs
     lower = next((r for r in range(rank - 1, -1, -1) if layers[r][1] > layers[r][0]), -1)
     upper = next((r for r in range(rank + 1, world) if layers[r][1] > layers[r][0]), -1)
-    host = l3b.make_cube_mesh(x, y, z[z0:z1 + 1], order=p)
+    local_axes = axes[:-1] + [cut[z0:z1 + 1]]
+    host = l3b.make_square_mesh(*local_axes, order=p) if dim == 2 else l3b.make_cube_mesh(*local_axes, order=p)
     nodes0, verts = np.array(host.nodes, dtype=np.int64), np.array(host.verts)
     sb = np.array(host.side_boundaries)
     n_elems, n_nodes = host.n_elems, host.n_nodes
     # lattice coordinates of every local node from the element's position and the node's place in it
-    ex = np.searchsorted(x, verts[:, 0, 0])
-    ey = np.searchsorted(y, verts[:, 0, 1])
-    ez = np.searchsorted(z, verts[:, 0, 2])
-    a = np.arange((p + 1) ** 3)
-    li, lj, lk = a % (p + 1), (a // (p + 1)) % (p + 1), a // (p + 1) ** 2
-    lat = np.zeros((n_nodes, 3), dtype=np.int64)
-    lat[nodes0.ravel(), 0] = (ex[:, None] * p + li[None, :]).ravel()
-    lat[nodes0.ravel(), 1] = (ey[:, None] * p + lj[None, :]).ravel()
-    lat[nodes0.ravel(), 2] = (ez[:, None] * p + lk[None, :]).ravel()
-    # ownership: the plane shared with the slab below belongs to the lower rank
-    ghost = (lat[:, 2] == z0 * p) if lower >= 0 else np.zeros(n_nodes, dtype=bool)
-    plane_key = lat[:, 1] * (len(x) * p + 1) + lat[:, 0]
+    a = np.arange(nn)
+    lat = np.zeros((n_nodes, dim), dtype=np.int64)
+    el_pos = []
+    for d in range(dim):
+        ed = np.searchsorted(axes[d], verts[:, 0, d])
+        el_pos.append(ed)
+        lat[nodes0.ravel(), d] = (ed[:, None] * p + ((a // (p + 1) ** d) % (p + 1))[None, :]).ravel()
+    ec = el_pos[-1]
+    # ownership: the plane (line) shared with the slab below belongs to the lower rank
+    ghost = (lat[:, -1] == z0 * p) if lower >= 0 else np.zeros(n_nodes, dtype=bool)
+    stride = len(axes[0]) * p + 1
+    plane_key = lat[:, 0] if dim == 2 else lat[:, 1] * stride + lat[:, 0]
     owned_ids = np.nonzero(~ghost)[0]
     ghost_ids = np.nonzero(ghost)[0]
     ghost_ids = ghost_ids[np.argsort(plane_key[ghost_ids], kind="stable")]
@@ -104,18 +108,20 @@ def make_slab(x, y, z, order, rank, world) -> Slab:
     nodes = perm[nodes0].astype(np.uint32)
     lat_new = np.empty_like(lat)
     lat_new[perm] = lat
-    top = np.nonzero(lat_new[:, 2] == z1 * p)[0] if upper >= 0 else np.zeros(0, dtype=np.int64)
-    top = top[np.argsort((lat_new[top, 1] * (len(x) * p + 1) + lat_new[top, 0]), kind="stable")]
-    # the z faces between slabs are not physical boundaries (sides 0 = z-, 1 = z+, mesh/ElementTraits.hpp:88-93)
+    top = np.nonzero(lat_new[:, -1] == z1 * p)[0] if upper >= 0 else np.zeros(0, dtype=np.int64)
+    top_key = lat_new[top, 0] if dim == 2 else lat_new[top, 1] * stride + lat_new[top, 0]
+    top = top[np.argsort(top_key, kind="stable")]
+    # the faces between slabs are not physical boundaries (sides 0 = low, 1 = high of the cut direction in both element types,
+    # mesh/ElementTraits.hpp:88-93, 118-137)
     no_bnd = np.uint16(0xFFFF)
     if lower >= 0:
-        sb[ez == z0, 0] = no_bnd
+        sb[ec == z0, 0] = no_bnd
     if upper >= 0:
-        sb[ez == z1 - 1, 1] = no_bnd
+        sb[ec == z1 - 1, 1] = no_bnd
     touches_ghost = (nodes >= len(owned_ids)).any(axis=1)
     n_border = int(touches_ghost.sum())
     assert not touches_ghost[n_border:].any(), "border elements are expected to be the first layer of the slab"
-    return Slab(rank, world, p, n_elems, n_nodes, len(owned_ids), nodes, verts, sb, lat_new, n_border, top, lower, upper)
+    return Slab(rank, world, p, dim, n_elems, n_nodes, len(owned_ids), nodes, verts, sb, lat_new, n_border, top, lower, upper)
 
 
 class _DevicePtr:
@@ -201,7 +207,7 @@ class SlabOperator:
         self.n_local_dofs, self.n_owned_dofs = self.halo.n_local_dofs, self.halo.n_owned_dofs
         self.mesh = self.sys = None
         if slab.n_elems > 0:
-            self.mesh = l3b.Mesh(ctx, 3, slab.order, slab.verts, slab.nodes, slab.side_boundaries, slab.n_local_nodes, slab.n_owned_nodes)
+            self.mesh = l3b.Mesh(ctx, slab.dim, slab.order, slab.verts, slab.nodes, slab.side_boundaries, slab.n_local_nodes, slab.n_owned_nodes)
             mask = np.zeros(self.n_local_dofs, dtype=np.uint8)
             if dirichlet_boundary_ids:
                 mask[slab.dirichlet_nodes(dirichlet_boundary_ids) * dofs_per_node] = 1  # dof 0 (T), benchmarks/Diffusion3D.hpp:102-104
@@ -307,7 +313,12 @@ class SlabAssembledOperator:
     sparse product, Export-sum of the ghost rows, the global diagonal and rhs the Export-sums of the local ones. The reference
     export-adds the shared ROWS to their owners at endAssembly instead (AssembledSystem.hpp:384-389): same operator, same halo."""
 
-    def __init__(self, ctx, slab: Slab, dofs_per_node, kernel, dirichlet_boundary_ids=(), dirichlet_value=0.0):
+    def __init__(self, ctx, slab: Slab, dofs_per_node, kernel, dirichlet_boundary_ids=(), dirichlet_value=0.0, *, field_data=None,
+                 dirichlet=None):
+        """kernel: a name, or a list of dicts (name, boundary_ids, asm_opts, dof_inds, field_inds, time) assembled in turn (domain and
+        boundary kernels of one problem); field_data: (n_fields, n_local_nodes) nodal values in the slab's numbering, ghosts included
+        (post/FieldAccess.hpp: the values at ghost nodes must be current); dirichlet: (local dofs, values) instead of the
+        (boundary ids -> dof 0 = value) short form"""
         import torch
 
         self.torch, self.ctx, self.slab, self.dpn = torch, ctx, slab, dofs_per_node
@@ -315,12 +326,19 @@ class SlabAssembledOperator:
         self.halo = Halo(slab, dofs_per_node, dev, ctx)
         self.n_local_dofs, self.n_owned_dofs = self.halo.n_local_dofs, self.halo.n_owned_dofs
         self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-        self.mesh = l3b.Mesh(ctx, 3, slab.order, slab.verts, slab.nodes, slab.side_boundaries, slab.n_local_nodes, slab.n_owned_nodes)
+        self.mesh = l3b.Mesh(ctx, slab.dim, slab.order, slab.verts, slab.nodes, slab.side_boundaries, slab.n_local_nodes, slab.n_owned_nodes)
         self.sys = l3b.AssembledSystem(ctx, self.mesh, dofs_per_node, 1)
+        self.fields = ctx.upload_fields(field_data) if field_data is not None else None
         self.sys.beginAssembly()
-        self.sys.assembleProblem(kernel)
-        dofs = slab.dirichlet_nodes(dirichlet_boundary_ids) * dofs_per_node if dirichlet_boundary_ids else np.zeros(0, dtype=np.int64)
-        self.sys.endAssemblyRanked(dofs.astype(np.int32), np.full((len(dofs), 1), dirichlet_value), self.n_owned_dofs)
+        for k in ([dict(name=kernel)] if isinstance(kernel, str) else kernel):
+            self.sys.assembleProblem(k["name"], k.get("boundary_ids", ()), self.fields if l3b.kernel_info(k["name"])["n_fields"] else None,
+                                     k.get("field_inds"), k.get("dof_inds"), k.get("asm_opts", l3b.AssemblyOptions()), k.get("time", 0.0))
+        if dirichlet is not None:
+            dofs, vals = np.asarray(dirichlet[0], dtype=np.int64), np.asarray(dirichlet[1], dtype=np.float64).reshape(-1, 1)
+        else:
+            dofs = slab.dirichlet_nodes(dirichlet_boundary_ids) * dofs_per_node if dirichlet_boundary_ids else np.zeros(0, dtype=np.int64)
+            vals = np.full((len(dofs), 1), dirichlet_value)
+        self.sys.endAssemblyRanked(dofs.astype(np.int32), vals, self.n_owned_dofs)
         self.rhs = _device_view(self.sys.device_rhs, self.n_local_dofs, dev)
         self.diag = torch.zeros(self.n_local_dofs, dtype=torch.float64, device=dev)
         torch.cuda.current_stream().synchronize()
@@ -344,8 +362,8 @@ class SlabAssembledOperator:
                 halo.export_y(y)
                 halo.unpack_add(y)
 
-    def solve(self, tol=1e-6, max_iters=10000):
-        """CG + Jacobi over all ranks on the assembled matrix (solve/BelosSolvers.hpp:116-123)"""
+    def solve(self, tol=1e-6, max_iters=10000, gmres=False, restart_length=250, max_restarts=39):
+        """CG (or, gmres=True, restarted GMRES) + Jacobi over all ranks on the assembled matrix (solve/BelosSolvers.hpp:116-131)"""
         import torch.distributed as dist
 
         torch = self.torch
@@ -362,6 +380,10 @@ class SlabAssembledOperator:
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(_device_view(sp, n, dev))
 
-        res, it = self.ctx.pcg(self.n_local_dofs, self.n_owned_dofs, apply, allreduce if multi else None, self.diag.data_ptr(),
-                               self.rhs.data_ptr(), x.data_ptr(), tol, max_iters)
+        if gmres:
+            res, it = self.ctx.gmres(self.n_local_dofs, self.n_owned_dofs, apply, allreduce if multi else None, self.diag.data_ptr(),
+                                     self.rhs.data_ptr(), x.data_ptr(), tol, restart_length, max_restarts, max_iters)
+        else:
+            res, it = self.ctx.pcg(self.n_local_dofs, self.n_owned_dofs, apply, allreduce if multi else None, self.diag.data_ptr(),
+                                   self.rhs.data_ptr(), x.data_ptr(), tol, max_iters)
         return x, res, it

@@ -114,3 +114,25 @@ def test_two_process_nccl_apply_matches_single_gpu():
                           "--master-port", "29533", script], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "SLAB_APPLY_OK" in out.stdout
+
+
+def test_two_process_karman_assembled_gmres():
+    """BASELINE configs[3] partitioned: steady Navier-Stokes kernel + outlet kernel assembled on y-strips, distributed GMRES (NCCL)"""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mp_slab_karman.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29537", script], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "SLAB_KARMAN_OK" in out.stdout
+
+
+def test_one_process_karman_worker():
+    """the same worker on one rank (one GPU): the callback-driven GMRES against the library's own driver"""
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mp_slab_karman.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=1", "--master-addr", "127.0.0.1",
+                          "--master-port", "29539", script], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "SLAB_KARMAN_OK" in out.stdout

