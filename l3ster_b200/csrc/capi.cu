@@ -2031,6 +2031,8 @@ int l3b_cond_create(l3b_context* ctx, l3b_asm* elem_sys, l3b_asm* cond_sys, int6
         ctx->checkStatus();
         const int nId = n_int * elem_sys->dpn;
         const int nPd    = n_bnd * elem_sys->dpn;
+        if (nId > 256)
+            fail(L3B_ERR_INVALID_ARG, "static condensation: more than 256 interior dofs per element are not supported by this kernel");
         c->smem_condense = condSmemBytes(nId, nPd, elem_sys->n_rhs, true);
         if (c->smem_condense > 113 * 1024) // K_ii does not fit shared memory (two CTAs per SM): invert it in a global work buffer
         {

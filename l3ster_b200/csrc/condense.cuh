@@ -119,19 +119,29 @@ __global__ void __launch_bounds__(cond_threads, 2) condenseKernel(const __grid_c
         if (not(pkk > 0.) and tid == 0)
             atomicOr(c.status, status_degenerate_element);
         const double piv = 1. / pkk;
+        // a warp per row, a lane per column: the pivot row stays in registers over the rows (up to 8 x 32 columns)
+        constexpr int MAXC = 8;
+        double        rv[MAXC];
+#pragma unroll
+        for (int t = 0; t < MAXC; ++t)
+            rv[t] = lane + 32 * t < nId ? rowv[lane + 32 * t] : 0.;
         for (int i = warp; i < nId; i += n_warps)
         {
-            const double f = -colv[i] * piv;
-            for (int j = lane; j < nId; j += 32)
+            double* const Mi = M + i * ldM;
+            if (i == k)
             {
-                double v;
-                if (i == k)
-                    v = j == k ? piv : rowv[j] * piv;
-                else if (j == k)
-                    v = f;
-                else
-                    v = fma(f, rowv[j], M[i * ldM + j]);
-                M[i * ldM + j] = v;
+#pragma unroll
+                for (int t = 0; t < MAXC; ++t)
+                    if (lane + 32 * t < nId)
+                        Mi[lane + 32 * t] = lane + 32 * t == k ? piv : rv[t] * piv;
+            }
+            else
+            {
+                const double f = -colv[i] * piv;
+#pragma unroll
+                for (int t = 0; t < MAXC; ++t)
+                    if (lane + 32 * t < nId)
+                        Mi[lane + 32 * t] = lane + 32 * t == k ? f : fma(f, rv[t], Mi[lane + 32 * t]);
             }
         }
         __syncthreads();
