@@ -40,7 +40,7 @@ def run(kind, orders=(1, 2, 3, 4, 5, 6)):
         line = {"order": p, "kernel": kind}
         if kind != "mf":
             # elements so that the CRS stays below ~6 GB
-            n = {1: 40, 2: 28, 3: 20, 4: 14, 5: 10, 6: 8}[p]
+            n = {1: 40, 2: 28, 3: 20, 4: 14, 5: 10, 6: 8, 7: 6, 8: 5}[p]
             host = l3b.make_cube_mesh(node_dist(n), order=p)
             mesh = ctx.upload_mesh(host)
             a = l3b.AssembledSystem(ctx, mesh, U, 1, host.node_graph())
@@ -54,7 +54,7 @@ def run(kind, orders=(1, 2, 3, 4, 5, 6)):
                          "tflops_reference_count": ref_flops(p) * host.n_elems / (k_ms * 1e-3) / 1e12})
             del a
         if kind in ("dmma", "mf"):  # the matrix-free apply of the same order, once
-            nm = {1: 128, 2: 96, 3: 80, 4: 64, 5: 48, 6: 40}[p]
+            nm = {1: 128, 2: 96, 3: 80, 4: 64, 5: 48, 6: 40, 7: 32, 8: 28}[p]
             hm = l3b.make_cube_mesh(node_dist(nm), order=p)
             mm = ctx.upload_mesh(hm)
             mask = np.zeros(hm.n_nodes * U, dtype=np.uint8)
@@ -82,11 +82,60 @@ def run(kind, orders=(1, 2, 3, 4, 5, 6)):
         print(json.dumps(line), flush=True)
 
 
+def run_quads(orders=(1, 2, 3, 4, 5, 6, 7, 8)):
+    """the 2-D half: quads, diffusion (U = 3, E = 4): assembly (the kernel the size rule picks) and matrix-free apply per order"""
+    import torch
+
+    ctx = l3b.Context(0)
+    U2, E2 = 3, 4
+    for p in orders:
+        n = max(16, 2048 // p)
+        host = l3b.make_square_mesh(node_dist(n), order=p)
+        mesh = ctx.upload_mesh(host)
+        a = l3b.AssembledSystem(ctx, mesh, U2, 1, host.node_graph())
+        ms = []
+        for it in range(5):
+            a.beginAssembly()
+            a.assembleProblem("bench_diffusion2d")
+            ms.append(a.last_kernel_ms)
+        k_ms = float(np.mean(ms[2:]))
+        nn = (p + 1) ** 2
+        L = nn * U2
+        flops = nn * (8 * nn + 5 * L * E2 + (L + 1) ** 2 / 2 * (2 * E2 + 1))  # LocalAssemblyBenchmarks.cpp:71-75 with D = 2
+        line = {"order": p, "kernel": "quad", "assembly_kernel": "dmma" if nn >= 32 else "dfma", "elements": host.n_elems, "kernel_ms": k_ms,
+                "elements_per_s": host.n_elems / (k_ms * 1e-3), "tflops_reference_count": flops * host.n_elems / (k_ms * 1e-3) / 1e12}
+        del a
+        mask = np.zeros(host.n_nodes * U2, dtype=np.uint8)
+        mask[host.boundary_nodes([1, 2, 3, 4]) * U2] = 1
+        s = l3b.MatrixFreeSystem(ctx, mesh, U2, 1, mask, None)
+        s.assembleProblem("bench_diffusion2d")
+        s.endAssembly()
+        x = torch.rand(s.n_dofs, dtype=torch.float64, device="cuda")
+        y = torch.zeros_like(x)
+        torch.cuda.synchronize()
+        stream = torch.cuda.ExternalStream(ctx.stream)
+        for _ in range(3):
+            s.apply_device(x.data_ptr(), y.data_ptr())
+        ctx.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(10):
+            s.apply_device(x.data_ptr(), y.data_ptr())
+        e1.record(stream)
+        ctx.synchronize()
+        t = e0.elapsed_time(e1) / 10
+        line.update({"mf_dofs": s.n_dofs, "mf_ms_per_apply": t, "mf_gdofs_per_s": s.n_dofs / (t * 1e-3) / 1e9})
+        print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 2:  # e.g. `order_sweep.py mf 4 5 6`: the matrix-free apply only, these orders
+    if len(sys.argv) > 1 and sys.argv[1] == "quad":
+        run_quads(tuple(int(a) for a in sys.argv[2:]) or (1, 2, 3, 4, 5, 6, 7, 8))
+    elif len(sys.argv) > 2:  # e.g. `order_sweep.py mf 4 5 6`: the matrix-free apply only, these orders
         run(sys.argv[1], tuple(int(a) for a in sys.argv[2:]))
     elif len(sys.argv) > 1:
         run(sys.argv[1])
     else:
-        run("dmma")
+        run("dmma", (1, 2, 3, 4, 5, 6, 7, 8))
         subprocess.run([sys.executable, os.path.abspath(__file__), "dfma"], env=dict(os.environ, L3B_ASM_FMA="1"), check=True)
+        run_quads()
