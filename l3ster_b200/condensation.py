@@ -73,17 +73,21 @@ class CondensedAssembledSystem:
             self._fields.append(fields)
         self.local.assembleProblem(kernel, boundary_ids, fields, field_inds, dof_inds, asm_opts, time)
 
-    def endAssembly(self, dirichlet_dofs=None, dirichlet_vals=None):
-        """dirichlet_dofs in the numbering node * dofs_per_node + d of the mesh; they must sit on primary nodes (domain boundaries do)"""
+    def endAssembly(self, dirichlet_dofs=None, dirichlet_vals=None, n_owned_primary_dofs=None):
+        """dirichlet_dofs in the numbering node * dofs_per_node + d of the mesh; they must sit on primary nodes (domain boundaries do).
+        n_owned_primary_dofs: on a rank that also holds ghost rows (l3b_asm_end_assembly_ranked), in condensed numbering"""
         self.ctx._chk(lib().l3b_cond_condense(self._h))
-        if dirichlet_dofs is None or len(dirichlet_dofs) == 0:
-            self.condensed.endAssembly()
-            return
-        d = np.asarray(dirichlet_dofs, dtype=np.int64)
-        prim = self.prim_of[d // self.dofs_per_node]
-        if (prim < 0).any():
-            raise L3BError(2, "a Dirichlet dof sits on an element-interior node: it has no row in the condensed system")
-        self.condensed.endAssembly((prim * self.dofs_per_node + d % self.dofs_per_node).astype(np.int32), dirichlet_vals)
+        cd, vals = None, None
+        if dirichlet_dofs is not None and len(dirichlet_dofs) > 0:
+            d = np.asarray(dirichlet_dofs, dtype=np.int64)
+            prim = self.prim_of[d // self.dofs_per_node]
+            if (prim < 0).any():
+                raise L3BError(2, "a Dirichlet dof sits on an element-interior node: it has no row in the condensed system")
+            cd, vals = (prim * self.dofs_per_node + d % self.dofs_per_node).astype(np.int32), dirichlet_vals
+        if n_owned_primary_dofs is None:
+            self.condensed.endAssembly(cd, vals)
+        else:
+            self.condensed.endAssemblyRanked(cd, vals, n_owned_primary_dofs)
 
     def recover(self, x_condensed):
         """nodal solution over all mesh nodes, (n_nodes * dofs_per_node, n_rhs), from the solution of the condensed system"""

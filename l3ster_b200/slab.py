@@ -307,6 +307,14 @@ class SlabOperator:
         self.launches = n
 
 
+class _SlabAsHost:
+    """the slab's arrays under the names CondensedAssembledSystem reads from a HostMesh"""
+
+    def __init__(self, slab: Slab):
+        self.dim, self.order, self.nodes, self.verts, self.side_boundaries = slab.dim, slab.order, slab.nodes, slab.verts, slab.side_boundaries
+        self.n_nodes, self.n_elems = slab.n_local_nodes, slab.n_elems
+
+
 class SlabAssembledOperator:
     """Assembled system of one slab (BASELINE configs[1] on more than one GPU): every rank assembles its elements into the rows of
     its local nodes [owned | ghost] (`assembleProblem`, no exchange — as in the reference); the global operator is Import x, local
@@ -314,31 +322,54 @@ class SlabAssembledOperator:
     export-adds the shared ROWS to their owners at endAssembly instead (AssembledSystem.hpp:384-389): same operator, same halo."""
 
     def __init__(self, ctx, slab: Slab, dofs_per_node, kernel, dirichlet_boundary_ids=(), dirichlet_value=0.0, *, field_data=None,
-                 dirichlet=None):
+                 dirichlet=None, condensed=False):
         """kernel: a name, or a list of dicts (name, boundary_ids, asm_opts, dof_inds, field_inds, time) assembled in turn (domain and
         boundary kernels of one problem); field_data: (n_fields, n_local_nodes) nodal values in the slab's numbering, ghosts included
         (post/FieldAccess.hpp: the values at ghost nodes must be current); dirichlet: (local dofs, values) instead of the
-        (boundary ids -> dof 0 = value) short form"""
+        (boundary ids -> dof 0 = value) short form; condensed: CondensationPolicy::ElementBoundary — the operator then lives on the
+        primary (element-boundary) nodes of the slab, [owned | ghost] like the nodes (every ghost node is a primary one), and
+        `recover` returns the nodal solution"""
         import torch
 
         self.torch, self.ctx, self.slab, self.dpn = torch, ctx, slab, dofs_per_node
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.halo = Halo(slab, dofs_per_node, dev, ctx)
-        self.n_local_dofs, self.n_owned_dofs = self.halo.n_local_dofs, self.halo.n_owned_dofs
         self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-        self.mesh = l3b.Mesh(ctx, slab.dim, slab.order, slab.verts, slab.nodes, slab.side_boundaries, slab.n_local_nodes, slab.n_owned_nodes)
-        self.sys = l3b.AssembledSystem(ctx, self.mesh, dofs_per_node, 1)
-        self.fields = ctx.upload_fields(field_data) if field_data is not None else None
-        self.sys.beginAssembly()
-        for k in ([dict(name=kernel)] if isinstance(kernel, str) else kernel):
-            self.sys.assembleProblem(k["name"], k.get("boundary_ids", ()), self.fields if l3b.kernel_info(k["name"])["n_fields"] else None,
-                                     k.get("field_inds"), k.get("dof_inds"), k.get("asm_opts", l3b.AssemblyOptions()), k.get("time", 0.0))
+        kernels = [dict(name=kernel)] if isinstance(kernel, str) else kernel
         if dirichlet is not None:
             dofs, vals = np.asarray(dirichlet[0], dtype=np.int64), np.asarray(dirichlet[1], dtype=np.float64).reshape(-1, 1)
         else:
             dofs = slab.dirichlet_nodes(dirichlet_boundary_ids) * dofs_per_node if dirichlet_boundary_ids else np.zeros(0, dtype=np.int64)
             vals = np.full((len(dofs), 1), dirichlet_value)
-        self.sys.endAssemblyRanked(dofs.astype(np.int32), vals, self.n_owned_dofs)
+        self.cs = None
+        if condensed:
+            import dataclasses
+
+            from .condensation import CondensedAssembledSystem
+
+            self.cs = CondensedAssembledSystem(ctx, _SlabAsHost(slab), dofs_per_node)
+            n_owned_prim = int((self.cs.primary_nodes < slab.n_owned_nodes).sum())  # local ids are [owned | ghost]: owned primaries first
+            assert (self.cs.prim_of[slab.n_owned_nodes:] >= 0).all(), "ghost nodes lie on element boundaries"
+            send_up = self.cs.prim_of[slab.send_up_nodes] if len(slab.send_up_nodes) else slab.send_up_nodes
+            pslab = dataclasses.replace(slab, n_local_nodes=len(self.cs.primary_nodes), n_owned_nodes=n_owned_prim, send_up_nodes=send_up)
+            self.halo = Halo(pslab, dofs_per_node, dev, ctx)
+            self.n_local_dofs, self.n_owned_dofs = self.halo.n_local_dofs, self.halo.n_owned_dofs
+            self.cs.beginAssembly()
+            for k in kernels:
+                self.cs.assembleProblem(k["name"], k.get("boundary_ids", ()), field_data if l3b.kernel_info(k["name"])["n_fields"] else None,
+                                        k.get("field_inds"), k.get("dof_inds"), k.get("asm_opts", l3b.AssemblyOptions()), k.get("time", 0.0))
+            self.cs.endAssembly(dofs, vals, n_owned_primary_dofs=self.n_owned_dofs)
+            self.mesh, self.sys = self.cs.local_mesh, self.cs.condensed
+        else:
+            self.halo = Halo(slab, dofs_per_node, dev, ctx)
+            self.n_local_dofs, self.n_owned_dofs = self.halo.n_local_dofs, self.halo.n_owned_dofs
+            self.mesh = l3b.Mesh(ctx, slab.dim, slab.order, slab.verts, slab.nodes, slab.side_boundaries, slab.n_local_nodes, slab.n_owned_nodes)
+            self.sys = l3b.AssembledSystem(ctx, self.mesh, dofs_per_node, 1)
+            self.fields = ctx.upload_fields(field_data) if field_data is not None else None
+            self.sys.beginAssembly()
+            for k in kernels:
+                self.sys.assembleProblem(k["name"], k.get("boundary_ids", ()), self.fields if l3b.kernel_info(k["name"])["n_fields"] else None,
+                                         k.get("field_inds"), k.get("dof_inds"), k.get("asm_opts", l3b.AssemblyOptions()), k.get("time", 0.0))
+            self.sys.endAssemblyRanked(dofs.astype(np.int32), vals, self.n_owned_dofs)
         self.rhs = _device_view(self.sys.device_rhs, self.n_local_dofs, dev)
         self.diag = torch.zeros(self.n_local_dofs, dtype=torch.float64, device=dev)
         torch.cuda.current_stream().synchronize()
@@ -349,6 +380,17 @@ class SlabAssembledOperator:
                     self.halo.export_y(v)
                     self.halo.unpack_add(v)
         ctx.synchronize()
+
+    def recover(self, x):
+        """condensed operator only: nodal solution over the slab's local nodes (n_local_nodes * dofs_per_node, host) from the condensed
+        solution x over the primary dofs; the ghost primaries are refreshed from their owners first"""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            if self.slab.world > 1:
+                self.halo.pack(x)
+                self.halo.import_x(x)
+        self.ctx.synchronize()
+        return self.cs.recover(x.cpu().numpy())[:, 0]
 
     def apply(self, x, y):
         """y[owned] = (A x)[owned]; x[ghost] is overwritten by the Import. Asynchronous on the context stream."""

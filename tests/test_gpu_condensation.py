@@ -123,3 +123,19 @@ def test_dirichlet_on_interior_node_is_rejected(ctx):
     interior_node = int(host.nodes[0, 4])  # the centre node of the first p=2 quad
     with pytest.raises(l3b.L3BError):
         cs.endAssembly(np.array([interior_node * 3], dtype=np.int32), np.zeros((1, 1)))
+
+
+def test_condensed_slab_operator_on_one_rank(ctx):
+    """SlabAssembledOperator(condensed=True), the multi-rank form of the condensed system, on a single slab: same solution as
+    CondensedAssembledSystem and as the uncondensed slab operator (distributed: tests/mp_slab_apply.py)"""
+    from l3ster_b200.slab import SlabAssembledOperator, make_slab
+
+    x1, y1, z1 = np.linspace(0, 1, 3), np.linspace(0, 1.1, 3), np.linspace(0, 1.3, 4)
+    slab = make_slab(x1, y1, z1, 3, 0, 1)
+    bnd = [1, 2, 3, 4, 5, 6]
+    full = SlabAssembledOperator(ctx, slab, 4, "bench_diffusion3d", bnd)
+    cond = SlabAssembledOperator(ctx, slab, 4, "bench_diffusion3d", bnd, condensed=True)
+    xf, res_f, it_f = full.solve(tol=1e-11)
+    xc, res_c, it_c = cond.solve(tol=1e-11)
+    assert res_f <= 1e-11 and res_c <= 1e-11 and cond.n_local_dofs < full.n_local_dofs
+    assert rel_err(cond.recover(xc), xf.cpu().numpy()) < 1e-9

@@ -133,7 +133,7 @@ def test_two_dimensional_strips_cover_the_square():
                 assert (s.nodes[: s.n_border_elems] >= s.n_owned_nodes).any(axis=1).all()
                 assert not (s.nodes[s.n_border_elems:] >= s.n_owned_nodes).any()
                 if s.lower >= 0:
-                    assert (s.side_boundaries[:, 0] != 1).all() or True
+                    assert (s.side_boundaries[:, 0] == 0xFFFF).all()  # no strip below the first one touches the bottom boundary
                     assert s.n_ghost_nodes == stride
                 if s.upper >= 0:
                     assert len(s.send_up_nodes) == stride
