@@ -172,7 +172,9 @@ def main():
     ap.add_argument("--n-mf", type=int, default=64, help="elements per edge, matrix-free workload (per GPU)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workload")
     ap.add_argument("--cg-max-iters", type=int, default=10000, help="matrix-free workload: iteration cap of the CG solve timed after the applies (0 = skip)")
-    ap.add_argument("--condensed", action="store_true", help="assembly workload: also time CondensationPolicy::ElementBoundary")
+    ap.add_argument("--no-condensed", dest="condensed", action="store_false",
+                    help="assembly workload: skip the CondensationPolicy::ElementBoundary figure (assembly + per-element Schur complements)")
+    ap.add_argument("--condensed", dest="condensed", action="store_true", default=True, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
