@@ -19,7 +19,7 @@ namespace l3b
 {
 constexpr int cond_threads = 256;
 constexpr int cond_wcols = 16;               // columns of K_ip per pass of W = K_ii^-1 K_ip
-constexpr int cond_tm = 32, cond_tn = 64;    // tile of the Schur update S = K_pp - K_pi W (2 x 4 outputs per thread)
+constexpr int cond_tm = 64, cond_tn = 64;    // tile of the Schur update S = K_pp - K_pi W (two passes of 2 x 4 outputs per thread)
 
 struct CondArgs
 {
@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(cond_threads, 2) condenseKernel(const __grid_c
         }
     }
 
-    // ---- 3: S = K_pp - K_pi W in 32 x 64 tiles from shared memory (2 x 4 outputs per thread), straight into the condensed CRS; the
+    // ---- 3: S = K_pp - K_pi W in 64 x 64 tiles from shared memory (two passes of 2 x 4 outputs per thread: each W tile loaded from global
+    // serves 64 rows, the accumulators stay at 8 registers' worth), straight into the condensed CRS; the
     // condensed rhs f_p - K_pi g rides on the K_pi tile
     double* As = smem;                          // [cond_tm][nId + 1]: K_pi rows of the tile
     double* Bs = smem + cond_tm * (nId + 1);    // [nId][cond_tn]: W columns of the tile
@@ -265,45 +266,51 @@ __global__ void __launch_bounds__(cond_threads, 2) condenseKernel(const __grid_c
             __syncthreads();
             if (use_pf and q0 + cond_tn < nPd)
                 loadTile(q0 + cond_tn);
-            // thread tile: rows 2 ty, 2 ty + 1; columns 2 tx, 2 tx + 1, 32 + 2 tx, 33 + 2 tx (16-byte stride between threads: no bank conflicts)
-            double acc[2][4] = {{0., 0., 0., 0.}, {0., 0., 0., 0.}};
-#pragma unroll 2
-            for (int i = 0; i < nId; ++i)
+            // thread tile: rows 2 ty, 2 ty + 1 of each 32-row half; columns 2 tx, 2 tx + 1, 32 + 2 tx, 33 + 2 tx (16-byte stride between threads)
+            for (int half = 0; half < cond_tm / 32; ++half)
             {
-                const double  a0 = As[(2 * ty) * ldA + i], a1 = As[(2 * ty + 1) * ldA + i];
-                const double2 b0 = *reinterpret_cast< const double2* >(Bs + i * cond_tn + 2 * tx);
-                const double2 b1 = *reinterpret_cast< const double2* >(Bs + i * cond_tn + cond_tn / 2 + 2 * tx);
-                acc[0][0] = fma(a0, b0.x, acc[0][0]);
-                acc[0][1] = fma(a0, b0.y, acc[0][1]);
-                acc[0][2] = fma(a0, b1.x, acc[0][2]);
-                acc[0][3] = fma(a0, b1.y, acc[0][3]);
-                acc[1][0] = fma(a1, b0.x, acc[1][0]);
-                acc[1][1] = fma(a1, b0.y, acc[1][1]);
-                acc[1][2] = fma(a1, b1.x, acc[1][2]);
-                acc[1][3] = fma(a1, b1.y, acc[1][3]);
-            }
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr)
-            {
-                const int p = p0 + 2 * ty + rr;
-                if (p >= nPd)
+                const int r0 = 32 * half + 2 * ty;
+                if (p0 + 32 * half >= nPd or q0 + cond_tn <= p0 + 32 * half) // rows past the end, or a tile wholly left of this half's diagonal
                     continue;
-                const int       ib = p % c.nB, u = p / c.nB, ro = pRow[p];
-                const long long A = prim_e[ib], np = c.node_ptr[A], deg = c.node_ptr[A + 1] - np;
-                double* const   rowp = c.vals + U * (U * np + u * deg);
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc)
+                double acc[2][4] = {{0., 0., 0., 0.}, {0., 0., 0., 0.}};
+#pragma unroll 2
+                for (int i = 0; i < nId; ++i)
                 {
-                    const int q = q0 + (cc / 2) * (cond_tn / 2) + 2 * tx + cc % 2;
-                    if (q >= nPd or q < p)
+                    const double  a0 = As[r0 * ldA + i], a1 = As[(r0 + 1) * ldA + i];
+                    const double2 b0 = *reinterpret_cast< const double2* >(Bs + i * cond_tn + 2 * tx);
+                    const double2 b1 = *reinterpret_cast< const double2* >(Bs + i * cond_tn + cond_tn / 2 + 2 * tx);
+                    acc[0][0] = fma(a0, b0.x, acc[0][0]);
+                    acc[0][1] = fma(a0, b0.y, acc[0][1]);
+                    acc[0][2] = fma(a0, b1.x, acc[0][2]);
+                    acc[0][3] = fma(a0, b1.y, acc[0][3]);
+                    acc[1][0] = fma(a1, b0.x, acc[1][0]);
+                    acc[1][1] = fma(a1, b0.y, acc[1][1]);
+                    acc[1][2] = fma(a1, b1.x, acc[1][2]);
+                    acc[1][3] = fma(a1, b1.y, acc[1][3]);
+                }
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+                {
+                    const int p = p0 + r0 + rr;
+                    if (p >= nPd)
                         continue;
-                    const int    ib2 = q % c.nB, v2 = q / c.nB;
-                    const double sv  = ke[ro + pCol[q]] - acc[rr][cc];
-                    atomicAdd(rowp + v2 * deg + pos_e[ib * c.nB + ib2], sv);
-                    if (q > p)
+                    const int       ib = p % c.nB, u = p / c.nB, ro = pRow[p];
+                    const long long A = prim_e[ib], np = c.node_ptr[A], deg = c.node_ptr[A + 1] - np;
+                    double* const   rowp = c.vals + U * (U * np + u * deg);
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc)
                     {
-                        const long long A2 = prim_e[ib2], np2 = c.node_ptr[A2], deg2 = c.node_ptr[A2 + 1] - np2;
-                        atomicAdd(c.vals + U * (U * np2 + v2 * deg2) + u * deg2 + pos_e[ib2 * c.nB + ib], sv);
+                        const int q = q0 + (cc / 2) * (cond_tn / 2) + 2 * tx + cc % 2;
+                        if (q >= nPd or q < p)
+                            continue;
+                        const int    ib2 = q % c.nB, v2 = q / c.nB;
+                        const double sv  = ke[ro + pCol[q]] - acc[rr][cc];
+                        atomicAdd(rowp + v2 * deg + pos_e[ib * c.nB + ib2], sv);
+                        if (q > p)
+                        {
+                            const long long A2 = prim_e[ib2], np2 = c.node_ptr[A2], deg2 = c.node_ptr[A2 + 1] - np2;
+                            atomicAdd(c.vals + U * (U * np2 + v2 * deg2) + u * deg2 + pos_e[ib2 * c.nB + ib], sv);
+                        }
                     }
                 }
             }
