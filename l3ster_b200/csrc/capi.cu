@@ -1996,6 +1996,7 @@ struct l3b_cond
     DevBuf< uint16_t > pos;
     DevBuf< double >   work;
     size_t             smem_condense = 0;
+    int                maxc = 8;
     bool               condensed = false;
 };
 extern "C" {
@@ -2041,8 +2042,18 @@ int l3b_cond_create(l3b_context* ctx, l3b_asm* elem_sys, l3b_asm* cond_sys, int6
             if (c->smem_condense > 220 * 1024)
                 fail(L3B_ERR_INVALID_ARG, "static condensation: the element's interior block is too large for this kernel");
         }
-        if (c->smem_condense > 48 * 1024)
-            cudaCheck(cudaFuncSetAttribute(condenseKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(c->smem_condense)), "smem");
+        c->maxc = nId <= 32 ? 1 : nId <= 64 ? 2 : nId <= 128 ? 4 : 8;
+        const auto raise = [&](auto kernel) {
+            if (c->smem_condense > 48 * 1024)
+                cudaCheck(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(c->smem_condense)), "smem");
+        };
+        switch (c->maxc)
+        {
+        case 1: raise(condenseKernel< 1 >); break;
+        case 2: raise(condenseKernel< 2 >); break;
+        case 4: raise(condenseKernel< 4 >); break;
+        default: raise(condenseKernel< 8 >);
+        }
         cudaCheck(cudaStreamSynchronize(ctx->stream), "cond create");
         *out = c.release();
     });
@@ -2079,7 +2090,14 @@ int l3b_cond_condense(l3b_cond* c)
             a.ld_c      = c->cond_sys->n_dofs;
             a.work      = c->work.ptr;
             a.status    = c->ctx->status.ptr;
-            condenseKernel<<< static_cast< unsigned >(c->n_elems), cond_threads, c->smem_condense, c->ctx->stream >>>(a);
+            const auto launch = [&](auto kernel) { kernel<<< static_cast< unsigned >(c->n_elems), cond_threads, c->smem_condense, c->ctx->stream >>>(a); };
+            switch (c->maxc)
+            {
+            case 1: launch(condenseKernel< 1 >); break;
+            case 2: launch(condenseKernel< 2 >); break;
+            case 4: launch(condenseKernel< 4 >); break;
+            default: launch(condenseKernel< 8 >);
+            }
             cudaCheck(cudaGetLastError(), "condense");
         }
         c->ctx->checkStatus();

@@ -68,6 +68,8 @@ __device__ __forceinline__ long long keIndex(const CondArgs& c, long long e, int
 // One CTA per element. Interior dofs i = (interior node i / U, unknown i % U); primary dofs are enumerated dof-major, q = v nB + ib,
 // so that consecutive q are consecutive doubles of a row of K_e. After the kernel the element-local storage holds W = K_ii^-1 K_ip in
 // place of K_ip and g = K_ii^-1 f_i in place of f_i: x_i = g - W x_p is all the recovery needs.
+// MAXC: 32-column groups of K_ii a lane covers in the inverse (the host picks the smallest of 1, 2, 4, 8 with 32 MAXC >= interior dofs)
+template < int MAXC >
 __global__ void __launch_bounds__(cond_threads, 2) condenseKernel(const __grid_constant__ CondArgs c)
 {
     extern __shared__ __align__(16) double smem[];
@@ -119,8 +121,7 @@ __global__ void __launch_bounds__(cond_threads, 2) condenseKernel(const __grid_c
         if (not(pkk > 0.) and tid == 0)
             atomicOr(c.status, status_degenerate_element);
         const double piv = 1. / pkk;
-        // a warp per row, a lane per column: the pivot row stays in registers over the rows (up to 8 x 32 columns)
-        constexpr int MAXC = 8;
+        // a warp per row, a lane per column: the pivot row stays in registers over the rows
         double        rv[MAXC];
 #pragma unroll
         for (int t = 0; t < MAXC; ++t)
