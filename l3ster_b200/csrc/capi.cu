@@ -461,6 +461,11 @@ __global__ void extractDiagKernel(const long long* node_ptr, const uint32_t* nod
     diag[row] = vals[beg + d * deg + lo];
 }
 
+// one thread per item (kernels without a grid-stride loop): exact block count, at least 1 so that empty ranks launch harmlessly
+unsigned blocksFor(long long n, int block = 256)
+{
+    return static_cast< unsigned >(std::max< long long >(1, (n + block - 1) / block));
+}
 unsigned gridFor(long long n, int block = 256)
 {
     const long long g = (n + block - 1) / block;
@@ -1411,12 +1416,12 @@ int l3b_asm_create(l3b_context* ctx, l3b_mesh* mesh, int dpn, int n_rhs, const i
         s->node_ptr_host.assign(node_ptr, node_ptr + N + 1);
         s->node_nbr.upload(node_nbr, node_ptr[N], ctx->stream);
         s->row_ptr.alloc(s->n_dofs + 1);
-        rowPtrKernel<<< static_cast< unsigned >((s->n_dofs + 1 + 255) / 256), 256, 0, ctx->stream >>>(s->node_ptr.ptr, N, dpn, s->row_ptr.ptr);
+        rowPtrKernel<<< blocksFor(s->n_dofs + 1), 256, 0, ctx->stream >>>(s->node_ptr.ptr, N, dpn, s->row_ptr.ptr);
         s->values.alloc(s->nnz);
         s->rhs.alloc(s->n_dofs * n_rhs);
         const long long n_pos = mesh->n_elems * mesh->nn * mesh->nn;
         s->slot_pos.alloc(n_pos);
-        slotMapKernel<<< static_cast< unsigned >((n_pos + 255) / 256), 256, 0, ctx->stream >>>(mesh->nodes.ptr, mesh->n_elems, mesh->nn,
+        slotMapKernel<<< blocksFor(n_pos), 256, 0, ctx->stream >>>(mesh->nodes.ptr, mesh->n_elems, mesh->nn,
                                                                                            s->node_ptr.ptr, s->node_nbr.ptr,
                                                                                            s->slot_pos.ptr, ctx->status.ptr);
         cudaCheck(cudaGetLastError(), "slot map");
@@ -1443,7 +1448,7 @@ int l3b_crs_create(l3b_context* ctx, int64_t n_nodes, int dpn, int n_rhs, const 
         s->node_ptr_host.assign(node_ptr, node_ptr + n_nodes + 1);
         s->node_nbr.upload(node_nbr, node_ptr[n_nodes], ctx->stream);
         s->row_ptr.alloc(s->n_dofs + 1);
-        rowPtrKernel<<< static_cast< unsigned >((s->n_dofs + 1 + 255) / 256), 256, 0, ctx->stream >>>(s->node_ptr.ptr, n_nodes, dpn, s->row_ptr.ptr);
+        rowPtrKernel<<< blocksFor(s->n_dofs + 1), 256, 0, ctx->stream >>>(s->node_ptr.ptr, n_nodes, dpn, s->row_ptr.ptr);
         s->values.alloc(s->nnz);
         s->rhs.alloc(s->n_dofs * n_rhs);
         cudaCheck(cudaGetLastError(), "crs create");
@@ -1520,7 +1525,7 @@ int l3b_asm_end_assembly_ranked(l3b_asm* sys, int64_t n_dir, const int32_t* dofs
             d_mask.upload(mask.data(), mask.size(), sys->ctx->stream);
             d_bc.upload(bc.data(), bc.size(), sys->ctx->stream);
             const long long threads = sys->n_dofs * 32;
-            dirichletAlgebraicKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
+            dirichletAlgebraicKernel<<< blocksFor(threads), 256, 0, sys->ctx->stream >>>(
                 sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, d_mask.ptr, d_bc.ptr, sys->rhs.ptr,
                 sys->n_dofs, sys->n_rhs, n_owned_dofs);
             cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "Dirichlet BC application");
@@ -1567,7 +1572,7 @@ int l3b_asm_spmv(l3b_asm* sys, const double* x, double* y)
         DevBuf< double > dx(sys->n_dofs), dy(sys->n_dofs);
         dx.upload(x, sys->n_dofs, sys->ctx->stream);
         const long long threads = sys->n_dofs * 32;
-        spmvKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
+        spmvKernel<<< blocksFor(threads), 256, 0, sys->ctx->stream >>>(
             sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, dx.ptr, dy.ptr);
         dy.download(y, sys->n_dofs, sys->ctx->stream);
         cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "spmv");
@@ -1581,13 +1586,13 @@ int l3b_asm_solve_gmres(l3b_asm* sys, double tol, int restart_length, int max_re
             fail(L3B_ERR_STATE, "`solve()` was called before `endAssembly()`");
         const auto       n = sys->n_dofs;
         DevBuf< double > diag(n), dx(n);
-        extractDiagKernel<<< static_cast< unsigned >((n + 255) / 256), 256, 0, sys->ctx->stream >>>(
+        extractDiagKernel<<< blocksFor(n), 256, 0, sys->ctx->stream >>>(
             sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, diag.ptr);
         const long long threads = n * 32;
         gmres(
             sys->ctx, n, n,
             [&](const double* in, double* out) {
-                spmvKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
+                spmvKernel<<< blocksFor(threads), 256, 0, sys->ctx->stream >>>(
                     sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, in, out);
             },
             [](double*, int) {}, diag.ptr, sys->rhs.ptr, dx.ptr, tol, restart_length, max_restarts, max_iters, achieved_tol, iters);
@@ -1599,7 +1604,7 @@ int l3b_asm_spmv_device(l3b_asm* sys, const double* x, double* y)
 {
     return guardedCtx(sys->ctx, [&] {
         const long long threads = sys->n_dofs * 32;
-        spmvKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
+        spmvKernel<<< blocksFor(threads), 256, 0, sys->ctx->stream >>>(
             sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, x, y);
         cudaCheck(cudaGetLastError(), "spmv");
     });
@@ -1607,7 +1612,7 @@ int l3b_asm_spmv_device(l3b_asm* sys, const double* x, double* y)
 int l3b_asm_diag_device(l3b_asm* sys, double* diag)
 {
     return guardedCtx(sys->ctx, [&] {
-        extractDiagKernel<<< static_cast< unsigned >((sys->n_dofs + 255) / 256), 256, 0, sys->ctx->stream >>>(
+        extractDiagKernel<<< blocksFor(sys->n_dofs), 256, 0, sys->ctx->stream >>>(
             sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, diag);
         cudaCheck(cudaGetLastError(), "diagonal");
     });
@@ -1623,13 +1628,13 @@ int l3b_asm_solve_cg(l3b_asm* sys, double tol, int max_iters, double* x, double*
             fail(L3B_ERR_STATE, "`solve()` was called before `endAssembly()`");
         const auto       n = sys->n_dofs;
         DevBuf< double > diag(n), dx(n);
-        extractDiagKernel<<< static_cast< unsigned >((n + 255) / 256), 256, 0, sys->ctx->stream >>>(
+        extractDiagKernel<<< blocksFor(n), 256, 0, sys->ctx->stream >>>(
             sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, diag.ptr);
         const long long threads = n * 32;
         pcg(
             sys->ctx, n, n,
             [&](const double* in, double* out, double*) {
-                spmvKernel<<< static_cast< unsigned >((threads + 255) / 256), 256, 0, sys->ctx->stream >>>(
+                spmvKernel<<< blocksFor(threads), 256, 0, sys->ctx->stream >>>(
                     sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, in, out);
                 return false; // p.Ap by a dot-product pass
             },
@@ -2026,7 +2031,7 @@ int l3b_cond_create(l3b_context* ctx, l3b_asm* elem_sys, l3b_asm* cond_sys, int6
         const long long n_pos = n_elems * n_bnd * n_bnd;
         c->pos.alloc(std::max< long long >(n_pos, 1));
         if (n_pos > 0)
-            slotMapKernel<<< static_cast< unsigned >((n_pos + 255) / 256), 256, 0, ctx->stream >>>(
+            slotMapKernel<<< blocksFor(n_pos), 256, 0, ctx->stream >>>(
                 c->elem_prim.ptr, n_elems, n_bnd, cond_sys->node_ptr.ptr, cond_sys->node_nbr.ptr, c->pos.ptr, ctx->status.ptr);
         cudaCheck(cudaGetLastError(), "slot map");
         ctx->checkStatus();

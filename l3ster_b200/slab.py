@@ -133,6 +133,8 @@ def _device_view(ptr, n, device):
     """zero-copy torch view of n doubles of device memory owned by the library"""
     import torch
 
+    if not ptr or n == 0:  # an empty rank: the library holds no storage
+        return torch.empty(0, dtype=torch.float64, device=device)
     return torch.as_tensor(_DevicePtr(ptr, n), device=device)
 
 

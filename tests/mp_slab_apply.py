@@ -145,6 +145,23 @@ def main():
         print(f"condensed distributed CG: {its_c} iterations on {cop.n_owned_dofs} of {aop.n_owned_dofs} owned dofs (uncondensed: {its_a} iterations); "
               f"recovered solution vs uncondensed rel diff {err3:.2e}")
         ok = ok and bool(np.isfinite(err3) and err3 < 1e-7 and res_c <= 1e-10 and its_c <= its_a)
+    # ---- fewer element layers than ranks (tests/EmptyPartitionTest.cpp:10-49, both condensation policies): the empty ranks take part in
+    # the reductions with zero dofs; the solution is the one-rank solution
+    z_one = z1[:2]
+    for cond in (False, True):
+        eslab = make_slab(x1, y1, z_one, P2, rank, world)
+        eop = SlabAssembledOperator(ctx, eslab, U, "bench_diffusion3d", BND, condensed=cond)
+        xe, res_e, its_e = eop.solve(tol=1e-10, max_iters=2000)
+        mine = float(torch.sum(xe[: eop.n_owned_dofs] ** 2).item()) if eop.n_owned_dofs else 0.0
+        tot = torch.tensor([mine, float(eslab.n_elems)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot)
+        if rank == 0:
+            wslab = make_slab(x1, y1, z_one, P2, 0, 1)
+            wop_e = SlabAssembledOperator(ctx, wslab, U, "bench_diffusion3d", BND, condensed=cond)
+            xw_e, _, its_we = wop_e.solve(tol=1e-10, max_iters=2000)
+            ref = float(torch.sum(xw_e ** 2).item())
+            print(f"one element layer over {world} ranks (condensed={cond}): {its_e} iterations (one rank {its_we}), |x|^2 {tot[0].item():.12e} vs {ref:.12e}")
+            ok = ok and bool(abs(tot[0].item() - ref) <= 1e-8 * ref and abs(its_e - its_we) <= 1 and int(tot[1].item()) == wslab.n_elems)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
