@@ -136,3 +136,19 @@ def test_one_process_karman_worker():
                           "--master-port", "29539", script], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "SLAB_KARMAN_OK" in out.stdout
+
+
+def test_assembled_operators_on_an_empty_rank():
+    """tests/EmptyPartitionTest.cpp:10-49: a rank without elements builds its (empty) assembled system under both condensation policies
+    and can take part in the solves (the distributed solve with an empty rank runs in tests/mp_slab_apply.py)"""
+    from l3ster_b200.slab import SlabAssembledOperator
+
+    ctx = l3b.Context(0)
+    x = np.linspace(0, 1, 3)
+    slab = make_slab(x, x, x, 2, 2, 3)  # 2 element layers over 3 ranks
+    assert slab.n_elems == 0
+    for cond in (False, True):
+        op = SlabAssembledOperator(ctx, slab, 4, "bench_diffusion3d", [1, 2, 3, 4, 5, 6], condensed=cond)
+        assert op.n_local_dofs == 0 and op.n_owned_dofs == 0
+        xs, res, its = op.solve(tol=1e-8)
+        assert its == 0 and xs.numel() == 0
