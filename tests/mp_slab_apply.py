@@ -162,6 +162,19 @@ def main():
             ref = float(torch.sum(xw_e ** 2).item())
             print(f"one element layer over {world} ranks (condensed={cond}): {its_e} iterations (one rank {its_we}), |x|^2 {tot[0].item():.12e} vs {ref:.12e}")
             ok = ok and bool(abs(tot[0].item() - ref) <= 1e-8 * ref and abs(its_e - its_we) <= 1 and int(tot[1].item()) == wslab.n_elems)
+    # the matrix-free operator with an empty rank
+    eslab = make_slab(x1, y1, z_one, P2, rank, world)
+    emf = SlabOperator(ctx, eslab, U, "bench_diffusion3d", BND)
+    xm, res_m, its_m = emf.solve(tol=1e-10, max_iters=2000)
+    mine = float(torch.sum(xm[: emf.n_owned_dofs] ** 2).item()) if emf.n_owned_dofs else 0.0
+    tot = torch.tensor([mine], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tot)
+    if rank == 0:
+        wmf = SlabOperator(ctx, make_slab(x1, y1, z_one, P2, 0, 1), U, "bench_diffusion3d", BND)
+        xw_m, _, its_wm = wmf.solve(tol=1e-10, max_iters=2000)
+        ref = float(torch.sum(xw_m ** 2).item())
+        print(f"matrix-free, one element layer over {world} ranks: {its_m} iterations (one rank {its_wm}), |x|^2 {tot[0].item():.12e} vs {ref:.12e}")
+        ok = ok and bool(abs(tot[0].item() - ref) <= 1e-8 * ref and abs(its_m - its_wm) <= 1)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
