@@ -254,20 +254,39 @@ __global__ void dot2Kernel(const double* a, const double* b, const double* c, co
             atomicAdd(out + 1, s1);
     }
 }
-// r -= a Ap ; z = minv r ; out[0] += r.r ; out[1] += r.z     (a = rz / pAp read from device scalars)
+// r -= a Ap ; z = minv r ; out[0] += r.r ; out[1] += r.z     (a = rz / pAp read from device scalars). Two doubles per access: the
+// arrays are cudaMalloc'ed (16-byte aligned), an odd last element is handled by one thread.
 __global__ void cgUpdateKernel(double* r, double* z, const double* Ap, const double* minv, long long n, const double* scal /* [rz, pAp] */,
                                double* out)
 {
-    const double a  = scal[0] / scal[1];
-    double       s0 = 0., s1 = 0.;
-    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
+    const double    a  = scal[0] / scal[1];
+    double          s0 = 0., s1 = 0.;
+    const long long n2 = n / 2;
+    auto* const       r2  = reinterpret_cast< double2* >(r);
+    auto* const       z2  = reinterpret_cast< double2* >(z);
+    const auto* const Ap2 = reinterpret_cast< const double2* >(Ap);
+    const auto* const m2  = reinterpret_cast< const double2* >(minv);
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n2; i += static_cast< long long >(gridDim.x) * blockDim.x)
     {
-        const double ri = fma(-a, Ap[i], r[i]);
-        r[i]            = ri;
-        const double zi = minv[i] * ri;
-        z[i]            = zi;
-        s0              = fma(ri, ri, s0);
-        s1              = fma(ri, zi, s1);
+        const double2 q = Ap2[i], m = m2[i];
+        double2       ri = r2[i];
+        ri.x = fma(-a, q.x, ri.x);
+        ri.y = fma(-a, q.y, ri.y);
+        r2[i] = ri;
+        const double2 zi{m.x * ri.x, m.y * ri.y};
+        z2[i] = zi;
+        s0    = fma(ri.x, ri.x, fma(ri.y, ri.y, s0));
+        s1    = fma(ri.x, zi.x, fma(ri.y, zi.y, s1));
+    }
+    if ((n & 1) and blockIdx.x == 0 and threadIdx.x == 0)
+    {
+        const long long i  = n - 1;
+        const double    ri = fma(-a, Ap[i], r[i]);
+        r[i]               = ri;
+        const double zi    = minv[i] * ri;
+        z[i]               = zi;
+        s0                 = fma(ri, ri, s0);
+        s1                 = fma(ri, zi, s1);
     }
     s0 = blockSum(s0);
     s1 = blockSum(s1);
@@ -280,12 +299,26 @@ __global__ void cgUpdateKernel(double* r, double* z, const double* Ap, const dou
 // x += a p ; p = z + (rz_new / rz_old) p     (the x update rides on the pass that reads p anyway; scal = [rz_old, pAp, rr, rz_new])
 __global__ void cgDirectionKernel(double* x, double* p, const double* z, long long n, const double* scal)
 {
-    const double a = scal[0] / scal[1], b = scal[3] / scal[0];
-    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
+    const double    a = scal[0] / scal[1], b = scal[3] / scal[0];
+    const long long n2 = n / 2;
+    auto* const       x2 = reinterpret_cast< double2* >(x);
+    auto* const       p2 = reinterpret_cast< double2* >(p);
+    const auto* const z2 = reinterpret_cast< const double2* >(z);
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n2; i += static_cast< long long >(gridDim.x) * blockDim.x)
     {
-        const double pi = p[i];
-        x[i]            = fma(a, pi, x[i]);
-        p[i]            = fma(b, pi, z[i]);
+        const double2 pi = p2[i], zi = z2[i];
+        double2       xi = x2[i];
+        xi.x = fma(a, pi.x, xi.x);
+        xi.y = fma(a, pi.y, xi.y);
+        x2[i] = xi;
+        p2[i] = double2{fma(b, pi.x, zi.x), fma(b, pi.y, zi.y)};
+    }
+    if ((n & 1) and blockIdx.x == 0 and threadIdx.x == 0)
+    {
+        const long long i  = n - 1;
+        const double    pi = p[i];
+        x[i]               = fma(a, pi, x[i]);
+        p[i]               = fma(b, pi, z[i]);
     }
 }
 // x += a p     (last iteration: no next direction)
