@@ -235,15 +235,30 @@ __device__ __forceinline__ double blockSum(double v)
     __syncthreads();
     return v;
 }
-// out[0] += a.b ; out[1] += c.d (either pair may alias)
+// out[0] += a.b ; out[1] += c.d (either pair may alias); two doubles per access (cudaMalloc'ed arrays), odd tail by one thread
 __global__ void dot2Kernel(const double* a, const double* b, const double* c, const double* d, long long n, double* out)
 {
-    double s0 = 0., s1 = 0.;
-    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
+    double          s0 = 0., s1 = 0.;
+    const long long n2 = n / 2;
+    const auto* const a2 = reinterpret_cast< const double2* >(a);
+    const auto* const b2 = reinterpret_cast< const double2* >(b);
+    const auto* const c2 = reinterpret_cast< const double2* >(c);
+    const auto* const d2 = reinterpret_cast< const double2* >(d);
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n2; i += static_cast< long long >(gridDim.x) * blockDim.x)
     {
-        s0 = fma(a[i], b[i], s0);
+        const double2 u = a2[i], v = b2[i];
+        s0 = fma(u.x, v.x, fma(u.y, v.y, s0));
         if (c)
-            s1 = fma(c[i], d[i], s1);
+        {
+            const double2 w = c2[i], t = d2[i];
+            s1 = fma(w.x, t.x, fma(w.y, t.y, s1));
+        }
+    }
+    if ((n & 1) and blockIdx.x == 0 and threadIdx.x == 0)
+    {
+        s0 = fma(a[n - 1], b[n - 1], s0);
+        if (c)
+            s1 = fma(c[n - 1], d[n - 1], s1);
     }
     s0 = blockSum(s0);
     s1 = blockSum(s1);
