@@ -6,7 +6,9 @@
   * `matrix_free` (BASELINE configs[2]): sum-factorised operator apply, metric "matrix-free DOFs/s".
 
 One JSON line on stdout (rank 0). The line's `metric`/`value` belong to --workload; the other workload is reported in the
-`also` object of the same line with its own roofline. `--impl reference` times the CPU restatement of the reference
+`also` object of the same line with its own roofline. Extras beside the contract keys: `condensed` (assembly workload: the same
+elements under CondensationPolicy::ElementBoundary, assembly + per-element Schur complements, the policy
+benchmarks/Diffusion3DBenchmark.cpp runs) and `cg_solve` (matrix-free workload: the benchmark's full CG + Jacobi solve, tol 1e-6). `--impl reference` times the CPU restatement of the reference
 (oracle/, built -march=native on this host) on a bounded sample of the same workload.
 
 Timing: CUDA events on the library's stream, W warm-up steps, K timed steps between barriers, max over ranks.
