@@ -223,6 +223,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":  # the banner goes to stdout: keep it to one JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = l3b.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
