@@ -223,9 +223,18 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":  # the banner goes to stdout: keep it to one JSON line
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner to stdout when the communicator is created: send the C-level stdout to stderr until that has
+        # happened, so that stdout carries the one JSON line only
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.all_reduce(torch.zeros(1, device="cuda"))
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     ctx = l3b.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
 
