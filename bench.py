@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Benchmark of the hot path named in BASELINE.json (3-D diffusion, hex p=4, U=4, E=7):
 
-  * `assembly` (default, BASELINE configs[1]): element-local least-squares assembly fused with the CRS scatter,
-    metric "assembled elements/s";
-  * `matrix_free` (BASELINE configs[2]): sum-factorised operator apply, metric "matrix-free DOFs/s".
+  * `matrix_free` (default, BASELINE configs[2] — the configuration BASELINE quotes at 1/2/4/8 B200): sum-factorised operator apply
+    with its NCCL halo exchange, metric "matrix-free DOFs/s"; at N > 1 the line carries `parity_vs_n1` (the N-rank apply of a seeded
+    global vector against the one-rank apply of the same global mesh);
+  * `assembly` (BASELINE configs[1]): element-local least-squares assembly fused with the CRS scatter, metric "assembled elements/s".
 
 One JSON line on stdout (rank 0). The line's `metric`/`value` belong to --workload; the other workload is reported in the
 `also` object of the same line with its own roofline. Extras beside the contract keys: `condensed` (assembly workload: the same
@@ -35,10 +36,26 @@ Q = (P + 1) ** 3
 ASM_FLOPS_PER_ELEM = Q * (18 * NN + 7 * L * E + (L + 1) ** 2 / 2 * (2 * E + 1))  # 238.7 Mflop, reference's own DPFlops formula
 MF_FLOPS_PER_ELEM = 215e3  # reference formulation: back 45k + QP 120k + forward 45k + geometry 5k
 N_BND_NODES = NN - (P - 1) ** 3
+# multiply-adds the matrix-free kernel issues per element (sweeps + point stage), for the fp64-pipe fraction
+MF_EXECUTED_DFMA_PER_ELEM = 46.0e3
+# dram__bytes_read.sum + dram__bytes_write.sum per element of the two dominant kernels, from the ncu captures under profiles/
+MF_TRAFFIC_PER_ELEM = 5.99e3
+MF_TRAFFIC_SOURCE = "from profile: profiles/r1b_ncu_raw.txt (5.99 kB per element incl. the y read-modify-write), scaled to this launch"
+ASM_TRAFFIC_PER_ELEM = 3.57e6
+ASM_TRAFFIC_SOURCE = "from profile: profiles/r1b_ncu_raw.txt (3.57 MB per element), scaled to this launch"
 
 
 def mf_bytes_per_apply(n_dofs, n_elems):
     return 16 * n_dofs + n_elems * (192 + 4 * (N_BND_NODES + 1))  # x read + y write + vertices + compact node ids
+
+
+def workload_string(workload, n, world):
+    """config.workload — the same text in the product arm and in the reference arm"""
+    if workload == "assembly":
+        return (f"Diffusion3DBenchmark assembly + CRS scatter: cube [0,1]^3, {n}^3 hex p=4 per GPU, U=4, E=7, nq=5, "
+                f"CondensationPolicy::None")
+    return (f"Diffusion3DBenchmarkMatrixFree operator apply: {n} x {n} x {n * world} hex p=4 on [0,1]^2 x [0,{world}], "
+            f"U=4, E=7, nq=5, Dirichlet T=0 on the six faces, one z-slab of {n}^3 elements per GPU")
 
 
 def node_dist(n):
@@ -169,8 +186,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="assembly", choices=["assembly", "matrix_free"])
-    ap.add_argument("--n-asm", type=int, default=16, help="elements per edge, assembly workload (per GPU)")
+    ap.add_argument("--workload", default="matrix_free", choices=["assembly", "matrix_free"])
+    ap.add_argument("--n-asm", type=int, default=24, help="elements per edge, assembly workload (per GPU); 24^3 is the largest CRS that leaves room")
+    ap.add_argument("--n-parity", type=int, default=32, help="N > 1: edge of the cube whose N-slab apply is checked against the one-rank apply")
     ap.add_argument("--n-mf", type=int, default=64, help="elements per edge, matrix-free workload (per GPU)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workload")
     ap.add_argument("--cg-max-iters", type=int, default=10000, help="matrix-free workload: iteration cap of the CG solve timed after the applies (0 = skip)")
@@ -178,6 +196,7 @@ def main():
                     help="assembly workload: skip the CondensationPolicy::ElementBoundary figure (assembly + per-element Schur complements)")
     ap.add_argument("--condensed", dest="condensed", action="store_true", default=True, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-distorted", action="store_true", help="matrix-free workload: skip the distorted-mesh figure")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -204,13 +223,25 @@ def main():
         line = {"impl": "reference", "metric": metric[args.workload][0], "value": mean, "unit": best["unit"], "n_gpus": args.gpus,
                 "steps": n_steps, "warmup": max(args.warmup, 0), "ms_per_step": 1e3 * wall / n_steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"{args.workload}: cube [0,1]^3 hex p=4, benchmarks/Diffusion3D.hpp kernel; each step a bounded sample, "
-                                       f"see cpu_baseline.sample",
+                "config": {"workload": workload_string(args.workload, args.n_asm if args.workload == "assembly" else args.n_mf, max(args.gpus, 1)),
+                           "sample": "each step a bounded sample of this workload on the host cores, see cpu_baseline.sample",
                            "note": "the reference needs gcc >= 14, Eigen, Trilinos, oneTBB, MPI — none in this image — so its CPU path is "
                                    "timed through the oracle restatement (oracle/, -O3 -march=native, std::thread over the physical cores)"},
                 "cpu_baseline": dict(best, value=mean), "e2e": {"value": mean, "unit": best["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
+
+    # CPU baseline first (rank 0's host cores, at every N): the other ranks block in the rendezvous of init_process_group meanwhile, so
+    # nothing competes for the cores and nothing spins on a GPU
+    cpu_main = cpu_also = None
+    if rank == 0 and not args.no_cpu_baseline:
+        other_wl = "matrix_free" if args.workload == "assembly" else "assembly"
+        try:
+            cpu_main = cpu_reference(args.workload, physical_cores())
+            if not args.no_also:
+                cpu_also = cpu_reference(other_wl, physical_cores(), budget_s=8.0)
+        except Exception as exc:  # the baseline is a reported extra; never lose the GPU numbers over it
+            cpu_main = cpu_main or {"error": str(exc)}
 
     import torch
 
@@ -229,7 +260,9 @@ def main():
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            import datetime
+
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=15))
             dist.all_reduce(torch.zeros(1, device="cuda"))
             torch.cuda.synchronize()
         finally:
@@ -347,24 +380,24 @@ def main():
             "value": world * n_elems / (ms * 1e-3), "ms_per_step": ms,
             "e2e": {"value": world * n_elems / (wall_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": int(verts_np.nbytes),
                     "d2h_bytes_per_step": int(n_dofs_asm * 8),
-                    "what": "element geometry H2D (pinned) + beginAssembly + assembleProblem + rhs D2H (pinned) through the C ABI, wall clock"},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_dmma, "unit": "TFLOP/s", "frac": achieved / fp64_dmma,
-                         "traffic": 3.57e6 * n_elems,
+                    "what": "element geometry H2D (pinned) + beginAssembly + assembleProblem + rhs D2H (pinned) through the C ABI, wall clock; "
+                            "the CRS values (%.1f GB) stay on the device, where the solve runs" % (crs_nnz * 8 / 1e9)},
+            "roofline": {"bound": "tensor", "achieved": executed, "peak": fp64_dmma, "unit": "TFLOP/s", "frac": executed / fp64_dmma,
+                         "traffic": ASM_TRAFFIC_PER_ELEM * n_elems,
                          "kernel": "assembleDmmaKernel<bench_diffusion3d, hex p=4> (fp64 DMMA, mma.sync.m8n8k4.f64)", "kernel_ms": k_ms,
                          "algorithmic_flops_per_element": ASM_FLOPS_PER_ELEM,
                          "peak_source": "fp64 DMMA microkernel measured in this run (MEASURED_PEAKS.json carries bf16 and HBM figures only); "
                                         "DFMA and DMMA share one pipe on B200 (interleaved microkernel: %.1f TFLOP/s)" % ctx.microbench(3),
                          "fp64_fma_tflops_measured": fp64_fma,
-                         "executed_flops_per_element": asm_executed_flops_per_elem(), "executed_tflops": executed,
-                         "frac_executed": executed / fp64_dmma,
-                         "note": "`achieved` counts the reference's own DPFlops formula (dense symmetric rank update, "
-                                 "benchmarks/LocalAssemblyBenchmarks.cpp:71-75); the kernel skips the products with structurally zero "
-                                 "operator entries (33 of 112 equation x unknown-pair products survive), hence achieved > executed and "
-                                 "frac may exceed 1; frac_executed is the DMMA pipe share of the flops really issued",
-                         "traffic_source": "dram__bytes_read + write of profiles/r1b_ncu_raw.txt (3.57 MB per element), scaled to this launch"},
+                         "executed_flops_per_element": asm_executed_flops_per_elem(),
+                         "reference_count_tflops": achieved,
+                         "note": "`achieved` / `frac` count the multiply-adds the kernel really issues on the DMMA pipe (physical fraction); "
+                                 "`reference_count_tflops` is the same time against the reference's own DPFlops formula (dense symmetric "
+                                 "rank update, benchmarks/LocalAssemblyBenchmarks.cpp:71-75), larger because products with structurally "
+                                 "zero operator entries are skipped (33 of 112 equation x unknown-pair products survive)",
+                         "traffic_source": ASM_TRAFFIC_SOURCE},
             "gpu_launches": args.steps, "clocks": clocks, "condensed": condensed,
-            "config": {"workload": f"Diffusion3DBenchmark assembly + CRS scatter: cube [0,1]^3, {n}^3 hex p=4 per GPU, U=4, E=7, nq=5, "
-                                   f"CondensationPolicy::None", "elements_per_gpu": n_elems, "dofs_per_gpu": host.n_nodes * U,
+            "config": {"workload": workload_string("assembly", n, world), "elements_per_gpu": n_elems, "dofs_per_gpu": host.n_nodes * U,
                        "crs_nnz_per_gpu": crs_nnz, "l2": "CRS values (%.1f GB) larger than L2" % (crs_nnz * 8 / 1e9),
                        "step": "beginAssembly (zero values + rhs) + assembleProblem",
                        "multi_gpu": "one n^3 block per rank; assembleProblem has no exchange step in the reference either (shared rows are "
@@ -372,19 +405,61 @@ def main():
         }
 
     # ---- matrix-free workload (BASELINE configs[2]) -----------------------------------------------------------------
+    BND = [1, 2, 3, 4, 5, 6]  # Dirichlet T = 0 on the six faces (benchmarks/Diffusion3D.hpp:39-41)
+
+    def seeded_x(slab):
+        """a vector that is a function of the GLOBAL lattice position of a node, so that every rank (and the one-rank run of the same
+        global mesh) holds the same values at the nodes it shares"""
+        lat = slab.lattice.astype(np.float64)
+        base = np.sin(0.37 * lat[:, 0] + 1.0) * np.cos(0.23 * lat[:, 1] - 0.5) + np.sin(0.11 * lat[:, 2] + 0.3)
+        return (base[:, None] * (1.0 + 0.25 * np.arange(U))[None, :] + 0.1 * np.arange(U)[None, :]).ravel()
+
+    def parity_vs_n1():
+        """strong-scaling check of the halo'd apply: a cube of n_parity^3 elements cut into `world` z-slabs, y = A x of a seeded global
+        x; ||y||^2 and x.y summed over the owned dofs of all ranks against the same quantities of the one-rank apply of the whole cube
+        (rank 0 computes it after the distributed one). Relative differences, bar 1e-12."""
+        n = args.n_parity
+        xs = node_dist(n)
+        slab = make_slab(xs, xs, xs, P, rank, world)
+        op = SlabOperator(ctx, slab, U, "bench_diffusion3d", BND)
+        sums = torch.zeros(2, dtype=torch.float64, device="cuda")
+        if slab.n_elems > 0:
+            xd = torch.from_numpy(seeded_x(slab)).to("cuda")
+            yd = torch.zeros_like(xd)
+            torch.cuda.synchronize()
+            op.apply(xd, yd, 1.0, 0.0)
+            ctx.synchronize()
+            no = op.n_owned_dofs
+            sums = torch.stack([(yd[:no] * yd[:no]).sum(), (xd[:no] * yd[:no]).sum()])
+        dist.all_reduce(sums)
+        ref = torch.zeros(2, dtype=torch.float64, device="cuda")
+        if rank == 0:
+            whole = make_slab(xs, xs, xs, P, 0, 1)
+            wop = SlabOperator(ctx, whole, U, "bench_diffusion3d", BND)
+            xw = torch.from_numpy(seeded_x(whole)).to("cuda")
+            yw = torch.zeros_like(xw)
+            torch.cuda.synchronize()
+            wop.apply(xw, yw, 1.0, 0.0)
+            ctx.synchronize()
+            ref = torch.stack([(yw * yw).sum(), (xw * yw).sum()])
+        dist.broadcast(ref, 0)
+        rel = ((sums - ref).abs() / ref.abs()).cpu().numpy()
+        return {"ok": bool((rel < 1e-12).all()), "rel_diff_yy": float(rel[0]), "rel_diff_xy": float(rel[1]), "tolerance": 1e-12,
+                "mesh": f"{n}^3 hex p=4 cut into {world} z-slabs vs the same cube on one rank",
+                "what": "||A x||^2 and x.A x of a seeded global x, all-reduced over the owned dofs"}
+
     def run_mf():
         n = args.n_mf
         xs = node_dist(n)
-        # weak scaling: the mesh is n x n x (n * world), one z-slab of n layers per rank, halo exchange over NCCL
+        # weak scaling: the mesh is n x n x (n * world), one z-slab of n layers per rank, halo exchange over NCCL inside the library
         zs = node_dist(n) if world == 1 else np.concatenate([[0.0], np.cumsum(np.full(z_layers_mf, 1.0 / n))])
         slab = make_slab(xs, xs, zs, P, rank, world)
         t0 = time.perf_counter()
-        op = SlabOperator(ctx, slab, U, "bench_diffusion3d", [1, 2, 3, 4, 5, 6])  # Dirichlet T = 0 on the six faces (Diffusion3D.hpp:39-41)
+        op = SlabOperator(ctx, slab, U, "bench_diffusion3d", BND)
         ctx.synchronize()
         init_s = time.perf_counter() - t0
         n_local, n_owned, n_elems = op.n_local_dofs, op.n_owned_dofs, slab.n_elems
-        rng = np.random.default_rng(5489 + rank)
-        xh = torch.from_numpy(rng.uniform(-1, 1, size=n_local)).pin_memory()
+        xh = torch.from_numpy(seeded_x(slab)).pin_memory()
         yh = torch.empty(n_local, dtype=torch.float64).pin_memory()
         xd = xh.to("cuda")
         yd = torch.zeros_like(xd)
@@ -396,16 +471,30 @@ def main():
         ms, _, clocks = timed(step, args.steps, args.warmup)
         launches = op.launches
 
-        def step_e2e():  # host vectors in, host vector out: H2D x, apply (with halo exchange), D2H y
-            with torch.cuda.stream(stream):
-                xd.copy_(xh, non_blocking=True)
-            op.apply(xd, yd, 1.0, 0.0)
-            with torch.cuda.stream(stream):
-                yh.copy_(yd, non_blocking=True)
-            ctx.synchronize()
+        # the dominant kernel alone, live: K launches of the element phase over all of this rank's elements between two events
+        def step_kernel():
+            op.sys.apply_phase_device(xd.data_ptr(), yd.data_ptr(), l3b.APPLY_ELEMENTS, 0, n_elems)
+
+        k_ms, _, _ = timed(step_kernel, args.steps, 2)
+        # distorted mesh (every element non-affine: the general point stage instead of the axis-aligned one): device time of the same apply
+        distorted_ms = None
+        if world == 1 and not args.no_distorted:
+            verts = np.array(slab.verts)
+            bump = 0.15 / n
+            verts[..., 0] += bump * np.sin(2 * np.pi * verts[..., 1]) * np.sin(2 * np.pi * verts[..., 2])
+            verts[..., 1] += bump * np.sin(2 * np.pi * verts[..., 0]) * np.sin(2 * np.pi * verts[..., 2])
+            op.mesh.update_verts(np.ascontiguousarray(verts))
+            distorted_ms, _, _ = timed(step, args.steps, 2)
+            op.mesh.update_verts(np.ascontiguousarray(slab.verts))
+
+        xh_np, yh_np = xh.numpy(), yh.numpy()
+
+        def step_e2e():  # the reference-facing call with HOST buffers: l3b_mf_apply = H2D x, halo'd apply, D2H y, synchronised
+            op.sys.apply_raw(xh_np, yh_np, 1, 1.0, 0.0)
 
         _, wall_ms, _ = timed(step_e2e, args.steps, 1)
         owned_total = sum_over_ranks(float(n_owned))
+        parity = parity_vs_n1() if world > 1 else None
         cg = None
         if args.cg_max_iters > 0:
             # the benchmark's solve (benchmarks/Diffusion3D.hpp:115-118): CG + native Jacobi, tol 1e-6 (absolute), x0 = 0, rhs of the source f = 1
@@ -420,33 +509,45 @@ def main():
                 cg_s = min(cg_s, max_over_ranks(time.perf_counter() - t0))
             cg = {"iters": int(iters), "achieved_residual": float(res), "seconds": cg_s, "ms_per_iteration": cg_s * 1e3 / max(iters, 1),
                   "dofs_per_s": owned_total * iters / cg_s, "tol": 1e-6, "max_iters": args.cg_max_iters,
-                  "what": "full CG + Jacobi solve on the device, one operator apply (p.Ap fused) + 10 vector passes per iteration, wall clock, max over ranks, faster of two solves"}
-        gbs = mf_bytes_per_apply(n_owned, n_elems) / (ms * 1e-3) / 1e9
+                  "what": "full CG + Jacobi solve on the device (l3b_mf_solve_device: halo'd apply with p.Ap fused + 10 vector passes + "
+                          "ncclAllReduce of the dot products per iteration), wall clock, max over ranks, faster of two solves"}
+        bytes_alg = mf_bytes_per_apply(n_owned, n_elems)
+        gbs = bytes_alg / (k_ms * 1e-3) / 1e9
         fp64_fma = ctx.microbench(0)
-        return {
+        res = {
             "value": owned_total / (ms * 1e-3), "ms_per_step": ms,
             "e2e": {"value": owned_total / (wall_ms * 1e-3), "unit": "DOFs/s", "h2d_bytes_per_step": int(n_local * 8),
-                    "d2h_bytes_per_step": int(n_local * 8),
-                    "what": "pinned host x -> device, phased apply with halo exchange, device y -> pinned host, wall clock"},
+                    "d2h_bytes_per_step": int(n_local * 8), "ms_per_step": wall_ms,
+                    "what": "l3b_mf_apply through the C ABI with pinned HOST vectors: x H2D, apply (with halo exchange), y D2H, synchronised; "
+                            "wall clock, max over ranks — bound by the two PCIe copies, not by the kernel"},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                         "traffic": 5.99e3 * n_elems,
-                         "kernel": "mfHexPlanesKernel<bench_diffusion3d, hex p=4, nq=5> (+ memset of y, Dirichlet-row and halo pack/unpack kernels)",
-                         "algorithmic_bytes_per_dof": mf_bytes_per_apply(n_owned, n_elems) / max(n_owned, 1), "peak_source": hbm_src,
-                         "fp64_tflops_reference_formulation": MF_FLOPS_PER_ELEM * n_elems / (ms * 1e-3) / 1e12,
-                         "fp64_fma_peak_tflops_measured": fp64_fma,
-                         "note": "the p=4, U=4, E=7 apply is bound by the fp64 pipe, not HBM (SURVEY §7): ~46 k DFMA per element after "
-                                 "structural-zero elimination = 0.72 ms per 64^3 apply at the measured DFMA peak, i.e. 26 % of the HBM "
-                                 "roofline is the ceiling of this formulation",
-                         "traffic_source": "dram__bytes_read + write of profiles/r1b_ncu_raw.txt (5.99 kB per element incl. the y read-modify-write), "
-                                           "scaled to this launch"},
+                         "traffic": MF_TRAFFIC_PER_ELEM * n_elems if MF_TRAFFIC_PER_ELEM else None,
+                         "kernel": "mfHexPlanesKernel<bench_diffusion3d, hex p=4, nq=5>", "kernel_ms": k_ms,
+                         "algorithmic_bytes": bytes_alg, "algorithmic_bytes_per_dof": bytes_alg / max(n_owned, 1), "peak_source": hbm_src,
+                         "kernel_share_of_step": k_ms / ms,
+                         "fp64_pipe": {"executed_dfma_per_element": MF_EXECUTED_DFMA_PER_ELEM,
+                                       "executed_tflops": 2 * MF_EXECUTED_DFMA_PER_ELEM * n_elems / (k_ms * 1e-3) / 1e12,
+                                       "peak_tflops_measured": fp64_fma,
+                                       "frac": 2 * MF_EXECUTED_DFMA_PER_ELEM * n_elems / (k_ms * 1e-3) / 1e12 / fp64_fma,
+                                       "reference_formulation_tflops": MF_FLOPS_PER_ELEM * n_elems / (k_ms * 1e-3) / 1e12},
+                         "note": "contract roofline is HBM (north_star); the kernel itself is bound by the fp64 pipe (arithmetic intensity "
+                                 "~45 flop/B), so the fp64 fraction of the multiply-adds it really issues is reported beside it",
+                         "traffic_source": MF_TRAFFIC_SOURCE},
             "gpu_launches": launches * args.steps, "clocks": clocks, "cg_solve": cg,
-            "config": {"workload": f"Diffusion3DBenchmarkMatrixFree operator apply: {n} x {n} x {n * world} hex p=4 on [0,1]^2 x [0,{world}], "
-                                   f"U=4, E=7, nq=5, Dirichlet T=0 on the six faces, one z-slab of {n}^3 elements per GPU",
-                       "elements_per_gpu": n_elems, "owned_dofs_per_gpu": n_owned, "ghost_dofs_per_gpu": n_local - n_owned,
+            "config": {"workload": workload_string("matrix_free", n, world), "elements_per_gpu": n_elems, "owned_dofs_per_gpu": n_owned, "ghost_dofs_per_gpu": n_local - n_owned,
                        "l2": "x and y (%.0f MB each) larger than L2" % (n_local * 8 / 1e6), "init_diag_rhs_s": init_s,
-                       "multi_gpu": "NCCL point-to-point halo exchange (Import x / Export y of the interface plane, %.1f MB per direction) "
-                                    "overlapped with the interior elements" % ((n * P + 1) ** 2 * U * 8 / 1e6) if world > 1 else "single GPU"},
+                       "step": "y = A x: zero y, element kernel, Dirichlet rows" + ("; Import of x behind the zeroing, border elements, Export of y "
+                               "behind the interior elements, unpack-add" if world > 1 else ""),
+                       "multi_gpu": ("NCCL send/recv halo exchange inside the library (l3b_halo: Import x / Export y of the interface plane, "
+                                     "%.1f MB per direction), hidden behind the zeroing of y and the interior elements"
+                                     % ((n * P + 1) ** 2 * U * 8 / 1e6)) if world > 1 else "single GPU"},
         }
+        if distorted_ms is not None:
+            res["distorted_mesh"] = {"ms_per_step": distorted_ms, "value": owned_total / (distorted_ms * 1e-3),
+                                     "what": "the same apply with every element non-affine (general J^-1 per point instead of the axis-aligned path)"}
+        if parity is not None:
+            res["parity_vs_n1"] = parity
+        return res
 
     runners = {"assembly": run_assembly, "matrix_free": run_mf}
     main_res = runners[args.workload]()
@@ -460,18 +561,15 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": main_res["config"],
             "e2e": main_res["e2e"], "roofline": main_res["roofline"], "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"]}
-    for extra in ("cg_solve", "condensed"):
+    for extra in ("cg_solve", "condensed", "parity_vs_n1", "distorted_mesh"):
         if main_res.get(extra):
             line[extra] = main_res[extra]
     if also:
         line["also"] = also
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            line["cpu_baseline"] = cpu_reference(args.workload, physical_cores())
-            if also:
-                also["cpu_baseline"] = cpu_reference("matrix_free" if args.workload == "assembly" else "assembly", physical_cores(), budget_s=8.0)
-        except Exception as exc:  # the baseline is a reported extra; never lose the GPU numbers over it
-            line["cpu_baseline"] = {"error": str(exc)}
+    if cpu_main is not None:
+        line["cpu_baseline"] = cpu_main
+    if also and cpu_also is not None:
+        also["cpu_baseline"] = cpu_also
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

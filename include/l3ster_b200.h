@@ -39,7 +39,9 @@ typedef enum l3b_status
     L3B_ERR_GRAPH          = 6, /* entry not present in the sparsity graph */
     L3B_ERR_NOT_CONVERGED  = 7,
     L3B_ERR_NO_DEVICE      = 8,
-    L3B_ERR_SPARSITY       = 9 /* run-time guard of the compile-time operator sparsity probe tripped (kernel_interface.cuh) */
+    L3B_ERR_SPARSITY       = 9, /* run-time guard of the compile-time operator sparsity probe tripped (kernel_interface.cuh) */
+    L3B_ERR_SINGULAR       = 10, /* static condensation: singular interior block K_ii (the reference's inverse() would return garbage) */
+    L3B_ERR_COMM           = 11  /* NCCL failure, or a distributed entry point used without a communicator */
 } l3b_status;
 
 typedef struct l3b_context   l3b_context;
@@ -48,6 +50,8 @@ typedef struct l3b_mesh      l3b_mesh;
 typedef struct l3b_fields    l3b_fields;
 typedef struct l3b_asm       l3b_asm;
 typedef struct l3b_mf        l3b_mf;
+typedef struct l3b_comm      l3b_comm;
+typedef struct l3b_halo      l3b_halo;
 
 /* ---- context ----------------------------------------------------------------------------------------------------- */
 /* replaces util::L3sterScopeGuard's device-side duties (util/ScopeGuards.hpp:186-201). Fails with L3B_ERR_NO_DEVICE
@@ -58,6 +62,44 @@ const char* l3b_last_error(const l3b_context* ctx);
 const char* l3b_global_error(void); /* errors raised before a context exists */
 int         l3b_context_synchronize(l3b_context* ctx);
 void*       l3b_context_stream(l3b_context* ctx); /* cudaStream_t */
+
+/* ---- communicator (replaces comm/MpiComm.hpp:404-600 on the device data path: NCCL over NVLink, one rank per GPU) ------------ */
+/* NCCL is resolved at run time (libnccl.so.2, the copy already in the process if there is one); without it these calls return
+ * L3B_ERR_COMM and everything single-rank still works. Rank 0 draws the id and hands the bytes to the other ranks out of band (the
+ * reference's MPI_Bcast; torch.distributed in the tests); every rank then creates its communicator — collective over the ranks.
+ * Transfers run on a communication stream owned by the communicator, ordered against the context's stream with events. */
+#define L3B_COMM_ID_BYTES 128
+int  l3b_comm_unique_id(char id[L3B_COMM_ID_BYTES]);
+int  l3b_comm_create(l3b_context* ctx, int rank, int world, const char id[L3B_COMM_ID_BYTES], l3b_comm** out);
+int  l3b_comm_attach(l3b_context* ctx, void* nccl_comm /* an existing ncclComm_t; stays the caller's */, l3b_comm** out);
+void l3b_comm_destroy(l3b_comm* comm);
+int  l3b_comm_rank(const l3b_comm* comm);
+int  l3b_comm_size(const l3b_comm* comm);
+/* in-place sum over the ranks of n device doubles (MpiComm::allReduce, :452-466), ordered after the work on the context stream */
+int  l3b_comm_allreduce_sum(l3b_comm* comm, double* device_scalars, int n);
+
+/* ---- halo engine: comm::ImportExportContext + Import + Export (comm/ImportExport.hpp:29-72, 131-215, 296-470) ------------------
+ * Vectors cover the local dofs [owned | ghost] (n_owned + n_ghost rows, column-major, ld = n_owned + n_ghost). As in the reference's
+ * context (segmented ownership: every rank owns one contiguous global range, ghosts sorted by global id) the description has two halves:
+ *   owned neighbours : ranks holding ghost copies of my owned dofs; owned_inds[owned_ptr[k] .. owned_ptr[k+1]) = the local owned dofs
+ *                      shared with neighbour k, in the order the neighbour stores them (ascending global id) — packed for the Import,
+ *                      targets of the Export's combine (sum);
+ *   shared neighbours: ranks owning my ghost dofs; neighbour j's ghosts are the contiguous range
+ *                      [shared_offsets[j], shared_offsets[j+1]) of the ghost block — received in place by the Import, sent in place
+ *                      by the Export.
+ * A rank may be its own neighbour (NCCL copies locally). All right-hand sides travel in one ncclGroup per exchange. */
+int  l3b_halo_create(l3b_comm* comm, int64_t n_owned, int64_t n_ghost, int n_owned_nbrs, const int* owned_nbr_ranks,
+                     const int64_t* owned_ptr, const int32_t* owned_inds, int n_shared_nbrs, const int* shared_nbr_ranks,
+                     const int64_t* shared_offsets, l3b_halo** out);
+void l3b_halo_destroy(l3b_halo* halo);
+/* Import::postComms / wait (:296-384): begin packs on the context stream and posts the transfers on the communication stream; work
+ * queued on the context stream before _end overlaps them; after _end the ghost block of x holds the owners' values. */
+int l3b_halo_import_begin(l3b_halo* halo, double* x, int n_cols);
+int l3b_halo_import_end(l3b_halo* halo);
+/* Export::postRecvs / postSends / wait with AtomicSumInto (:403-470): begin (ordered after the work already on the context stream)
+ * posts the ghost block of y to the owners; _end waits and adds the received contributions into the owned dofs. */
+int l3b_halo_export_begin(l3b_halo* halo, double* y, int n_cols);
+int l3b_halo_export_end(l3b_halo* halo, double* y, int n_cols);
 
 /* ---- kernel registry (common/KernelInterface.hpp:13-20, 178-190) ---------------------------------------------------- */
 typedef struct l3b_kernel_info
@@ -143,16 +185,27 @@ int l3b_asm_spmv(l3b_asm* sys, const double* x, double* y);
  * matrix-free apply, and the global diagonal the Export-sum of the local ones. */
 int l3b_asm_spmv_device(l3b_asm* sys, const double* x, double* y);
 int l3b_asm_diag_device(l3b_asm* sys, double* diag);
+/* the halo of the row layout [owned | ghost]: l3b_asm_spmv_device, l3b_asm_diag_device and the solvers then act as the global operator
+ * (Import x, local product, Export-sum of the ghost rows; dots over the owned rows, all-reduced) */
+int l3b_asm_set_halo(l3b_asm* sys, l3b_halo* halo);
 double* l3b_asm_device_rhs(l3b_asm* sys);
 /* l3b_asm_end_assembly for a rank that also holds ghost rows: Dirichlet rows become identity rows for the first n_owned_dofs dofs
  * and zero rows for the ghost dofs (their owner holds the identity row; the Export-sum must add nothing to it) */
 int l3b_asm_end_assembly_ranked(l3b_asm* sys, int64_t n_dirichlet, const int32_t* dirichlet_dofs, const double* dirichlet_vals,
                                 int64_t n_owned_dofs);
-/* CG + native Jacobi on the assembled matrix (solve/BelosSolvers.hpp:116-123, NativePreconditioners.hpp:36-100) */
+/* CG + native Jacobi on the assembled matrix (solve/BelosSolvers.hpp:116-123, NativePreconditioners.hpp:36-100).
+ * x (host, n_dofs): in = initial guess — the reference hands Belos its persistent solution vector, so a repeated solve (time step,
+ * Newton iteration) starts from the previous solution (AssembledSystem.hpp:113-135); out = solution. A zero guess skips the apply for
+ * r0. With a halo (l3b_asm_set_halo) the solve runs over all ranks: dots over the owned rows, all-reduced through the communicator. */
 int l3b_asm_solve_cg(l3b_asm* sys, double tol, int max_iters, double* x /* host, n_dofs */, double* achieved_tol, int* iters);
 /* GMRES + native Jacobi on the assembled matrix (solve/BelosSolvers.hpp:125-131) */
 int l3b_asm_solve_gmres(l3b_asm* sys, double tol, int restart_length, int max_restarts, int max_iters, double* x, double* achieved_tol,
                         int* iters);
+/* the same solvers on a device vector over the local rows (the solution stays on the GPU between solves — the reference's
+ * AssembledSystem::solve + updateSolution round trip without the host copy): method 0 = CG, 1 = GMRES; x in = initial guess
+ * (x0_is_zero != 0: the caller vouches it is zero), out = solution with the ghost copies refreshed */
+int l3b_asm_solve_device(l3b_asm* sys, int method, double tol, int max_iters, int restart_length, int max_restarts, double* x, int x0_is_zero,
+                         double* achieved_tol, int* iters);
 /* timing of the last l3b_asm_assemble kernel launches (ms, CUDA events on the context stream) */
 double l3b_asm_last_kernel_ms(const l3b_asm* sys);
 
@@ -164,6 +217,11 @@ void l3b_mf_destroy(l3b_mf* sys);
 /* MatrixFreeSystem::assembleProblem: registers the kernel for init and apply (:585-787) */
 int l3b_mf_assemble(l3b_mf* sys, int kernel_id, l3b_asm_opts opts, double time, const int* dof_inds, const l3b_fields* fields,
                     const int* field_inds, const int* boundary_ids, int n_boundary_ids);
+/* More than one rank: the system takes the halo of its dof layout (mesh: n_owned_nodes / n_local_nodes; elements [0, n_border_elems)
+ * are the ones touching ghost nodes, mesh/SplitMesh.hpp) and from then on l3b_mf_end_assembly, l3b_mf_apply[_device] and the solvers work
+ * over all ranks like MatrixFreeSystem does (:887-941, 1019-1140): one call = pack + Import of x behind the pass that zeroes y, border
+ * elements, Export of y behind the interior elements, unpack-add, Dirichlet rows; dot products all-reduced. Call before endAssembly. */
+int l3b_mf_set_halo(l3b_mf* sys, l3b_halo* halo, int64_t n_border_elems);
 /* MatrixFreeSystem::endAssembly → computeDiagAndRhs (:877-941) */
 int l3b_mf_end_assembly(l3b_mf* sys);
 /* the same in two steps for more than one rank: _begin accumulates the element contributions to diag and rhs over the local
@@ -179,22 +237,31 @@ int l3b_mf_download(l3b_mf* sys, double* diag, double* rhs);
  * host version: copies x (and y if beta != 0) in, y out. */
 int l3b_mf_apply_device(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta);
 int l3b_mf_apply(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta);
-/* CG + native Jacobi, x0 = 0, rhs = system rhs column 0 (benchmarks/Diffusion3D.hpp:115-118) */
+/* single-column apply that also adds this rank's share of x^T A x (its elements, its owned Dirichlet dofs) to the device scalar
+ * `energy`: CG takes p.Ap from the quadrature-point stage instead of a dot-product pass (see l3b_mf_apply_phase_device) */
+int l3b_mf_apply_energy_device(l3b_mf* sys, const double* x, double* y, double alpha, double beta, double* energy);
+/* CG + native Jacobi, rhs = system rhs column 0 (benchmarks/Diffusion3D.hpp:115-118); x (host, n_dofs): in = initial guess (zero in the
+ * benchmark), out = solution over the local dofs, ghost copies refreshed. With a halo (l3b_mf_set_halo) the solve runs over all ranks. */
 int l3b_mf_solve_cg(l3b_mf* sys, double tol, int max_iters, double* x /* host */, double* achieved_tol, int* iters);
 int l3b_mf_solve_gmres(l3b_mf* sys, double tol, int restart_length, int max_restarts, int max_iters, double* x /* host */,
                        double* achieved_tol, int* iters);
+int l3b_mf_solve_device(l3b_mf* sys, int method, double tol, int max_iters, int restart_length, int max_restarts, double* x, int x0_is_zero,
+                        double* achieved_tol, int* iters); /* as l3b_asm_solve_device */
 /* The same apply split into the phases MatrixFreeSystem::applyImpl overlaps with its halo exchange (:1046-1122):
  *   L3B_APPLY_INIT     y <- beta y                                   (:1038)
  *   L3B_APPLY_ELEMENTS y[dofs(e)] += alpha K_e x[dofs(e)] for the domain elements e in [elem_begin, elem_end) — the caller passes
- *                      its interior range while comm::Import (owner -> ghost copies of x) is in flight, then the border range;
- *                      boundary kernels run with the range that contains element 0
+ *                      its interior range while comm::Import (owner -> ghost copies of x) is in flight, then the border range.
+ *                      Boundary kernels (side lists are not split) run once per apply: in the call that carries L3B_APPLY_BOUNDARY,
+ *                      or — without that bit anywhere — with the NON-EMPTY range that starts at element 0 (an empty range [0, 0),
+ *                      as a rank without border elements passes, never triggers them)
  *   L3B_APPLY_FINISH   Dirichlet identity rows y[d] += alpha x[d]    (:1087-1103)
  * All phases are asynchronous on the context stream; x, y are device pointers over the LOCAL dofs [owned | ghost]. */
 enum
 {
     L3B_APPLY_INIT     = 1,
     L3B_APPLY_ELEMENTS = 2,
-    L3B_APPLY_FINISH   = 4
+    L3B_APPLY_FINISH   = 4,
+    L3B_APPLY_BOUNDARY = 8 /* run the boundary kernels (their whole side list) in this call */
 };
 /* energy: NULL, or a device scalar to which the ELEMENTS and FINISH phases add x^T A x of column 0 — this rank's elements and owned
  * Dirichlet dofs, so that the sum over the phases and over the ranks is the global x^T A x (alpha and beta do not enter). CG uses it for
@@ -215,14 +282,17 @@ int l3b_vec_scatter_add(l3b_context* ctx, double* dst, int64_t ld, const int32_t
 typedef int (*l3b_apply_callback)(void* user, const double* x, double* y, double* energy);
 typedef int (*l3b_allreduce_callback)(void* user, double* scalars, int n);
 /* Restarted GMRES with the same callbacks: Belos "Pseudoblock GMRES" as solve/BelosSolvers.hpp:42-131 configures it ("Num Blocks" =
- * restart_length 250, "Maximum Restarts" 39 by default, solve/SolverInterface.hpp:26-37), left Jacobi preconditioner, x0 = 0,
+ * restart_length 250, "Maximum Restarts" 39 by default, solve/SolverInterface.hpp:26-37), left Jacobi preconditioner,
  * convergence on the preconditioned residual norm of the Givens recurrence (Belos' implicit test, absolute). */
+/* x: in = the initial guess (Belos takes the system's persistent solution vector, AssembledSystem.hpp:113-135), out = the solution;
+ * only its first n_owned entries are read and valid on return. x0_is_zero != 0: the caller vouches that the guess is zero (the first
+ * solve of the reference's benchmarks) — x is zeroed and the operator apply for r0 = b - A x0 is skipped. */
 int l3b_gmres_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_apply_callback apply, l3b_allreduce_callback allreduce,
                      void* user, const double* diag, const double* b, double* x, double tol, int restart_length, int max_restarts,
-                     int max_iters, double* achieved_tol, int* iters);
+                     int max_iters, int x0_is_zero, double* achieved_tol, int* iters);
 int l3b_pcg_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_apply_callback apply, l3b_allreduce_callback allreduce,
-                   void* user, const double* diag, const double* b, double* x, double tol, int max_iters, double* achieved_tol,
-                   int* iters);
+                   void* user, const double* diag, const double* b, double* x, double tol, int max_iters, int x0_is_zero,
+                   double* achieved_tol, int* iters);
 /* ---- integrals and norms of residual kernels (post/Integral.hpp:102-121 computeIntegral, post/NormL2.hpp:31-60 computeNormL2) ----
  * The kernel is a registered residual kernel `(const Input&, Rhs&) -> void` (common/KernelInterface.hpp:140-176); a domain kernel is
  * integrated over all elements of the mesh, a boundary kernel over the sides carrying one of `boundary_ids`. The integrand is

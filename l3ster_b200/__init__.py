@@ -52,7 +52,8 @@ class AssemblyOptions:
 APPLY_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
 ALLREDUCE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)
 _lib = None
-APPLY_INIT, APPLY_ELEMENTS, APPLY_FINISH = 1, 2, 4
+APPLY_INIT, APPLY_ELEMENTS, APPLY_FINISH, APPLY_BOUNDARY = 1, 2, 4, 8
+COMM_ID_BYTES = 128
 
 # every symbol include/l3ster_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
@@ -72,6 +73,9 @@ EXPORTED_SYMBOLS = [
     "l3b_gmres_device", "l3b_asm_solve_gmres", "l3b_mf_solve_gmres",
     "l3b_compute_integral", "l3b_compute_norm_l2",
     "l3b_crs_create", "l3b_cond_create", "l3b_cond_destroy", "l3b_cond_condense", "l3b_cond_recover",
+    "l3b_comm_unique_id", "l3b_comm_create", "l3b_comm_attach", "l3b_comm_destroy", "l3b_comm_rank", "l3b_comm_size", "l3b_comm_allreduce_sum",
+    "l3b_halo_create", "l3b_halo_destroy", "l3b_halo_import_begin", "l3b_halo_import_end", "l3b_halo_export_begin", "l3b_halo_export_end",
+    "l3b_mf_set_halo", "l3b_asm_set_halo", "l3b_mf_solve_device", "l3b_asm_solve_device", "l3b_mf_apply_energy_device",
 ]
 
 
@@ -155,7 +159,7 @@ def lib():
     L.l3b_mf_end_assembly_begin.argtypes = [vp]
     L.l3b_asm_solve_gmres.argtypes = [vp, dbl, i32, i32, i32, vp, C.POINTER(dbl), C.POINTER(i32)]
     L.l3b_mf_solve_gmres.argtypes = [vp, dbl, i32, i32, i32, vp, C.POINTER(dbl), C.POINTER(i32)]
-    L.l3b_gmres_device.argtypes = [vp, i64, i64, APPLY_CB, ALLREDUCE_CB, vp, vp, vp, vp, dbl, i32, i32, i32, C.POINTER(dbl), C.POINTER(i32)]
+    L.l3b_gmres_device.argtypes = [vp, i64, i64, APPLY_CB, ALLREDUCE_CB, vp, vp, vp, vp, dbl, i32, i32, i32, i32, C.POINTER(dbl), C.POINTER(i32)]
     L.l3b_asm_spmv_device.argtypes = [vp, vp, vp]
     L.l3b_asm_diag_device.argtypes = [vp, vp]
     L.l3b_asm_device_rhs.argtypes = [vp]
@@ -166,7 +170,27 @@ def lib():
     L.l3b_mf_device_diag.restype = vp
     L.l3b_mf_device_rhs.argtypes = [vp]
     L.l3b_mf_device_rhs.restype = vp
-    L.l3b_pcg_device.argtypes = [vp, i64, i64, APPLY_CB, ALLREDUCE_CB, vp, vp, vp, vp, dbl, i32, C.POINTER(dbl), C.POINTER(i32)]
+    L.l3b_pcg_device.argtypes = [vp, i64, i64, APPLY_CB, ALLREDUCE_CB, vp, vp, vp, vp, dbl, i32, i32, C.POINTER(dbl), C.POINTER(i32)]
+    L.l3b_comm_unique_id.argtypes = [vp]
+    L.l3b_comm_create.argtypes = [vp, i32, i32, vp, C.POINTER(vp)]
+    L.l3b_comm_attach.argtypes = [vp, vp, C.POINTER(vp)]
+    L.l3b_comm_destroy.argtypes = [vp]
+    L.l3b_comm_destroy.restype = None
+    L.l3b_comm_rank.argtypes = [vp]
+    L.l3b_comm_size.argtypes = [vp]
+    L.l3b_comm_allreduce_sum.argtypes = [vp, vp, i32]
+    L.l3b_halo_create.argtypes = [vp, i64, i64, i32, vp, vp, vp, i32, vp, vp, C.POINTER(vp)]
+    L.l3b_halo_destroy.argtypes = [vp]
+    L.l3b_halo_destroy.restype = None
+    L.l3b_halo_import_begin.argtypes = [vp, vp, i32]
+    L.l3b_halo_import_end.argtypes = [vp]
+    L.l3b_halo_export_begin.argtypes = [vp, vp, i32]
+    L.l3b_halo_export_end.argtypes = [vp, vp, i32]
+    L.l3b_mf_set_halo.argtypes = [vp, vp, i64]
+    L.l3b_asm_set_halo.argtypes = [vp, vp]
+    L.l3b_mf_apply_energy_device.argtypes = [vp, vp, vp, dbl, dbl, vp]
+    for f in ("l3b_mf_solve_device", "l3b_asm_solve_device"):
+        getattr(L, f).argtypes = [vp, i32, dbl, i32, i32, i32, vp, i32, C.POINTER(dbl), C.POINTER(i32)]
     L.l3b_vec_scatter_add.argtypes = [vp, vp, i64, vp, i64, i32, vp]
     L.l3b_mf_apply.argtypes = [vp, vp, vp, i32, dbl, dbl]
     L.l3b_mf_solve_cg.argtypes = [vp, dbl, i32, vp, C.POINTER(dbl), C.POINTER(i32)]
@@ -397,22 +421,25 @@ class Context:
 
         return APPLY_CB(_apply), (ALLREDUCE_CB(_reduce) if allreduce is not None else C.cast(None, ALLREDUCE_CB)), err
 
-    def pcg(self, n_local, n_owned, apply, allreduce, diag_ptr, b_ptr, x_ptr, tol=1e-6, max_iters=10000):
+    def pcg(self, n_local, n_owned, apply, allreduce, diag_ptr, b_ptr, x_ptr, tol=1e-6, max_iters=10000, x0_is_zero=True):
         """l3b_pcg_device: apply(x_ptr, y_ptr, energy_ptr) and allreduce(scalars_ptr, n) are Python callables working on device pointers;
-        apply returns True when it added this rank's share of x^T A x to the device scalar at energy_ptr (see l3b_apply_callback)"""
+        apply returns True when it added this rank's share of x^T A x to the device scalar at energy_ptr (see l3b_apply_callback);
+        x0_is_zero=False: the vector at x_ptr is the initial guess"""
         a_cb, r_cb, err = self._krylov_callbacks(apply, allreduce)
         at, it = C.c_double(), C.c_int()
-        rc = lib().l3b_pcg_device(self._h, n_local, n_owned, a_cb, r_cb, None, diag_ptr, b_ptr, x_ptr, tol, max_iters, C.byref(at), C.byref(it))
+        rc = lib().l3b_pcg_device(self._h, n_local, n_owned, a_cb, r_cb, None, diag_ptr, b_ptr, x_ptr, tol, max_iters, int(x0_is_zero),
+                                  C.byref(at), C.byref(it))
         if rc != 0:
             raise L3BError(rc, lib().l3b_last_error(self._h).decode() + (f" ({err[0]!r})" if err else ""))
         return at.value, it.value
 
-    def gmres(self, n_local, n_owned, apply, allreduce, diag_ptr, b_ptr, x_ptr, tol=1e-6, restart_length=250, max_restarts=39, max_iters=10000):
+    def gmres(self, n_local, n_owned, apply, allreduce, diag_ptr, b_ptr, x_ptr, tol=1e-6, restart_length=250, max_restarts=39, max_iters=10000,
+              x0_is_zero=True):
         """l3b_gmres_device with the same callbacks as pcg (the energy pointer is always null here)"""
         a_cb, r_cb, err = self._krylov_callbacks(apply, allreduce)
         at, it = C.c_double(), C.c_int()
         rc = lib().l3b_gmres_device(self._h, n_local, n_owned, a_cb, r_cb, None, diag_ptr, b_ptr, x_ptr, tol, restart_length, max_restarts,
-                                    max_iters, C.byref(at), C.byref(it))
+                                    max_iters, int(x0_is_zero), C.byref(at), C.byref(it))
         if rc != 0:
             raise L3BError(rc, lib().l3b_last_error(self._h).decode() + (f" ({err[0]!r})" if err else ""))
         return at.value, it.value
@@ -430,6 +457,97 @@ class Context:
     def upload_fields(self, data):
         """data: (n_fields, n_local_nodes) — post/SolutionManager.hpp:83-101 layout"""
         return Fields(self, data)
+
+
+class Comm:
+    """The rank's communicator (l3b_comm_*): NCCL, one rank per GPU. `Comm(ctx)` is the single-rank communicator;
+    `Comm.from_torch_distributed(ctx)` creates one over the ranks of the initialised torch.distributed group (the unique id is
+    drawn by rank 0 and broadcast through torch.distributed — the only thing torch carries)."""
+
+    def __init__(self, ctx: Context, rank=0, world=1, unique_id=None):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        if unique_id is None:
+            if world != 1:
+                raise ValueError("more than one rank needs the unique id drawn by rank 0 (Comm.unique_id())")
+            unique_id = Comm.unique_id()
+        buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        self._h = C.c_void_p()
+        ctx._chk(lib().l3b_comm_create(ctx._h, rank, world, buf, C.byref(self._h)))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        rc = lib().l3b_comm_unique_id(buf)
+        if rc != 0:
+            raise L3BError(rc, lib().l3b_global_error().decode())
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, ctx: Context):
+        import torch.distributed as dist
+
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return cls(ctx)
+        box = [Comm.unique_id() if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(ctx, dist.get_rank(), dist.get_world_size(), box[0])
+
+    def allreduce_sum(self, scalars_ptr, n):
+        self.ctx._chk(lib().l3b_comm_allreduce_sum(self._h, scalars_ptr, n))
+
+    def __del__(self):
+        try:
+            lib().l3b_comm_destroy(self._h)
+        except Exception:
+            pass
+
+
+class DeviceHalo:
+    """comm::ImportExportContext + Import + Export on the device (l3b_halo_*). owned: list of (rank, local owned dofs shared with it, in
+    the neighbour's ghost order); shared: list of (rank, offset, size) ranges of the ghost block owned by that rank."""
+
+    def __init__(self, comm: Comm, n_owned, n_ghost, owned, shared):
+        self.comm, self.n_owned, self.n_ghost = comm, int(n_owned), int(n_ghost)
+        o_ranks = np.array([r for r, _ in owned], dtype=np.int32)
+        o_ptr = np.zeros(len(owned) + 1, dtype=np.int64)
+        for k, (_, idx) in enumerate(owned):
+            o_ptr[k + 1] = o_ptr[k] + len(idx)
+        o_idx = np.concatenate([np.asarray(i, dtype=np.int32) for _, i in owned]) if owned else np.zeros(0, dtype=np.int32)
+        s_ranks = np.array([r for r, _, _ in shared], dtype=np.int32)
+        s_off = np.zeros(len(shared) + 1, dtype=np.int64)
+        for j, (_, off, size) in enumerate(shared):
+            if off != s_off[j]:
+                raise ValueError("the ghost ranges of the shared neighbours must tile the ghost block in order")
+            s_off[j + 1] = off + size
+        self._h = C.c_void_p()
+        comm.ctx._chk(lib().l3b_halo_create(comm._h, self.n_owned, self.n_ghost, len(owned), _p(o_ranks), _p(o_ptr), _p(np.ascontiguousarray(o_idx)),
+                                            len(shared), _p(s_ranks), _p(s_off), C.byref(self._h)))
+
+    def import_begin(self, x_ptr, n_cols=1):
+        self.comm.ctx._chk(lib().l3b_halo_import_begin(self._h, x_ptr, n_cols))
+
+    def import_end(self):
+        self.comm.ctx._chk(lib().l3b_halo_import_end(self._h))
+
+    def export_begin(self, y_ptr, n_cols=1):
+        self.comm.ctx._chk(lib().l3b_halo_export_begin(self._h, y_ptr, n_cols))
+
+    def export_end(self, y_ptr, n_cols=1):
+        self.comm.ctx._chk(lib().l3b_halo_export_end(self._h, y_ptr, n_cols))
+
+    def import_(self, x_ptr, n_cols=1):
+        self.import_begin(x_ptr, n_cols)
+        self.import_end()
+
+    def export_add(self, y_ptr, n_cols=1):
+        self.export_begin(y_ptr, n_cols)
+        self.export_end(y_ptr, n_cols)
+
+    def __del__(self):
+        try:
+            lib().l3b_halo_destroy(self._h)
+        except Exception:
+            pass
 
 
 class Mesh:
@@ -541,6 +659,18 @@ class AssembledSystem:
         v = None if n == 0 else np.ascontiguousarray(np.asarray(dirichlet_vals, dtype=np.float64).reshape(n, -1).T)
         self.ctx._chk(lib().l3b_asm_end_assembly(self._h, n, _p(d), _p(v)))
 
+    def solve_device(self, x_ptr, method="cg", tol=1e-6, max_iters=10000, restart_length=250, max_restarts=39, x0_is_zero=True):
+        """l3b_asm_solve_device: solution on the device over the local rows"""
+        at, it = C.c_double(), C.c_int()
+        self.ctx._chk(lib().l3b_asm_solve_device(self._h, {"cg": 0, "gmres": 1}[method], tol, max_iters, restart_length, max_restarts, x_ptr,
+                                                 int(x0_is_zero), C.byref(at), C.byref(it)))
+        return at.value, it.value
+
+    def set_halo(self, halo: "DeviceHalo | None"):
+        """rows [owned | ghost] over more than one rank: spmv_device, diag_device and the solvers become the global operator"""
+        self._halo = halo
+        self.ctx._chk(lib().l3b_asm_set_halo(self._h, halo._h if halo is not None else None))
+
     def endAssemblyRanked(self, dirichlet_dofs, dirichlet_vals, n_owned_dofs):
         """endAssembly on a rank that also holds ghost rows: ghost copies of Dirichlet rows become zero rows"""
         n = 0 if dirichlet_dofs is None else len(dirichlet_dofs)
@@ -583,18 +713,19 @@ class AssembledSystem:
         self.ctx._chk(lib().l3b_asm_spmv(self._h, _p(x), _p(y)))
         return y
 
-    def solve(self, tol=1e-6, max_iters=10000):
-        x = np.zeros(self.n_dofs)
+    def solve(self, tol=1e-6, max_iters=10000, x0=None):
+        """x0: initial guess (default zero); the reference starts a repeated solve from its previous solution"""
+        x = np.zeros(max(self.n_dofs, 1)) if x0 is None else np.array(x0, dtype=np.float64, copy=True).reshape(-1)
         at, it = C.c_double(), C.c_int()
         self.ctx._chk(lib().l3b_asm_solve_cg(self._h, tol, max_iters, _p(x), C.byref(at), C.byref(it)))
-        return x, at.value, it.value
+        return x[:self.n_dofs], at.value, it.value
 
-    def solve_gmres(self, tol=1e-6, restart_length=250, max_restarts=39, max_iters=10000):
+    def solve_gmres(self, tol=1e-6, restart_length=250, max_restarts=39, max_iters=10000, x0=None):
         """lstr::Gmres with the native Jacobi preconditioner (solve/BelosSolvers.hpp:125-131, SolverInterface.hpp:26-37 defaults)"""
-        x = np.zeros(self.n_dofs)
+        x = np.zeros(max(self.n_dofs, 1)) if x0 is None else np.array(x0, dtype=np.float64, copy=True).reshape(-1)
         at, it = C.c_double(), C.c_int()
         self.ctx._chk(lib().l3b_asm_solve_gmres(self._h, tol, restart_length, max_restarts, max_iters, _p(x), C.byref(at), C.byref(it)))
-        return x, at.value, it.value
+        return x[:self.n_dofs], at.value, it.value
 
     @property
     def last_kernel_ms(self):
@@ -625,6 +756,18 @@ class MatrixFreeSystem:
         kid, di, fh, fi, bi, nb = _kernel_args(kernel, dof_inds, fields, field_inds, boundary_ids)
         self._keepalive.append(fields)  # the system stores the device pointer (like FieldAccess references SolutionManager)
         self.ctx._chk(lib().l3b_mf_assemble(self._h, kid, asm_opts._c(), time, _p(di), fh, _p(fi), _p(bi), nb))
+
+    def solve_device(self, x_ptr, method="cg", tol=1e-6, max_iters=10000, restart_length=250, max_restarts=39, x0_is_zero=True):
+        """l3b_mf_solve_device: solution on the device over the local dofs"""
+        at, it = C.c_double(), C.c_int()
+        self.ctx._chk(lib().l3b_mf_solve_device(self._h, {"cg": 0, "gmres": 1}[method], tol, max_iters, restart_length, max_restarts, x_ptr,
+                                                int(x0_is_zero), C.byref(at), C.byref(it)))
+        return at.value, it.value
+
+    def set_halo(self, halo: "DeviceHalo | None", n_border_elems=0):
+        """more than one rank (l3b_mf_set_halo): endAssembly, apply and the solvers then work over all ranks"""
+        self._halo = halo
+        self.ctx._chk(lib().l3b_mf_set_halo(self._h, halo._h if halo is not None else None, n_border_elems))
 
     def endAssembly(self):
         self.ctx._chk(lib().l3b_mf_end_assembly(self._h))
@@ -668,7 +811,9 @@ class MatrixFreeSystem:
         if energy_ptr is None:
             self.ctx._chk(lib().l3b_mf_apply_device(self._h, x_ptr, y_ptr, n_cols, alpha, beta))
         else:
-            self.apply_phase_device(x_ptr, y_ptr, APPLY_INIT | APPLY_ELEMENTS | APPLY_FINISH, n_cols=n_cols, alpha=alpha, beta=beta, energy_ptr=energy_ptr)
+            if n_cols != 1:
+                raise ValueError("the energy is collected for single-column applies")
+            self.ctx._chk(lib().l3b_mf_apply_energy_device(self._h, x_ptr, y_ptr, alpha, beta, energy_ptr))
 
     def apply_phase_device(self, x_ptr, y_ptr, phases, elem_begin=0, elem_end=None, n_cols=1, alpha=1.0, beta=0.0, energy_ptr=None):
         """One phase of the apply (APPLY_INIT | APPLY_ELEMENTS | APPLY_FINISH) on device pointers over [owned | ghost] dofs; energy_ptr:
@@ -676,17 +821,18 @@ class MatrixFreeSystem:
         end = self.mesh.n_elems if elem_end is None else elem_end
         self.ctx._chk(lib().l3b_mf_apply_phase_device(self._h, x_ptr, y_ptr, n_cols, alpha, beta, phases, elem_begin, end, energy_ptr))
 
-    def solve(self, tol=1e-6, max_iters=10000):
-        x = np.zeros(self.n_dofs)
+    def solve(self, tol=1e-6, max_iters=10000, x0=None):
+        """x0: initial guess over the local dofs (default zero, the benchmark's first solve)"""
+        x = np.zeros(max(self.n_dofs, 1)) if x0 is None else np.array(x0, dtype=np.float64, copy=True).reshape(-1)
         at, it = C.c_double(), C.c_int()
         self.ctx._chk(lib().l3b_mf_solve_cg(self._h, tol, max_iters, _p(x), C.byref(at), C.byref(it)))
-        return x, at.value, it.value
+        return x[:self.n_dofs], at.value, it.value
 
-    def solve_gmres(self, tol=1e-6, restart_length=250, max_restarts=39, max_iters=10000):
-        x = np.zeros(self.n_dofs)
+    def solve_gmres(self, tol=1e-6, restart_length=250, max_restarts=39, max_iters=10000, x0=None):
+        x = np.zeros(max(self.n_dofs, 1)) if x0 is None else np.array(x0, dtype=np.float64, copy=True).reshape(-1)
         at, it = C.c_double(), C.c_int()
         self.ctx._chk(lib().l3b_mf_solve_gmres(self._h, tol, restart_length, max_restarts, max_iters, _p(x), C.byref(at), C.byref(it)))
-        return x, at.value, it.value
+        return x[:self.n_dofs], at.value, it.value
 
     @property
     def kernel_launches(self):

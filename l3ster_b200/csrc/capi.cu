@@ -2,6 +2,7 @@
 // Krylov layer. Host orchestration only — all element math lives in the kernels instantiated through register_kernel.cuh.
 #include "../../include/l3ster_b200.h"
 
+#include "comm.cuh"
 #include "mesh_host.hpp"
 #include "mf_hex_planes.cuh"
 #include "condense.cuh"
@@ -422,7 +423,12 @@ __global__ void slotMapKernel(const uint32_t* nodes, long long n_elems, int nn, 
     }
     if (lo >= end or node_nbr[lo] != want)
     {
-        atomicOr(status, 2);
+        atomicOr(status, status_graph_entry_missing);
+        return;
+    }
+    if (lo - beg > 0xFFFF) // more neighbours than the 16-bit slot position can address
+    {
+        atomicOr(status, status_slot_overflow);
         return;
     }
     pos[idx] = static_cast< uint16_t >(lo - beg);
@@ -602,6 +608,10 @@ struct l3b_context
             status.zero(stream);
             if (st & status_degenerate_element)
                 fail(L3B_ERR_DEGENERATE, "Encountered degenerate element ( |J| <= 0 )");
+            if (st & status_singular_interior)
+                fail(L3B_ERR_SINGULAR, "static condensation: the interior block K_ii of an element is singular (non-positive pivot)");
+            if (st & status_slot_overflow)
+                fail(L3B_ERR_GRAPH, "a node has more than 65535 neighbours: the 16-bit slot map cannot address its row");
             if (st & status_sparsity_violation)
                 fail(L3B_ERR_SPARSITY, "an operator entry found structurally zero by the compile-time probe was non-zero at run time: "
                                        "register the kernel with a functor that is not constexpr-evaluable, or fix the probe");
@@ -634,8 +644,170 @@ struct l3b_fields
     DevBuf< double > data;
 };
 
+// communicator: the NCCL communicator of this rank plus the library's communication stream (comm.cuh)
+struct l3b_comm
+{
+    l3b_context* ctx   = nullptr;
+    ncclComm_t   comm  = nullptr;
+    bool         owned = false; // created here (destroyed with the object) or attached (the caller's)
+    int          rank = 0, world = 1;
+    cudaStream_t stream = nullptr;                  // communication stream C
+    cudaEvent_t  ev_ready = nullptr, ev_done = nullptr; // for the all-reduce hop S -> C -> S
+    ~l3b_comm()
+    {
+        if (ev_ready)
+            cudaEventDestroy(ev_ready);
+        if (ev_done)
+            cudaEventDestroy(ev_done);
+        if (stream)
+            cudaStreamDestroy(stream);
+        if (owned and comm and l3b::comm::nccl().handle)
+            l3b::comm::nccl().CommDestroy(comm);
+    }
+};
+// comm::ImportExportContext + Import + Export of one dof layout (comm/ImportExport.hpp:29-72, 131-215)
+struct l3b_halo
+{
+    l3b_comm*                comm = nullptr;
+    long long                n_owned = 0, n_ghost = 0;
+    std::vector< int >       owned_nbrs, shared_nbrs;
+    std::vector< long long > owned_ptr, shared_off; // CSR offsets into owned_idx; offsets of the neighbours' ranges in the ghost block
+    DevBuf< int32_t >        owned_idx;
+    DevBuf< long long >      owned_ptr_dev;
+    DevBuf< double >         buf; // pack buffer of the Import, receive buffer of the Export
+    cudaEvent_t              ev_ready = nullptr, ev_done = nullptr;
+    bool active() const { return comm != nullptr and (not owned_nbrs.empty() or not shared_nbrs.empty()); }
+    ~l3b_halo()
+    {
+        if (ev_ready)
+            cudaEventDestroy(ev_ready);
+        if (ev_done)
+            cudaEventDestroy(ev_done);
+    }
+};
+
 namespace
 {
+void ncclCheck(ncclResult_t rc, const char* what)
+{
+    if (rc != ncclSuccess)
+        fail(L3B_ERR_COMM, std::string{what} + ": " + l3b::comm::nccl().GetErrorString(rc));
+}
+const l3b::comm::NcclApi& ncclApi()
+{
+    const auto& api = l3b::comm::nccl();
+    if (not api.handle)
+        fail(L3B_ERR_COMM, api.error);
+    return api;
+}
+void haloReserve(l3b_halo* h, int n_cols)
+{
+    const size_t need = static_cast< size_t >(h->owned_ptr.back()) * n_cols;
+    if (h->buf.n < need)
+    {
+        cudaCheck(cudaStreamSynchronize(h->comm->stream), "sync"); // a transfer may still read the old buffer
+        cudaCheck(cudaStreamSynchronize(h->comm->ctx->stream), "sync");
+        h->buf.alloc(need);
+    }
+}
+// one ncclGroup with every message of the exchange; `import`: owned -> ghost copies, else ghost -> owner contributions
+void haloTransfer(l3b_halo* h, double* v, int n_cols, bool import)
+{
+    const auto&     api = ncclApi();
+    auto* const     c   = h->comm;
+    const long long ld  = h->n_owned + h->n_ghost;
+    ncclCheck(api.GroupStart(), "ncclGroupStart");
+    for (size_t k = 0; k < h->owned_nbrs.size(); ++k)
+    {
+        const long long n_k = h->owned_ptr[k + 1] - h->owned_ptr[k];
+        for (int col = 0; col < n_cols and n_k > 0; ++col)
+        {
+            double* const chunk = h->buf.ptr + h->owned_ptr[k] * n_cols + col * n_k;
+            if (import)
+                ncclCheck(api.Send(chunk, n_k, ncclDouble, h->owned_nbrs[k], c->comm, c->stream), "ncclSend");
+            else
+                ncclCheck(api.Recv(chunk, n_k, ncclDouble, h->owned_nbrs[k], c->comm, c->stream), "ncclRecv");
+        }
+    }
+    for (size_t j = 0; j < h->shared_nbrs.size(); ++j)
+    {
+        const long long n_j = h->shared_off[j + 1] - h->shared_off[j];
+        for (int col = 0; col < n_cols and n_j > 0; ++col)
+        {
+            double* const range = v + h->n_owned + h->shared_off[j] + col * ld; // in place: the neighbour's ghosts are contiguous
+            if (import)
+                ncclCheck(api.Recv(range, n_j, ncclDouble, h->shared_nbrs[j], c->comm, c->stream), "ncclRecv");
+            else
+                ncclCheck(api.Send(range, n_j, ncclDouble, h->shared_nbrs[j], c->comm, c->stream), "ncclSend");
+        }
+    }
+    ncclCheck(api.GroupEnd(), "ncclGroupEnd");
+}
+// Import (comm/ImportExport.hpp:296-384): begin = pack + post, end = the context stream waits for the ghost values
+int haloImportBegin(l3b_halo* h, double* x, int n_cols)
+{
+    if (h == nullptr or not h->active())
+        return 0;
+    auto* const c = h->comm;
+    const auto  S = c->ctx->stream;
+    int         launches = 0;
+    haloReserve(h, n_cols);
+    if (h->owned_ptr.back() > 0)
+    {
+        l3b::comm::haloPackKernel<<< gridFor(h->owned_ptr.back() * n_cols, 256), 256, 0, S >>>(
+            x, h->n_owned + h->n_ghost, h->owned_idx.ptr, h->owned_ptr_dev.ptr, static_cast< int >(h->owned_nbrs.size()), n_cols, h->buf.ptr);
+        ++launches;
+    }
+    cudaCheck(cudaEventRecord(h->ev_ready, S), "event record");
+    cudaCheck(cudaStreamWaitEvent(c->stream, h->ev_ready, 0), "event wait");
+    haloTransfer(h, x, n_cols, true);
+    cudaCheck(cudaEventRecord(h->ev_done, c->stream), "event record");
+    return launches;
+}
+void haloImportEnd(l3b_halo* h)
+{
+    if (h == nullptr or not h->active())
+        return;
+    cudaCheck(cudaStreamWaitEvent(h->comm->ctx->stream, h->ev_done, 0), "event wait");
+}
+// Export (comm/ImportExport.hpp:403-470): begin = post (ordered after the work already on the context stream), end = wait + unpack-add
+void haloExportBegin(l3b_halo* h, double* y, int n_cols)
+{
+    if (h == nullptr or not h->active())
+        return;
+    auto* const c = h->comm;
+    haloReserve(h, n_cols);
+    cudaCheck(cudaEventRecord(h->ev_ready, c->ctx->stream), "event record");
+    cudaCheck(cudaStreamWaitEvent(c->stream, h->ev_ready, 0), "event wait");
+    haloTransfer(h, y, n_cols, false);
+    cudaCheck(cudaEventRecord(h->ev_done, c->stream), "event record");
+}
+int haloExportEnd(l3b_halo* h, double* y, int n_cols)
+{
+    if (h == nullptr or not h->active())
+        return 0;
+    const auto S = h->comm->ctx->stream;
+    cudaCheck(cudaStreamWaitEvent(S, h->ev_done, 0), "event wait");
+    if (h->owned_ptr.back() == 0)
+        return 0;
+    l3b::comm::haloUnpackAddKernel<<< gridFor(h->owned_ptr.back() * n_cols, 256), 256, 0, S >>>(
+        y, h->n_owned + h->n_ghost, h->owned_idx.ptr, h->owned_ptr_dev.ptr, static_cast< int >(h->owned_nbrs.size()), n_cols, h->buf.ptr);
+    return 1;
+}
+// in-place sum over the ranks of n device doubles, ordered after the work on the context stream and before what follows on it
+void commAllReduce(l3b_comm* c, double* scalars, int n)
+{
+    if (c == nullptr or c->world == 1 or n == 0)
+        return;
+    const auto& api = ncclApi();
+    const auto  S   = c->ctx->stream;
+    cudaCheck(cudaEventRecord(c->ev_ready, S), "event record");
+    cudaCheck(cudaStreamWaitEvent(c->stream, c->ev_ready, 0), "event wait");
+    ncclCheck(api.AllReduce(scalars, scalars, n, ncclDouble, ncclSum, c->comm, c->stream), "ncclAllReduce");
+    cudaCheck(cudaEventRecord(c->ev_done, c->stream), "event record");
+    cudaCheck(cudaStreamWaitEvent(S, c->ev_done, 0), "event wait");
+}
+
 struct WorkList
 {
     long long          n = 0;
@@ -800,6 +972,12 @@ struct l3b_asm
     bool                open = false;
     cudaEvent_t         ev0 = nullptr, ev1 = nullptr;
     double              last_ms = 0.;
+    // more than one rank (l3b_asm_set_halo): halo of the row layout [owned | ghost]
+    l3b_halo*           halo = nullptr;
+    long long           n_owned_dofs = -1; // -1: all rows owned
+    bool                rows_exported = false; // l3b_asm_export_shared_rows ran: owned rows are complete, ghost rows are spent
+    long long           ownedDofs() const { return n_owned_dofs < 0 ? n_dofs : n_owned_dofs; }
+    l3b_comm*           comm() const { return halo ? halo->comm : nullptr; }
     ~l3b_asm()
     {
         if (ev0)
@@ -826,15 +1004,45 @@ struct l3b_mf
     std::vector< KernelUse > uses;
     DevBuf< double >         work_x, work_y; // staging for the host-buffer apply
     int                      last_launches = 0;
+    // more than one rank (l3b_mf_set_halo): the halo of the dof layout [owned | ghost]; elements [0, n_border) touch ghost nodes
+    l3b_halo*                halo     = nullptr;
+    long long                n_border = 0;
+    long long                ownedDofs() const { return static_cast< long long >(mesh->n_owned_nodes) * dpn; }
+    l3b_comm*                comm() const { return halo ? halo->comm : nullptr; }
 };
 
 namespace
 {
+// every context-bearing entry point runs with the context's device current (and restores the caller's): two contexts in one
+// process, another host thread, or a framework that switches devices must not redirect allocations and launches
+struct DeviceGuard
+{
+    int prev = -1;
+    explicit DeviceGuard(const l3b_context* ctx)
+    {
+        if (ctx == nullptr)
+            return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess and cur != ctx->device)
+        {
+            prev = cur;
+            cudaSetDevice(ctx->device);
+        }
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0)
+            cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&)            = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 template < typename F >
 int guardedCtx(const l3b_context* ctx, F&& f)
 {
     try
     {
+        const DeviceGuard guard{ctx};
         f();
         return L3B_OK;
     }
@@ -858,18 +1066,20 @@ int guardedCtx(const l3b_context* ctx, F&& f)
 // their whole side list, with the range that contains element 0). `masked`: honour the Dirichlet mask (the operator apply) or not
 // (the Dirichlet lifting of the initialisation). Returns the number of kernels launched.
 int applyUse(l3b_mf* sys, const KernelUse& use, const double* x, double* y, int n_cols, double alpha, bool masked, double* energy, long long elem_begin,
-             long long elem_end)
+             long long elem_end, bool boundary_work)
 {
     auto*       ctx  = sys->ctx;
     const auto& info = kernelRegistry()[use.kernel_id].info;
     ElemArgs    a    = baseArgs(sys->mesh, use, sys->dpn, sys->n_dofs);
     if (info.is_boundary)
     {
-        if (elem_begin != 0) // the side work list is not split: it runs with the range that contains element 0
+        if (not boundary_work) // the side work list is not split: it runs once per apply, when the caller says so
             return 0;
     }
     else
     {
+        if (elem_end <= elem_begin)
+            return 0;
         a.first_elem = elem_begin;
         a.n_work     = elem_end - elem_begin;
     }
@@ -927,9 +1137,15 @@ void mfApplyPhases(l3b_mf* sys, const double* x, double* y, int n_cols, double a
             ++launches;
         }
     }
-    if (phases & L3B_APPLY_ELEMENTS)
+    // boundary kernels run with L3B_APPLY_BOUNDARY only (the public entry point adds the bit by its documented rule)
+    const bool boundary_work = (phases & L3B_APPLY_BOUNDARY) != 0;
+    if (phases & (L3B_APPLY_ELEMENTS | L3B_APPLY_BOUNDARY))
         for (const auto& use : sys->uses)
-            launches += applyUse(sys, use, x, y, n_cols, alpha, true, energy, elem_begin, elem_end);
+        {
+            const bool is_bnd = kernelRegistry()[use.kernel_id].info.is_boundary;
+            if (is_bnd ? boundary_work : (phases & L3B_APPLY_ELEMENTS) != 0)
+                launches += applyUse(sys, use, x, y, n_cols, alpha, true, energy, elem_begin, elem_end, boundary_work);
+        }
     if ((phases & L3B_APPLY_FINISH) and sys->has_bc and sys->n_dir > 0)
     {
         dirichletRowsListKernel<<< gridFor(sys->n_dir), 256, 0, ctx->stream >>>(sys->dir_list.ptr, sys->n_dir, x, y, sys->n_dofs, n_cols, alpha, energy,
@@ -939,9 +1155,35 @@ void mfApplyPhases(l3b_mf* sys, const double* x, double* y, int n_cols, double a
     cudaCheck(cudaGetLastError(), "operator apply");
     sys->last_launches = launches; // of this call
 }
+// The whole operator apply. One rank: one pass over all elements. With a halo (MatrixFreeSystem::applyImpl, :1019-1140):
+//     pack + post the Import of x | y <- beta y (the pass over y hides the Import) | wait | border elements + boundary kernels |
+//     post the Export of y | interior elements (hide the Export) | wait + unpack-add | Dirichlet rows
+// The reference runs interior elements first and polls for the Import; here the zeroing of y covers the Import and the long interior
+// launch covers the Export, so neither transfer is exposed. The ghost block of x is overwritten by the Import.
 void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta, double* energy = nullptr)
 {
-    mfApplyPhases(sys, x, y, n_cols, alpha, beta, L3B_APPLY_INIT | L3B_APPLY_ELEMENTS | L3B_APPLY_FINISH, 0, sys->mesh->n_elems, energy);
+    auto* const h = sys->halo;
+    if (h == nullptr or not h->active())
+    {
+        mfApplyPhases(sys, x, y, n_cols, alpha, beta, L3B_APPLY_INIT | L3B_APPLY_ELEMENTS | L3B_APPLY_BOUNDARY | L3B_APPLY_FINISH, 0, sys->mesh->n_elems, energy);
+        return;
+    }
+    int        launches = haloImportBegin(h, const_cast< double* >(x), n_cols);
+    const auto n_elems  = sys->mesh->n_elems;
+    mfApplyPhases(sys, x, y, n_cols, alpha, beta, L3B_APPLY_INIT, 0, 0);
+    launches += sys->last_launches;
+    haloImportEnd(h);
+    mfApplyPhases(sys, x, y, n_cols, alpha, beta, L3B_APPLY_ELEMENTS | L3B_APPLY_BOUNDARY, 0, sys->n_border, energy);
+    launches += sys->last_launches;
+    haloExportBegin(h, y, n_cols);
+    if (sys->n_border < n_elems)
+    {
+        mfApplyPhases(sys, x, y, n_cols, alpha, beta, L3B_APPLY_ELEMENTS, sys->n_border, n_elems, energy);
+        launches += sys->last_launches;
+    }
+    launches += haloExportEnd(h, y, n_cols);
+    mfApplyPhases(sys, x, y, n_cols, alpha, beta, L3B_APPLY_FINISH, 0, 0, energy);
+    sys->last_launches += launches;
 }
 
 // Preconditioned CG, Belos "Block CG" semantics for block size 1 (solve/BelosSolvers.hpp:76-89): left preconditioner,
@@ -965,9 +1207,18 @@ struct Event
     Event(const Event&)            = delete;
     Event& operator=(const Event&) = delete;
 };
+// r = b - Ap
+__global__ void residualKernel(double* r, const double* b, const double* Ap, long long n)
+{
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
+        r[i] = b[i] - Ap[i];
+}
+// x0_zero: the caller vouches that the initial guess is zero (the reference's first solve: m_solution starts at 0) — x is zeroed and the
+// apply for r0 = b - A x0 is skipped; otherwise x is the initial guess, as Belos takes the system's persistent solution vector
+// (AssembledSystem.hpp:113-135, solve/BelosSolvers.hpp: LinearProblem(A, x, b)). Only the owned part of x is valid on return.
 template < typename Apply, typename Reduce >
 void pcg(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Reduce&& reduce, const double* diag, const double* b,
-         double* x /* device */, double tol, int max_iters, double* achieved, int* iters)
+         double* x /* device */, double tol, int max_iters, double* achieved, int* iters, bool x0_zero = true)
 {
     // n = owned dofs: dots and updates run over those; p and Ap carry the ghost tail the operator needs
     DevBuf< double > r(n), z(n), p(n_local), Ap(n_local), minv(n);
@@ -979,9 +1230,18 @@ void pcg(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Reduce
     const auto s  = ctx->stream;
     const auto g  = gridFor(n);
     jacobiInvertKernel<<< g, 256, 0, s >>>(diag, minv.ptr, n, 1., 0.);
-    cudaCheck(cudaMemsetAsync(x, 0, n * sizeof(double), s), "memset");
     p.zero(s);
-    cudaCheck(cudaMemcpyAsync(r.ptr, b, n * sizeof(double), cudaMemcpyDeviceToDevice, s), "copy");
+    if (x0_zero)
+    {
+        cudaCheck(cudaMemsetAsync(x, 0, n * sizeof(double), s), "memset");
+        cudaCheck(cudaMemcpyAsync(r.ptr, b, n * sizeof(double), cudaMemcpyDeviceToDevice, s), "copy");
+    }
+    else
+    {
+        cudaCheck(cudaMemcpyAsync(p.ptr, x, n * sizeof(double), cudaMemcpyDeviceToDevice, s), "copy"); // p carries the ghost tail the operator fills
+        apply(p.ptr, Ap.ptr, nullptr);
+        residualKernel<<< g, 256, 0, s >>>(r.ptr, b, Ap.ptr, n);
+    }
     hadamardKernel<<< g, 256, 0, s >>>(z.ptr, minv.ptr, r.ptr, n);
     cudaCheck(cudaMemcpyAsync(p.ptr, z.ptr, n * sizeof(double), cudaMemcpyDeviceToDevice, s), "copy");
     cudaCheck(cudaMemsetAsync(sc, 0, 8 * sizeof(double), s), "memset");
@@ -1036,7 +1296,7 @@ void pcg(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Reduce
 // preconditioned residual from the Givens recurrence, against `tol`.
 template < typename Apply, typename Reduce >
 void gmres(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Reduce&& reduce, const double* diag, const double* b,
-           double* x /* device */, double tol, int restart, int max_restarts, int max_iters, double* achieved, int* iters)
+           double* x /* device */, double tol, int restart, int max_restarts, int max_iters, double* achieved, int* iters, bool x0_zero = true)
 {
     const int        m = std::max(1, restart);
     DevBuf< double > V(static_cast< size_t >(m + 1) * n), w(n_local), xin(n_local), minv(n), hd(m + 2);
@@ -1044,7 +1304,8 @@ void gmres(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Redu
     const auto       g = gridFor(n);
     std::vector< double > H(static_cast< size_t >(m + 1) * m, 0.), cs(m), sn(m), gvec(m + 1), hcol(m + 2), y(m);
     jacobiInvertKernel<<< g, 256, 0, s >>>(diag, minv.ptr, n, 1., 0.);
-    cudaCheck(cudaMemsetAsync(x, 0, n * sizeof(double), s), "memset");
+    if (x0_zero) // otherwise x is the initial guess (Belos: LinearProblem(A, x, b) with the system's persistent solution)
+        cudaCheck(cudaMemsetAsync(x, 0, n * sizeof(double), s), "memset");
     xin.zero(s);
     w.zero(s);
     int    it = 0, restarts = 0;
@@ -1145,6 +1406,58 @@ void gmres(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Redu
     *achieved = res;
     *iters    = it;
 }
+
+bool hostAllZero(const double* x, long long n)
+{
+    for (long long i = 0; i < n; ++i)
+        if (x[i] != 0.)
+            return false;
+    return true;
+}
+// ghost copies of a solution vector follow their owners (so that the whole local vector is valid on return)
+void refreshGhosts(l3b_halo* h, double* x)
+{
+    haloImportBegin(h, x, 1);
+    haloImportEnd(h);
+}
+// y = A x on the assembled rows. With a halo and rows [owned | ghost] kept as the rank's elements assembled them: Import x, local product,
+// Export-sum of the ghost rows; after l3b_asm_export_shared_rows the owned rows are complete and the Export is skipped.
+void asmSpmvDevice(l3b_asm* sys, const double* x, double* y)
+{
+    auto* const     h       = sys->halo;
+    const long long threads = sys->n_dofs * 32;
+    haloImportBegin(h, const_cast< double* >(x), 1);
+    haloImportEnd(h);
+    spmvKernel<<< blocksFor(threads), 256, 0, sys->ctx->stream >>>(sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, x, y);
+    if (not sys->rows_exported)
+    {
+        haloExportBegin(h, y, 1);
+        haloExportEnd(h, y, 1);
+    }
+    cudaCheck(cudaGetLastError(), "spmv");
+}
+// diagonal of the global operator over the local rows (owned part valid): the Export-sum of the local diagonals
+void asmDiagDevice(l3b_asm* sys, double* diag)
+{
+    extractDiagKernel<<< blocksFor(sys->n_dofs), 256, 0, sys->ctx->stream >>>(sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes,
+                                                                            sys->dpn, diag);
+    if (not sys->rows_exported)
+    {
+        haloExportBegin(sys->halo, diag, 1);
+        haloExportEnd(sys->halo, diag, 1);
+    }
+    cudaCheck(cudaGetLastError(), "diagonal");
+}
+// right-hand side of the global system over the owned rows: the Export-sum of the local one (a copy: the system's rhs stays as assembled)
+void asmGlobalRhs(l3b_asm* sys, double* rhs)
+{
+    cudaCheck(cudaMemcpyAsync(rhs, sys->rhs.ptr, sys->n_dofs * sizeof(double), cudaMemcpyDeviceToDevice, sys->ctx->stream), "copy");
+    if (not sys->rows_exported)
+    {
+        haloExportBegin(sys->halo, rhs, 1);
+        haloExportEnd(sys->halo, rhs, 1);
+    }
+}
 } // namespace
 
 extern "C"
@@ -1197,6 +1510,169 @@ int l3b_context_synchronize(l3b_context* ctx)
 void* l3b_context_stream(l3b_context* ctx)
 {
     return ctx->stream;
+}
+
+// ---- communicator and halo (comm.cuh)
+int l3b_comm_unique_id(char id[L3B_COMM_ID_BYTES])
+{
+    return guardedCtx(nullptr, [&] {
+        static_assert(sizeof(ncclUniqueId) == L3B_COMM_ID_BYTES);
+        ncclUniqueId uid;
+        ncclCheck(ncclApi().GetUniqueId(&uid), "ncclGetUniqueId");
+        std::memcpy(id, &uid, sizeof(uid));
+    });
+}
+static void commFinishSetup(l3b_comm* c)
+{
+    cudaCheck(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream create");
+    cudaCheck(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming), "event create");
+    cudaCheck(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming), "event create");
+}
+int l3b_comm_create(l3b_context* ctx, int rank, int world, const char id[L3B_COMM_ID_BYTES], l3b_comm** out)
+{
+    return guardedCtx(ctx, [&] {
+        if (world < 1 or rank < 0 or rank >= world)
+            fail(L3B_ERR_INVALID_ARG, "l3b_comm_create: invalid rank / world size");
+        auto c   = std::make_unique< l3b_comm >();
+        c->ctx   = ctx;
+        c->rank  = rank;
+        c->world = world;
+        ncclUniqueId uid;
+        std::memcpy(&uid, id, sizeof(uid));
+        ncclCheck(ncclApi().CommInitRank(&c->comm, world, uid, rank), "ncclCommInitRank");
+        c->owned = true;
+        commFinishSetup(c.get());
+        *out = c.release();
+    });
+}
+int l3b_comm_attach(l3b_context* ctx, void* nccl_comm, l3b_comm** out)
+{
+    return guardedCtx(ctx, [&] {
+        if (nccl_comm == nullptr)
+            fail(L3B_ERR_INVALID_ARG, "l3b_comm_attach: null communicator");
+        auto c  = std::make_unique< l3b_comm >();
+        c->ctx  = ctx;
+        c->comm = static_cast< ncclComm_t >(nccl_comm);
+        ncclCheck(ncclApi().CommCount(c->comm, &c->world), "ncclCommCount");
+        ncclCheck(ncclApi().CommUserRank(c->comm, &c->rank), "ncclCommUserRank");
+        commFinishSetup(c.get());
+        *out = c.release();
+    });
+}
+void l3b_comm_destroy(l3b_comm* c)
+{
+    if (c == nullptr)
+        return;
+    const DeviceGuard guard{c->ctx};
+    if (c->stream)
+        cudaStreamSynchronize(c->stream);
+    delete c;
+}
+int l3b_comm_rank(const l3b_comm* c)
+{
+    return c ? c->rank : 0;
+}
+int l3b_comm_size(const l3b_comm* c)
+{
+    return c ? c->world : 1;
+}
+int l3b_comm_allreduce_sum(l3b_comm* c, double* device_scalars, int n)
+{
+    return guardedCtx(c ? c->ctx : nullptr, [&] { commAllReduce(c, device_scalars, n); });
+}
+int l3b_halo_create(l3b_comm* c, int64_t n_owned, int64_t n_ghost, int n_owned_nbrs, const int* owned_nbr_ranks, const int64_t* owned_ptr,
+                    const int32_t* owned_inds, int n_shared_nbrs, const int* shared_nbr_ranks, const int64_t* shared_offsets, l3b_halo** out)
+{
+    return guardedCtx(c ? c->ctx : nullptr, [&] {
+        if (c == nullptr)
+            fail(L3B_ERR_COMM, "l3b_halo_create needs a communicator");
+        if (n_owned < 0 or n_ghost < 0 or n_owned_nbrs < 0 or n_shared_nbrs < 0)
+            fail(L3B_ERR_INVALID_ARG, "l3b_halo_create: negative size");
+        auto h     = std::make_unique< l3b_halo >();
+        h->comm    = c;
+        h->n_owned = n_owned;
+        h->n_ghost = n_ghost;
+        h->owned_nbrs.assign(owned_nbr_ranks, owned_nbr_ranks + n_owned_nbrs);
+        h->shared_nbrs.assign(shared_nbr_ranks, shared_nbr_ranks + n_shared_nbrs);
+        h->owned_ptr.assign(1, 0);
+        h->shared_off.assign(1, 0);
+        if (n_owned_nbrs > 0)
+            h->owned_ptr.assign(owned_ptr, owned_ptr + n_owned_nbrs + 1);
+        if (n_shared_nbrs > 0)
+            h->shared_off.assign(shared_offsets, shared_offsets + n_shared_nbrs + 1);
+        for (int r : h->owned_nbrs)
+            if (r < 0 or r >= c->world)
+                fail(L3B_ERR_INVALID_ARG, "l3b_halo_create: neighbour rank out of range");
+        for (int r : h->shared_nbrs)
+            if (r < 0 or r >= c->world)
+                fail(L3B_ERR_INVALID_ARG, "l3b_halo_create: neighbour rank out of range");
+        if (h->owned_ptr.front() != 0 or h->shared_off.front() != 0 or h->shared_off.back() > n_ghost)
+            fail(L3B_ERR_INVALID_ARG, "l3b_halo_create: offsets do not fit the dof layout");
+        for (size_t k = 0; k + 1 < h->owned_ptr.size(); ++k)
+            if (h->owned_ptr[k] > h->owned_ptr[k + 1])
+                fail(L3B_ERR_INVALID_ARG, "l3b_halo_create: offsets must ascend");
+        for (size_t k = 0; k + 1 < h->shared_off.size(); ++k)
+            if (h->shared_off[k] > h->shared_off[k + 1])
+                fail(L3B_ERR_INVALID_ARG, "l3b_halo_create: offsets must ascend");
+        const long long n_idx = h->owned_ptr.back();
+        for (long long i = 0; i < n_idx; ++i)
+            if (owned_inds[i] < 0 or owned_inds[i] >= n_owned)
+                fail(L3B_ERR_INVALID_ARG, "l3b_halo_create: a packed index is not an owned dof");
+        const auto S = c->ctx->stream;
+        h->owned_idx.alloc(std::max< long long >(n_idx, 1));
+        h->owned_idx.upload(owned_inds, n_idx, S);
+        h->owned_ptr_dev.alloc(h->owned_ptr.size());
+        h->owned_ptr_dev.upload(h->owned_ptr.data(), h->owned_ptr.size(), S);
+        cudaCheck(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming), "event create");
+        cudaCheck(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming), "event create");
+        cudaCheck(cudaStreamSynchronize(S), "halo upload");
+        *out = h.release();
+    });
+}
+void l3b_halo_destroy(l3b_halo* h)
+{
+    if (h == nullptr)
+        return;
+    const DeviceGuard guard{h->comm->ctx};
+    cudaStreamSynchronize(h->comm->stream);
+    cudaStreamSynchronize(h->comm->ctx->stream);
+    delete h;
+}
+int l3b_halo_import_begin(l3b_halo* h, double* x, int n_cols)
+{
+    return guardedCtx(h->comm->ctx, [&] { haloImportBegin(h, x, n_cols); });
+}
+int l3b_halo_import_end(l3b_halo* h)
+{
+    return guardedCtx(h->comm->ctx, [&] { haloImportEnd(h); });
+}
+int l3b_halo_export_begin(l3b_halo* h, double* y, int n_cols)
+{
+    return guardedCtx(h->comm->ctx, [&] { haloExportBegin(h, y, n_cols); });
+}
+int l3b_halo_export_end(l3b_halo* h, double* y, int n_cols)
+{
+    return guardedCtx(h->comm->ctx, [&] { haloExportEnd(h, y, n_cols); });
+}
+int l3b_mf_set_halo(l3b_mf* sys, l3b_halo* halo, int64_t n_border_elems)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (halo != nullptr and (halo->n_owned != sys->ownedDofs() or halo->n_owned + halo->n_ghost != sys->n_dofs))
+            fail(L3B_ERR_INVALID_ARG, "l3b_mf_set_halo: the halo does not describe this system's dof layout [owned | ghost]");
+        if (n_border_elems < 0 or n_border_elems > sys->mesh->n_elems)
+            fail(L3B_ERR_INVALID_ARG, "l3b_mf_set_halo: border element count out of range");
+        sys->halo     = halo;
+        sys->n_border = n_border_elems;
+    });
+}
+int l3b_asm_set_halo(l3b_asm* sys, l3b_halo* halo)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (halo != nullptr and halo->n_owned + halo->n_ghost != sys->n_dofs)
+            fail(L3B_ERR_INVALID_ARG, "l3b_asm_set_halo: the halo does not describe this system's row layout [owned | ghost]");
+        sys->halo         = halo;
+        sys->n_owned_dofs = halo ? halo->n_owned : -1;
+    });
 }
 
 // ---- registry
@@ -1626,44 +2102,67 @@ int l3b_asm_spmv(l3b_asm* sys, const double* x, double* y)
         cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "spmv");
     });
 }
-int l3b_asm_solve_gmres(l3b_asm* sys, double tol, int restart_length, int max_restarts, int max_iters, double* x, double* achieved_tol,
-                        int* iters)
+// method 0: CG, 1: restarted GMRES — both with native Jacobi; x on the device over the local rows, in = initial guess, out = solution
+int l3b_asm_solve_device(l3b_asm* sys, int method, double tol, int max_iters, int restart_length, int max_restarts, double* x, int x0_is_zero,
+                         double* achieved_tol, int* iters)
 {
     return guardedCtx(sys->ctx, [&] {
         if (sys->open)
             fail(L3B_ERR_STATE, "`solve()` was called before `endAssembly()`");
+        if (method != 0 and method != 1)
+            fail(L3B_ERR_INVALID_ARG, "solver method: 0 (CG) or 1 (GMRES)");
         const auto       n = sys->n_dofs;
-        DevBuf< double > diag(n), dx(n);
-        extractDiagKernel<<< blocksFor(n), 256, 0, sys->ctx->stream >>>(
-            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, diag.ptr);
-        const long long threads = n * 32;
-        gmres(
-            sys->ctx, n, n,
-            [&](const double* in, double* out) {
-                spmvKernel<<< blocksFor(threads), 256, 0, sys->ctx->stream >>>(
-                    sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, in, out);
-            },
-            [](double*, int) {}, diag.ptr, sys->rhs.ptr, dx.ptr, tol, restart_length, max_restarts, max_iters, achieved_tol, iters);
-        dx.download(x, n, sys->ctx->stream);
+        DevBuf< double > diag(std::max< long long >(n, 1)), rhs(std::max< long long >(n, 1));
+        asmDiagDevice(sys, diag.ptr);
+        asmGlobalRhs(sys, rhs.ptr);
+        const auto reduce = [&](double* sc, int k) { commAllReduce(sys->comm(), sc, k); };
+        if (method == 0)
+            pcg(
+                sys->ctx, n, sys->ownedDofs(),
+                [&](const double* in, double* out, double*) {
+                    asmSpmvDevice(sys, in, out);
+                    return false; // p.Ap by a dot-product pass
+                },
+                reduce, diag.ptr, rhs.ptr, x, tol, max_iters, achieved_tol, iters, x0_is_zero != 0);
+        else
+            gmres(
+                sys->ctx, n, sys->ownedDofs(), [&](const double* in, double* out) { asmSpmvDevice(sys, in, out); }, reduce, diag.ptr, rhs.ptr, x, tol,
+                restart_length, max_restarts, max_iters, achieved_tol, iters, x0_is_zero != 0);
+        refreshGhosts(sys->halo, x);
+        cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "solve"); // diag and rhs die here
+    });
+}
+static int asmSolveHost(l3b_asm* sys, int method, double tol, int max_iters, int restart_length, int max_restarts, double* x, double* achieved_tol,
+                        int* iters)
+{
+    DevBuf< double > dx;
+    const int        rc = guardedCtx(sys->ctx, [&] {
+        dx.alloc(std::max< long long >(sys->n_dofs, 1));
+        dx.upload(x, sys->n_dofs, sys->ctx->stream);
+    });
+    if (rc != L3B_OK)
+        return rc;
+    const int rc2 = l3b_asm_solve_device(sys, method, tol, max_iters, restart_length, max_restarts, dx.ptr, hostAllZero(x, sys->ownedDofs()),
+                                         achieved_tol, iters);
+    if (rc2 != L3B_OK)
+        return rc2;
+    return guardedCtx(sys->ctx, [&] {
+        dx.download(x, sys->n_dofs, sys->ctx->stream);
         cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "solve");
     });
 }
+int l3b_asm_solve_gmres(l3b_asm* sys, double tol, int restart_length, int max_restarts, int max_iters, double* x, double* achieved_tol,
+                        int* iters)
+{
+    return asmSolveHost(sys, 1, tol, max_iters, restart_length, max_restarts, x, achieved_tol, iters);
+}
 int l3b_asm_spmv_device(l3b_asm* sys, const double* x, double* y)
 {
-    return guardedCtx(sys->ctx, [&] {
-        const long long threads = sys->n_dofs * 32;
-        spmvKernel<<< blocksFor(threads), 256, 0, sys->ctx->stream >>>(
-            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, x, y);
-        cudaCheck(cudaGetLastError(), "spmv");
-    });
+    return guardedCtx(sys->ctx, [&] { asmSpmvDevice(sys, x, y); });
 }
 int l3b_asm_diag_device(l3b_asm* sys, double* diag)
 {
-    return guardedCtx(sys->ctx, [&] {
-        extractDiagKernel<<< blocksFor(sys->n_dofs), 256, 0, sys->ctx->stream >>>(
-            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, diag);
-        cudaCheck(cudaGetLastError(), "diagonal");
-    });
+    return guardedCtx(sys->ctx, [&] { asmDiagDevice(sys, diag); });
 }
 double* l3b_asm_device_rhs(l3b_asm* sys)
 {
@@ -1671,25 +2170,7 @@ double* l3b_asm_device_rhs(l3b_asm* sys)
 }
 int l3b_asm_solve_cg(l3b_asm* sys, double tol, int max_iters, double* x, double* achieved_tol, int* iters)
 {
-    return guardedCtx(sys->ctx, [&] {
-        if (sys->open)
-            fail(L3B_ERR_STATE, "`solve()` was called before `endAssembly()`");
-        const auto       n = sys->n_dofs;
-        DevBuf< double > diag(n), dx(n);
-        extractDiagKernel<<< blocksFor(n), 256, 0, sys->ctx->stream >>>(
-            sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, diag.ptr);
-        const long long threads = n * 32;
-        pcg(
-            sys->ctx, n, n,
-            [&](const double* in, double* out, double*) {
-                spmvKernel<<< blocksFor(threads), 256, 0, sys->ctx->stream >>>(
-                    sys->node_ptr.ptr, sys->node_nbr.ptr, sys->values.ptr, sys->n_nodes, sys->dpn, in, out);
-                return false; // p.Ap by a dot-product pass
-            },
-            [](double*, int) {}, diag.ptr, sys->rhs.ptr, dx.ptr, tol, max_iters, achieved_tol, iters);
-        dx.download(x, n, sys->ctx->stream);
-        cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "solve");
-    });
+    return asmSolveHost(sys, 0, tol, max_iters, 1, 0, x, achieved_tol, iters);
 }
 double l3b_asm_last_kernel_ms(const l3b_asm* sys)
 {
@@ -1792,7 +2273,7 @@ int l3b_mf_end_assembly_begin(l3b_mf* sys)
             const bool fast = use.inst->init_fast != nullptr and not force_dense;
             cudaCheck((fast ? use.inst->init_fast : use.inst->init)(kernelRegistry()[use.kernel_id].object.get(), a, ctx->stream), "init launch");
             if (fast and sys->lift_needed)
-                applyUse(sys, use, sys->dir_g.ptr, sys->rhs.ptr, sys->n_rhs, -1., false, nullptr, 0, sys->mesh->n_elems);
+                applyUse(sys, use, sys->dir_g.ptr, sys->rhs.ptr, sys->n_rhs, -1., false, nullptr, 0, sys->mesh->n_elems, true);
         }
         cudaCheck(cudaGetLastError(), "init");
     });
@@ -1813,7 +2294,16 @@ int l3b_mf_end_assembly_finish(l3b_mf* sys)
 }
 int l3b_mf_end_assembly(l3b_mf* sys)
 {
-    const int rc = l3b_mf_end_assembly_begin(sys);
+    int rc = l3b_mf_end_assembly_begin(sys);
+    if (rc != L3B_OK)
+        return rc;
+    // more than one rank: the ghost parts of diag and rhs go to their owners (MatrixFreeSystem.hpp:925-938)
+    rc = guardedCtx(sys->ctx, [&] {
+        haloExportBegin(sys->halo, sys->diag.ptr, 1);
+        haloExportEnd(sys->halo, sys->diag.ptr, 1);
+        haloExportBegin(sys->halo, sys->rhs.ptr, sys->n_rhs);
+        haloExportEnd(sys->halo, sys->rhs.ptr, sys->n_rhs);
+    });
     return rc != L3B_OK ? rc : l3b_mf_end_assembly_finish(sys);
 }
 double* l3b_mf_device_diag(l3b_mf* sys)
@@ -1826,7 +2316,7 @@ double* l3b_mf_device_rhs(l3b_mf* sys)
 }
 int l3b_gmres_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_apply_callback apply, l3b_allreduce_callback allreduce,
                      void* user, const double* diag, const double* b, double* x, double tol, int restart_length, int max_restarts,
-                     int max_iters, double* achieved_tol, int* iters)
+                     int max_iters, int x0_is_zero, double* achieved_tol, int* iters)
 {
     return guardedCtx(ctx, [&] {
         if (apply == nullptr or n_owned > n_local or n_owned < 0 or restart_length < 1)
@@ -1842,27 +2332,61 @@ int l3b_gmres_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_app
                 if (allreduce != nullptr and allreduce(user, sc, n) != 0)
                     fail(L3B_ERR_INVALID_ARG, "l3b_gmres_device: the all-reduce callback failed");
             },
-            diag, b, x, tol, restart_length, max_restarts, max_iters, achieved_tol, iters);
+            diag, b, x, tol, restart_length, max_restarts, max_iters, achieved_tol, iters, x0_is_zero != 0);
     });
 }
-int l3b_mf_solve_gmres(l3b_mf* sys, double tol, int restart_length, int max_restarts, int max_iters, double* x, double* achieved_tol, int* iters)
+int l3b_mf_solve_device(l3b_mf* sys, int method, double tol, int max_iters, int restart_length, int max_restarts, double* x, int x0_is_zero,
+                        double* achieved_tol, int* iters)
 {
     return guardedCtx(sys->ctx, [&] {
         if (not sys->closed)
             fail(L3B_ERR_STATE, "`solve()` was called before `endAssembly()`");
         if (sys->n_rhs != 1)
-            fail(L3B_ERR_INVALID_ARG, "the GMRES driver handles one right-hand side");
-        DevBuf< double > dx(sys->n_dofs);
-        gmres(
-            sys->ctx, sys->n_dofs, sys->n_dofs, [&](const double* in, double* out) { mfApplyDevice(sys, in, out, 1, 1., 0.); },
-            [](double*, int) {}, sys->diag.ptr, sys->rhs.ptr, dx.ptr, tol, restart_length, max_restarts, max_iters, achieved_tol, iters);
+            fail(L3B_ERR_INVALID_ARG, "the Krylov drivers handle one right-hand side");
+        if (method != 0 and method != 1)
+            fail(L3B_ERR_INVALID_ARG, "solver method: 0 (CG) or 1 (GMRES)");
+        const auto reduce = [&](double* sc, int k) { commAllReduce(sys->comm(), sc, k); };
+        if (method == 0)
+            pcg(
+                sys->ctx, sys->n_dofs, sys->ownedDofs(),
+                [&](const double* in, double* out, double* energy) {
+                    mfApplyDevice(sys, in, out, 1, 1., 0., energy);
+                    return energy != nullptr; // p.Ap comes out of the apply
+                },
+                reduce, sys->diag.ptr, sys->rhs.ptr, x, tol, max_iters, achieved_tol, iters, x0_is_zero != 0);
+        else
+            gmres(
+                sys->ctx, sys->n_dofs, sys->ownedDofs(), [&](const double* in, double* out) { mfApplyDevice(sys, in, out, 1, 1., 0.); }, reduce,
+                sys->diag.ptr, sys->rhs.ptr, x, tol, restart_length, max_restarts, max_iters, achieved_tol, iters, x0_is_zero != 0);
+        refreshGhosts(sys->halo, x);
+    });
+}
+static int mfSolveHost(l3b_mf* sys, int method, double tol, int max_iters, int restart_length, int max_restarts, double* x, double* achieved_tol,
+                       int* iters)
+{
+    DevBuf< double > dx;
+    const int        rc = guardedCtx(sys->ctx, [&] {
+        dx.alloc(std::max< long long >(sys->n_dofs, 1));
+        dx.upload(x, sys->n_dofs, sys->ctx->stream);
+    });
+    if (rc != L3B_OK)
+        return rc;
+    const int rc2 = l3b_mf_solve_device(sys, method, tol, max_iters, restart_length, max_restarts, dx.ptr, hostAllZero(x, sys->ownedDofs()),
+                                        achieved_tol, iters);
+    if (rc2 != L3B_OK)
+        return rc2;
+    return guardedCtx(sys->ctx, [&] {
         dx.download(x, sys->n_dofs, sys->ctx->stream);
         cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "solve");
     });
 }
+int l3b_mf_solve_gmres(l3b_mf* sys, double tol, int restart_length, int max_restarts, int max_iters, double* x, double* achieved_tol, int* iters)
+{
+    return mfSolveHost(sys, 1, tol, max_iters, restart_length, max_restarts, x, achieved_tol, iters);
+}
 int l3b_pcg_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_apply_callback apply, l3b_allreduce_callback allreduce,
-                   void* user, const double* diag, const double* b, double* x, double tol, int max_iters, double* achieved_tol,
-                   int* iters)
+                   void* user, const double* diag, const double* b, double* x, double tol, int max_iters, int x0_is_zero,
+                   double* achieved_tol, int* iters)
 {
     return guardedCtx(ctx, [&] {
         if (apply == nullptr or n_owned > n_local or n_owned < 0)
@@ -1879,7 +2403,7 @@ int l3b_pcg_device(l3b_context* ctx, int64_t n_local, int64_t n_owned, l3b_apply
                 if (allreduce != nullptr and allreduce(user, sc, n) != 0)
                     fail(L3B_ERR_INVALID_ARG, "l3b_pcg_device: the all-reduce callback failed");
             },
-            diag, b, x, tol, max_iters, achieved_tol, iters);
+            diag, b, x, tol, max_iters, achieved_tol, iters, x0_is_zero != 0);
     });
 }
 int l3b_mf_download(l3b_mf* sys, double* diag, double* rhs)
@@ -1896,10 +2420,21 @@ int l3b_mf_apply_device(l3b_mf* sys, const double* x, double* y, int n_cols, dou
 {
     return guardedCtx(sys->ctx, [&] { mfApplyDevice(sys, x, y, n_cols, alpha, beta); });
 }
+int l3b_mf_apply_energy_device(l3b_mf* sys, const double* x, double* y, double alpha, double beta, double* energy)
+{
+    return guardedCtx(sys->ctx, [&] { mfApplyDevice(sys, x, y, 1, alpha, beta, energy); });
+}
 int l3b_mf_apply_phase_device(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta, int phases, int64_t elem_begin,
                               int64_t elem_end, double* energy)
 {
-    return guardedCtx(sys->ctx, [&] { mfApplyPhases(sys, x, y, n_cols, alpha, beta, phases, elem_begin, elem_end, energy); });
+    return guardedCtx(sys->ctx, [&] {
+        // boundary kernels: with L3B_APPLY_BOUNDARY, or with a NON-EMPTY element range that starts at element 0 — an empty range never
+        // triggers them, so a caller without border elements (range [0, 0) followed by [0, n)) does not run them twice
+        int ph = phases;
+        if ((ph & L3B_APPLY_ELEMENTS) != 0 and elem_begin == 0 and elem_end > 0)
+            ph |= L3B_APPLY_BOUNDARY;
+        mfApplyPhases(sys, x, y, n_cols, alpha, beta, ph, elem_begin, elem_end, energy);
+    });
 }
 int l3b_vec_gather(l3b_context* ctx, const double* src, int64_t ld, const int32_t* idx, int64_t n, int n_cols, double* dst)
 {
@@ -1937,22 +2472,7 @@ int l3b_mf_apply(l3b_mf* sys, const double* x, double* y, int n_cols, double alp
 }
 int l3b_mf_solve_cg(l3b_mf* sys, double tol, int max_iters, double* x, double* achieved_tol, int* iters)
 {
-    return guardedCtx(sys->ctx, [&] {
-        if (not sys->closed)
-            fail(L3B_ERR_STATE, "`solve()` was called before `endAssembly()`");
-        if (sys->n_rhs != 1)
-            fail(L3B_ERR_INVALID_ARG, "the CG driver handles one right-hand side");
-        DevBuf< double > dx(sys->n_dofs);
-        pcg(
-            sys->ctx, sys->n_dofs, sys->n_dofs,
-            [&](const double* in, double* out, double* energy) {
-                mfApplyDevice(sys, in, out, 1, 1., 0., energy);
-                return true; // p.Ap comes out of the apply
-            },
-            [](double*, int) {}, sys->diag.ptr, sys->rhs.ptr, dx.ptr, tol, max_iters, achieved_tol, iters);
-        dx.download(x, sys->n_dofs, sys->ctx->stream);
-        cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "solve");
-    });
+    return mfSolveHost(sys, 0, tol, max_iters, 1, 0, x, achieved_tol, iters);
 }
 int64_t l3b_mf_num_dofs(const l3b_mf* sys)
 {

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(cond_threads, 2) condenseKernel(const __grid_c
         __syncthreads();
         const double pkk = colv[k];
         if (not(pkk > 0.) and tid == 0)
-            atomicOr(c.status, status_degenerate_element);
+            atomicOr(c.status, status_singular_interior);
         const double piv = 1. / pkk;
         // a warp per row, a lane per column: the pivot row stays in registers over the rows
         double        rv[MAXC];

@@ -29,7 +29,9 @@ enum StatusBits : int
 {
     status_degenerate_element = 1, // "Encountered degenerate element ( |J| <= 0 )" (AssembleLocalSystem.hpp:249)
     status_graph_entry_missing = 2,
-    status_sparsity_violation  = 4 // an operator entry the compile-time probe found structurally zero was non-zero at run time
+    status_sparsity_violation  = 4, // an operator entry the compile-time probe found structurally zero was non-zero at run time
+    status_slot_overflow       = 8, // a node with more than 65535 neighbours (slot positions are 16-bit)
+    status_singular_interior   = 16 // static condensation: non-positive pivot in K_ii
 };
 
 // Everything an element kernel needs. Plain pointers and sizes only.

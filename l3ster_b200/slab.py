@@ -195,6 +195,26 @@ class Halo:
         self._p2p(y[self.n_owned_dofs:] if self.n_ghost_dofs else None, self.slab.lower, self.recv_up, self.slab.upper)
 
 
+def comm_of(ctx):
+    """the context's communicator over the torch.distributed ranks (created once; NCCL in the library, torch only ships the id)"""
+    if getattr(ctx, "_slab_comm", None) is None:
+        ctx._slab_comm = l3b.Comm.from_torch_distributed(ctx)
+    return ctx._slab_comm
+
+
+def device_halo(ctx, slab: Slab, dofs_per_node, n_owned_nodes=None, n_local_nodes=None, send_up_nodes=None):
+    """l3b_halo of the slab's dof layout: the top plane is shared with the upper rank (packed in (y, x) order = the order of the upper
+    rank's ghost block), the ghost block is owned by the lower rank"""
+    n_owned_nodes = slab.n_owned_nodes if n_owned_nodes is None else n_owned_nodes
+    n_local_nodes = slab.n_local_nodes if n_local_nodes is None else n_local_nodes
+    send_up_nodes = slab.send_up_nodes if send_up_nodes is None else send_up_nodes
+    up = (np.asarray(send_up_nodes)[:, None] * dofs_per_node + np.arange(dofs_per_node)[None, :]).ravel().astype(np.int32)
+    n_ghost = (n_local_nodes - n_owned_nodes) * dofs_per_node
+    owned = [(slab.upper, up)] if slab.upper >= 0 and len(up) else []
+    shared = [(slab.lower, 0, n_ghost)] if slab.lower >= 0 and n_ghost else []
+    return l3b.DeviceHalo(comm_of(ctx), n_owned_nodes * dofs_per_node, n_ghost, owned, shared)
+
+
 class SlabOperator:
     """Matrix-free operator of one slab with the overlap of MatrixFreeSystem::applyImpl (:1046-1122): the interior elements run
     while the Import is in flight, then the border elements, then the Export-sum. Vectors are device tensors over the local
@@ -216,98 +236,43 @@ class SlabOperator:
             self.sys = l3b.MatrixFreeSystem(ctx, self.mesh, dofs_per_node, 1, mask, None)
             self.sys.assembleProblem(kernel)
         self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-        self.comm = torch.cuda.Stream(device=dev)
         self.launches = 0
-        self.split_interior = os.environ.get("L3B_SLAB_SPLIT", "0") == "1"  # measured on 2 B200: 1.70 ms unsplit, 2.03 ms split
+        self.comm = comm_of(ctx) if slab.world > 1 else None  # collective: every rank, also an empty one
         self.diag = self.rhs = None
         if self.sys is not None:
-            # computeDiagAndRhs (MatrixFreeSystem.hpp:877-941): element contributions, Export-sum of the ghost parts, Dirichlet dofs
-            self.sys.endAssemblyBegin()
+            if slab.world > 1:
+                self.dev_halo = device_halo(ctx, slab, dofs_per_node)
+                self.sys.set_halo(self.dev_halo, slab.n_border_elems)
+            # computeDiagAndRhs (MatrixFreeSystem.hpp:877-941): element contributions, Export-sum of the ghost parts, Dirichlet dofs —
+            # one library call (l3b_mf_end_assembly)
+            self.sys.endAssembly()
             self.diag = _device_view(self.sys.device_diag, self.n_local_dofs, dev)
             self.rhs = _device_view(self.sys.device_rhs, self.n_local_dofs, dev)
-            if slab.world > 1:
-                with torch.cuda.stream(self.stream):
-                    for v in (self.diag, self.rhs):
-                        self.halo.export_y(v)
-                        self.halo.unpack_add(v)
-            self.sys.endAssemblyFinish()
-        elif slab.world > 1:
-            pass  # an empty rank has no neighbours: nothing to exchange
 
-    def solve(self, tol=1e-6, max_iters=10000):
-        """CG + native Jacobi over all ranks (benchmarks/Diffusion3D.hpp:115-118): the library's PCG driver with this operator's
-        apply and an NCCL all-reduce for the dot products. Returns (x over the local dofs, achieved residual norm, iterations)."""
-        import torch.distributed as dist
-
+    def solve(self, tol=1e-6, max_iters=10000, x0=None):
+        """CG + native Jacobi over all ranks (benchmarks/Diffusion3D.hpp:115-118): l3b_mf_solve_device — the library's PCG driver with the
+        halo'd apply and ncclAllReduce for the dot products. Returns (x over the local dofs, achieved residual norm, iterations)."""
         torch = self.torch
         dev = torch.device("cuda", torch.cuda.current_device())
-        x = torch.zeros(max(self.n_local_dofs, 1), dtype=torch.float64, device=dev)
+        x = torch.zeros(max(self.n_local_dofs, 1), dtype=torch.float64, device=dev) if x0 is None else x0
         torch.cuda.current_stream().synchronize()  # torch filled x on its own stream; the library's stream does not wait for it
-        multi = self.slab.world > 1 and dist.is_initialized()
-
-        def apply(xp, yp, energy_ptr):
-            xv = _device_view(xp, self.n_local_dofs, dev)
-            yv = _device_view(yp, self.n_local_dofs, dev)
-            self.apply(xv, yv, energy_ptr=energy_ptr)
-            return True  # p.Ap comes out of the element kernels: no dot-product pass
-
-        def allreduce(sp, n):
-            with torch.cuda.stream(self.stream):
-                dist.all_reduce(_device_view(sp, n, dev))
-
         if self.sys is None:  # empty rank (tests/EmptyPartitionTest.cpp): zero dofs, it takes part in the reductions only
-            res, it = self.ctx.pcg(0, 0, lambda xp, yp, ep: False, allreduce if multi else None, None, None, x.data_ptr(), tol, max_iters)
+            def allreduce(sp, n):
+                self.comm.allreduce_sum(sp, n)
+
+            res, it = self.ctx.pcg(0, 0, lambda xp, yp, ep: False, allreduce if self.comm is not None else None, None, None, x.data_ptr(), tol, max_iters)
             return x[:0], res, it
-        res, it = self.ctx.pcg(self.n_local_dofs, self.n_owned_dofs, apply, allreduce if multi else None, self.sys.device_diag,
-                               self.sys.device_rhs, x.data_ptr(), tol, max_iters)
+        res, it = self.sys.solve_device(x.data_ptr(), "cg", tol, max_iters, x0_is_zero=x0 is None)
         return x, res, it
 
     def apply(self, x, y, alpha=1.0, beta=0.0, energy_ptr=None):
-        """y[owned] = alpha (A x)[owned] + beta y[owned]; x[ghost] is overwritten by the Import. Asynchronous. energy_ptr: device scalar
-        that receives this rank's share of x^T A x (l3b_mf_apply_phase_device)."""
-        torch, s, sys_, halo = self.torch, self.slab, self.sys, self.halo
-        if sys_ is None:
+        """y[owned] = alpha (A x)[owned] + beta y[owned]; x[ghost] is overwritten by the Import. Asynchronous on the context stream: ONE
+        library call (l3b_mf_apply_device with the system's halo: pack + Import behind the zeroing of y, border elements, Export behind
+        the interior elements, unpack-add, Dirichlet rows). energy_ptr: device scalar that receives this rank's share of x^T A x."""
+        if self.sys is None:
             return
-        S, Cs = self.stream, self.comm
-        if s.world == 1 or (s.lower < 0 and s.upper < 0):  # no neighbours: one launch over all elements
-            with torch.cuda.stream(S):
-                sys_.apply_device(x.data_ptr(), y.data_ptr(), 1, alpha, beta, energy_ptr=energy_ptr)
-            self.launches = sys_.kernel_launches
-            return
-        # all interior elements run while the Import is in flight; the 2 MB Export is left exposed — splitting the interior in two
-        # (L3B_SLAB_SPLIT=1: one half hides the Import, one the Export) costs a third launch and measured slower
-        half = s.n_border_elems + (s.n_elems - s.n_border_elems) // 2 if self.split_interior else s.n_elems
-        xp, yp = x.data_ptr(), y.data_ptr()
-        n = 0
-        with torch.cuda.stream(S):
-            n += halo.pack(x)
-            ev_packed = S.record_event()
-        with torch.cuda.stream(Cs):
-            Cs.wait_event(ev_packed)
-            halo.import_x(x)
-            ev_imported = Cs.record_event()
-        with torch.cuda.stream(S):
-            sys_.apply_phase_device(xp, yp, l3b.APPLY_INIT, 0, 0, alpha=alpha, beta=beta)
-            n += sys_.kernel_launches
-            sys_.apply_phase_device(xp, yp, l3b.APPLY_ELEMENTS, s.n_border_elems, half, alpha=alpha, energy_ptr=energy_ptr)
-            n += sys_.kernel_launches
-            S.wait_event(ev_imported)
-            sys_.apply_phase_device(xp, yp, l3b.APPLY_ELEMENTS, 0, s.n_border_elems, alpha=alpha, energy_ptr=energy_ptr)
-            n += sys_.kernel_launches
-            ev_border = S.record_event()
-        with torch.cuda.stream(Cs):
-            Cs.wait_event(ev_border)
-            halo.export_y(y)
-            ev_exported = Cs.record_event()
-        with torch.cuda.stream(S):
-            if half < s.n_elems:
-                sys_.apply_phase_device(xp, yp, l3b.APPLY_ELEMENTS, half, s.n_elems, alpha=alpha, energy_ptr=energy_ptr)
-                n += sys_.kernel_launches
-            S.wait_event(ev_exported)
-            n += halo.unpack_add(y)
-            sys_.apply_phase_device(xp, yp, l3b.APPLY_FINISH, 0, 0, alpha=alpha, energy_ptr=energy_ptr)
-            n += sys_.kernel_launches
-        self.launches = n
+        self.sys.apply_device(x.data_ptr(), y.data_ptr(), 1, alpha, beta, energy_ptr=energy_ptr)
+        self.launches = self.sys.kernel_launches
 
 
 class _SlabAsHost:
@@ -354,8 +319,8 @@ class SlabAssembledOperator:
             assert (self.cs.prim_of[slab.n_owned_nodes:] >= 0).all(), "ghost nodes lie on element boundaries"
             send_up = self.cs.prim_of[slab.send_up_nodes] if len(slab.send_up_nodes) else slab.send_up_nodes
             pslab = dataclasses.replace(slab, n_local_nodes=len(self.cs.primary_nodes), n_owned_nodes=n_owned_prim, send_up_nodes=send_up)
-            self.halo = Halo(pslab, dofs_per_node, dev, ctx)
-            self.n_local_dofs, self.n_owned_dofs = self.halo.n_local_dofs, self.halo.n_owned_dofs
+            self.n_local_dofs, self.n_owned_dofs = pslab.n_local_nodes * dofs_per_node, pslab.n_owned_nodes * dofs_per_node
+            self.dev_halo = device_halo(ctx, pslab, dofs_per_node) if slab.world > 1 else None
             self.cs.beginAssembly()
             for k in kernels:
                 self.cs.assembleProblem(k["name"], k.get("boundary_ids", ()), field_data if l3b.kernel_info(k["name"])["n_fields"] else None,
@@ -363,8 +328,8 @@ class SlabAssembledOperator:
             self.cs.endAssembly(dofs, vals, n_owned_primary_dofs=self.n_owned_dofs)
             self.mesh, self.sys = self.cs.local_mesh, self.cs.condensed
         else:
-            self.halo = Halo(slab, dofs_per_node, dev, ctx)
-            self.n_local_dofs, self.n_owned_dofs = self.halo.n_local_dofs, self.halo.n_owned_dofs
+            self.n_local_dofs, self.n_owned_dofs = slab.n_local_nodes * dofs_per_node, slab.n_owned_nodes * dofs_per_node
+            self.dev_halo = device_halo(ctx, slab, dofs_per_node) if slab.world > 1 else None
             self.mesh = l3b.Mesh(ctx, slab.dim, slab.order, slab.verts, slab.nodes, slab.side_boundaries, slab.n_local_nodes, slab.n_owned_nodes)
             self.sys = l3b.AssembledSystem(ctx, self.mesh, dofs_per_node, 1)
             self.fields = ctx.upload_fields(field_data) if field_data is not None else None
@@ -373,62 +338,53 @@ class SlabAssembledOperator:
                 self.sys.assembleProblem(k["name"], k.get("boundary_ids", ()), self.fields if l3b.kernel_info(k["name"])["n_fields"] else None,
                                          k.get("field_inds"), k.get("dof_inds"), k.get("asm_opts", l3b.AssemblyOptions()), k.get("time", 0.0))
             self.sys.endAssemblyRanked(dofs.astype(np.int32), vals, self.n_owned_dofs)
-        self.rhs = _device_view(self.sys.device_rhs, self.n_local_dofs, dev)
+        if self.dev_halo is not None:
+            self.sys.set_halo(self.dev_halo)  # spmv_device, diag_device and the solvers now act over all ranks
+        self.rhs = _device_view(self.sys.device_rhs, self.n_local_dofs, dev).clone()
         self.diag = torch.zeros(self.n_local_dofs, dtype=torch.float64, device=dev)
         torch.cuda.current_stream().synchronize()
-        with torch.cuda.stream(self.stream):
-            self.sys.diag_device(self.diag.data_ptr())
-            if slab.world > 1:
-                for v in (self.diag, self.rhs):
-                    self.halo.export_y(v)
-                    self.halo.unpack_add(v)
+        self.sys.diag_device(self.diag.data_ptr())  # global diagonal: Export-sum of the local ones
+        if self.dev_halo is not None:
+            self.dev_halo.export_add(self.rhs.data_ptr())  # global rhs on the owned rows (a copy; the system keeps its own)
         ctx.synchronize()
 
     def recover(self, x):
         """condensed operator only: nodal solution over the slab's local nodes (n_local_nodes * dofs_per_node, host) from the condensed
         solution x over the primary dofs; the ghost primaries are refreshed from their owners first"""
-        torch = self.torch
-        with torch.cuda.stream(self.stream):
-            if self.slab.world > 1:
-                self.halo.pack(x)
-                self.halo.import_x(x)
+        if self.dev_halo is not None:
+            self.dev_halo.import_(x.data_ptr())
         self.ctx.synchronize()
         return self.cs.recover(x.cpu().numpy())[:, 0]
 
     def apply(self, x, y):
-        """y[owned] = (A x)[owned]; x[ghost] is overwritten by the Import. Asynchronous on the context stream."""
-        torch, halo = self.torch, self.halo
-        with torch.cuda.stream(self.stream):
-            if self.slab.world > 1:
-                halo.pack(x)
-                halo.import_x(x)
-            self.sys.spmv_device(x.data_ptr(), y.data_ptr())
-            if self.slab.world > 1:
-                halo.export_y(y)
-                halo.unpack_add(y)
+        """y[owned] = (A x)[owned]; x[ghost] is overwritten by the Import. Asynchronous on the context stream (l3b_asm_spmv_device with
+        the system's halo: Import x, local sparse product, Export-sum of the ghost rows)."""
+        self.sys.spmv_device(x.data_ptr(), y.data_ptr())
 
-    def solve(self, tol=1e-6, max_iters=10000, gmres=False, restart_length=250, max_restarts=39):
-        """CG (or, gmres=True, restarted GMRES) + Jacobi over all ranks on the assembled matrix (solve/BelosSolvers.hpp:116-131)"""
-        import torch.distributed as dist
-
+    def solve(self, tol=1e-6, max_iters=10000, gmres=False, restart_length=250, max_restarts=39, callbacks=False):
+        """CG (or, gmres=True, restarted GMRES) + Jacobi over all ranks on the assembled matrix (solve/BelosSolvers.hpp:116-131):
+        l3b_asm_solve_device; callbacks=True drives the same iteration through l3b_pcg_device / l3b_gmres_device with this object's
+        apply and the communicator's all-reduce (the entry points a user with an operator of their own binds to)."""
         torch = self.torch
         dev = torch.device("cuda", torch.cuda.current_device())
-        x = torch.zeros(self.n_local_dofs, dtype=torch.float64, device=dev)
+        x = torch.zeros(max(self.n_local_dofs, 1), dtype=torch.float64, device=dev)
         torch.cuda.current_stream().synchronize()  # torch filled x on its own stream; the library's stream does not wait for it
-        multi = self.slab.world > 1 and dist.is_initialized()
+        if not callbacks:
+            res, it = self.sys.solve_device(x.data_ptr(), "gmres" if gmres else "cg", tol, max_iters, restart_length, max_restarts)
+            return x[:self.n_local_dofs], res, it
+        comm = comm_of(self.ctx) if self.slab.world > 1 else None
 
         def apply(xp, yp, _energy_ptr):
-            self.apply(_device_view(xp, self.n_local_dofs, dev), _device_view(yp, self.n_local_dofs, dev))
+            self.sys.spmv_device(xp, yp)
             return False
 
         def allreduce(sp, n):
-            with torch.cuda.stream(self.stream):
-                dist.all_reduce(_device_view(sp, n, dev))
+            comm.allreduce_sum(sp, n)
 
         if gmres:
-            res, it = self.ctx.gmres(self.n_local_dofs, self.n_owned_dofs, apply, allreduce if multi else None, self.diag.data_ptr(),
+            res, it = self.ctx.gmres(self.n_local_dofs, self.n_owned_dofs, apply, allreduce if comm else None, self.diag.data_ptr(),
                                      self.rhs.data_ptr(), x.data_ptr(), tol, restart_length, max_restarts, max_iters)
         else:
-            res, it = self.ctx.pcg(self.n_local_dofs, self.n_owned_dofs, apply, allreduce if multi else None, self.diag.data_ptr(),
+            res, it = self.ctx.pcg(self.n_local_dofs, self.n_owned_dofs, apply, allreduce if comm else None, self.diag.data_ptr(),
                                    self.rhs.data_ptr(), x.data_ptr(), tol, max_iters)
-        return x, res, it
+        return x[:self.n_local_dofs], res, it

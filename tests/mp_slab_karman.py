@@ -78,8 +78,9 @@ def main():
     if rank == 0:
         whole = make_slab(xs, ys, None, P, 0, 1)
         wop = problem(ctx, whole, xs, ys)
-        xw, res_w, its_w = wop.solve(tol=TOL, max_iters=4000, gmres=True, restart_length=RESTART)
-        xd, res_d, its_d = wop.sys.solve_gmres(tol=TOL, restart_length=RESTART, max_iters=4000)  # the library's own driver, host vectors
+        # one rank: the callback-driven driver (l3b_gmres_device with this operator's apply) against the library's own (host vectors)
+        xw, res_w, its_w = wop.solve(tol=TOL, max_iters=4000, gmres=True, restart_length=RESTART, callbacks=True)
+        xd, res_d, its_d = wop.sys.solve_gmres(tol=TOL, restart_length=RESTART, max_iters=4000)
         ctx.synchronize()
         wkey = whole.lattice[:, 0] + stride * whole.lattice[:, 1]
         n_all = stride * (NY * P + 1)
