@@ -749,6 +749,83 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
         }
 #else
         // ---- E: z-projection + scatter (MatrixFreeSystem.hpp:494-537): relaxed fp64 atomics (RED), Dirichlet rows skipped
+#ifndef L3B_HEX_NO_RED_TRANSPOSE
+        // U == 4, contiguous dofs: the four dofs of a node are one 32-byte sector. A thread owns the 4 x NB results of its nodal column;
+        // issued as they are, every lane of a RED hits its own sector (32 wavefronts in the L1 per instruction). A 4 x 4 transpose over
+        // each group of four lanes (two shuffle stages) gives lane g the unknown g of the four columns of its group, so the four lanes
+        // of a group add into ONE sector: 8 wavefronts per RED instruction instead of 32.
+        if (U == 4 and vec_vals)
+        {
+            const int  g       = tid & 3;
+            const bool me_ok   = col_on and node_thr;
+            const bool odd1    = (g & 1) != 0, odd2 = (g & 2) != 0;
+#pragma unroll
+            for (int r = 0; r < NRHS; ++r)
+            {
+                double out[4][NB];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                {
+                    double v[NQ];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+                        v[q] = me_ok ? s_V[((r * U + u) * NQ + q) * (EPB * PSZ) + col_off] : 0.;
+#pragma unroll
+                    for (int k = 0; k < NB; ++k)
+                    {
+                        double acc = v[0] * tab.interp[k * NQ];
+#pragma unroll
+                        for (int q = 1; q < NQ; ++q)
+                            acc = fma(v[q], tab.interp[k * NQ + q], acc);
+                        out[u][k] = acc * args.alpha;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NB; ++k)
+                {
+                    // stage 1: lanes g ^ 1 swap the (0,1) and (2,3) index pairs; stage 2: lanes g ^ 2 swap (0,2) and (1,3)
+                    {
+                        const double s0 = odd1 ? out[0][k] : out[1][k], s1 = odd1 ? out[2][k] : out[3][k];
+                        const double r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                        if (odd1)
+                            out[0][k] = r0, out[2][k] = r1;
+                        else
+                            out[1][k] = r0, out[3][k] = r1;
+                    }
+                    {
+                        const double s0 = odd2 ? out[0][k] : out[2][k], s1 = odd2 ? out[1][k] : out[3][k];
+                        const double r0 = __shfl_xor_sync(0xffffffffu, s0, 2), r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+                        if (odd2)
+                            out[0][k] = r0, out[1][k] = r1;
+                        else
+                            out[2][k] = r0, out[3][k] = r1;
+                    }
+                }
+                // out[m][k] now holds unknown g of the column owned by lane (group base + m)
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                {
+                    const int  tm    = (tid & ~3) + m;
+                    const int  slotm = tm / CT, ccm = tm % CT;
+                    const int  cim = ccm % NQ, cjm = ccm / NQ;
+                    const bool okm = tm < EPB * CT and slotm < n_active and cim < NB and cjm < NB;
+                    const unsigned long long dbm = __shfl_sync(0xffffffffu, dirbits, m, 4);
+                    if (okm)
+                    {
+                        const uint32_t* ids = s_ids + ((it % RING) * EPB + slotm) * NN + cjm * NB + cim;
+#pragma unroll
+                        for (int k = 0; k < NB; ++k)
+                        {
+                            const long long node = ids[k * NB * NB];
+                            if (not((dbm >> (k * U + g)) & 1ull))
+                                atomicAdd(args.y + node * U + g + r * args.ld, out[m][k]);
+                        }
+                    }
+                }
+            }
+        }
+        else
+#endif
         if (col_on and node_thr)
         {
             const bool flagged = flagOf(it);

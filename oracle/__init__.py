@@ -48,7 +48,7 @@ class Oracle:
         lib.orc_ref_basis_value.restype = C.c_double
         lib.orc_ref_basis_der.restype = C.c_double
         lib.orc_boundary_jacobian.restype = C.c_double
-        for name in ("orc_mesh_cube", "orc_mesh_square", "orc_mesh_single", "orc_mesh_from_arrays", "orc_asm_create", "orc_mf_create"):
+        for name in ("orc_mesh_cube", "orc_mesh_square", "orc_mesh_single", "orc_mesh_from_arrays", "orc_mesh_from_nodes", "orc_asm_create", "orc_mf_create"):
             getattr(lib, name).restype = C.c_void_p
         lib.orc_asm_nnz.restype = C.c_longlong
 
@@ -242,6 +242,15 @@ class Oracle:
         bd = np.ascontiguousarray(bnd_domains, dtype=np.int32)
         bi = np.ascontiguousarray(bnd_ids, dtype=np.int64)
         h = self.lib.orc_mesh_from_arrays(et, len(coords), _ptr(coords), len(elems), _ptr(elems), len(be), _ptr(be), _ptr(bd), _ptr(bi), order)
+        if not h:
+            raise RuntimeError(self.lib.orc_last_error().decode())
+        return OracleMesh(self, h)
+
+    def mesh_from_nodes(self, et, order, n_nodes, elem_nodes, elem_verts):
+        """mesh of order `order` straight from element node lists + vertices (no conversion, no boundary elements)"""
+        en = np.ascontiguousarray(elem_nodes, dtype=np.uint64)
+        ev = np.ascontiguousarray(elem_verts, dtype=np.float64)
+        h = self.lib.orc_mesh_from_nodes(et, order, C.c_longlong(n_nodes), C.c_longlong(en.shape[0]), _ptr(en), _ptr(ev))
         if not h:
             raise RuntimeError(self.lib.orc_last_error().decode())
         return OracleMesh(self, h)

@@ -324,6 +324,30 @@ void* orc_mesh_single(int et, int order, const double* verts)
     });
     return ret;
 }
+// a mesh of order `order` given directly by its element node lists (lexicographic local order, numbering as mesh::convertMeshToOrder
+// would produce it) and element vertices — no conversion and no boundary elements: for parity tests at sizes where the geometric node
+// matching of the conversion (restated faithfully, and quadratic-ish in practice) would take minutes; the numbering itself is pinned at
+// small sizes by comparing the two generators
+void* orc_mesh_from_nodes(int et, int order, long long n_nodes, long long n_elems, const unsigned long long* elem_nodes, const double* elem_verts)
+{
+    void* ret = nullptr;
+    guarded([&] {
+        Mesh       m;
+        const auto t = static_cast< ElementType >(et);
+        m.et         = t;
+        m.order      = order;
+        m.n_nodes    = static_cast< std::size_t >(n_nodes);
+        m.n_elems    = static_cast< std::size_t >(n_elems);
+        const auto npe = static_cast< std::size_t >(numNodes(t, order));
+        m.elem_nodes.assign(elem_nodes, elem_nodes + m.n_elems * npe);
+        m.elem_verts.assign(elem_verts, elem_verts + m.n_elems * (1u << et) * 3);
+        m.elem_ids.resize(m.n_elems);
+        for (std::size_t e = 0; e < m.n_elems; ++e)
+            m.elem_ids[e] = static_cast< n_id_t >(e);
+        ret = new MeshHandle{std::move(m)};
+    });
+    return ret;
+}
 // an order-1 mesh given by arrays (what mesh::readMesh produces: node coordinates, volume elements with vertex lists in lexicographic
 // order, boundary elements with their domain ids; ids: volume elements 0.., boundary elements as given), converted to `order` and
 // boundary-matched — the general path of mesh/ConvertMeshToOrder.hpp, for unstructured parity tests
