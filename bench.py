@@ -500,17 +500,21 @@ def main():
             # the benchmark's solve (benchmarks/Diffusion3D.hpp:115-118): CG + native Jacobi, tol 1e-6 (absolute), x0 = 0, rhs of the source f = 1
             del yd
             op.solve(1e-6, 2)  # loads the solver's kernels
-            cg_s = float("inf")
-            for _ in range(2):  # two solves, the faster one is reported (run-to-run spread of the whole solve: ~5 %)
+            cg_s, cg_all = float("inf"), []
+            cg_sampler = ClockSampler(local_rank)
+            cg_sampler.start()
+            for _ in range(3):  # three solves, the fastest one is reported, all are listed (a 2 s solve can run into the power cap)
                 barrier()
                 t0 = time.perf_counter()
                 _, res, iters = op.solve(1e-6, args.cg_max_iters)
                 ctx.synchronize()
-                cg_s = min(cg_s, max_over_ranks(time.perf_counter() - t0))
+                cg_all.append(max_over_ranks(time.perf_counter() - t0))
+                cg_s = min(cg_s, cg_all[-1])
+            cg_clocks = cg_sampler.stop()
             cg = {"iters": int(iters), "achieved_residual": float(res), "seconds": cg_s, "ms_per_iteration": cg_s * 1e3 / max(iters, 1),
-                  "dofs_per_s": owned_total * iters / cg_s, "tol": 1e-6, "max_iters": args.cg_max_iters,
+                  "dofs_per_s": owned_total * iters / cg_s, "tol": 1e-6, "max_iters": args.cg_max_iters, "seconds_all": cg_all, "clocks": cg_clocks,
                   "what": "full CG + Jacobi solve on the device (l3b_mf_solve_device: halo'd apply with p.Ap fused + 10 vector passes + "
-                          "ncclAllReduce of the dot products per iteration), wall clock, max over ranks, faster of two solves"}
+                          "ncclAllReduce of the dot products per iteration), wall clock, max over ranks, fastest of three solves"}
         bytes_alg = mf_bytes_per_apply(n_owned, n_elems)
         gbs = bytes_alg / (k_ms * 1e-3) / 1e9
         fp64_fma = ctx.microbench(0)
