@@ -145,6 +145,33 @@ int  l3b_node_graph(int64_t n_nodes, int64_t n_elems, int nodes_per_elem, const 
 int  l3b_graph_expand(int64_t n_nodes, const int64_t* ptr, const uint32_t* nbr, int dofs_per_node, int64_t* row_ptr, int32_t* col_ind);
 void l3b_free(void* p);
 
+/* ---- partition import (mesh/PartitionMesh.hpp:322-440, dofs/NodeToDofMap.hpp:144-163, comm/ImportExport.hpp:29-72,
+ *      algsys/SparsityGraph.hpp:83-278) --------------------------------------------------------------------------------------------
+ * The reference partitions with METIS_PartMeshNodal (third party, not rebuilt); this takes the partition vectors from outside —
+ * epart[element] and, optionally, npart[node] (NULL: the lowest part among the elements holding the node) — and performs the
+ * deterministic rest exactly as the reference does: node assignment incl. the repair of "disjoint" nodes, the global renumbering that
+ * gives every rank one contiguous id range, local numbering [owned | ghost by global id], neighbour lists for the halo engine, the
+ * row-complete sparsity graph of the owned rows with the column map the neighbours' contributions induce, and the receive plan of
+ * the shared-row export. `nodes` is the global order-p connectivity (every rank builds the same object: no set-up communication).
+ * Views: extended = 0: [owned | ghost] (matrix-free system); extended = 1: [owned | ghost + extra columns] (assembled system). */
+typedef struct l3b_partition l3b_partition;
+int  l3b_partition_create(int dim, int order, int64_t n_nodes, int64_t n_elems, const uint32_t* nodes, int n_parts, const int32_t* epart,
+                          const int32_t* npart, l3b_partition** out);
+void l3b_partition_destroy(l3b_partition* p);
+/* new_id[n_nodes]: input node id -> global id (renumberNodes); npart[n_nodes] after the repair; dist[n_parts + 1]: rank r owns
+ * [dist[r], dist[r+1]). Any pointer may be NULL. */
+int l3b_partition_node_map(const l3b_partition* p, int64_t* new_id, int32_t* npart, int64_t* dist);
+/* info: [n_elems, n_border_elems, n_owned_nodes, n_local_nodes, n_owned_nbrs, n_shared_nbrs, n_nodes_in_owned_lists, first owned gid] */
+int l3b_partition_rank_info(const l3b_partition* p, int rank, int extended, int64_t info[8]);
+/* the rank's elements (global element ids, border elements first), their node lists in local ids, local id -> global id */
+int l3b_partition_rank_mesh(const l3b_partition* p, int rank, int extended, int64_t* elem_ids, uint32_t* nodes, int64_t* local_to_global);
+/* node-level description for l3b_halo_create (multiply by dofs_per_node for the dof-level lists) */
+int l3b_partition_rank_halo(const l3b_partition* p, int rank, int extended, int* owned_nbr_ranks, int64_t* owned_ptr, int32_t* owned_nodes,
+                            int* shared_nbr_ranks, int64_t* shared_offsets);
+/* extended view: node graph for l3b_asm_create (owned rows complete, ghost rows as the rank's elements fill them, extra rows empty)
+ * and, optionally, the receive plan of l3b_asm_export_shared_rows. Arrays are malloc'ed by the library; release with l3b_free. */
+int l3b_partition_rank_graph(const l3b_partition* p, int rank, int64_t** ptr, uint32_t** nbr, int64_t** export_entry_ptr, uint32_t** export_pos);
+
 /* ---- device mesh (mesh/LocalMeshView.hpp:13-57: vertices + local node ids + side → boundary id) ---------------------- */
 int  l3b_mesh_upload(l3b_context* ctx, int dim, int order, int64_t n_elems, const double* verts, const uint32_t* nodes,
                      const uint16_t* side_boundaries /* may be NULL */, int64_t n_local_nodes, int64_t n_owned_nodes, l3b_mesh** out);
@@ -185,6 +212,12 @@ int l3b_asm_spmv(l3b_asm* sys, const double* x, double* y);
  * matrix-free apply, and the global diagonal the Export-sum of the local ones. */
 int l3b_asm_spmv_device(l3b_asm* sys, const double* x, double* y);
 int l3b_asm_diag_device(l3b_asm* sys, double* diag);
+/* AssembledSystem::endAssembly's export of the shared rows (m_matrix->endAssembly(), m_rhs->endAssembly(): AssembledSystem.hpp:384-389).
+ * Needs the halo (l3b_asm_set_halo) and a system created on l3b_partition_rank_graph's graph. Every rank sends the values of its ghost
+ * rows (contiguous per owner) and the ghost block of its rhs to the owners, which add them into their rows through the receive plan
+ * (recv_entry_ptr / recv_pos of l3b_partition_rank_graph). Afterwards the owned rows are the reference's row-complete owner matrix
+ * (l3b_asm_download), ghost rows are zero, and spmv / solvers skip the Export of y. Call between assembleProblem and endAssembly. */
+int l3b_asm_export_shared_rows(l3b_asm* sys, const int64_t* recv_entry_ptr, const uint32_t* recv_pos);
 /* the halo of the row layout [owned | ghost]: l3b_asm_spmv_device, l3b_asm_diag_device and the solvers then act as the global operator
  * (Import x, local product, Export-sum of the ghost rows; dots over the owned rows, all-reduced) */
 int l3b_asm_set_halo(l3b_asm* sys, l3b_halo* halo);

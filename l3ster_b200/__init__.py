@@ -76,6 +76,8 @@ EXPORTED_SYMBOLS = [
     "l3b_comm_unique_id", "l3b_comm_create", "l3b_comm_attach", "l3b_comm_destroy", "l3b_comm_rank", "l3b_comm_size", "l3b_comm_allreduce_sum",
     "l3b_halo_create", "l3b_halo_destroy", "l3b_halo_import_begin", "l3b_halo_import_end", "l3b_halo_export_begin", "l3b_halo_export_end",
     "l3b_mf_set_halo", "l3b_asm_set_halo", "l3b_mf_solve_device", "l3b_asm_solve_device", "l3b_mf_apply_energy_device",
+    "l3b_partition_create", "l3b_partition_destroy", "l3b_partition_node_map", "l3b_partition_rank_info", "l3b_partition_rank_mesh",
+    "l3b_partition_rank_halo", "l3b_partition_rank_graph", "l3b_asm_export_shared_rows",
 ]
 
 
@@ -189,6 +191,15 @@ def lib():
     L.l3b_mf_set_halo.argtypes = [vp, vp, i64]
     L.l3b_asm_set_halo.argtypes = [vp, vp]
     L.l3b_mf_apply_energy_device.argtypes = [vp, vp, vp, dbl, dbl, vp]
+    L.l3b_partition_create.argtypes = [i32, i32, i64, i64, vp, i32, vp, vp, C.POINTER(vp)]
+    L.l3b_partition_destroy.argtypes = [vp]
+    L.l3b_partition_destroy.restype = None
+    L.l3b_partition_node_map.argtypes = [vp, vp, vp, vp]
+    L.l3b_partition_rank_info.argtypes = [vp, i32, i32, vp]
+    L.l3b_partition_rank_mesh.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.l3b_partition_rank_halo.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    L.l3b_partition_rank_graph.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.l3b_asm_export_shared_rows.argtypes = [vp, vp, vp]
     for f in ("l3b_mf_solve_device", "l3b_asm_solve_device"):
         getattr(L, f).argtypes = [vp, i32, dbl, i32, i32, i32, vp, i32, C.POINTER(dbl), C.POINTER(i32)]
     L.l3b_vec_scatter_add.argtypes = [vp, vp, i64, vp, i64, i32, vp]
@@ -623,6 +634,7 @@ class AssembledSystem:
         self.ctx, self.mesh, self.dofs_per_node, self.n_rhs = ctx, mesh, dofs_per_node, n_rhs
         self.node_ptr, self.node_nbr = graph if graph is not None else node_graph(mesh.n_local_nodes, mesh.nodes)
         self.n_dofs = mesh.n_local_nodes * dofs_per_node
+        self._halo = None
         self._h = C.c_void_p()
         ctx._chk(lib().l3b_asm_create(ctx._h, mesh._h, dofs_per_node, n_rhs, _p(self.node_ptr), _p(self.node_nbr), C.byref(self._h)))
         self.nnz = int(lib().l3b_asm_nnz(self._h))
@@ -634,6 +646,7 @@ class AssembledSystem:
         self.ctx, self.mesh, self.dofs_per_node, self.n_rhs = ctx, None, dofs_per_node, n_rhs
         self.node_ptr, self.node_nbr = graph
         self.n_dofs = n_nodes * dofs_per_node
+        self._halo = None
         self._h = C.c_void_p()
         ctx._chk(lib().l3b_crs_create(ctx._h, n_nodes, dofs_per_node, n_rhs, _p(self.node_ptr), _p(self.node_nbr), C.byref(self._h)))
         self.nnz = int(lib().l3b_asm_nnz(self._h))
@@ -665,6 +678,12 @@ class AssembledSystem:
         self.ctx._chk(lib().l3b_asm_solve_device(self._h, {"cg": 0, "gmres": 1}[method], tol, max_iters, restart_length, max_restarts, x_ptr,
                                                  int(x0_is_zero), C.byref(at), C.byref(it)))
         return at.value, it.value
+
+    def export_shared_rows(self, recv_entry_ptr, recv_pos):
+        """l3b_asm_export_shared_rows: ghost-row values and the ghost block of the rhs go to their owners (AssembledSystem.hpp:384-389)"""
+        ep = np.ascontiguousarray(recv_entry_ptr, dtype=np.int64)
+        rp = np.ascontiguousarray(recv_pos, dtype=np.uint32)
+        self.ctx._chk(lib().l3b_asm_export_shared_rows(self._h, _p(ep), _p(rp)))
 
     def set_halo(self, halo: "DeviceHalo | None"):
         """rows [owned | ghost] over more than one rank: spmv_device, diag_device and the solvers become the global operator"""

@@ -4,6 +4,7 @@
 
 #include "comm.cuh"
 #include "mesh_host.hpp"
+#include "partition_host.hpp"
 #include "mf_hex_planes.cuh"
 #include "condense.cuh"
 #include "registry.hpp"
@@ -806,6 +807,34 @@ void commAllReduce(l3b_comm* c, double* scalars, int n)
     ncclCheck(api.AllReduce(scalars, scalars, n, ncclDouble, ncclSum, c->comm, c->stream), "ncclAllReduce");
     cudaCheck(cudaEventRecord(c->ev_done, c->stream), "event record");
     cudaCheck(cudaStreamWaitEvent(S, c->ev_done, 0), "event wait");
+}
+
+// shared-row export, receive side: the neighbour's values of my rows arrive in ITS layout (node block of dpn rows, each column-dof-major
+// over its deg columns); entry (j-th received node, k-th column there) goes to position pos of my row of that node
+__global__ void rowExportAddKernel(const double* buf, const long long* entry_ptr, const int32_t* row_node, const uint32_t* pos, long long n_nodes_recv,
+                                   int dpn, const long long* node_ptr, double* vals)
+{
+    const long long n_entries = entry_ptr[n_nodes_recv];
+    for (long long t = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; t < n_entries; t += static_cast< long long >(gridDim.x) * blockDim.x)
+    {
+        long long lo = 0, hi = n_nodes_recv; // received node j of entry t: last j with entry_ptr[j] <= t
+        while (hi - lo > 1)
+        {
+            const long long mid = (lo + hi) / 2;
+            if (entry_ptr[mid] <= t)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const long long deg_s = entry_ptr[lo + 1] - entry_ptr[lo], k = t - entry_ptr[lo];
+        const long long n     = row_node[lo];
+        const long long deg_r = node_ptr[n + 1] - node_ptr[n];
+        const double*   src   = buf + static_cast< long long >(dpn) * dpn * entry_ptr[lo];
+        double*         dst   = vals + static_cast< long long >(dpn) * dpn * node_ptr[n];
+        for (int d = 0; d < dpn; ++d)
+            for (int v = 0; v < dpn; ++v)
+                atomicAdd(dst + (static_cast< long long >(d) * dpn + v) * deg_r + pos[t], src[(static_cast< long long >(d) * dpn + v) * deg_s + k]);
+    }
 }
 
 struct WorkList
@@ -1994,7 +2023,8 @@ int l3b_asm_begin_assembly(l3b_asm* sys)
     return guardedCtx(sys->ctx, [&] {
         sys->values.zero(sys->ctx->stream);
         sys->rhs.zero(sys->ctx->stream);
-        sys->open = true;
+        sys->open          = true;
+        sys->rows_exported = false;
     });
 }
 int l3b_asm_assemble(l3b_asm* sys, int kernel_id, l3b_asm_opts opts, double time, const int* dof_inds, const l3b_fields* fields,
@@ -2554,6 +2584,212 @@ int l3b_compute_norm_l2(l3b_context* ctx, l3b_mesh* mesh, int kernel_id, l3b_asm
                         const int* field_inds, const int* boundary_ids, int n_boundary_ids, double* out)
 {
     return guardedCtx(ctx, [&] { integrate(ctx, mesh, kernel_id, opts, time, fields, field_inds, boundary_ids, n_boundary_ids, true, out); });
+}
+}
+
+
+// ---- partition import (partition_host.hpp)
+struct l3b_partition
+{
+    host::Partition part;
+};
+extern "C" {
+int l3b_partition_create(int dim, int order, int64_t n_nodes, int64_t n_elems, const uint32_t* nodes, int n_parts, const int32_t* epart,
+                         const int32_t* npart, l3b_partition** out)
+{
+    return guardedCtx(nullptr, [&] {
+        if ((dim != 2 and dim != 3) or order < 1 or n_parts < 1)
+            fail(L3B_ERR_INVALID_ARG, "l3b_partition_create: invalid dimension, order or part count");
+        *out = new l3b_partition{host::makePartition(dim, order, n_nodes, n_elems, nodes, n_parts, epart, npart)};
+    });
+}
+void l3b_partition_destroy(l3b_partition* p)
+{
+    delete p;
+}
+int l3b_partition_node_map(const l3b_partition* p, int64_t* new_id, int32_t* npart, int64_t* dist)
+{
+    return guardedCtx(nullptr, [&] {
+        if (new_id)
+            std::copy(p->part.new_id.begin(), p->part.new_id.end(), new_id);
+        if (npart)
+            std::copy(p->part.npart.begin(), p->part.npart.end(), npart);
+        if (dist)
+            std::copy(p->part.dist.begin(), p->part.dist.end(), dist);
+    });
+}
+static void checkRank(const l3b_partition* p, int rank)
+{
+    if (rank < 0 or rank >= p->part.n_parts)
+        fail(L3B_ERR_INVALID_ARG, "partition: rank out of range");
+}
+int l3b_partition_rank_info(const l3b_partition* p, int rank, int extended, int64_t info[8])
+{
+    return guardedCtx(nullptr, [&] {
+        checkRank(p, rank);
+        const auto& P = p->part;
+        const auto  h = host::makeHaloLists(P, rank, extended != 0);
+        info[0]       = static_cast< int64_t >(P.ranks[rank].elems.size());
+        info[1]       = P.ranks[rank].n_border;
+        info[2]       = P.nOwned(rank);
+        info[3]       = P.nLocal(rank, extended != 0);
+        info[4]       = static_cast< int64_t >(h.owned_nbrs.size());
+        info[5]       = static_cast< int64_t >(h.shared_nbrs.size());
+        info[6]       = h.owned_ptr.back();
+        info[7]       = P.dist[rank];
+    });
+}
+int l3b_partition_rank_mesh(const l3b_partition* p, int rank, int extended, int64_t* elem_ids, uint32_t* nodes, int64_t* local_to_global)
+{
+    return guardedCtx(nullptr, [&] {
+        checkRank(p, rank);
+        const auto& P  = p->part;
+        const auto& R  = P.ranks[rank];
+        const bool  ex = extended != 0;
+        for (size_t i = 0; i < R.elems.size(); ++i)
+        {
+            if (elem_ids)
+                elem_ids[i] = R.elems[i];
+            if (nodes)
+                for (int a = 0; a < P.nn; ++a)
+                    nodes[i * P.nn + a] = static_cast< uint32_t >(P.localId(rank, ex, P.new_id[P.nodes[R.elems[i] * P.nn + a]]));
+        }
+        if (local_to_global)
+        {
+            const long long no = P.nOwned(rank);
+            for (long long l = 0; l < no; ++l)
+                local_to_global[l] = P.dist[rank] + l;
+            const auto& g = P.ghostsOf(rank, ex);
+            std::copy(g.begin(), g.end(), local_to_global + no);
+        }
+    });
+}
+int l3b_partition_rank_halo(const l3b_partition* p, int rank, int extended, int* owned_nbr_ranks, int64_t* owned_ptr, int32_t* owned_nodes,
+                            int* shared_nbr_ranks, int64_t* shared_offsets)
+{
+    return guardedCtx(nullptr, [&] {
+        checkRank(p, rank);
+        const auto h = host::makeHaloLists(p->part, rank, extended != 0);
+        std::copy(h.owned_nbrs.begin(), h.owned_nbrs.end(), owned_nbr_ranks);
+        std::copy(h.owned_ptr.begin(), h.owned_ptr.end(), owned_ptr);
+        std::copy(h.owned_nodes.begin(), h.owned_nodes.end(), owned_nodes);
+        std::copy(h.shared_nbrs.begin(), h.shared_nbrs.end(), shared_nbr_ranks);
+        std::copy(h.shared_off.begin(), h.shared_off.end(), shared_offsets);
+    });
+}
+int l3b_partition_rank_graph(const l3b_partition* p, int rank, int64_t** ptr, uint32_t** nbr, int64_t** export_entry_ptr, uint32_t** export_pos)
+{
+    return guardedCtx(nullptr, [&] {
+        checkRank(p, rank);
+        const auto g = host::makeRankGraph(p->part, rank);
+        const auto dup = [](const auto& v, auto** out) {
+            using T = std::remove_pointer_t< std::remove_pointer_t< decltype(out) > >;
+            *out    = static_cast< T* >(std::malloc(std::max< size_t >(1, v.size()) * sizeof(T)));
+            if (not *out)
+                fail(L3B_ERR_INVALID_ARG, "out of host memory");
+            for (size_t i = 0; i < v.size(); ++i)
+                (*out)[i] = static_cast< T >(v[i]);
+        };
+        dup(g.ptr, ptr);
+        dup(g.nbr, nbr);
+        if (export_entry_ptr and export_pos)
+        {
+            const auto h    = host::makeHaloLists(p->part, rank, true);
+            const auto plan = host::makeRowExportPlan(p->part, rank, h, g);
+            dup(plan.entry_ptr, export_entry_ptr);
+            dup(plan.pos, export_pos);
+        }
+    });
+}
+// Tpetra FECrsMatrix::endAssembly / FEMultiVector::endAssembly as AssembledSystem::endAssembly calls them (AssembledSystem.hpp:384-389):
+// the values of the shared (ghost) rows and the ghost block of the rhs go to the owners and are ADDED there; afterwards the owned rows
+// are complete (the reference's row-complete owner matrix, what l3b_asm_download returns) and the ghost rows are zero.
+int l3b_asm_export_shared_rows(l3b_asm* sys, const int64_t* recv_entry_ptr, const uint32_t* recv_pos)
+{
+    return guardedCtx(sys->ctx, [&] {
+        auto* const h = sys->halo;
+        if (not sys->open)
+            fail(L3B_ERR_STATE, "l3b_asm_export_shared_rows: call between `assembleProblem()` and `endAssembly()`");
+        if (sys->rows_exported)
+            fail(L3B_ERR_STATE, "l3b_asm_export_shared_rows was called twice");
+        if (h == nullptr)
+            fail(L3B_ERR_COMM, "l3b_asm_export_shared_rows needs the halo of the row layout (l3b_asm_set_halo)");
+        const int       dpn = sys->dpn;
+        const long long bs  = static_cast< long long >(dpn) * dpn;
+        if (h->n_owned % dpn != 0)
+            fail(L3B_ERR_INVALID_ARG, "row export: the halo is not node-blocked");
+        const long long n_owned_nodes = h->n_owned / dpn;
+        const auto&     np            = sys->node_ptr_host;
+        // rhs first: the ordinary Export-sum of the ghost block
+        haloExportBegin(h, sys->rhs.ptr, sys->n_rhs);
+        haloExportEnd(h, sys->rhs.ptr, sys->n_rhs);
+        if (h->active())
+        {
+            const auto&     api = ncclApi();
+            auto* const     c   = h->comm;
+            const auto      S   = sys->ctx->stream;
+            const long long n_recv_nodes = h->owned_ptr.back() / dpn;
+            // receive buffer + device copies of the plan
+            const long long n_entries = n_recv_nodes > 0 ? recv_entry_ptr[n_recv_nodes] : 0;
+            DevBuf< double >    buf(std::max< long long >(1, n_entries * bs));
+            DevBuf< long long > d_ptr(n_recv_nodes + 1);
+            DevBuf< int32_t >   d_row(std::max< long long >(1, n_recv_nodes));
+            DevBuf< uint32_t >  d_pos(std::max< long long >(1, n_entries));
+            std::vector< int32_t > row_node(n_recv_nodes);
+            {
+                std::vector< int32_t > idx(h->owned_ptr.back());
+                h->owned_idx.download(idx.data(), idx.size(), S);
+                cudaCheck(cudaStreamSynchronize(S), "halo index read");
+                for (long long j = 0; j < n_recv_nodes; ++j)
+                {
+                    row_node[j] = idx[j * dpn] / dpn;
+                    for (int d = 0; d < dpn; ++d)
+                        if (idx[j * dpn + d] != row_node[j] * dpn + d)
+                            fail(L3B_ERR_INVALID_ARG, "row export: the halo is not node-blocked");
+                }
+            }
+            static_assert(sizeof(long long) == sizeof(int64_t));
+            if (n_recv_nodes > 0)
+                d_ptr.upload(reinterpret_cast< const long long* >(recv_entry_ptr), n_recv_nodes + 1, S);
+            else
+                d_ptr.zero(S);
+            d_row.upload(row_node.data(), row_node.size(), S);
+            d_pos.upload(recv_pos, n_entries, S);
+            cudaCheck(cudaEventRecord(h->ev_ready, S), "event record");
+            cudaCheck(cudaStreamWaitEvent(c->stream, h->ev_ready, 0), "event wait");
+            ncclCheck(api.GroupStart(), "ncclGroupStart");
+            for (size_t k = 0; k < h->owned_nbrs.size(); ++k)
+            {
+                const long long j0 = h->owned_ptr[k] / dpn, j1 = h->owned_ptr[k + 1] / dpn;
+                const long long cnt = (recv_entry_ptr[j1] - recv_entry_ptr[j0]) * bs;
+                if (cnt > 0)
+                    ncclCheck(api.Recv(buf.ptr + recv_entry_ptr[j0] * bs, cnt, ncclDouble, h->owned_nbrs[k], c->comm, c->stream), "ncclRecv");
+            }
+            for (size_t j = 0; j < h->shared_nbrs.size(); ++j)
+            {
+                const long long n0 = n_owned_nodes + h->shared_off[j] / dpn, n1 = n_owned_nodes + h->shared_off[j + 1] / dpn;
+                const long long cnt = (np[n1] - np[n0]) * bs;
+                if (cnt > 0)
+                    ncclCheck(api.Send(sys->values.ptr + np[n0] * bs, cnt, ncclDouble, h->shared_nbrs[j], c->comm, c->stream), "ncclSend");
+            }
+            ncclCheck(api.GroupEnd(), "ncclGroupEnd");
+            cudaCheck(cudaEventRecord(h->ev_done, c->stream), "event record");
+            cudaCheck(cudaStreamWaitEvent(S, h->ev_done, 0), "event wait");
+            if (n_entries > 0)
+                rowExportAddKernel<<< gridFor(n_entries), 256, 0, S >>>(buf.ptr, d_ptr.ptr, d_row.ptr, d_pos.ptr, n_recv_nodes, dpn, sys->node_ptr.ptr,
+                                                                       sys->values.ptr);
+            cudaCheck(cudaGetLastError(), "row export");
+            // the ghost rows are spent
+            const long long tail = (np[sys->n_nodes] - np[n_owned_nodes]) * bs;
+            if (tail > 0)
+                cudaCheck(cudaMemsetAsync(sys->values.ptr + np[n_owned_nodes] * bs, 0, tail * sizeof(double), S), "memset");
+            const long long n_ghost_dofs = sys->n_dofs - h->n_owned;
+            for (int col = 0; col < sys->n_rhs and n_ghost_dofs > 0; ++col)
+                cudaCheck(cudaMemsetAsync(sys->rhs.ptr + h->n_owned + col * sys->n_dofs, 0, n_ghost_dofs * sizeof(double), S), "memset");
+            cudaCheck(cudaStreamSynchronize(S), "row export"); // the staging buffers die here
+        }
+        sys->rows_exported = true;
+    });
 }
 }
 

@@ -205,6 +205,8 @@ def comm_of(ctx):
 def device_halo(ctx, slab: Slab, dofs_per_node, n_owned_nodes=None, n_local_nodes=None, send_up_nodes=None):
     """l3b_halo of the slab's dof layout: the top plane is shared with the upper rank (packed in (y, x) order = the order of the upper
     rank's ghost block), the ghost block is owned by the lower rank"""
+    if hasattr(slab, "owned_halo") and n_owned_nodes is None:  # a partition.RankView: general neighbour lists
+        return slab.device_halo(comm_of(ctx), dofs_per_node)
     n_owned_nodes = slab.n_owned_nodes if n_owned_nodes is None else n_owned_nodes
     n_local_nodes = slab.n_local_nodes if n_local_nodes is None else n_local_nodes
     send_up_nodes = slab.send_up_nodes if send_up_nodes is None else send_up_nodes
@@ -331,20 +333,31 @@ class SlabAssembledOperator:
             self.n_local_dofs, self.n_owned_dofs = slab.n_local_nodes * dofs_per_node, slab.n_owned_nodes * dofs_per_node
             self.dev_halo = device_halo(ctx, slab, dofs_per_node) if slab.world > 1 else None
             self.mesh = l3b.Mesh(ctx, slab.dim, slab.order, slab.verts, slab.nodes, slab.side_boundaries, slab.n_local_nodes, slab.n_owned_nodes)
-            self.sys = l3b.AssembledSystem(ctx, self.mesh, dofs_per_node, 1)
+            # a partition.RankView in the extended numbering: the reference's row-complete owner matrix — the graph of the owned rows
+            # holds every rank's contributions (SparsityGraph.hpp:83-278) and the shared rows are export-added at endAssembly
+            # (AssembledSystem.hpp:384-389); otherwise every rank keeps the ghost rows its elements filled
+            self.row_export = bool(getattr(slab, "extended", False))
+            graph = plan = None
+            if self.row_export:
+                graph, plan = slab.part.rank_graph(slab.rank)
+            self.sys = l3b.AssembledSystem(ctx, self.mesh, dofs_per_node, 1, graph)
+            if self.dev_halo is not None:
+                self.sys.set_halo(self.dev_halo)  # spmv_device, diag_device and the solvers now act over all ranks
             self.fields = ctx.upload_fields(field_data) if field_data is not None else None
             self.sys.beginAssembly()
             for k in kernels:
                 self.sys.assembleProblem(k["name"], k.get("boundary_ids", ()), self.fields if l3b.kernel_info(k["name"])["n_fields"] else None,
                                          k.get("field_inds"), k.get("dof_inds"), k.get("asm_opts", l3b.AssemblyOptions()), k.get("time", 0.0))
+            if self.row_export and self.dev_halo is not None:
+                self.sys.export_shared_rows(*plan)
             self.sys.endAssemblyRanked(dofs.astype(np.int32), vals, self.n_owned_dofs)
-        if self.dev_halo is not None:
-            self.sys.set_halo(self.dev_halo)  # spmv_device, diag_device and the solvers now act over all ranks
+        if self.dev_halo is not None and self.sys._halo is None:
+            self.sys.set_halo(self.dev_halo)
         self.rhs = _device_view(self.sys.device_rhs, self.n_local_dofs, dev).clone()
         self.diag = torch.zeros(self.n_local_dofs, dtype=torch.float64, device=dev)
         torch.cuda.current_stream().synchronize()
-        self.sys.diag_device(self.diag.data_ptr())  # global diagonal: Export-sum of the local ones
-        if self.dev_halo is not None:
+        self.sys.diag_device(self.diag.data_ptr())  # global diagonal: Export-sum of the local ones (or the complete owned rows')
+        if self.dev_halo is not None and not getattr(self, "row_export", False):
             self.dev_halo.export_add(self.rhs.data_ptr())  # global rhs on the owned rows (a copy; the system keeps its own)
         ctx.synchronize()
 

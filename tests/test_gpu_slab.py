@@ -129,6 +129,21 @@ def test_two_process_karman_assembled_gmres():
     assert "SLAB_KARMAN_OK" in out.stdout
 
 
+@pytest.mark.parametrize("nproc", [1, 2, 4])
+def test_partition_import_worker(nproc):
+    """tests/mp_partition.py: ragged external partition -> views, halo'd matrix-free apply + CG, row-complete assembled matrix with the
+    shared-row export, all against the oracle's single-rank objects (one rank: the same code with an empty halo)"""
+    import torch
+
+    if torch.cuda.device_count() < nproc:
+        pytest.skip(f"needs {nproc} GPUs (gpurun --gpus {nproc})")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mp_partition.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+                          "--master-port", str(29541 + nproc), script], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "PARTITION_OK" in out.stdout
+
+
 def test_one_process_karman_worker():
     """the same worker on one rank (one GPU): the callback-driven GMRES against the library's own driver"""
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mp_slab_karman.py")
