@@ -445,6 +445,7 @@ def main():
         dist.broadcast(ref, 0)
         rel = ((sums - ref).abs() / ref.abs()).cpu().numpy()
         return {"ok": bool((rel < 1e-12).all()), "rel_diff_yy": float(rel[0]), "rel_diff_xy": float(rel[1]), "tolerance": 1e-12,
+                "yy": float(sums[0]), "xy": float(sums[1]), "yy_one_rank": float(ref[0]), "xy_one_rank": float(ref[1]),
                 "mesh": f"{n}^3 hex p=4 cut into {world} z-slabs vs the same cube on one rank",
                 "what": "||A x||^2 and x.A x of a seeded global x, all-reduced over the owned dofs"}
 

@@ -137,6 +137,70 @@ struct AdiabaticBC2D
     }
 };
 
+// 3-D boundary equation kernel on the dofs (T, qx, qy, qz) of the diffusion system. Equation 0: adiabatic wall q.n = 0 — the 3-D form
+// of tests/Kernels.hpp:120-128. Equation 1: a Robin condition written with DERIVATIVE operators and the normal, dT/dn + h T = h T_inf(x)
+// — the 3-D form of the Neumann kernel of examples/06-matrix-free/source.cpp:79-86 plus a point-dependent right-hand side, so that
+// A0, A1..A3, the normal and the physical point of the boundary quadrature are all exercised.
+struct RobinBC3D
+{
+    template < typename In, typename Out >
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
+    {
+        const auto& [vals, ders, point, normal] = in;
+        auto& [operators, rhs]                  = out;
+        auto& [A0, A1, A2, A3]                  = operators;
+        constexpr double h = 0.5;
+        A0(0, 1) = normal[0];
+        A0(0, 2) = normal[1];
+        A0(0, 3) = normal[2];
+        A0(1, 0) = h;
+        A1(1, 0) = normal[0];
+        A2(1, 0) = normal[1];
+        A3(1, 0) = normal[2];
+        rhs(1, 0) = h * (1. + point.space.x() + 2. * point.space.y() - point.space.z());
+    }
+};
+
+// benchmarks/Kernels.hpp:3-65 — the incompressible Navier-Stokes kernel of LocalAssemblyBenchmarks.cpp:41-87 (velocity-vorticity-pressure
+// first-order system: U = 7 unknowns (u, v, w, p, ox, oy, oz), E = 8 equations, linearised about the n_fields = 7 nodal fields)
+struct NS3D
+{
+    template < typename In, typename Out >
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
+    {
+        const auto& [vals, ders, point]             = in;
+        const auto& [u, v, w, p, ox, oy, oz]        = vals;
+        const auto& [x_ders, y_ders, z_ders]        = ders;
+        const auto& [ux, vx, wx, px, oxx, oyx, ozx] = x_ders;
+        const auto& [uy, vy, wy, py, oxy, oyy, ozy] = y_ders;
+        const auto& [uz, vz, wz, pz, oxz, oyz, ozz] = z_ders;
+        auto& [operators, rhs] = out;
+        auto& [A0, A1, A2, A3] = operators;
+        constexpr double Re_inv = 1e-3;
+        // momentum (rows 0-2): convection linearised about the fields, pressure gradient, curl of the vorticity
+        A0(0, 0) = ux, A0(0, 1) = uy, A0(0, 2) = uz;
+        A0(1, 0) = vx, A0(1, 1) = vy, A0(1, 2) = vz;
+        A0(2, 0) = wx, A0(2, 1) = wy, A0(2, 2) = wz;
+        A1(0, 0) = u, A1(1, 1) = u, A1(2, 2) = u;
+        A2(0, 0) = v, A2(1, 1) = v, A2(2, 2) = v;
+        A3(0, 0) = w, A3(1, 1) = w, A3(2, 2) = w;
+        A1(0, 3) = 1., A2(0, 3) = 1., A3(0, 3) = 1.;
+        A2(0, 6) = Re_inv, A3(0, 5) = -Re_inv;
+        A1(1, 6) = -Re_inv, A3(1, 4) = Re_inv;
+        A1(2, 5) = Re_inv, A2(2, 4) = -Re_inv;
+        // vorticity definition (rows 3-5)
+        A0(3, 4) = 1., A2(3, 2) = 1., A3(3, 1) = -1.;
+        A0(4, 5) = 1., A1(4, 2) = -1., A3(4, 0) = 1.;
+        A0(5, 6) = 1., A1(5, 1) = 1., A2(5, 0) = -1.;
+        // continuity (row 6), solenoidal vorticity (row 7)
+        A1(6, 0) = 1., A2(6, 1) = 1., A3(6, 2) = 1.;
+        A1(7, 4) = 1., A2(7, 5) = 1., A3(7, 6) = 1.;
+        rhs(0, 0) = u * ux + v * uy + w * uz;
+        rhs(1, 0) = u * vx + v * vy + w * vz;
+        rhs(2, 0) = u * wx + v * wy + w * wz;
+    }
+};
+
 // examples/02-diffusion-2D/source.cpp:45-67
 struct Example02Domain
 {
@@ -264,69 +328,6 @@ struct KarmanOutlet // on the dofs (u, v, p)
         A0(1, 2) = -ny;
         A1(1, 1) = karman::nu * nx;
         A2(1, 1) = karman::nu * ny;
-    }
-};
-
-// benchmarks/Kernels.hpp:3-65
-struct NS3D
-{
-    template < typename In, typename Out >
-    L3B_HD constexpr void operator()(const In& in, Out& out) const
-    {
-        const auto& [vals, ders, point]             = in;
-        const auto& [u, v, w, p, ox, oy, oz]        = vals;
-        const auto& [x_ders, y_ders, z_ders]        = ders;
-        const auto& [ux, vx, wx, px, oxx, oyx, ozx] = x_ders;
-        const auto& [uy, vy, wy, py, oxy, oyy, ozy] = y_ders;
-        const auto& [uz, vz, wz, pz, oxz, oyz, ozz] = z_ders;
-        auto& [operators, rhs] = out;
-        auto& [A0, A1, A2, A3] = operators;
-        constexpr double Re_inv = 1e-3;
-        A0(0, 0) = ux;
-        A0(0, 1) = uy;
-        A0(0, 2) = uz;
-        A0(1, 0) = vx;
-        A0(1, 1) = vy;
-        A0(1, 2) = vz;
-        A0(2, 0) = wx;
-        A0(2, 1) = wy;
-        A0(2, 2) = wz;
-        A0(3, 4) = 1.;
-        A0(4, 5) = 1.;
-        A0(5, 6) = 1.;
-        A1(0, 0) = u;
-        A1(0, 3) = 1.;
-        A1(1, 1) = u;
-        A1(1, 6) = -Re_inv;
-        A1(2, 2) = u;
-        A1(2, 5) = Re_inv;
-        A1(4, 2) = -1.;
-        A1(5, 1) = 1.;
-        A1(6, 0) = 1.;
-        A1(7, 4) = 1.;
-        A2(0, 0) = v;
-        A2(0, 3) = 1.;
-        A2(0, 6) = Re_inv;
-        A2(1, 1) = v;
-        A2(2, 2) = v;
-        A2(2, 4) = -Re_inv;
-        A2(3, 2) = 1.;
-        A2(5, 0) = -1.;
-        A2(6, 1) = 1.;
-        A2(7, 5) = 1.;
-        A3(0, 0) = w;
-        A3(0, 3) = 1.;
-        A3(0, 5) = -Re_inv;
-        A3(1, 1) = w;
-        A3(1, 4) = Re_inv;
-        A3(2, 2) = w;
-        A3(3, 1) = -1.;
-        A3(4, 0) = 1.;
-        A3(6, 2) = 1.;
-        A3(7, 6) = 1.;
-        rhs[0] = u * ux + v * uy + w * uz;
-        rhs[1] = u * vx + v * vy + w * vz;
-        rhs[2] = u * wx + v * wy + w * wz;
     }
 };
 

@@ -117,6 +117,25 @@ void adiabatic_bc_2D(In in, Out out)
     A0(0, 2) = in.normal[1];
 }
 
+// 3-D boundary kernel on (T, qx, qy, qz): row 0 the 3-D form of tests/Kernels.hpp:120-128 (adiabatic wall), row 1 a Robin condition
+// in derivative form, the 3-D form of examples/06-matrix-free/source.cpp:79-86 with a point-dependent right-hand side
+void robin_bc_3D(In in, Out out)
+{
+    auto& A0 = out.operators[0];
+    auto& A1 = out.operators[1];
+    auto& A2 = out.operators[2];
+    auto& A3 = out.operators[3];
+    constexpr double h = 0.5;
+    A0(0, 1)   = in.normal[0];
+    A0(0, 2)   = in.normal[1];
+    A0(0, 3)   = in.normal[2];
+    A0(1, 0)   = h;
+    A1(1, 0)   = in.normal[0];
+    A2(1, 0)   = in.normal[1];
+    A3(1, 0)   = in.normal[2];
+    out.rhs[1] = h * (1. + in.space[0] + 2. * in.space[1] - in.space[2]);
+}
+
 // examples/02-diffusion-2D/source.cpp:45-67
 void example02_domain(In, Out out)
 {
@@ -354,6 +373,7 @@ std::map< std::string, Kernel > makeRegistry()
     r["diffusion_kernel_3D_var"] = Kernel{{3, 7, 4, 1, 1}, false, diffusion_kernel_3D_var};
     r["bench_diffusion3d"]       = Kernel{{3, 7, 4, 0, 1}, false, diffusion_kernel_3D< true >};
     r["adiabatic_bc_2D"]         = Kernel{{2, 1, 3, 0, 1}, true, adiabatic_bc_2D};
+    r["robin_bc_3D"]             = Kernel{{3, 2, 4, 0, 1}, true, robin_bc_3D};
     r["example02_domain"]        = Kernel{{2, 4, 3, 0, 1}, false, example02_domain};
     r["example02_bc"]            = Kernel{{2, 1, 3, 0, 1}, true, example02_bc};
     r["ns3d_kernel"]             = Kernel{{3, 8, 7, 7, 1}, false, ns3d_kernel};

@@ -28,6 +28,10 @@ CASES = [
     ("diffusion_kernel_2D", "diffusion_kernel_2D", 2, 3, 4, l3b.AssemblyOptions(value_order=2), 2),
     ("diffusion_kernel_2D_var", "diffusion_kernel_2D_var", 2, 3, 3, l3b.AssemblyOptions(), 2),
     ("dense_probe_2D", "dense_probe_2D", 2, 4, 2, l3b.AssemblyOptions(value_order=1, derivative_order=1), 1),
+    # BASELINE configs[4], benchmarks/LocalAssemblyBenchmarks.cpp:41-87: NS3D, U = 7, E = 8, n_fields = 7, QO = 4p - 1 (= AssemblyOptions{1, 1})
+    ("ns3d_kernel", "ns3d_kernel", 3, 2, 2, l3b.AssemblyOptions(value_order=1, derivative_order=1), 1),
+    ("ns3d_kernel", "ns3d_kernel", 3, 2, 3, l3b.AssemblyOptions(), 1),
+    ("ns3d_kernel", "ns3d_kernel", 3, 1, 4, l3b.AssemblyOptions(value_order=1, derivative_order=1), 1),
 ]
 
 
@@ -294,3 +298,32 @@ def test_assembly_state_machine_and_argument_errors(ctx):
         mf.assembleProblem("example02_domain")
     with pytest.raises(l3b.L3BError):  # 2 columns into a 1-rhs system
         mf.apply(np.zeros((pm.n_nodes * 3, 2)))
+
+
+@pytest.mark.parametrize("p", [2, 4])
+def test_3d_boundary_equation_kernel_assembled(ctx, p):
+    """a 3-D boundary EQUATION kernel (robin_bc_3D: adiabatic row + Robin row with derivative operators, normal and boundary point)
+    assembled with the domain kernel into one CRS matrix, on a distorted hex mesh: assembleLocalSystem(BoundaryElementView),
+    AssembleLocalSystem.hpp:258-280 + mapBoundary"""
+    pm = PairedMesh(3, default_dists(3, 2), p)
+    mesh = pm.upload(ctx)
+    U = 4
+    bnd = [1, 2, 4, 5]
+    s = l3b.AssembledSystem(ctx, mesh, U)
+    s.beginAssembly()
+    s.assembleProblem("bench_diffusion3d")
+    s.assembleProblem("robin_bc_3D", boundary_ids=bnd)
+    so = pm.orc.assembled_system(U)
+    so.assemble("bench_diffusion3d", n_threads=4)
+    vd, rd = so.get()
+    vd, rd = vd.copy(), rd.copy()
+    so.assemble("robin_bc_3D", boundary_ids=bnd, n_threads=4)
+    v_o, r_o = so.get()
+    v_g, r_g = s.download()
+    assert rel_err(v_g, v_o) < TOL and rel_err(r_g, r_o) < TOL
+    assert np.linalg.norm(v_o - vd) > 1e-3 * np.linalg.norm(vd) and np.linalg.norm(r_o - rd) > 0  # the boundary kernel contributes
+    # the boundary kernel alone (its contribution is not hidden behind the domain kernel's larger entries)
+    s.beginAssembly()
+    s.assembleProblem("robin_bc_3D", boundary_ids=bnd)
+    v_b, r_b = s.download()
+    assert rel_err(v_b, v_o - vd) < 1e-10 and rel_err(r_b, r_o - rd) < 1e-10

@@ -46,6 +46,10 @@ CASES = [
     ("diffusion_kernel_2D_var", "diffusion_kernel_2D_var", 2, 3, 3, l3b.AssemblyOptions(), 2),
     ("dense_probe_2D", "dense_probe_2D", 2, 4, 2, l3b.AssemblyOptions(value_order=1, derivative_order=1), 1),
     ("example02_domain", "example02_domain", 2, 4, 4, l3b.AssemblyOptions(), 1),
+    # benchmarks/LocalOperatorEvaluationBenchmarks.cpp / LocalAssemblyBenchmarks.cpp:41-87: NS3D, U = 7, E = 8, n_fields = 7
+    ("ns3d_kernel", "ns3d_kernel", 3, 2, 2, l3b.AssemblyOptions(value_order=1, derivative_order=1), 1),
+    ("ns3d_kernel", "ns3d_kernel", 3, 2, 3, l3b.AssemblyOptions(), 1),
+    ("ns3d_kernel", "ns3d_kernel", 3, 1, 4, l3b.AssemblyOptions(), 1),
 ]
 
 
@@ -291,3 +295,33 @@ def test_apply_energy_is_x_dot_Ax(ctx, case, strategy):
     s.apply_phase_device(x.data_ptr(), y.data_ptr(), l3b.APPLY_FINISH, 0, 0, energy_ptr=e.data_ptr())
     ctx.synchronize()
     assert abs(e.item() - xAx) <= 1e-12 * abs(xAx)
+
+
+@pytest.mark.parametrize("p", [2, 3])
+def test_3d_boundary_equation_kernel_matrix_free(ctx, p):
+    """robin_bc_3D next to the domain kernel in the matrix-free operator (boundary kernels take evaluateLocalOperator on the parent
+    element, MatrixFreeSystem.hpp:539-551, 690-709): apply, diag and rhs against the oracle, with Dirichlet dofs"""
+    pm = PairedMesh(3, default_dists(3, 2), p)
+    mesh = pm.upload(ctx)
+    U = 4
+    bnd = [1, 2, 4, 5]
+    mask, dvals = _dirichlet(pm, U, [3, 6], [0], 1, 5)
+    s = l3b.MatrixFreeSystem(ctx, mesh, U, 1, mask, dvals)
+    s.assembleProblem("bench_diffusion3d")
+    s.assembleProblem("robin_bc_3D", boundary_ids=bnd)
+    s.endAssembly()
+    so = pm.orc.matrix_free_system(U, 1, mask, dvals)
+    so.add_kernel("bench_diffusion3d")
+    so.add_kernel("robin_bc_3D", boundary_ids=bnd)
+    diag_o, rhs_o = so.init(n_threads=4)
+    diag_g, rhs_g = s.download()
+    assert rel_err(diag_g, diag_o) < TOL and rel_err(rhs_g, rhs_o) < TOL
+    x = np.random.default_rng(2).uniform(-1, 1, size=(pm.n_nodes * U, 1))
+    assert rel_err(s.apply(x), so.apply(x, n_threads=4)) < TOL
+    # and the boundary kernel's share alone
+    sb = l3b.MatrixFreeSystem(ctx, mesh, U, 1, None, None)
+    sb.assembleProblem("robin_bc_3D", boundary_ids=bnd)
+    sb.endAssembly()
+    sob = pm.orc.matrix_free_system(U, 1, None, None)
+    sob.add_kernel("robin_bc_3D", boundary_ids=bnd)
+    assert rel_err(sb.apply(x), sob.apply(x, n_threads=4)) < TOL
