@@ -218,17 +218,16 @@ def device_halo(ctx, slab: Slab, dofs_per_node, n_owned_nodes=None, n_local_node
 
 
 class SlabOperator:
-    """Matrix-free operator of one slab with the overlap of MatrixFreeSystem::applyImpl (:1046-1122): the interior elements run
-    while the Import is in flight, then the border elements, then the Export-sum. Vectors are device tensors over the local
-    dofs [owned | ghost]."""
+    """Matrix-free operator of one rank (a Slab, or a partition.RankView of an imported partition) with the overlap of
+    MatrixFreeSystem::applyImpl (:1046-1122) inside the library: Import behind the zeroing of y, border elements, Export behind the
+    interior elements. Vectors are device tensors over the local dofs [owned | ghost]."""
 
     def __init__(self, ctx, slab: Slab, dofs_per_node, kernel, dirichlet_boundary_ids=()):
         import torch
 
         self.torch, self.ctx, self.slab, self.dpn = torch, ctx, slab, dofs_per_node
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.halo = Halo(slab, dofs_per_node, dev, ctx)
-        self.n_local_dofs, self.n_owned_dofs = self.halo.n_local_dofs, self.halo.n_owned_dofs
+        self.n_local_dofs, self.n_owned_dofs = slab.n_local_nodes * dofs_per_node, slab.n_owned_nodes * dofs_per_node
         self.mesh = self.sys = None
         if slab.n_elems > 0:
             self.mesh = l3b.Mesh(ctx, slab.dim, slab.order, slab.verts, slab.nodes, slab.side_boundaries, slab.n_local_nodes, slab.n_owned_nodes)
