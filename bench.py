@@ -449,6 +449,70 @@ def main():
                 "mesh": f"{n}^3 hex p=4 cut into {world} z-slabs vs the same cube on one rank",
                 "what": "||A x||^2 and x.A x of a seeded global x, all-reduced over the owned dofs"}
 
+    def ragged_partition_parity():
+        """the general-partition path at this N (partition import, general neighbour lists, shared-row export): a 4^3 hex p=4 cube cut
+        by a ragged, non-slab epart; matrix-free apply and the row-complete assembled matrix (l3b_asm_export_shared_rows) against the
+        same objects on one rank (rank 0), relative differences"""
+        from l3ster_b200.partition import Partition, bisection_epart
+        from l3ster_b200.slab import SlabAssembledOperator
+
+        host = l3b.make_cube_mesh(node_dist(4), order=P)
+        rng = np.random.default_rng(2024)
+        ep = bisection_epart(host.verts.mean(axis=1), world)
+        flip = rng.random(host.n_elems) < 0.2
+        ep[flip] = rng.integers(0, world, size=int(flip.sum()))
+        part = Partition(3, P, host.n_nodes, host.nodes, host.verts, host.side_boundaries, world, ep.astype(np.int32))
+
+        def seeded_g(gids):
+            g = gids.astype(np.float64)
+            return (np.sin(0.37 * g + 1.0)[:, None] * (1.0 + 0.25 * np.arange(U))[None, :] + 0.1 * np.arange(U)[None, :]).ravel()
+
+        view = part.rank_view(rank, False)
+        op = SlabOperator(ctx, view, U, "bench_diffusion3d", BND)
+        no = view.n_owned_nodes * U
+        xd = torch.from_numpy(seeded_g(view.gids)).to("cuda")
+        yd = torch.zeros_like(xd)
+        torch.cuda.synchronize()
+        op.apply(xd, yd, 1.0, 0.0)
+        ctx.synchronize()
+        viewx = part.rank_view(rank, True)
+        aop = SlabAssembledOperator(ctx, viewx, U, "bench_diffusion3d", BND)
+        nox = viewx.n_owned_nodes * U
+        xa = torch.from_numpy(seeded_g(viewx.gids)).to("cuda")
+        ya = torch.zeros_like(xa)
+        torch.cuda.synchronize()
+        aop.apply(xa, ya)
+        ctx.synchronize()
+        vals, _ = aop.sys.download()
+        row_ptr, _ = aop.sys.graph()
+        # owned parts, placed by global id, summed over ranks (every dof is owned exactly once)
+        full = torch.zeros(3, host.n_nodes * U, dtype=torch.float64, device="cuda")
+        full[0, view.first_gid * U:view.first_gid * U + no] = yd[:no]
+        full[1, viewx.first_gid * U:viewx.first_gid * U + nox] = ya[:nox]
+        row_sq = np.add.reduceat(vals[:row_ptr[nox]] ** 2, row_ptr[:nox]) if nox else np.zeros(0)
+        full[2, viewx.first_gid * U:viewx.first_gid * U + nox] = torch.from_numpy(row_sq).to("cuda")
+        dist.all_reduce(full)
+        out = None
+        if rank == 0:
+            gnodes = part.new_id[host.nodes.astype(np.int64)].astype(np.uint32)
+            whole = Partition(3, P, host.n_nodes, gnodes, host.verts, host.side_boundaries, 1, np.zeros(host.n_elems, dtype=np.int32))
+            wv = whole.rank_view(0, True)
+            wop = SlabOperator(ctx, whole.rank_view(0, False), U, "bench_diffusion3d", BND)
+            xw = torch.from_numpy(seeded_g(wv.gids)).to("cuda")
+            yw = torch.zeros_like(xw)
+            torch.cuda.synchronize()
+            wop.apply(xw, yw, 1.0, 0.0)
+            ctx.synchronize()
+            wa = SlabAssembledOperator(ctx, wv, U, "bench_diffusion3d", BND)
+            wvals, _ = wa.sys.download()
+            wrp, _ = wa.sys.graph()
+            wrow_sq = torch.from_numpy(np.add.reduceat(wvals ** 2, wrp[:-1])).to("cuda")
+            rel = lambda a, b: float(torch.linalg.norm(a - b) / torch.linalg.norm(b))  # noqa: E731
+            out = {"mf_apply": rel(full[0], yw), "assembled_apply": rel(full[1], yw), "assembled_row_norms": rel(full[2], wrow_sq),
+                   "elements_per_rank": [int((ep == r).sum()) for r in range(world)], "tolerance": 1e-12}
+            out["ok"] = bool(max(out["mf_apply"], out["assembled_apply"], out["assembled_row_norms"]) < 1e-12)
+        return out
+
     def run_mf():
         n = args.n_mf
         xs = node_dist(n)
@@ -496,6 +560,11 @@ def main():
         _, wall_ms, _ = timed(step_e2e, args.steps, 1)
         owned_total = sum_over_ranks(float(n_owned))
         parity = parity_vs_n1() if world > 1 else None
+        if parity is not None:
+            rp = ragged_partition_parity()
+            if rank == 0:
+                parity["ragged_partition"] = rp
+                parity["ok"] = bool(parity["ok"] and rp["ok"])
         cg = None
         if args.cg_max_iters > 0:
             # the benchmark's solve (benchmarks/Diffusion3D.hpp:115-118): CG + native Jacobi, tol 1e-6 (absolute), x0 = 0, rhs of the source f = 1
