@@ -144,6 +144,21 @@ def test_partition_import_worker(nproc):
     assert "PARTITION_OK" in out.stdout
 
 
+@pytest.mark.parametrize("nproc", [1, 2])
+def test_real_karman_mesh_partitioned_worker(nproc):
+    """tests/mp_karman_mesh.py: BASELINE configs[3] on the real examples/07-karman-2D mesh, partitioned, row-complete assembled matrix,
+    GMRES over NCCL"""
+    import torch
+
+    if torch.cuda.device_count() < nproc:
+        pytest.skip(f"needs {nproc} GPUs (gpurun --gpus {nproc})")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mp_karman_mesh.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+                          "--master-port", str(29551 + nproc), script], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "KARMAN_MESH_OK" in out.stdout
+
+
 def test_one_process_karman_worker():
     """the same worker on one rank (one GPU): the callback-driven GMRES against the library's own driver"""
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mp_slab_karman.py")
