@@ -179,6 +179,29 @@ int  l3b_mesh_upload(l3b_context* ctx, int dim, int order, int64_t n_elems, cons
 int  l3b_mesh_update_verts(l3b_mesh* mesh, const double* verts);
 void l3b_mesh_destroy(l3b_mesh* mesh);
 
+/* element -> domain id (mesh/Domain.hpp): with it, the `ids` of l3b_asm_assemble / l3b_mf_assemble select the elements a DOMAIN kernel
+ * visits (AssembledSystem::assembleProblem(kernel, domain_ids, ...), MeshPartition::visit(..., domain_ids)); without it, or with zero ids,
+ * a domain kernel visits every element. NULL clears. */
+int l3b_mesh_set_element_domains(l3b_mesh* mesh, const int32_t* domain_ids);
+
+/* ---- dof maps for problem definitions with inactive (node, dof) pairs and several domains ------------------------------------------
+ * ProblemDefinition -> NodeToGlobalDofMap -> sparsity graph (dofs/NodeToDofMap.hpp:144-163, 188-264, 335-357,
+ * algsys/SparsityGraph.hpp:25-81; tests/MultiDomainTest.cpp, tests/SparsityGraphTest.cpp:99-146). Definition i activates the dofs of bit
+ * mask def_dof_masks[i] on the nodes of the elements whose domain id — and of the element sides whose boundary id — is one of
+ * def_domain_ids[def_ptr[i] .. def_ptr[i+1]). The map numbers the ACTIVE pairs node-major from base_dof (the reference's global dofs:
+ * pass the number of active pairs of the lower ranks as base, nodes in global-id order) and holds the reference's compact CRS graph
+ * (per definition the clique of element nodes x its dofs, rows sorted). Device storage stays padded (node * dofs_per_node + d): see
+ * l3b_asm_set_dofmap / l3b_asm_download_compact for the translation; for the matrix-free system pass the inactive pairs in the
+ * Dirichlet mask with zero values. */
+typedef struct l3b_dofmap l3b_dofmap;
+int  l3b_dofmap_create(int dim, int order, int64_t n_nodes, int64_t n_elems, const uint32_t* nodes, const int32_t* elem_domains /* NULL: all 0 */,
+                       const uint16_t* side_boundaries /* may be NULL */, int dofs_per_node, int n_defs, const int* def_ptr,
+                       const int* def_domain_ids, const uint32_t* def_dof_masks, int64_t base_dof, l3b_dofmap** out);
+void l3b_dofmap_destroy(l3b_dofmap* map);
+int  l3b_dofmap_info(const l3b_dofmap* map, int64_t info[4]); /* [n_dofs, graph nnz, n_nodes, dofs_per_node] */
+/* active[n_nodes * dpn]; dof[n_nodes * dpn] (compact id or -1); row_ptr[n_dofs + 1]; col_ind[nnz] (compact local ids). NULL = skip */
+int  l3b_dofmap_get(const l3b_dofmap* map, uint8_t* active, int64_t* dof, int64_t* row_ptr, int32_t* col_ind);
+
 /* ---- nodal fields (post/SolutionManager.hpp:54-101, post/FieldAccess.hpp:10-53): field-major [n_fields][n_local_nodes] */
 int  l3b_fields_upload(l3b_context* ctx, int64_t n_local_nodes, int n_fields, const double* data, l3b_fields** out);
 int  l3b_fields_update(l3b_fields* f, const double* data);
@@ -193,7 +216,8 @@ void    l3b_asm_destroy(l3b_asm* sys);
 int64_t l3b_asm_nnz(const l3b_asm* sys);
 int     l3b_asm_begin_assembly(l3b_asm* sys); /* AssembledSystem::beginAssembly: zero matrix and rhs */
 /* AssembledSystem::assembleProblem (:406-436). dof_inds: kernel unknown u → system dof (NULL = identity);
- * boundary kernels: ids of the boundaries to visit. */
+ * boundary_ids: the ids of the domains to visit — boundary ids for a boundary kernel, element domain ids for a domain kernel on a mesh
+ * with l3b_mesh_set_element_domains (none given: every element). */
 int l3b_asm_assemble(l3b_asm* sys, int kernel_id, l3b_asm_opts opts, double time, const int* dof_inds, const l3b_fields* fields,
                      const int* field_inds, const int* boundary_ids, int n_boundary_ids);
 /* AssembledSystem::endAssembly (:373-397) with algebraic Dirichlet BCs (bcs/DirichletBC.hpp:82-150): rows → identity,
@@ -212,6 +236,10 @@ int l3b_asm_spmv(l3b_asm* sys, const double* x, double* y);
  * matrix-free apply, and the global diagonal the Export-sum of the local ones. */
 int l3b_asm_spmv_device(l3b_asm* sys, const double* x, double* y);
 int l3b_asm_diag_device(l3b_asm* sys, double* diag);
+/* l3b_asm_set_dofmap: endAssembly closes the inactive (node, dof) pairs as identity rows with zero rhs (they receive no contributions);
+ * l3b_asm_download_compact: values over the dof map's compact graph + rhs over its dofs — the reference's matrix, bit-exact graph. */
+int l3b_asm_set_dofmap(l3b_asm* sys, const l3b_dofmap* map);
+int l3b_asm_download_compact(l3b_asm* sys, const l3b_dofmap* map, double* values, double* rhs);
 /* AssembledSystem::endAssembly's export of the shared rows (m_matrix->endAssembly(), m_rhs->endAssembly(): AssembledSystem.hpp:384-389).
  * Needs the halo (l3b_asm_set_halo) and a system created on l3b_partition_rank_graph's graph. Every rank sends the values of its ghost
  * rows (contiguous per owner) and the ghost block of its rhs to the owners, which add them into their rows through the receive plan

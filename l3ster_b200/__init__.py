@@ -78,6 +78,8 @@ EXPORTED_SYMBOLS = [
     "l3b_mf_set_halo", "l3b_asm_set_halo", "l3b_mf_solve_device", "l3b_asm_solve_device", "l3b_mf_apply_energy_device",
     "l3b_partition_create", "l3b_partition_destroy", "l3b_partition_node_map", "l3b_partition_rank_info", "l3b_partition_rank_mesh",
     "l3b_partition_rank_halo", "l3b_partition_rank_graph", "l3b_asm_export_shared_rows",
+    "l3b_mesh_set_element_domains", "l3b_dofmap_create", "l3b_dofmap_destroy", "l3b_dofmap_info", "l3b_dofmap_get", "l3b_asm_set_dofmap",
+    "l3b_asm_download_compact",
 ]
 
 
@@ -200,6 +202,14 @@ def lib():
     L.l3b_partition_rank_halo.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     L.l3b_partition_rank_graph.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.l3b_asm_export_shared_rows.argtypes = [vp, vp, vp]
+    L.l3b_mesh_set_element_domains.argtypes = [vp, vp]
+    L.l3b_dofmap_create.argtypes = [i32, i32, i64, i64, vp, vp, vp, i32, i32, vp, vp, vp, i64, C.POINTER(vp)]
+    L.l3b_dofmap_destroy.argtypes = [vp]
+    L.l3b_dofmap_destroy.restype = None
+    L.l3b_dofmap_info.argtypes = [vp, vp]
+    L.l3b_dofmap_get.argtypes = [vp, vp, vp, vp, vp]
+    L.l3b_asm_set_dofmap.argtypes = [vp, vp]
+    L.l3b_asm_download_compact.argtypes = [vp, vp, vp, vp]
     for f in ("l3b_mf_solve_device", "l3b_asm_solve_device"):
         getattr(L, f).argtypes = [vp, i32, dbl, i32, i32, i32, vp, i32, C.POINTER(dbl), C.POINTER(i32)]
     L.l3b_vec_scatter_add.argtypes = [vp, vp, i64, vp, i64, i32, vp]
@@ -470,6 +480,60 @@ class Context:
         return Fields(self, data)
 
 
+class DofMap:
+    """ProblemDefinition -> NodeToGlobalDofMap -> sparsity graph (l3b_dofmap_*): `definitions` is a list of (domain ids, dof indices) —
+    ProblemDefinition::define(domains, dofs). Attributes: active (n_nodes, dpn) bool, dof (n_nodes, dpn) compact ids or -1, n_dofs,
+    row_ptr / col_ind (the reference's compact CRS graph)."""
+
+    def __init__(self, dim, order, n_nodes, nodes, elem_domains, side_boundaries, dofs_per_node, definitions, base_dof=0):
+        nodes = np.ascontiguousarray(nodes, dtype=np.uint32)
+        ed = None if elem_domains is None else np.ascontiguousarray(elem_domains, dtype=np.int32)
+        sb = None if side_boundaries is None else np.ascontiguousarray(side_boundaries, dtype=np.uint16)
+        ptr = np.zeros(len(definitions) + 1, dtype=np.int32)
+        ids, masks = [], []
+        for i, (doms, dofs) in enumerate(definitions):
+            ids += list(doms)
+            ptr[i + 1] = len(ids)
+            masks.append(sum(1 << int(d) for d in dofs))
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        masks = np.ascontiguousarray(masks, dtype=np.uint32)
+        self._h = C.c_void_p()
+        rc = lib().l3b_dofmap_create(dim, order, n_nodes, nodes.shape[0], _p(nodes), _p(ed), _p(sb), dofs_per_node, len(definitions), _p(ptr),
+                                     _p(ids), _p(masks), base_dof, C.byref(self._h))
+        if rc != 0:
+            raise L3BError(rc, lib().l3b_global_error().decode())
+        info = np.zeros(4, dtype=np.int64)
+        lib().l3b_dofmap_info(self._h, _p(info))
+        self.n_dofs, nnz, self.n_nodes, self.dofs_per_node = map(int, info)
+        active = np.zeros((self.n_nodes, dofs_per_node), dtype=np.uint8)
+        self.dof = np.zeros((self.n_nodes, dofs_per_node), dtype=np.int64)
+        self.row_ptr = np.zeros(self.n_dofs + 1, dtype=np.int64)
+        self.col_ind = np.zeros(nnz, dtype=np.int32)
+        lib().l3b_dofmap_get(self._h, _p(active), _p(self.dof), _p(self.row_ptr), _p(self.col_ind))
+        self.active = active.astype(bool)
+        self.base_dof = base_dof
+
+    def padded_dirichlet(self, mask=None, vals=None, n_rhs=1):
+        """Dirichlet mask / values over the PADDED dofs with the inactive pairs closed (mask 1, value 0): what MatrixFreeSystem takes"""
+        m = np.zeros(self.n_nodes * self.dofs_per_node, dtype=np.uint8) if mask is None else np.array(mask, dtype=np.uint8).ravel()
+        v = np.zeros((len(m), n_rhs)) if vals is None else np.array(vals, dtype=np.float64).reshape(len(m), -1)
+        inactive = ~self.active.ravel()
+        m[inactive] = 1
+        v[inactive] = 0.0
+        return m, v
+
+    def compact(self, padded):
+        """padded vector(s) (n_nodes * dpn [, n_cols]) -> compact (n_dofs [, n_cols])"""
+        padded = np.asarray(padded)
+        return padded.reshape(self.n_nodes * self.dofs_per_node, -1)[self.active.ravel()].reshape((self.n_dofs,) + padded.shape[1:])
+
+    def __del__(self):
+        try:
+            lib().l3b_dofmap_destroy(self._h)
+        except Exception:
+            pass
+
+
 class Comm:
     """The rank's communicator (l3b_comm_*): NCCL, one rank per GPU. `Comm(ctx)` is the single-rank communicator;
     `Comm.from_torch_distributed(ctx)` creates one over the ranks of the initialised torch.distributed group (the unique id is
@@ -578,6 +642,11 @@ class Mesh:
         """computeNormL2 (post/NormL2.hpp:31-60); on more than one rank sum the squares over the ranks"""
         return self._integrate(lib().l3b_compute_norm_l2, kernel, boundary_ids, fields, field_inds, asm_opts, time)
 
+    def set_element_domains(self, domain_ids):
+        """element -> domain id: domain kernels can then be restricted to domains (assembleProblem(kernel, domain_ids, ...))"""
+        d = None if domain_ids is None else np.ascontiguousarray(domain_ids, dtype=np.int32)
+        self.ctx._chk(lib().l3b_mesh_set_element_domains(self._h, _p(d)))
+
     def update_verts(self, verts):
         """new vertex coordinates, same connectivity (H2D copy, no reallocation)"""
         self.ctx._chk(lib().l3b_mesh_update_verts(self._h, verts.ctypes.data))
@@ -678,6 +747,18 @@ class AssembledSystem:
         self.ctx._chk(lib().l3b_asm_solve_device(self._h, {"cg": 0, "gmres": 1}[method], tol, max_iters, restart_length, max_restarts, x_ptr,
                                                  int(x0_is_zero), C.byref(at), C.byref(it)))
         return at.value, it.value
+
+    def set_dofmap(self, dofmap: "DofMap | None"):
+        """inactive (node, dof) pairs are closed as identity rows at endAssembly"""
+        self._dofmap = dofmap
+        self.ctx._chk(lib().l3b_asm_set_dofmap(self._h, dofmap._h if dofmap is not None else None))
+
+    def download_compact(self, dofmap: "DofMap"):
+        """(values over dofmap's compact CRS graph, rhs (n_dofs, n_rhs)): the reference's matrix"""
+        vals = np.zeros(len(dofmap.col_ind))
+        rhs = np.zeros((self.n_rhs, dofmap.n_dofs))
+        self.ctx._chk(lib().l3b_asm_download_compact(self._h, dofmap._h, _p(vals), _p(rhs)))
+        return vals, rhs.T.copy()
 
     def export_shared_rows(self, recv_entry_ptr, recv_pos):
         """l3b_asm_export_shared_rows: ghost-row values and the ghost block of the rhs go to their owners (AssembledSystem.hpp:384-389)"""

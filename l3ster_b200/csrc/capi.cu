@@ -5,6 +5,7 @@
 #include "comm.cuh"
 #include "mesh_host.hpp"
 #include "partition_host.hpp"
+#include "dofmap_host.hpp"
 #include "mf_hex_planes.cuh"
 #include "condense.cuh"
 #include "registry.hpp"
@@ -635,6 +636,7 @@ struct l3b_mesh
     DevBuf< uint32_t >  nodes;
     DevBuf< double >    hex_geo; // dim 3: per-element geometry record of the planes + columns apply kernel
     std::vector< uint16_t > side_bnd; // host copy, used to build boundary work lists
+    std::vector< int32_t >  elem_domains; // host copy (l3b_mesh_set_element_domains), empty = one domain
 };
 
 struct l3b_fields
@@ -854,6 +856,8 @@ struct KernelUse
     const l3b_fields*           fields = nullptr;
     int                         field_inds[max_fields]{};
     std::shared_ptr< WorkList > boundary_work; // boundary kernels only
+    std::shared_ptr< WorkList > domain_work;   // domain kernels restricted to some element domains: ascending element ids
+    std::vector< int32_t >      domain_elems;  // host copy of that list (to cut it to an element range)
 };
 
 // the (element, side) pairs lying on the given boundary ids (the reference's BoundaryView, mesh/BoundaryView.hpp)
@@ -940,6 +944,23 @@ KernelUse makeUse(l3b_mesh* mesh, int dofs_per_node, int n_rhs, int kernel_id, l
     }
     if (info.is_boundary)
         use.boundary_work = makeBoundaryWork(mesh, boundary_ids, n_boundary_ids);
+    else if (n_boundary_ids > 0 and not mesh->elem_domains.empty())
+    {
+        // assembleProblem(kernel, domain_ids, ...): the elements of the listed domains only (mesh.visit(..., domain_ids))
+        for (long long e = 0; e < mesh->n_elems; ++e)
+            for (int k = 0; k < n_boundary_ids; ++k)
+                if (mesh->elem_domains[e] == boundary_ids[k])
+                {
+                    use.domain_elems.push_back(static_cast< int32_t >(e));
+                    break;
+                }
+        auto wl = std::make_shared< WorkList >();
+        wl->n   = static_cast< long long >(use.domain_elems.size());
+        wl->elems.alloc(std::max< size_t >(1, use.domain_elems.size()));
+        wl->elems.upload(use.domain_elems.data(), use.domain_elems.size(), mesh->ctx->stream);
+        cudaCheck(cudaStreamSynchronize(mesh->ctx->stream), "work list upload");
+        use.domain_work = std::move(wl);
+    }
     return use;
 }
 
@@ -965,6 +986,11 @@ ElemArgs baseArgs(l3b_mesh* mesh, const KernelUse& use, int dofs_per_node, long 
         a.n_work     = use.boundary_work->n;
         a.work_elems = use.boundary_work->elems.ptr;
         a.work_sides = use.boundary_work->sides.ptr;
+    }
+    else if (use.domain_work)
+    {
+        a.n_work     = use.domain_work->n;
+        a.work_elems = use.domain_work->elems.ptr;
     }
     else
     {
@@ -1004,7 +1030,8 @@ struct l3b_asm
     // more than one rank (l3b_asm_set_halo): halo of the row layout [owned | ghost]
     l3b_halo*           halo = nullptr;
     long long           n_owned_dofs = -1; // -1: all rows owned
-    bool                rows_exported = false; // l3b_asm_export_shared_rows ran: owned rows are complete, ghost rows are spent
+    bool                rows_exported = false;
+    const host::DofMap* dofmap = nullptr; // l3b_asm_set_dofmap: inactive (node, dof) pairs are closed as identity rows // l3b_asm_export_shared_rows ran: owned rows are complete, ghost rows are spent
     long long           ownedDofs() const { return n_owned_dofs < 0 ? n_dofs : n_owned_dofs; }
     l3b_comm*           comm() const { return halo ? halo->comm : nullptr; }
     ~l3b_asm()
@@ -1109,8 +1136,22 @@ int applyUse(l3b_mf* sys, const KernelUse& use, const double* x, double* y, int 
     {
         if (elem_end <= elem_begin)
             return 0;
-        a.first_elem = elem_begin;
-        a.n_work     = elem_end - elem_begin;
+        if (use.domain_work)
+        {
+            // the part of the (ascending) domain list that falls into [elem_begin, elem_end)
+            const auto& el = use.domain_elems;
+            const auto  lo = std::lower_bound(el.begin(), el.end(), static_cast< int32_t >(elem_begin)) - el.begin();
+            const auto  hi = std::lower_bound(el.begin(), el.end(), static_cast< int32_t >(std::min< long long >(elem_end, 0x7fffffff))) - el.begin();
+            if (hi <= lo)
+                return 0;
+            a.work_elems = use.domain_work->elems.ptr + lo;
+            a.n_work     = hi - lo;
+        }
+        else
+        {
+            a.first_elem = elem_begin;
+            a.n_work     = elem_end - elem_begin;
+        }
     }
     a.x              = x;
     a.y              = y;
@@ -2062,10 +2103,14 @@ int l3b_asm_end_assembly_ranked(l3b_asm* sys, int64_t n_dir, const int32_t* dofs
     return guardedCtx(sys->ctx, [&] {
         if (not sys->open)
             fail(L3B_ERR_STATE, "`endAssembly()` was called more than once");
-        if (n_dir > 0)
+        const bool close_inactive = sys->dofmap != nullptr and sys->dofmap->n_dofs < sys->n_dofs;
+        if (n_dir > 0 or close_inactive)
         {
             std::vector< uint8_t > mask(sys->n_dofs, 0);
             std::vector< double >  bc(static_cast< size_t >(sys->n_dofs) * sys->n_rhs, 0.);
+            if (close_inactive) // homogeneous "Dirichlet" rows: identity, rhs 0; their columns are empty anyway
+                for (long long i = 0; i < sys->n_dofs; ++i)
+                    mask[i] = sys->dofmap->active[i] ? 0 : 1;
             for (int64_t i = 0; i < n_dir; ++i)
             {
                 if (dofs[i] < 0 or dofs[i] >= sys->n_dofs)
@@ -2789,6 +2834,127 @@ int l3b_asm_export_shared_rows(l3b_asm* sys, const int64_t* recv_entry_ptr, cons
             cudaCheck(cudaStreamSynchronize(S), "row export"); // the staging buffers die here
         }
         sys->rows_exported = true;
+    });
+}
+}
+
+// ---- dof maps with inactive dofs / several domains (dofmap_host.hpp)
+struct l3b_dofmap
+{
+    host::DofMap map;
+};
+extern "C" {
+int l3b_mesh_set_element_domains(l3b_mesh* mesh, const int32_t* domain_ids)
+{
+    return guardedCtx(mesh->ctx, [&] {
+        if (domain_ids)
+            mesh->elem_domains.assign(domain_ids, domain_ids + mesh->n_elems);
+        else
+            mesh->elem_domains.clear();
+    });
+}
+int l3b_dofmap_create(int dim, int order, int64_t n_nodes, int64_t n_elems, const uint32_t* nodes, const int32_t* elem_domains,
+                      const uint16_t* side_boundaries, int dofs_per_node, int n_defs, const int* def_ptr, const int* def_domain_ids,
+                      const uint32_t* def_dof_masks, int64_t base_dof, l3b_dofmap** out)
+{
+    return guardedCtx(nullptr, [&] {
+        if ((dim != 2 and dim != 3) or order < 1 or n_defs < 1)
+            fail(L3B_ERR_INVALID_ARG, "l3b_dofmap_create: invalid dimension, order or definition count");
+        host::ProblemDefinition def;
+        def.ptr.assign(def_ptr, def_ptr + n_defs + 1);
+        def.ids.assign(def_domain_ids, def_domain_ids + def_ptr[n_defs]);
+        def.mask.assign(def_dof_masks, def_dof_masks + n_defs);
+        *out = new l3b_dofmap{host::makeDofMap(dim, order, n_nodes, n_elems, nodes, elem_domains, side_boundaries, dofs_per_node, def, base_dof)};
+    });
+}
+void l3b_dofmap_destroy(l3b_dofmap* m)
+{
+    delete m;
+}
+int l3b_dofmap_info(const l3b_dofmap* m, int64_t info[4])
+{
+    info[0] = m->map.n_dofs;
+    info[1] = static_cast< int64_t >(m->map.col_ind.size());
+    info[2] = m->map.n_nodes;
+    info[3] = m->map.dpn;
+    return L3B_OK;
+}
+int l3b_dofmap_get(const l3b_dofmap* m, uint8_t* active, int64_t* dof, int64_t* row_ptr, int32_t* col_ind)
+{
+    return guardedCtx(nullptr, [&] {
+        if (active)
+            std::copy(m->map.active.begin(), m->map.active.end(), active);
+        if (dof)
+            std::copy(m->map.dof.begin(), m->map.dof.end(), dof);
+        if (row_ptr)
+            std::copy(m->map.row_ptr.begin(), m->map.row_ptr.end(), row_ptr);
+        if (col_ind)
+            std::copy(m->map.col_ind.begin(), m->map.col_ind.end(), col_ind);
+    });
+}
+// the system closes every inactive (node, dof) pair as an identity row with zero rhs at endAssembly
+int l3b_asm_set_dofmap(l3b_asm* sys, const l3b_dofmap* m)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (m != nullptr and (m->map.n_nodes != sys->n_nodes or m->map.dpn != sys->dpn))
+            fail(L3B_ERR_INVALID_ARG, "l3b_asm_set_dofmap: the dof map does not belong to this system's nodes");
+        sys->dofmap = m ? &m->map : nullptr;
+    });
+}
+// values and rhs in the reference's COMPACT numbering: CRS over the dof map's graph (row_ptr / col_ind of l3b_dofmap_get), rhs
+// n_dofs x n_rhs column-major. Entries of the padded storage outside the compact graph must be zero (they are: no kernel writes there;
+// the identity rows of the inactive pairs are not part of the compact system) — checked, L3B_ERR_GRAPH otherwise.
+int l3b_asm_download_compact(l3b_asm* sys, const l3b_dofmap* m, double* values, double* rhs)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (m == nullptr or m->map.n_nodes != sys->n_nodes or m->map.dpn != sys->dpn)
+            fail(L3B_ERR_INVALID_ARG, "l3b_asm_download_compact: the dof map does not belong to this system's nodes");
+        const auto&           M   = m->map;
+        const int             dpn = sys->dpn;
+        std::vector< double > pv(sys->nnz), pr(sys->rhs.n);
+        sys->values.download(pv.data(), pv.size(), sys->ctx->stream);
+        sys->rhs.download(pr.data(), pr.size(), sys->ctx->stream);
+        std::vector< uint32_t > nbr(sys->node_nbr.n);
+        sys->node_nbr.download(nbr.data(), nbr.size(), sys->ctx->stream);
+        cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "download");
+        const auto&              np = sys->node_ptr_host;
+        std::vector< long long > node_of(M.n_dofs), d_of(M.n_dofs);
+        for (long long n = 0; n < M.n_nodes; ++n)
+            for (int d = 0; d < dpn; ++d)
+                if (M.dof[n * dpn + d] >= 0)
+                {
+                    node_of[M.dof[n * dpn + d] - M.base_dof] = n;
+                    d_of[M.dof[n * dpn + d] - M.base_dof]    = d;
+                }
+        double kept2 = 0., all2 = 0.;
+        for (double v : pv)
+            all2 += v * v;
+        for (long long r = 0; r < M.n_dofs; ++r)
+        {
+            const long long n = node_of[r], d = d_of[r], deg = np[n + 1] - np[n];
+            const long long base = static_cast< long long >(dpn) * (dpn * np[n] + d * deg);
+            for (long long k = M.row_ptr[r]; k < M.row_ptr[r + 1]; ++k)
+            {
+                const long long c = M.col_ind[k], cn = node_of[c], cv = d_of[c];
+                const auto      it = std::lower_bound(nbr.begin() + np[n], nbr.begin() + np[n + 1], static_cast< uint32_t >(cn));
+                if (it == nbr.begin() + np[n + 1] or *it != cn)
+                    fail(L3B_ERR_GRAPH, "compact download: a column of the compact graph is missing from the padded storage");
+                const double v = pv[base + cv * deg + (it - (nbr.begin() + np[n]))];
+                kept2 += v * v;
+                if (values)
+                    values[k] = v;
+            }
+            if (rhs)
+                for (int col = 0; col < sys->n_rhs; ++col)
+                    rhs[r + col * M.n_dofs] = pr[n * dpn + d + col * sys->n_dofs];
+        }
+        // identity rows of closed (inactive) pairs are the only padded entries allowed outside the compact graph
+        double closed2 = 0.;
+        if (not sys->open and sys->dofmap == &M)
+            for (size_t i = 0; i < M.active.size(); ++i)
+                closed2 += M.active[i] ? 0. : 1.;
+        if (std::fabs(all2 - kept2 - closed2) > 1e-20 * std::max(all2, 1.))
+            fail(L3B_ERR_GRAPH, "compact download: the padded storage holds non-zero entries outside the compact sparsity graph");
     });
 }
 }

@@ -201,6 +201,20 @@ struct NS3D
     }
 };
 
+// tests/MultiDomainTest.cpp:38-46: one unknown, A0 = 1, rhs = the value to set (the test captures it in the lambda; a registered functor
+// is stateless, so the value travels as the `time` argument of assembleProblem)
+struct MultiDomainMass
+{
+    template < typename In, typename Out >
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
+    {
+        auto& [operators, rhs] = out;
+        auto& [A0, A1, A2]     = operators;
+        A0(0, 0)               = 1.;
+        rhs(0, 0)              = in.point.time;
+    }
+};
+
 // examples/02-diffusion-2D/source.cpp:45-67
 struct Example02Domain
 {

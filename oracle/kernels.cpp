@@ -136,6 +136,13 @@ void robin_bc_3D(In in, Out out)
     out.rhs[1] = h * (1. + in.space[0] + 2. * in.space[1] - in.space[2]);
 }
 
+// tests/MultiDomainTest.cpp:38-46 (the value to set travels as the time argument)
+void multidomain_mass(In in, Out out)
+{
+    out.operators[0](0, 0) = 1.;
+    out.rhs[0]             = in.time;
+}
+
 // examples/02-diffusion-2D/source.cpp:45-67
 void example02_domain(In, Out out)
 {
@@ -374,6 +381,7 @@ std::map< std::string, Kernel > makeRegistry()
     r["bench_diffusion3d"]       = Kernel{{3, 7, 4, 0, 1}, false, diffusion_kernel_3D< true >};
     r["adiabatic_bc_2D"]         = Kernel{{2, 1, 3, 0, 1}, true, adiabatic_bc_2D};
     r["robin_bc_3D"]             = Kernel{{3, 2, 4, 0, 1}, true, robin_bc_3D};
+    r["multidomain_mass"]        = Kernel{{2, 1, 1, 0, 1}, false, multidomain_mass};
     r["example02_domain"]        = Kernel{{2, 4, 3, 0, 1}, false, example02_domain};
     r["example02_bc"]            = Kernel{{2, 1, 3, 0, 1}, true, example02_bc};
     r["ns3d_kernel"]             = Kernel{{3, 8, 7, 7, 1}, false, ns3d_kernel};
