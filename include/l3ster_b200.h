@@ -365,6 +365,21 @@ int l3b_compute_integral(l3b_context* ctx, l3b_mesh* mesh, int kernel_id, l3b_as
                          const int* field_inds, const int* boundary_ids, int n_boundary_ids, double* out);
 int l3b_compute_norm_l2(l3b_context* ctx, l3b_mesh* mesh, int kernel_id, l3b_asm_opts opts, double time, const l3b_fields* fields,
                         const int* field_inds, const int* boundary_ids, int n_boundary_ids, double* out);
+/* ---- nodal values of residual kernels (algsys/ComputeValuesAtNodes.hpp:316-721) and solution -> fields ------------------------------
+ * computeValuesAtNodes: the residual kernel is evaluated at the nodes of the elements of the domains `ids` (domain kernel; no ids = all
+ * elements) or of the element sides on the boundaries `ids` (boundary kernel, with the outward normal); equation eq of the result is
+ * written to dof (node, dof_inds[eq]) of `values` (device, padded dofs over the local nodes, leading dimension ld, n_rhs columns);
+ * nodes shared by several elements get the average of their contributions; other dofs of `values` are left alone. halo (may be NULL):
+ * the contributions of ghost nodes are combined at the owners and the result copied back. This is what setDirichletBCValues(kernel,
+ * boundaries, dof_inds) and setValues(...) of the reference's systems do. */
+int l3b_compute_values_at_nodes(l3b_context* ctx, l3b_mesh* mesh, int kernel_id, double time, const l3b_fields* fields, const int* field_inds,
+                                const int* ids, int n_ids, int dofs_per_node, const int* dof_inds, double* values, int64_t ld, l3b_halo* halo);
+/* updateSolution (AssembledSystem.hpp:140-160, MatrixFreeSystem.hpp:1231-1273) without leaving the device: field field_inds[i] <- dof
+ * dof_inds[i] of the solution vector x (device, padded local dofs, e.g. the x of l3b_asm_solve_device); l3b_fields_device exposes the
+ * field storage [n_fields][n_local_nodes] */
+int     l3b_update_solution(l3b_context* ctx, const double* x, int dofs_per_node, const int* dof_inds, int n, l3b_fields* fields, const int* field_inds);
+double* l3b_fields_device(l3b_fields* f);
+
 /* ---- static condensation, CondensationPolicy::ElementBoundary (algsys/StaticCondensationManager.hpp:135-535) ---------------------
  * The element matrices are assembled, with the ordinary l3b_asm_* calls, into an element-local system: an l3b_asm over the same
  * elements with node ids e * nodes_per_elem + a (every element its own nodes: the CRS is then the dense K_e, block by block). The

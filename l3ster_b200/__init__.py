@@ -79,7 +79,7 @@ EXPORTED_SYMBOLS = [
     "l3b_partition_create", "l3b_partition_destroy", "l3b_partition_node_map", "l3b_partition_rank_info", "l3b_partition_rank_mesh",
     "l3b_partition_rank_halo", "l3b_partition_rank_graph", "l3b_asm_export_shared_rows",
     "l3b_mesh_set_element_domains", "l3b_dofmap_create", "l3b_dofmap_destroy", "l3b_dofmap_info", "l3b_dofmap_get", "l3b_asm_set_dofmap",
-    "l3b_asm_download_compact",
+    "l3b_asm_download_compact", "l3b_compute_values_at_nodes", "l3b_update_solution", "l3b_fields_device",
 ]
 
 
@@ -210,6 +210,10 @@ def lib():
     L.l3b_dofmap_get.argtypes = [vp, vp, vp, vp, vp]
     L.l3b_asm_set_dofmap.argtypes = [vp, vp]
     L.l3b_asm_download_compact.argtypes = [vp, vp, vp, vp]
+    L.l3b_compute_values_at_nodes.argtypes = [vp, vp, i32, dbl, vp, vp, vp, i32, i32, vp, vp, i64, vp]
+    L.l3b_update_solution.argtypes = [vp, vp, i32, vp, i32, vp, vp]
+    L.l3b_fields_device.argtypes = [vp]
+    L.l3b_fields_device.restype = vp
     for f in ("l3b_mf_solve_device", "l3b_asm_solve_device"):
         getattr(L, f).argtypes = [vp, i32, dbl, i32, i32, i32, vp, i32, C.POINTER(dbl), C.POINTER(i32)]
     L.l3b_vec_scatter_add.argtypes = [vp, vp, i64, vp, i64, i32, vp]
@@ -642,6 +646,18 @@ class Mesh:
         """computeNormL2 (post/NormL2.hpp:31-60); on more than one rank sum the squares over the ranks"""
         return self._integrate(lib().l3b_compute_norm_l2, kernel, boundary_ids, fields, field_inds, asm_opts, time)
 
+    def computeValuesAtNodes(self, kernel, values_ptr, dofs_per_node, ids=(), dof_inds=None, fields=None, field_inds=None, time=0.0, ld=None,
+                             halo=None):
+        """l3b_compute_values_at_nodes: nodal values of a residual kernel into the (device, padded) vector at values_ptr"""
+        info = kernel_info(kernel)
+        di = _iarr(dof_inds, info["n_equations"])
+        fi = _iarr(field_inds, info["n_fields"])
+        bi = _iarr(list(ids))
+        ld = self.n_local_nodes * dofs_per_node if ld is None else ld
+        self.ctx._chk(lib().l3b_compute_values_at_nodes(self.ctx._h, self._h, info["id"], time, fields._h if fields is not None else None, _p(fi),
+                                                        _p(bi), 0 if bi is None else len(bi), dofs_per_node, _p(di), values_ptr, ld,
+                                                        halo._h if halo is not None else None))
+
     def set_element_domains(self, domain_ids):
         """element -> domain id: domain kernels can then be restricted to domains (assembleProblem(kernel, domain_ids, ...))"""
         d = None if domain_ids is None else np.ascontiguousarray(domain_ids, dtype=np.int32)
@@ -680,6 +696,15 @@ class Fields:
     def update(self, data):
         data = np.ascontiguousarray(data, dtype=np.float64)
         self.ctx._chk(lib().l3b_fields_update(self._h, _p(data)))
+
+    @property
+    def device_ptr(self):
+        return lib().l3b_fields_device(self._h)
+
+    def update_from_solution(self, x_ptr, dofs_per_node, dof_inds, field_inds):
+        """updateSolution on the device: field field_inds[i] <- dof dof_inds[i] of the solution vector at x_ptr"""
+        di, fi = _iarr(dof_inds), _iarr(field_inds, len(dof_inds))
+        self.ctx._chk(lib().l3b_update_solution(self.ctx._h, x_ptr, dofs_per_node, _p(di), len(di), self._h, _p(fi)))
 
     def __del__(self):
         try:

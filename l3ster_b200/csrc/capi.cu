@@ -599,6 +599,34 @@ struct l3b_context
         cudaCheck(cudaStreamSynchronize(stream), "table upload");
         return *dense.emplace(key, std::move(d)).first->second;
     }
+    // dense tables at the NODE locations (basis::getBasisAtNodes, mesh::getNodeLocations): point a = local node a
+    std::map< std::pair< int, int >, std::unique_ptr< DenseDev > > node_tabs;
+    const DenseDev& nodeTables(int dim, int order)
+    {
+        auto it = node_tabs.find({dim, order});
+        if (it != node_tabs.end())
+            return *it->second;
+        const auto                gll = tables::gllNodes(order + 1);
+        const int                 nb = order + 1, nn = cpow(nb, dim);
+        std::vector< tables::ld > p(static_cast< size_t >(nn) * dim), w(nn, 1);
+        for (int a = 0; a < nn; ++a)
+        {
+            int rem = a;
+            for (int d = 0; d < dim; ++d, rem /= nb)
+                p[static_cast< size_t >(a) * dim + d] = gll[rem % nb];
+        }
+        const auto t = tables::makeDenseTables(dim, order, p, w);
+        auto       d = std::make_unique< DenseDev >();
+        d->n_qp      = t.n_qp;
+        d->vals.alloc(t.values.size());
+        d->ders.alloc(t.derivatives.size());
+        d->pts.alloc(t.points.size());
+        d->vals.upload(t.values.data(), t.values.size(), stream);
+        d->ders.upload(t.derivatives.data(), t.derivatives.size(), stream);
+        d->pts.upload(t.points.data(), t.points.size(), stream);
+        cudaCheck(cudaStreamSynchronize(stream), "table upload");
+        return *node_tabs.emplace(std::make_pair(dim, order), std::move(d)).first->second;
+    }
     // read-and-clear the device status word; translate to the reference's exceptions
     void checkStatus()
     {
@@ -811,6 +839,25 @@ void commAllReduce(l3b_comm* c, double* scalars, int n)
     cudaCheck(cudaStreamWaitEvent(S, c->ev_done, 0), "event wait");
 }
 
+// values /= counts where a contribution arrived (averageElementContributions, ComputeValuesAtNodes.hpp:112-154)
+__global__ void averageKernel(double* values, const double* counts, long long n, long long ld, int n_cols)
+{
+    for (long long i = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; i < n; i += static_cast< long long >(gridDim.x) * blockDim.x)
+        if (counts[i] > 0.)
+            for (int c = 0; c < n_cols; ++c)
+                values[i + c * ld] /= counts[i];
+}
+// updateSolution (algsys/MatrixFreeSystem.hpp:1231-1273, AssembledSystem::updateSolution): dof columns of the solution -> nodal fields
+__global__ void updateSolutionKernel(const double* x, long long n_nodes, int dpn, const int* dof_inds, const int* field_inds, int n, double* fields,
+                                     long long field_stride)
+{
+    for (long long t = blockIdx.x * static_cast< long long >(blockDim.x) + threadIdx.x; t < n_nodes * n; t += static_cast< long long >(gridDim.x) * blockDim.x)
+    {
+        const long long node = t % n_nodes;
+        const int       i    = static_cast< int >(t / n_nodes);
+        fields[node + field_inds[i] * field_stride] = x[node * dpn + dof_inds[i]];
+    }
+}
 // shared-row export, receive side: the neighbour's values of my rows arrive in ITS layout (node block of dpn rows, each column-dof-major
 // over its deg columns); entry (j-th received node, k-th column there) goes to position pos of my row of that node
 __global__ void rowExportAddKernel(const double* buf, const long long* entry_ptr, const int32_t* row_node, const uint32_t* pos, long long n_nodes_recv,
@@ -1559,6 +1606,7 @@ void l3b_context_destroy(l3b_context* ctx)
         return;
     cudaSetDevice(ctx->device);
     ctx->dense.clear();
+    ctx->node_tabs.clear();
     ctx->status.release();
     ctx->scalars.release();
     if (ctx->stream)
@@ -2955,6 +3003,121 @@ int l3b_asm_download_compact(l3b_asm* sys, const l3b_dofmap* m, double* values, 
                 closed2 += M.active[i] ? 0. : 1.;
         if (std::fabs(all2 - kept2 - closed2) > 1e-20 * std::max(all2, 1.))
             fail(L3B_ERR_GRAPH, "compact download: the padded storage holds non-zero entries outside the compact sparsity graph");
+    });
+}
+}
+
+// ---- nodal values of residual kernels, solution -> fields
+extern "C" {
+// computeValuesAtNodes (algsys/ComputeValuesAtNodes.hpp:316-593, 595-721): what AssembledSystem / MatrixFreeSystem::setDirichletBCValues
+// and setValues call to turn a residual kernel into nodal values
+int l3b_compute_values_at_nodes(l3b_context* ctx, l3b_mesh* mesh, int kernel_id, double time, const l3b_fields* fields, const int* field_inds,
+                                const int* ids, int n_ids, int dofs_per_node, const int* dof_inds, double* values, int64_t ld, l3b_halo* halo)
+{
+    return guardedCtx(ctx, [&] {
+        auto& reg = kernelRegistry();
+        if (kernel_id < 0 or kernel_id >= static_cast< int >(reg.size()))
+            fail(L3B_ERR_INVALID_ARG, "invalid kernel id");
+        const auto& entry = reg[kernel_id];
+        const auto& info  = entry.info;
+        if (not info.is_residual)
+            fail(L3B_ERR_INVALID_ARG, "kernel '" + info.name + "' is an equation kernel, nodal values take residual kernels");
+        if (info.dim != mesh->dim)
+            fail(L3B_ERR_INVALID_ARG, "The dimensions of the kernel do not match the dimensions of the domain");
+        KernelUse use;
+        use.kernel_id = kernel_id;
+        use.inst      = entry.find(mesh->order, 0);
+        if (not use.inst or not use.inst->values_at_nodes)
+            fail(L3B_ERR_NO_INSTANCE, "residual kernel '" + info.name + "' is not compiled for order " + std::to_string(mesh->order));
+        use.time = time;
+        for (int eq = 0; eq < info.n_equations; ++eq)
+        {
+            use.dof_inds[eq] = dof_inds ? dof_inds[eq] : eq;
+            if (use.dof_inds[eq] < 0 or use.dof_inds[eq] >= dofs_per_node)
+                fail(L3B_ERR_INVALID_ARG, "dof index out of range");
+        }
+        if (info.n_fields > 0)
+        {
+            if (not fields or fields->n_nodes != mesh->n_local_nodes)
+                fail(L3B_ERR_INVALID_ARG, "kernel needs external fields over the mesh's local nodes");
+            for (int f = 0; f < info.n_fields; ++f)
+            {
+                use.field_inds[f] = field_inds ? field_inds[f] : f;
+                if (use.field_inds[f] < 0 or use.field_inds[f] >= fields->n_fields)
+                    fail(L3B_ERR_INVALID_ARG, "field index out of range");
+            }
+            use.fields = fields;
+        }
+        if (info.is_boundary)
+            use.boundary_work = makeBoundaryWork(mesh, ids, n_ids);
+        else if (n_ids > 0 and not mesh->elem_domains.empty())
+        {
+            for (long long e = 0; e < mesh->n_elems; ++e)
+                for (int k = 0; k < n_ids; ++k)
+                    if (mesh->elem_domains[e] == ids[k])
+                    {
+                        use.domain_elems.push_back(static_cast< int32_t >(e));
+                        break;
+                    }
+            auto wl = std::make_shared< WorkList >();
+            wl->n   = static_cast< long long >(use.domain_elems.size());
+            wl->elems.alloc(std::max< size_t >(1, use.domain_elems.size()));
+            wl->elems.upload(use.domain_elems.data(), use.domain_elems.size(), ctx->stream);
+            cudaCheck(cudaStreamSynchronize(ctx->stream), "work list upload");
+            use.domain_work = std::move(wl);
+        }
+        const long long  n_dofs = mesh->n_local_nodes * dofs_per_node;
+        DevBuf< double > counts(std::max< long long >(n_dofs, 1));
+        counts.zero(ctx->stream);
+        ElemArgs a  = baseArgs(mesh, use, dofs_per_node, ld);
+        const auto& t = ctx->nodeTables(mesh->dim, mesh->order);
+        a.tab_vals  = t.vals.ptr;
+        a.tab_ders  = t.ders.ptr;
+        a.tab_pts   = t.pts.ptr;
+        a.n_qp      = t.n_qp;
+        a.y         = values;
+        a.diag      = counts.ptr;
+        for (int pass = 0; pass < 2; ++pass)
+        {
+            a.n_cols = pass;
+            cudaCheck(use.inst->values_at_nodes(entry.object.get(), a, ctx->stream), "values at nodes");
+        }
+        // over ranks: contributions and counts of ghost nodes go to the owners, the averages come back (exchangeElementContributions, :156-194)
+        haloExportBegin(halo, values, info.n_rhs);
+        haloExportEnd(halo, values, info.n_rhs);
+        haloExportBegin(halo, counts.ptr, 1);
+        haloExportEnd(halo, counts.ptr, 1);
+        if (n_dofs > 0)
+            averageKernel<<< gridFor(n_dofs), 256, 0, ctx->stream >>>(values, counts.ptr, n_dofs, ld, info.n_rhs);
+        cudaCheck(cudaGetLastError(), "values at nodes");
+        haloImportBegin(halo, values, info.n_rhs);
+        haloImportEnd(halo);
+        cudaCheck(cudaStreamSynchronize(ctx->stream), "values at nodes"); // `counts` dies here
+    });
+}
+double* l3b_fields_device(l3b_fields* f)
+{
+    return f->data.ptr;
+}
+// AssembledSystem / MatrixFreeSystem::updateSolution on the device: field field_inds[i] <- dof dof_inds[i] of the (padded) solution
+// vector x over the local dofs; nothing leaves the GPU between a solve and the next assembly that reads the fields
+int l3b_update_solution(l3b_context* ctx, const double* x, int dofs_per_node, const int* dof_inds, int n, l3b_fields* fields, const int* field_inds)
+{
+    return guardedCtx(ctx, [&] {
+        if (n <= 0 or n > max_unknowns)
+            fail(L3B_ERR_INVALID_ARG, "l3b_update_solution: between 1 and 8 components per call");
+        for (int i = 0; i < n; ++i)
+            if (dof_inds[i] < 0 or dof_inds[i] >= dofs_per_node or field_inds[i] < 0 or field_inds[i] >= fields->n_fields)
+                fail(L3B_ERR_INVALID_ARG, "l3b_update_solution: index out of range");
+        DevBuf< int > idx(2 * n);
+        std::vector< int > h(dof_inds, dof_inds + n);
+        h.insert(h.end(), field_inds, field_inds + n);
+        idx.upload(h.data(), h.size(), ctx->stream);
+        if (fields->n_nodes > 0)
+            updateSolutionKernel<<< gridFor(fields->n_nodes * n), 256, 0, ctx->stream >>>(x, fields->n_nodes, dofs_per_node, idx.ptr, idx.ptr + n, n,
+                                                                                         fields->data.ptr, fields->n_nodes);
+        cudaCheck(cudaGetLastError(), "update solution");
+        cudaCheck(cudaStreamSynchronize(ctx->stream), "update solution"); // the index buffer dies here
     });
 }
 }

@@ -407,6 +407,17 @@ struct KarmanFlowRate
         out[0] = u * nx + v * ny;
     }
 };
+// examples/07-karman-2D/source.cpp:167-171: parabolic inlet velocity profile, the kernel of setDirichletBCValues(kernel_inlet, {inlet}, {IU, IV})
+struct KarmanInlet
+{
+    template < typename In, typename Out >
+    L3B_HD constexpr void operator()(const In& in, Out& out) const
+    {
+        const double y = in.point.space.y();
+        out[0]         = 1.5 * (1. - y * y);
+        out[1]         = 0.;
+    }
+};
 // not in the reference: polynomial / field probes with closed-form integrals on boxes (same bodies as oracle/kernels.cpp)
 struct IntegrandProbe2D
 {

@@ -9,3 +9,4 @@ L3B_REGISTER_DOMAIN_RESIDUAL_KERNEL(integrand_probe_2D, kernels::IntegrandProbe2
 L3B_REGISTER_DOMAIN_RESIDUAL_KERNEL(integrand_probe_3D, kernels::IntegrandProbe3D, (KernelParams{.dimension = 3, .n_equations = 3, .n_fields = 2}), 1, 2, 3, 4);
 L3B_REGISTER_BOUNDARY_RESIDUAL_KERNEL(boundary_probe_2D, kernels::BoundaryProbe2D, (KernelParams{.dimension = 2, .n_equations = 3, .n_fields = 2}), 1, 2, 4);
 L3B_REGISTER_BOUNDARY_RESIDUAL_KERNEL(boundary_probe_3D, kernels::BoundaryProbe3D, (KernelParams{.dimension = 3, .n_equations = 3, .n_fields = 2}), 1, 2, 3, 4);
+L3B_REGISTER_BOUNDARY_RESIDUAL_KERNEL(karman_inlet, kernels::KarmanInlet, (KernelParams{.dimension = 2, .n_equations = 2}), 2, 4);

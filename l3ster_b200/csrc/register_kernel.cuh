@@ -194,6 +194,19 @@ cudaError_t launchIntegrate(const void* obj, const ElemArgs& args, cudaStream_t 
     return cudaGetLastError();
 }
 
+template < typename KernelT, int DIM, int P >
+cudaError_t launchValuesAtNodes(const void* obj, const ElemArgs& args, cudaStream_t stream)
+{
+    using Cfg = IntegrateCfg< KernelT, DIM, P >;
+    if (args.n_work == 0)
+        return cudaSuccess;
+    constexpr auto fn = valuesAtNodesKernel< KernelT, DIM, P >;
+    if (const auto err = raiseSmemLimit< fn >(Cfg::smem_bytes); err != cudaSuccess)
+        return err;
+    fn<<< static_cast< unsigned >(args.n_work), local_threads, Cfg::smem_bytes, stream >>>(*static_cast< const KernelT* >(obj), args);
+    return cudaGetLastError();
+}
+
 template < int P_, int NQ_ >
 struct PQ
 {
@@ -254,6 +267,8 @@ int registerResidualKernel(const char* name, const KernelT& kernel)
         inst.order     = P;
         inst.nq        = 0;
         inst.integrate = launchIntegrate< KernelT, params.dimension, P >;
+        if constexpr (KernelT::parameters.n_equations <= static_cast< size_t >(max_unknowns))
+            inst.values_at_nodes = launchValuesAtNodes< KernelT, KernelT::parameters.dimension, P >;
         entry.instances.push_back(inst);
     };
     (add(std::integral_constant< int, orders >{}), ...);

@@ -35,6 +35,7 @@ struct KernelInstance
     ElemLaunch init_fast = nullptr; // domain kernels: diag + F_e without the Dirichlet lifting (mf_init.cuh)
     ElemLaunch assemble = nullptr;
     ElemLaunch integrate = nullptr; // residual kernels only; nq == 0: any quadrature size (dense tables at run time)
+    ElemLaunch values_at_nodes = nullptr; // residual kernels only: computeValuesAtNodes
     // work per launch unit, for occupancy/grid decisions and reporting
     int mf_elems_per_block = 1, asm_blocks_per_elem = 1;
 };

@@ -332,6 +332,17 @@ class OracleMesh:
     def matrix_free_system(self, U, n_rhs=1, is_dirichlet=None, dirichlet_vals=None):
         return OracleMatrixFree(self, U, n_rhs, is_dirichlet, dirichlet_vals)
 
+    def values_at_nodes(self, kernel, values, dofs_per_node, boundary_ids=(), dof_inds=None, fields=None, field_inds=None, time=0.0):
+        """computeValuesAtNodes (algsys/ComputeValuesAtNodes.hpp:316-506): `values` (n_nodes * dpn, n_rhs) is updated in place and returned"""
+        v = np.array(np.asarray(values, dtype=np.float64).reshape(self.n_nodes * dofs_per_node, -1).T, order="C", copy=True)
+        f = None if fields is None else np.ascontiguousarray(fields, dtype=np.float64)
+        b = np.ascontiguousarray(list(boundary_ids) or [0], dtype=np.int32)
+        fi = None if field_inds is None else np.ascontiguousarray(field_inds, dtype=np.int32)
+        di = None if dof_inds is None else np.ascontiguousarray(dof_inds, dtype=np.int32)
+        self.orc._chk(self.orc.lib.orc_values_at_nodes(self.h, kernel.encode(), C.c_double(time), _ptr(f), _ptr(fi), len(boundary_ids), _ptr(b),
+                                                       dofs_per_node, _ptr(di), _ptr(v)))
+        return v.T.copy()
+
 
 class OracleAssembled:
     def __init__(self, mesh: OracleMesh, U, n_rhs):

@@ -547,6 +547,21 @@ int orc_compute_integral(void* mesh_h, const char* kernel, int value_order, int 
     });
 }
 
+int orc_values_at_nodes(void* mesh_h, const char* kernel, double time, const double* fields, const int* field_inds, int n_bnd_ids,
+                        const int* bnd_ids, int dpn, const int* dof_inds, double* values)
+{
+    return guarded([&] {
+        const auto&        mesh = static_cast< MeshHandle* >(mesh_h)->mesh;
+        const auto&        k    = getKernel(kernel);
+        std::vector< int > fi, di(k.params.n_equations);
+        if (field_inds)
+            fi.assign(field_inds, field_inds + k.params.n_fields);
+        for (int eq = 0; eq < k.params.n_equations; ++eq)
+            di[eq] = dof_inds ? dof_inds[eq] : eq;
+        computeValuesAtNodes(mesh, k, time, fields, fi, {bnd_ids, bnd_ids + n_bnd_ids}, dpn, di, values);
+    });
+}
+
 // ---- matrix-free system
 void* orc_mf_create(void* mesh_h, int U, int n_rhs, const unsigned char* is_dirichlet, const double* dirichlet_vals)
 {

@@ -1,3 +1,4 @@
+#include <tuple>
 // CPU ORACLE — test infrastructure only (see l3ster_oracle.hpp). mapping/ and element-local algsys/ restatement.
 #include "l3ster_oracle.hpp"
 
@@ -630,4 +631,58 @@ void precomputeOperatorDiagonalAndRhs(const Kernel&         kernel,
         }
     }
 }
+// algsys/ComputeValuesAtNodes.hpp:316-369, 450-506 with detail::zeroOut (:92-110) and the averaging of :112-154, single rank
+void computeValuesAtNodes(const Mesh& mesh, const Kernel& kernel, val_t time, const val_t* fields, const std::vector< int >& field_inds,
+                          const std::vector< int >& boundary_ids, int dpn, const std::vector< int >& dof_inds, val_t* values)
+{
+    const int         nn = mesh.nodesPerElem(), NF = kernel.params.n_fields, E = kernel.params.n_equations, R = kernel.params.n_rhs;
+    const std::size_t ld = mesh.n_nodes * static_cast< std::size_t >(dpn);
+    const auto        rb = makeRefBasisAtNodes(mesh.et, mesh.order);
+    std::vector< val_t >  node_vals(static_cast< std::size_t >(nn) * std::max(NF, 1));
+    std::vector< double > n_contribs(ld, 0.);
+    // (element, side, local nodes to visit)
+    std::vector< std::tuple< std::size_t, int, std::vector< int > > > work;
+    if (not kernel.is_boundary)
+    {
+        std::vector< int > all(nn);
+        for (int a = 0; a < nn; ++a)
+            all[a] = a;
+        for (std::size_t e = 0; e < mesh.n_elems; ++e)
+            work.emplace_back(e, -1, all);
+    }
+    else
+        for (const auto& b : mesh.boundary)
+            if (std::find(boundary_ids.begin(), boundary_ids.end(), b.domain_id) != boundary_ids.end())
+                work.emplace_back(b.parent, b.side, sideNodeInds(mesh.et, mesh.order, b.side));
+    for (const auto& [e, side, locals] : work) // zeroOut
+        for (int a : locals)
+            for (int eq = 0; eq < E; ++eq)
+                for (int r = 0; r < R; ++r)
+                    values[mesh.elem_nodes[e * nn + a] * dpn + dof_inds[eq] + r * ld] = 0.;
+    QpEval qp{kernel, nn};
+    for (const auto& [e, side, locals] : work)
+    {
+        const n_id_t* el_nodes = &mesh.elem_nodes[e * nn];
+        for (int a = 0; a < nn; ++a)
+            for (int f = 0; f < NF; ++f)
+                node_vals[static_cast< std::size_t >(a) * NF + f] =
+                    fields[el_nodes[a] + static_cast< std::size_t >(field_inds.empty() ? f : field_inds[f]) * mesh.n_nodes];
+        for (int a : locals)
+        {
+            qp.eval(kernel, mesh.et, &mesh.elem_verts[e * (1u << nativeDim(mesh.et)) * 3], node_vals.data(), rb, a, time, side);
+            for (int eq = 0; eq < E; ++eq)
+            {
+                const std::size_t dof = el_nodes[a] * dpn + dof_inds[eq];
+                n_contribs[dof] += 1.;
+                for (int r = 0; r < R; ++r)
+                    values[dof + r * ld] += qp.F[eq + r * E];
+            }
+        }
+    }
+    for (std::size_t dof = 0; dof < ld; ++dof)
+        if (n_contribs[dof] > 0.)
+            for (int r = 0; r < R; ++r)
+                values[dof + r * ld] /= n_contribs[dof];
+}
+
 } // namespace orc

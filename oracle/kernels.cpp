@@ -338,6 +338,12 @@ void karman_flowrate(In in, Out out)
 {
     out.rhs[0] = in.field_vals[0] * in.normal[0] + in.field_vals[1] * in.normal[1];
 }
+// examples/07-karman-2D/source.cpp:167-171
+void karman_inlet(In in, Out out)
+{
+    out.rhs[0] = 1.5 * (1. - in.space[1] * in.space[1]);
+    out.rhs[1] = 0.;
+}
 // not in the reference: polynomial / field probes with closed-form integrals on boxes
 void integrand_probe_2D(In in, Out out)
 {
@@ -370,6 +376,7 @@ std::map< std::string, Kernel > makeRegistry()
     r["diffusion2d_error_dom"]   = Kernel{{2, 3, 0, 3, 1}, false, diffusion2d_error};
     r["diffusion2d_error_bnd"]   = Kernel{{2, 3, 0, 3, 1}, true, diffusion2d_error};
     r["karman_flowrate"]         = Kernel{{2, 1, 0, 2, 1}, true, karman_flowrate};
+    r["karman_inlet"]            = Kernel{{2, 2, 0, 0, 1}, true, karman_inlet};
     r["integrand_probe_2D"]      = Kernel{{2, 3, 0, 2, 1}, false, integrand_probe_2D};
     r["integrand_probe_3D"]      = Kernel{{3, 3, 0, 2, 1}, false, integrand_probe_3D};
     r["boundary_probe_2D"]       = Kernel{{2, 3, 0, 2, 1}, true, boundary_probe_2D};

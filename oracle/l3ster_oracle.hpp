@@ -106,6 +106,7 @@ struct RefBasisAtQuad
 };
 RefBasisAtQuad makeRefBasisAtDomainQuad(ElementType et, int order, int quad_order);             // ReferenceElementBasisAtQuadrature.hpp:10-19
 RefBasisAtQuad makeRefBasisAtBoundaryQuad(ElementType et, int order, int quad_order, int side); // ReferenceElementBasisAtQuadrature.hpp:56-96
+RefBasisAtQuad makeRefBasisAtNodes(ElementType et, int order); // basis::getBasisAtNodes, at mesh::getNodeLocations
 
 // ---------------------------------------------------------------------------------------------------------------------
 // mapping/
@@ -314,6 +315,10 @@ void assembleGlobalSystem(AssembledSystem& sys, const Kernel& kernel, const Asse
                           const std::vector< int >& dof_inds = {}, const std::vector< int >& field_inds = {});
 // post/Integral.hpp:55-121 computeIntegral and post/NormL2.hpp:31-60 computeNormL2 on one rank: quadrature order opts.order(EO) — not
 // doubled as in the assembly (Integral.hpp:66-69); the norm doubles both option orders, squares the components and takes square roots
+// algsys/ComputeValuesAtNodes.hpp:316-369 (domain kernel) / :450-506 (boundary kernel): zero the visited dofs, add the kernel's value at
+// every node of every visited element (side), count, average. values: [n_nodes * dpn][n_rhs] column-major, in/out.
+void computeValuesAtNodes(const Mesh& mesh, const Kernel& kernel, val_t time, const val_t* fields, const std::vector< int >& field_inds,
+                          const std::vector< int >& boundary_ids, int dpn, const std::vector< int >& dof_inds, val_t* values);
 std::vector< val_t > computeIntegral(const Mesh& mesh, const Kernel& kernel, const AssemblyOptions& opts, val_t time, const val_t* fields,
                                      const std::vector< int >& boundary_ids, const std::vector< int >& field_inds, bool norm_l2);
 // bcs/DirichletBC.hpp:82-150 — algebraic Dirichlet application (row/col zeroing, rhs lifting)

@@ -334,6 +334,26 @@ RefBasisAtQuad evalAtQuadrature(ElementType et, int order, Quadrature quad)
 }
 } // namespace
 
+// basis::getBasisAtNodes + mesh::getNodeLocations (basisfun/ReferenceBasisAtNodes.hpp, mesh/NodeReferenceLocation.hpp:31-44): the basis
+// and its reference derivatives at the element's own node locations; "point" a is local node a, weights are not used
+RefBasisAtQuad makeRefBasisAtNodes(ElementType et, int order)
+{
+    const int   dim = nativeDim(et), nb = order + 1, nn = numNodes(et, order);
+    const auto& gll = lobattoAbsc(nb);
+    Quadrature  pts;
+    pts.dim  = dim;
+    pts.size = nn;
+    pts.points.assign(static_cast< std::size_t >(nn) * dim, 0.);
+    pts.weights.assign(nn, 1.);
+    for (int a = 0; a < nn; ++a)
+    {
+        int rem = a;
+        for (int d = 0; d < dim; ++d, rem /= nb)
+            pts.points[static_cast< std::size_t >(a) * dim + d] = gll[rem % nb];
+    }
+    return evalAtQuadrature(et, order, std::move(pts));
+}
+
 // basisfun/ReferenceElementBasisAtQuadrature.hpp:10-19
 RefBasisAtQuad makeRefBasisAtDomainQuad(ElementType et, int order, int quad_order)
 {

@@ -93,3 +93,54 @@ def test_kernel_kind_errors(ctx):
         mesh.computeIntegral("diffusion2d_error_dom")  # fields missing
     with pytest.raises(l3b.L3BError):
         mesh.computeIntegral("integrand_probe_3D")  # dimension mismatch
+
+
+@pytest.mark.parametrize("dim,p,kernel,bnd", [(2, 2, "integrand_probe_2D", None), (2, 4, "integrand_probe_2D", None), (3, 2, "integrand_probe_3D", None),
+                                              (2, 4, "boundary_probe_2D", [1, 4]), (3, 3, "boundary_probe_3D", [2, 5, 6])])
+def test_values_at_nodes_match_oracle(dim, p, kernel, bnd):
+    """computeValuesAtNodes (algsys/ComputeValuesAtNodes.hpp:316-506): residual kernels (fields, gradients, point, time, normal) evaluated
+    at the nodes of the visited elements / sides on a distorted mesh, averaged over the elements sharing a node, written to chosen dofs of
+    a 4-dof-per-node vector; untouched dofs keep their values"""
+    import torch
+
+    ctx = l3b.Context(0)
+    pm = PairedMesh(dim, default_dists(dim, 3), p)
+    mesh = pm.upload(ctx)
+    dpn, dof_inds, time = 4, [2, 0, 3], 0.6
+    fdata = np.random.default_rng(3).uniform(-1, 1, size=(2, pm.n_nodes))
+    v0 = np.random.default_rng(4).uniform(-1, 1, size=pm.n_nodes * dpn)
+    vd = torch.from_numpy(v0.copy()).cuda()
+    torch.cuda.synchronize()
+    mesh.computeValuesAtNodes(kernel, vd.data_ptr(), dpn, ids=bnd or (), dof_inds=dof_inds, fields=ctx.upload_fields(fdata), time=time)
+    ctx.synchronize()
+    vo = pm.orc.values_at_nodes(kernel, v0.reshape(-1, 1), dpn, boundary_ids=bnd or (), dof_inds=dof_inds, fields=fdata, time=time)[:, 0]
+    got = vd.cpu().numpy()
+    assert rel_err(got, vo) < 1e-12
+    touched = got != v0
+    if bnd is None:
+        assert touched.reshape(-1, dpn)[:, dof_inds].all() and not touched.reshape(-1, dpn)[:, 1].any()
+    else:
+        on = np.zeros(pm.n_nodes, dtype=bool)
+        on[pm.host.boundary_nodes(bnd)] = True
+        assert not touched.reshape(-1, dpn)[~on].any() and touched.reshape(-1, dpn)[on][:, dof_inds].any()
+
+
+def test_update_solution_on_the_device():
+    """updateSolution (AssembledSystem.hpp:140-160): dof columns of the solution vector -> nodal fields, without leaving the GPU"""
+    import torch
+
+    ctx = l3b.Context(0)
+    n_nodes, dpn = 1000, 4
+    x = np.random.default_rng(0).uniform(-1, 1, size=n_nodes * dpn)
+    f0 = np.random.default_rng(1).uniform(-1, 1, size=(6, n_nodes))
+    fields = ctx.upload_fields(f0)
+    xd = torch.from_numpy(x).cuda()
+    torch.cuda.synchronize()
+    fields.update_from_solution(xd.data_ptr(), dpn, [0, 1, 3], [2, 5, 0])
+    ctx.synchronize()
+    from l3ster_b200.slab import _DevicePtr
+
+    view = torch.as_tensor(_DevicePtr(fields.device_ptr, f0.size), device="cuda").cpu().numpy().reshape(f0.shape)
+    want = f0.copy()
+    want[2], want[5], want[0] = x[0::dpn], x[1::dpn], x[3::dpn]
+    assert np.array_equal(view, want)
