@@ -3135,6 +3135,7 @@ struct l3b_cond
     DevBuf< double >   work;
     size_t             smem_condense = 0;
     int                maxc = 8;
+    bool               large = false; // more than 256 interior dofs per element: condenseLargeKernel
     bool               condensed = false;
 };
 extern "C" {
@@ -3171,7 +3172,21 @@ int l3b_cond_create(l3b_context* ctx, l3b_asm* elem_sys, l3b_asm* cond_sys, int6
         const int nId = n_int * elem_sys->dpn;
         const int nPd    = n_bnd * elem_sys->dpn;
         if (nId > 256)
-            fail(L3B_ERR_INVALID_ARG, "static condensation: more than 256 interior dofs per element are not supported by this kernel");
+        {
+            // hex p >= 6 at U = 4 (benchmarks/Diffusion3DBenchmark.cpp ships p = 6: 500 interior dofs): the blocked kernel, K_ii^-1 in a
+            // global work buffer
+            c->large         = true;
+            c->smem_condense = condLargeSmemBytes(nId, nPd, elem_sys->n_rhs);
+            if (c->smem_condense > 220 * 1024)
+                fail(L3B_ERR_INVALID_ARG, "static condensation: the element's interior block is too large for this kernel");
+            c->work.alloc(n_elems * static_cast< long long >(nId) * condLdM(nId));
+            if (c->smem_condense > 48 * 1024)
+                cudaCheck(cudaFuncSetAttribute(condenseLargeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast< int >(c->smem_condense)),
+                          "smem");
+            cudaCheck(cudaStreamSynchronize(ctx->stream), "cond create");
+            *out = c.release();
+            return;
+        }
         c->smem_condense = condSmemBytes(nId, nPd, elem_sys->n_rhs, true);
         if (c->smem_condense > 113 * 1024) // K_ii does not fit shared memory (two CTAs per SM): invert it in a global work buffer
         {
@@ -3229,6 +3244,9 @@ int l3b_cond_condense(l3b_cond* c)
             a.work      = c->work.ptr;
             a.status    = c->ctx->status.ptr;
             const auto launch = [&](auto kernel) { kernel<<< static_cast< unsigned >(c->n_elems), cond_threads, c->smem_condense, c->ctx->stream >>>(a); };
+            if (c->large)
+                launch(condenseLargeKernel);
+            else
             switch (c->maxc)
             {
             case 1: launch(condenseKernel< 1 >); break;

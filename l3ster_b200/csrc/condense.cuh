@@ -319,6 +319,186 @@ __global__ void __launch_bounds__(cond_threads, 2) condenseKernel(const __grid_c
     }
 }
 
+
+// ---- elements with MANY interior dofs (more than 256: hex p >= 6 at U = 4, the configuration benchmarks/Diffusion3DBenchmark.cpp ships) --------
+// Same three steps, blocked so that nothing of size nId^2 or nId x tile has to fit shared memory: K_ii^-1 lives in the global work
+// buffer (2 MB per resident element at nId = 500: L2-resident), the pivot row and column of each Gauss-Jordan step and the K_ip / K_pi /
+// W tiles go through shared memory in chunks of cond_kc interior dofs.
+constexpr int cond_kc = 64;                  // interior dofs per chunk of the tile contractions
+constexpr int cond_lt = 32;                  // tile edge of the Schur update in the large kernel
+inline size_t condLargeSmemBytes(int nId, int nPd, int n_rhs)
+{
+    const size_t ldM = condLdM(nId);
+    const size_t p12 = 2 * ldM + ldM * n_rhs + static_cast< size_t >(nId) * cond_wcols;
+    const size_t p3  = static_cast< size_t >(cond_lt) * (cond_kc + 1) + static_cast< size_t >(cond_kc) * cond_lt;
+    const size_t dbl = ((p12 > p3 ? p12 : p3) + 1) & ~size_t{1};
+    return dbl * sizeof(double) + 2 * static_cast< size_t >(nId + nPd) * sizeof(int);
+}
+__global__ void __launch_bounds__(cond_threads) condenseLargeKernel(const __grid_constant__ CondArgs c)
+{
+    extern __shared__ __align__(16) double smem[];
+    const long long e   = blockIdx.x;
+    const int       tid = threadIdx.x, T = cond_threads, lane = tid & 31, warp = tid >> 5, n_warps = T / 32;
+    const int       U = c.U, nId = c.nI * U, nPd = c.nB * U, ldM = condLdM(nId);
+    const size_t    p12 = 2 * static_cast< size_t >(ldM) + static_cast< size_t >(ldM) * c.n_rhs + static_cast< size_t >(nId) * cond_wcols;
+    const size_t    p3  = static_cast< size_t >(cond_lt) * (cond_kc + 1) + static_cast< size_t >(cond_kc) * cond_lt;
+    int* const      iRow = reinterpret_cast< int* >(smem + (((p12 > p3 ? p12 : p3) + 1) & ~size_t{1}));
+    int* const      iCol = iRow + nId;
+    int* const      pRow = iCol + nId;
+    int* const      pCol = pRow + nPd;
+    for (int i = tid; i < nId; i += T)
+    {
+        const int a = c.int_idx[i / U], u = i % U;
+        iRow[i]     = (a * U + u) * U * c.NN;
+        iCol[i]     = u * c.NN + a;
+    }
+    for (int q = tid; q < nPd; q += T)
+    {
+        const int b = c.bnd_idx[q % c.nB], v = q / c.nB;
+        pRow[q]     = (b * U + v) * U * c.NN;
+        pCol[q]     = v * c.NN + b;
+    }
+    double* const   ke     = c.ke + e * c.NN * c.NN * U * U;
+    double* const   fe     = c.fe + e * c.NN * U;
+    double* const   M      = c.work + static_cast< long long >(blockIdx.x) * nId * ldM;
+    double* const   colv   = smem;
+    double* const   rowv   = colv + ldM;
+    double* const   g      = rowv + ldM;
+    double* const   Ks     = g + ldM * c.n_rhs;
+    const uint32_t* prim_e = c.elem_prim + e * c.nB;
+    const auto      feOff  = [&](int row_off) { return row_off / (U * c.NN); };
+    __syncthreads();
+    // ---- 1: K_ii^-1 in place (Gauss-Jordan, no pivoting: symmetric positive definite)
+    for (int i = warp; i < nId; i += n_warps)
+        for (int j = lane; j < ldM; j += 32)
+            M[i * ldM + j] = j < nId ? ke[iRow[i] + iCol[j]] : 0.;
+    __syncthreads();
+    for (int k = 0; k < nId; ++k)
+    {
+        for (int i = tid; i < nId; i += T)
+        {
+            colv[i] = M[i * ldM + k];
+            rowv[i] = M[k * ldM + i];
+        }
+        __syncthreads();
+        const double pkk = colv[k];
+        if (not(pkk > 0.) and tid == 0)
+            atomicOr(c.status, status_singular_interior);
+        const double piv = 1. / pkk;
+        for (int i = warp; i < nId; i += n_warps)
+        {
+            double* const Mi = M + i * ldM;
+            const double  f  = i == k ? 0. : -colv[i] * piv;
+            for (int j = lane; j < nId; j += 32)
+                Mi[j] = i == k ? (j == k ? piv : rowv[j] * piv) : (j == k ? f : fma(f, rowv[j], Mi[j]));
+        }
+        __syncthreads();
+    }
+    // g = K_ii^-1 f_i over f_i
+    for (int idx = tid; idx < nId * c.n_rhs; idx += T)
+    {
+        const int i = idx % nId, r = idx / nId;
+        double    acc = 0.;
+        for (int j = 0; j < nId; ++j)
+            acc = fma(M[i * ldM + j], fe[feOff(iRow[j]) + r * c.ld_e], acc);
+        g[i + r * ldM] = acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nId * c.n_rhs; idx += T)
+    {
+        const int i = idx % nId, r = idx / nId;
+        fe[feOff(iRow[i]) + r * c.ld_e] = g[i + r * ldM];
+    }
+    // ---- 2: W = K_ii^-1 K_ip over K_ip, cond_wcols columns at a time (a thread: one column, rows strided over the thread groups)
+    {
+        const int ql = tid % cond_wcols, grp = tid / cond_wcols, n_grp = T / cond_wcols;
+        for (int q0 = 0; q0 < nPd; q0 += cond_wcols)
+        {
+            const int q = q0 + ql, qc = q < nPd ? pCol[q] : 0;
+            __syncthreads();
+            for (int j = grp; j < nId; j += n_grp)
+                Ks[j * cond_wcols + ql] = q < nPd ? ke[iRow[j] + qc] : 0.;
+            __syncthreads();
+            for (int i = grp; i < nId; i += n_grp)
+            {
+                double acc = 0.;
+                for (int j = 0; j < nId; ++j)
+                    acc = fma(M[j * ldM + i], Ks[j * cond_wcols + ql], acc); // symmetric inverse: column i read as row-strided
+                if (q < nPd)
+                    ke[iRow[i] + qc] = acc;
+            }
+        }
+    }
+    __syncthreads();
+    // condensed rhs: f_p - K_pi g
+    for (int idx = tid; idx < nPd * c.n_rhs; idx += T)
+    {
+        const int p = idx % nPd, col = idx / nPd;
+        double    acc = fe[feOff(pRow[p]) + col * c.ld_e];
+        for (int i = 0; i < nId; ++i)
+            acc = fma(-ke[pRow[p] + iCol[i]], fe[feOff(iRow[i]) + col * c.ld_e], acc);
+        atomicAdd(c.rhs + static_cast< long long >(prim_e[p % c.nB]) * U + p / c.nB + col * c.ld_c, acc);
+    }
+    // ---- 3: S = K_pp - K_pi W, 32 x 32 tiles, interior dofs in chunks of cond_kc; upper triangle formed, mirrored on scatter
+    double* const   As    = smem;                            // [cond_lt][cond_kc + 1]
+    double* const   Bs    = smem + cond_lt * (cond_kc + 1);  // [cond_kc][cond_lt]
+    const int       tx = tid % 16, ty = tid / 16;            // thread: rows 2 ty, 2 ty + 1; columns 2 tx, 2 tx + 1
+    const uint16_t* pos_e = c.pos + e * c.nB * c.nB;
+    for (int p0 = 0; p0 < nPd; p0 += cond_lt)
+        for (int q0 = p0; q0 < nPd; q0 += cond_lt)
+        {
+            double acc[2][2] = {{0., 0.}, {0., 0.}};
+            for (int k0 = 0; k0 < nId; k0 += cond_kc)
+            {
+                __syncthreads();
+                for (int idx = tid; idx < cond_lt * cond_kc; idx += T)
+                {
+                    const int r = idx / cond_kc, k = idx % cond_kc, p = p0 + r, i = k0 + k;
+                    As[r * (cond_kc + 1) + k] = p < nPd and i < nId ? ke[pRow[p] + iCol[i]] : 0.;
+                }
+                for (int idx = tid; idx < cond_kc * cond_lt; idx += T)
+                {
+                    const int k = idx / cond_lt, cq = idx % cond_lt, q = q0 + cq, i = k0 + k;
+                    Bs[k * cond_lt + cq] = q < nPd and i < nId ? ke[iRow[i] + pCol[q]] : 0.;
+                }
+                __syncthreads();
+#pragma unroll 4
+                for (int k = 0; k < cond_kc; ++k)
+                {
+                    const double a0 = As[(2 * ty) * (cond_kc + 1) + k], a1 = As[(2 * ty + 1) * (cond_kc + 1) + k];
+                    const double b0 = Bs[k * cond_lt + 2 * tx], b1 = Bs[k * cond_lt + 2 * tx + 1];
+                    acc[0][0] = fma(a0, b0, acc[0][0]);
+                    acc[0][1] = fma(a0, b1, acc[0][1]);
+                    acc[1][0] = fma(a1, b0, acc[1][0]);
+                    acc[1][1] = fma(a1, b1, acc[1][1]);
+                }
+            }
+            for (int rr = 0; rr < 2; ++rr)
+            {
+                const int p = p0 + 2 * ty + rr;
+                if (p >= nPd)
+                    continue;
+                const int       ib = p % c.nB, u = p / c.nB, ro = pRow[p];
+                const long long A = prim_e[ib], np = c.node_ptr[A], deg = c.node_ptr[A + 1] - np;
+                double* const   rowp = c.vals + U * (U * np + u * deg);
+                for (int cc = 0; cc < 2; ++cc)
+                {
+                    const int q = q0 + 2 * tx + cc;
+                    if (q >= nPd or q < p)
+                        continue;
+                    const int    ib2 = q % c.nB, v2 = q / c.nB;
+                    const double sv  = ke[ro + pCol[q]] - acc[rr][cc];
+                    atomicAdd(rowp + v2 * deg + pos_e[ib * c.nB + ib2], sv);
+                    if (q > p)
+                    {
+                        const long long A2 = prim_e[ib2], np2 = c.node_ptr[A2], deg2 = c.node_ptr[A2 + 1] - np2;
+                        atomicAdd(c.vals + U * (U * np2 + v2 * deg2) + u * deg2 + pos_e[ib2 * c.nB + ib], sv);
+                    }
+                }
+            }
+        }
+}
+
 // x_i = K_ii^-1 (f_i - K_ip x_p) = g - W x_p per element (StaticCondensationManager.hpp:420-535), with g and W as condenseKernel left
 // them; out: nodal solution over the mesh's nodes, out[node * U + u + r * ld_out]; primary values are copied from the condensed
 // solution. One CTA per element.

@@ -31,6 +31,8 @@ CASES = [
     ("bench_diffusion3d", None, 3, 2, 2, l3b.AssemblyOptions()),
     ("bench_diffusion3d", None, 3, 1, 4, l3b.AssemblyOptions()),
     ("dense_probe_3D", None, 3, 2, 2, l3b.AssemblyOptions()),
+    ("bench_diffusion3d", None, 3, 1, 5, l3b.AssemblyOptions()),  # 256 interior dofs: the largest the register-resident inverse takes
+    ("bench_diffusion3d", None, 3, 1, 6, l3b.AssemblyOptions()),  # 500 interior dofs (the shipped benchmark's order): the blocked kernel
 ]
 
 
@@ -89,6 +91,35 @@ def test_condensed_solve_equals_uncondensed_solve(ctx):
     assert tol_f <= 1e-12 and tol_c <= 1e-12
     assert cs.n_primary_dofs < full.n_dofs and it_c <= it_f  # fewer unknowns, better conditioned (the point of the policy)
     assert rel_err(x_cond, x_full) < 1e-9
+
+
+def test_diffusion3d_benchmark_as_shipped(ctx):
+    """benchmarks/Diffusion3DBenchmark.cpp:6 + Diffusion3D.hpp:8-118 as shipped: hex p = 6, CondensationPolicy::ElementBoundary, Dirichlet
+    T = 0 on the six faces, CG + Jacobi to 1e-6 (4^3 elements here instead of 6^3 to keep the test short; 500 interior dofs per element).
+    The nodal solution must equal the matrix-free (uncondensed) solve of the same problem."""
+    n, p, U = 4, 6, 4
+    dx, x, nd = 1.0 / n, 0.0, []
+    for _ in range(n + 1):
+        nd.append(x)
+        x += dx
+    host = l3b.make_cube_mesh(np.array(nd), order=p)
+    bc_nodes = host.boundary_nodes([1, 2, 3, 4, 5, 6])
+    cs = CondensedAssembledSystem(ctx, host, U)
+    cs.beginAssembly()
+    cs.assembleProblem("bench_diffusion3d")
+    cs.endAssembly((bc_nodes * U).astype(np.int32), np.zeros((len(bc_nodes), 1)))
+    x_cond, tol_c, it_c = cs.solve(tol=1e-10)
+    assert tol_c <= 1e-10
+    mask = np.zeros(host.n_nodes * U, dtype=np.uint8)
+    mask[bc_nodes * U] = 1
+    mf = l3b.MatrixFreeSystem(ctx, ctx.upload_mesh(host), U, 1, mask, None)
+    mf.assembleProblem("bench_diffusion3d")
+    mf.endAssembly()
+    x_mf, tol_m, it_m = mf.solve(tol=1e-10)
+    assert tol_m <= 1e-10 and it_c < it_m  # fewer, better conditioned unknowns
+    assert cs.n_primary_dofs < host.n_nodes * U
+    assert rel_err(x_cond, x_mf) < 1e-7
+    assert np.abs(x_mf[0::U]).max() > 1e-3
 
 
 def test_diffusion2d_condensed_end_to_end(ctx):
