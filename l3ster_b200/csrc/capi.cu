@@ -11,6 +11,8 @@
 #include "registry.hpp"
 #include "tables.hpp"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -56,6 +58,16 @@ void cudaCheck(cudaError_t err, const char* what)
     if (err != cudaSuccess)
         fail(L3B_ERR_CUDA, std::string{what} + ": " + cudaGetErrorString(err));
 }
+
+// NVTX ranges named after the reference's Caliper regions (util/Caliper.hpp: L3STER_PROFILE_FUNCTION / _REGION_BEGIN), so that a
+// timeline of this library reads like a Caliper report of the reference. NVTX v3 is header-only: no tool attached, no cost.
+struct ProfileRegion
+{
+    explicit ProfileRegion(const char* name) { nvtxRangePushA(name); }
+    ~ProfileRegion() { nvtxRangePop(); }
+    ProfileRegion(const ProfileRegion&)            = delete;
+    ProfileRegion& operator=(const ProfileRegion&) = delete;
+};
 
 template < typename T >
 struct DevBuf
@@ -1265,6 +1277,7 @@ void mfApplyPhases(l3b_mf* sys, const double* x, double* y, int n_cols, double a
         }
     if ((phases & L3B_APPLY_FINISH) and sys->has_bc and sys->n_dir > 0)
     {
+        const ProfileRegion region{"Impose Dirichlet BCs"}; // MatrixFreeSystem.hpp:1101-1104
         dirichletRowsListKernel<<< gridFor(sys->n_dir), 256, 0, ctx->stream >>>(sys->dir_list.ptr, sys->n_dir, x, y, sys->n_dofs, n_cols, alpha, energy,
                                                                                 static_cast< long long >(sys->mesh->n_owned_nodes) * sys->dpn);
         ++launches;
@@ -1279,6 +1292,7 @@ void mfApplyPhases(l3b_mf* sys, const double* x, double* y, int n_cols, double a
 // launch covers the Export, so neither transfer is exposed. The ghost block of x is overwritten by the Import.
 void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta, double* energy = nullptr)
 {
+    const ProfileRegion region{"Evaluate matrix-free operator"}; // MatrixFreeSystem.hpp:1032-1139
     auto* const h = sys->halo;
     if (h == nullptr or not h->active())
     {
@@ -2120,6 +2134,7 @@ int l3b_asm_assemble(l3b_asm* sys, int kernel_id, l3b_asm_opts opts, double time
                      const int* field_inds, const int* boundary_ids, int n_boundary_ids)
 {
     return guardedCtx(sys->ctx, [&] {
+        const ProfileRegion region{"assembleGlobalSystem"}; // AssembleGlobalSystem.hpp:32, 74
         if (not sys->open)
             fail(L3B_ERR_STATE, "`assembleProblem()` was called before `beginAssembly()`");
         if (sys->mesh == nullptr)
@@ -2149,6 +2164,7 @@ int l3b_asm_end_assembly(l3b_asm* sys, int64_t n_dir, const int32_t* dofs, const
 int l3b_asm_end_assembly_ranked(l3b_asm* sys, int64_t n_dir, const int32_t* dofs, const double* vals, int64_t n_owned_dofs)
 {
     return guardedCtx(sys->ctx, [&] {
+        const ProfileRegion region{"Dirichlet BCs"}; // AssembledSystem.hpp:349-353 (inside endAssembly, :376)
         if (not sys->open)
             fail(L3B_ERR_STATE, "`endAssembly()` was called more than once");
         const bool close_inactive = sys->dofmap != nullptr and sys->dofmap->n_dofs < sys->n_dofs;
@@ -2230,6 +2246,7 @@ int l3b_asm_solve_device(l3b_asm* sys, int method, double tol, int max_iters, in
                          double* achieved_tol, int* iters)
 {
     return guardedCtx(sys->ctx, [&] {
+        const ProfileRegion region{"solve"}; // AssembledSystem::solve (AssembledSystem.hpp:115)
         if (sys->open)
             fail(L3B_ERR_STATE, "`solve()` was called before `endAssembly()`");
         if (method != 0 and method != 1)
@@ -2373,6 +2390,7 @@ int l3b_mf_assemble(l3b_mf* sys, int kernel_id, l3b_asm_opts opts, double time, 
 int l3b_mf_end_assembly_begin(l3b_mf* sys)
 {
     return guardedCtx(sys->ctx, [&] {
+        const ProfileRegion region{"computeDiagAndRhs"}; // MatrixFreeSystem.hpp:887-941
         if (sys->closed)
             fail(L3B_ERR_STATE, "`endAssembly()` was called more than once");
         auto* ctx = sys->ctx;
@@ -2462,6 +2480,7 @@ int l3b_mf_solve_device(l3b_mf* sys, int method, double tol, int max_iters, int 
                         double* achieved_tol, int* iters)
 {
     return guardedCtx(sys->ctx, [&] {
+        const ProfileRegion region{"solve"}; // MatrixFreeSystem::solve
         if (not sys->closed)
             fail(L3B_ERR_STATE, "`solve()` was called before `endAssembly()`");
         if (sys->n_rhs != 1)
@@ -2800,6 +2819,7 @@ int l3b_partition_rank_graph(const l3b_partition* p, int rank, int64_t** ptr, ui
 int l3b_asm_export_shared_rows(l3b_asm* sys, const int64_t* recv_entry_ptr, const uint32_t* recv_pos)
 {
     return guardedCtx(sys->ctx, [&] {
+        const ProfileRegion region{"Matrix"}; // AssembledSystem.hpp:384-389: regions "RHS" and "Matrix" of endAssembly
         auto* const h = sys->halo;
         if (not sys->open)
             fail(L3B_ERR_STATE, "l3b_asm_export_shared_rows: call between `assembleProblem()` and `endAssembly()`");
@@ -3171,9 +3191,9 @@ int l3b_cond_create(l3b_context* ctx, l3b_asm* elem_sys, l3b_asm* cond_sys, int6
         ctx->checkStatus();
         const int nId = n_int * elem_sys->dpn;
         const int nPd    = n_bnd * elem_sys->dpn;
-        if (nId > 256)
+        if (nId > 256 or condSmemBytes(nId, nPd, elem_sys->n_rhs, false) > 220 * 1024)
         {
-            // hex p >= 6 at U = 4 (benchmarks/Diffusion3DBenchmark.cpp ships p = 6: 500 interior dofs): the blocked kernel, K_ii^-1 in a
+            // more interior dofs than the register-resident inverse (256) or the 64 x 64 Schur tiles (shared memory) take: hex p >= 5 at U = 4 (benchmarks/Diffusion3DBenchmark.cpp ships p = 6: 500 interior dofs): the blocked kernel, K_ii^-1 in a
             // global work buffer
             c->large         = true;
             c->smem_condense = condLargeSmemBytes(nId, nPd, elem_sys->n_rhs);
@@ -3220,6 +3240,7 @@ void l3b_cond_destroy(l3b_cond* c)
 int l3b_cond_condense(l3b_cond* c)
 {
     return guardedCtx(c->ctx, [&] {
+        const ProfileRegion region{"Static condensation"}; // AssembledSystem.hpp:379-383
         if (not c->elem_sys->open or not c->cond_sys->open)
             fail(L3B_ERR_STATE, "l3b_cond_condense: both systems must be open for assembly");
         if (c->n_elems > 0)

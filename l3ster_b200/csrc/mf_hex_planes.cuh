@@ -810,16 +810,22 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
                     const int  cim = ccm % NQ, cjm = ccm / NQ;
                     const bool okm = tm < EPB * CT and slotm < n_active and cim < NB and cjm < NB;
                     const unsigned long long dbm = __shfl_sync(0xffffffffu, dirbits, m, 4);
-                    if (okm)
-                    {
-                        const uint32_t* ids = s_ids + ((it % RING) * EPB + slotm) * NN + cjm * NB + cim;
+                    const uint32_t* ids = s_ids + ((it % RING) * EPB + (okm ? slotm : 0)) * NN + (okm ? cjm * NB + cim : 0);
+                    uint32_t        nd[NB];
 #pragma unroll
-                        for (int k = 0; k < NB; ++k)
-                        {
-                            const long long node = ids[k * NB * NB];
-                            if (not((dbm >> (k * U + g)) & 1ull))
-                                atomicAdd(args.y + node * U + g + r * args.ld, out[m][k]);
-                        }
+                    for (int k = 0; k < NB; ++k)
+                        nd[k] = ids[k * NB * NB];
+                    double* const yb = args.y + g + r * args.ld;
+#pragma unroll
+                    for (int k = 0; k < NB; ++k)
+                    {
+                        const int go = okm and not((dbm >> (k * U + g)) & 1ull);
+#if defined(L3B_HEX_PROBE_PLAIN_STORES) // timing probe only (wrong results): what the apply costs without the atomic units
+                        if (go)
+                            yb[static_cast< long long >(nd[k]) * U] = out[m][k];
+#else
+                        redAddIf(yb + static_cast< long long >(nd[k]) * U, out[m][k], go); // predicated RED: no branch around it
+#endif
                     }
                 }
             }
