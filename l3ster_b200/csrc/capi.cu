@@ -1158,6 +1158,9 @@ int guardedCtx(const l3b_context* ctx, F&& f)
     try
     {
         const DeviceGuard guard{ctx};
+        // a stale, non-sticky error left in this thread by another library (NCCL's peer probing leaves cudaErrorInvalidDevice on a
+        // one-GPU box) must not be blamed on the next launch checked with cudaGetLastError
+        (void)cudaGetLastError();
         f();
         return L3B_OK;
     }

@@ -100,6 +100,26 @@ struct MfHexCfg
     static constexpr int  min_blocks  = smem_bytes <= 112 * 1024 ? 2 : 1;
 #endif
     static constexpr bool supported   = CT <= 49 and smem_bytes <= 220 * 1024;
+    // Warpgroup slicing (L3B_HEX_WG, nq = 5 instances): ONE CTA per SM made of WG independent 128-thread groups, each running the whole
+    // pipeline on its own batches with its own shared-memory slice and named barrier — a "virtual CTA". What it buys over WG resident
+    // CTAs: registers move between the groups (setmaxnreg): a group holds reg_base registers per thread in the phases A, B, D, E and
+    // reg_points only while it is in the quadrature-point stage C, so three groups fit where two 240-register CTAs did.
+#if defined(L3B_HEX_WG)
+    static constexpr int  WG = (CT == 25 and threads == 128 and 3 * smem_bytes <= 225 * 1024) ? L3B_HEX_WG : 1;
+#else
+    static constexpr int  WG = 1;
+#endif
+#ifndef L3B_HEX_REG_BASE
+#define L3B_HEX_REG_BASE 128
+#endif
+#ifndef L3B_HEX_REG_POINTS
+#define L3B_HEX_REG_POINTS 240
+#endif
+    static constexpr int    reg_base = L3B_HEX_REG_BASE, reg_points = L3B_HEX_REG_POINTS;
+    static constexpr size_t wg_stride_doubles = ((smem_bytes + 15) / 16) * 2; // slice of one group, 16-byte aligned
+    static constexpr size_t launch_smem    = WG > 1 ? WG * wg_stride_doubles * sizeof(double) : smem_bytes;
+    static constexpr int    launch_threads = WG * threads;
+    static constexpr int    launch_min_blocks = WG > 1 ? 1 : min_blocks;
     // second copy of the point stage for axis-aligned elements: measured per order (ms per apply with / without, profiles/r1_final_summary.md):
     // p=4 1.50 / 1.63, but p=3 1.52 / 1.44, p=2 1.21 / 1.19, p=5 2.09 / 1.75 (at the 255-register limit the extra code costs more than
     // the saved multiply-adds) — so only the nq = 5 instances carry it
@@ -164,7 +184,7 @@ __device__ __forceinline__ void cpAsyncWaitAll()
 // ENERGY: also accumulate x^T A x (ElemArgs::energy). A separate instantiation: the plain apply keeps its registers (240 at p = 4;
 // one more live double costs 6 registers and 3 % of the apply).
 template < typename KernelT, int P, int NQ, int NRHS, bool ENERGY = false >
-__global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfHexCfg< KernelT, P, NQ, NRHS >::min_blocks)
+__global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::launch_threads, MfHexCfg< KernelT, P, NQ, NRHS >::launch_min_blocks)
     mfHexPlanesKernel(const KernelT kernel, const __grid_constant__ ElemArgs args, const __grid_constant__ SumFactTables< P + 1, NQ > tab)
 {
     using Cfg = MfHexCfg< KernelT, P, NQ, NRHS >;
@@ -172,7 +192,10 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
     constexpr int E = Cfg::E, U = Cfg::U, NF = Cfg::NF, NB = Cfg::NB, F0 = Cfg::F0, NN = Cfg::NN;
     constexpr int CT = Cfg::CT, PSZ = Cfg::PSZ, EPB = Cfg::EPB, AS = Cfg::AS, NPL = Cfg::NPL, NPLF = Cfg::NPLF;
     constexpr int T = Cfg::threads, RING = Cfg::RING;
-    extern __shared__ double smem[];
+    extern __shared__ double smem_all[];
+    constexpr int   WG      = Cfg::WG;
+    const int       wg      = WG > 1 ? threadIdx.x / T : 0;                  // warpgroup = virtual CTA
+    double* const   smem    = smem_all + wg * (WG > 1 ? Cfg::wg_stride_doubles : 0);
     double* const   s_V     = smem;
     double* const   s_DX    = smem + AS;
     double* const   s_DY    = smem + 2 * AS;
@@ -180,10 +203,20 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
     uint32_t* const s_ids   = reinterpret_cast< uint32_t* >(smem + Cfg::off_u32);
     uint32_t* const s_mask  = s_ids + Cfg::ids_words;
     uint32_t* const s_flag  = s_mask + Cfg::mask_words;
+    // barrier over the group's T threads (named barrier wg + 1 when the CTA holds several groups)
+    const auto groupSync = [&] {
+        if constexpr (WG > 1)
+            asm volatile("bar.sync %0, %1;" ::"r"(wg + 1), "n"(T) : "memory");
+        else
+            __syncthreads();
+    };
+    if constexpr (WG > 1)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::reg_base));
 
-    const int       tid       = threadIdx.x;
+    const int       tid       = WG > 1 ? threadIdx.x % T : threadIdx.x;
+    const long long vblock    = static_cast< long long >(blockIdx.x) * WG + wg, vgrid = static_cast< long long >(gridDim.x) * WG;
     const long long n_batches = (args.n_work + EPB - 1) / EPB;
-    const int       n_it      = static_cast< int >((n_batches - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const int       n_it      = static_cast< int >((n_batches - vblock + vgrid - 1) / vgrid);
     // column role
     const int  slot    = tid / CT;
     const int  cc      = tid % CT;
@@ -195,7 +228,7 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
     const bool vec_vals   = args.contiguous_dofs != 0 and U % 2 == 0;
     const bool stage_mask = vec_vals and U == 4 and args.dir_mask != nullptr;
 
-    const auto batchOf = [&](int i) { return static_cast< long long >(blockIdx.x) + static_cast< long long >(i) * gridDim.x; };
+    const auto batchOf = [&](int i) { return vblock + static_cast< long long >(i) * vgrid; };
     // element handled by this thread's slot in iteration i, or -1
     const auto elemOf = [&](int i) -> long long {
         const long long wi = batchOf(i) * EPB + slot;
@@ -292,7 +325,7 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
     prefetchGeo(0);
     cpAsyncCommit();
     cpAsyncWaitAll();
-    __syncthreads();
+    groupSync();
 #ifndef L3B_HEX_NO_X_PREFETCH
     loadX(0);
 #endif
@@ -397,7 +430,7 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
                 }
             }
         }
-        __syncthreads();
+        groupSync();
 
         // ---- software pipeline: geometry of the next batch, node ids of the one after
         if (it + 1 < n_it)
@@ -471,9 +504,11 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
                     py[qy * NQ + qx] = dy;
                 }
         }
-        __syncthreads();
+        groupSync();
 
         // ---- C: quadrature-point stage along the z-column (SumFactorization.hpp:614-756)
+        if constexpr (WG > 1)
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::reg_points)); // waits until the CTA's pool has them
         if (col_on)
         {
             const bool   affine = geo[hex_geo_affine] != 0.;
@@ -644,7 +679,9 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
             if (violated)
                 atomicOr(args.status, status_sparsity_violation);
         }
-        __syncthreads();
+        if constexpr (WG > 1)
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::reg_base));
+        groupSync();
 
         // ---- software pipeline: gather of the next batch into registers (consumed by A of the next iteration)
 #ifndef L3B_HEX_NO_X_PREFETCH
@@ -709,7 +746,7 @@ __global__ void __launch_bounds__(MfHexCfg< KernelT, P, NQ, NRHS >::threads, MfH
                     pv[j * NQ + i] = acc;
                 }
         }
-        __syncthreads();
+        groupSync();
 
 #ifdef L3B_HEX_SCATTER_TASKS
         // ---- E: z-projection + scatter (MatrixFreeSystem.hpp:494-537): relaxed fp64 atomics (RED), Dirichlet rows skipped.

@@ -77,23 +77,23 @@ cudaError_t launchMfHexImpl(const void* obj, const ElemArgs& args, const SumFact
 {
     using Cfg         = MfHexCfg< KernelT, P, NQ, NC >;
     constexpr auto fn = mfHexPlanesKernel< KernelT, P, NQ, NC, ENERGY >;
-    if (const auto err = raiseSmemLimit< fn >(Cfg::smem_bytes); err != cudaSuccess)
+    if (const auto err = raiseSmemLimit< fn >(Cfg::launch_smem); err != cudaSuccess)
         return err;
     static const cudaError_t carveout =
         cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, static_cast< int >(cudaSharedmemCarveoutMaxShared));
     if (carveout != cudaSuccess)
         return carveout;
-    // persistent grid: one CTA per resident slot of the device, batches strided over the grid
+    // persistent grid: one CTA per resident slot of the device, batches strided over the (virtual) CTAs
     static const int resident = [] {
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, Cfg::threads, Cfg::smem_bytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, Cfg::launch_threads, Cfg::launch_smem);
         return std::max(1, sms * std::max(1, per_sm));
     }();
     const long long n_batches = (args.n_work + Cfg::EPB - 1) / Cfg::EPB;
-    const auto      grid      = static_cast< unsigned >(std::min< long long >(n_batches, resident));
-    fn<<< grid, Cfg::threads, Cfg::smem_bytes, stream >>>(*static_cast< const KernelT* >(obj), args, tab);
+    const auto      grid      = static_cast< unsigned >(std::min< long long >((n_batches + Cfg::WG - 1) / Cfg::WG, resident));
+    fn<<< grid, Cfg::launch_threads, Cfg::launch_smem, stream >>>(*static_cast< const KernelT* >(obj), args, tab);
     return cudaGetLastError();
 }
 template < typename KernelT, int P, int NQ, int NC >

@@ -82,6 +82,71 @@ def run(kind, orders=(1, 2, 3, 4, 5, 6)):
         print(json.dumps(line), flush=True)
 
 
+def executed_flops(eq_sets, n_eq_total, nn, q):
+    """multiply-adds x 2 the DMMA assembly kernel issues per element (assemble_dmma.cuh): per unknown pair (u <= v) the equations
+    E_u ∩ E_v, 32 x 32 warp tiles of the TM x TN node tiles (for u == v: warp tiles above the diagonal skipped),
+    quadrature points padded to whole chunks"""
+    tn = 128 if nn > 64 else 64 if nn > 32 else 32
+    n_blk = -(-nn // tn)
+    kcmax = max(32, 4 * n_eq_total)
+    macs = 0.0
+    for u in range(len(eq_sets)):
+        for v in range(u, len(eq_sets)):
+            n_eq = len(eq_sets[u] & eq_sets[v])
+            if n_eq == 0:
+                continue
+            qc = min(32, (kcmax // n_eq) & ~3)
+            k_rows = -(-q // qc) * qc * n_eq
+            units = 0.0
+            for rb in range(n_blk):
+                for cb in range(n_blk):
+                    if u == v and cb * tn > rb * tn + tn - 1:
+                        continue
+                    for wy in range(tn // 32):
+                        for wx in range(tn // 32):
+                            r0, c0 = rb * tn + wy * 32, cb * tn + wx * 32
+                            if u == v and c0 > r0 + 31:
+                                continue
+                            units += 1.0  # (a diagonal warp tile issues 10 of its 16 DMMA tiles; counted whole, as bench.py does)
+            macs += units * 32 * 32 * k_rows
+    return 2.0 * macs
+
+
+NS3D_EQS = [{0, 1, 2, 4, 5, 6}, {0, 1, 2, 3, 5, 6}, {0, 1, 2, 3, 4, 6}, {0}, {1, 2, 3, 7}, {0, 2, 4, 7}, {0, 1, 5, 7}]  # benchmarks/Kernels.hpp:3-65
+
+
+def run_ns3d(orders=(2, 4)):
+    """BASELINE configs[4] as the reference's harness runs it (benchmarks/LocalAssemblyBenchmarks.cpp:41-87): NS3D kernel, U = 7, E = 8,
+    n_fields = 7, quadrature order 4p - 1 (= AssemblyOptions{1, 1}, nq = 2p), DPFlops counter of :71-75"""
+    ctx = l3b.Context(0)
+    U7, E8, NF = 7, 8, 7
+    opts = l3b.AssemblyOptions(value_order=1, derivative_order=1)
+    peak = ctx.microbench(1)
+    for p in orders:
+        n = {2: 16, 3: 10, 4: 6}[p]
+        host = l3b.make_cube_mesh(node_dist(n), order=p)
+        mesh = ctx.upload_mesh(host)
+        fields = ctx.upload_fields(np.random.default_rng(0).uniform(-1, 1, size=(NF, host.n_nodes)))
+        a = l3b.AssembledSystem(ctx, mesh, U7, 1, host.node_graph())
+        ms = []
+        for it in range(5):
+            a.beginAssembly()
+            a.assembleProblem("ns3d_kernel", fields=fields, asm_opts=opts)
+            ms.append(a.last_kernel_ms)
+        k_ms = float(np.mean(ms[2:]))
+        nn, q = (p + 1) ** 3, (2 * p) ** 3
+        L = nn * U7
+        ref = q * (18 * nn + 8 * NF * nn + 7 * L * E8 + (L + 1) ** 2 / 2 * (2 * E8 + 1))
+        ex = executed_flops(NS3D_EQS, E8, nn, q)
+        print(json.dumps({"order": p, "kernel": "ns3d", "assembly_kernel": "dmma" if nn >= 32 else "dfma", "elements": host.n_elems, "nq": 2 * p,
+                          "kernel_ms": k_ms, "elements_per_s": host.n_elems / (k_ms * 1e-3),
+                          "tflops_reference_count": ref * host.n_elems / (k_ms * 1e-3) / 1e12,
+                          "executed_tflops": ex * host.n_elems / (k_ms * 1e-3) / 1e12 if nn >= 32 else None,
+                          "dmma_peak_tflops_measured": peak,
+                          "frac_executed": ex * host.n_elems / (k_ms * 1e-3) / 1e12 / peak if nn >= 32 else None}), flush=True)
+        del a
+
+
 def run_quads(orders=(1, 2, 3, 4, 5, 6, 7, 8)):
     """the 2-D half: quads, diffusion (U = 3, E = 4): assembly (the kernel the size rule picks) and matrix-free apply per order"""
     import torch
@@ -129,7 +194,9 @@ def run_quads(orders=(1, 2, 3, 4, 5, 6, 7, 8)):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "quad":
+    if len(sys.argv) > 1 and sys.argv[1] == "ns3d":
+        run_ns3d(tuple(int(a) for a in sys.argv[2:]) or (2, 4))
+    elif len(sys.argv) > 1 and sys.argv[1] == "quad":
         run_quads(tuple(int(a) for a in sys.argv[2:]) or (1, 2, 3, 4, 5, 6, 7, 8))
     elif len(sys.argv) > 2:  # e.g. `order_sweep.py mf 4 5 6`: the matrix-free apply only, these orders
         run(sys.argv[1], tuple(int(a) for a in sys.argv[2:]))
@@ -139,3 +206,4 @@ if __name__ == "__main__":
         run("dmma", (1, 2, 3, 4, 5, 6, 7, 8))
         subprocess.run([sys.executable, os.path.abspath(__file__), "dfma"], env=dict(os.environ, L3B_ASM_FMA="1"), check=True)
         run_quads()
+        run_ns3d()
