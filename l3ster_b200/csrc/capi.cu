@@ -13,7 +13,9 @@
 
 #include <nvtx3/nvToolsExt.h>
 
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -549,6 +551,36 @@ struct l3b_context
     mutable std::string err;
     DevBuf< int >       status;
     DevBuf< double >    scalars; // Krylov scalars
+    // Work vectors of the Krylov drivers, kept between solves: a time loop solves the same system again and again, a fresh set of
+    // cudaMalloc'ed 0.5 GB vectors per solve costs tens of milliseconds of allocator time — and lands at different relative offsets
+    // every time, which showed as a 2.4 - 3.3 ms spread of the CG iteration (the five streams of the vector passes collide in the
+    // memory system when their bases line up). One slab, vectors carved out with staggered starts.
+    DevBuf< double >    krylov_ws;
+    double*             pinned_scalars = nullptr; // 8 doubles of page-locked host memory for the drivers' read-backs (cudaMallocHost and
+                                                  // cudaFreeHost synchronise the device and cost up to a second with tens of GB mapped:
+                                                  // once per context, not once per solve)
+    cudaEvent_t         krylov_event   = nullptr;
+    double*             pinnedScalars()
+    {
+        if (pinned_scalars == nullptr)
+            cudaCheck(cudaMallocHost(&pinned_scalars, 8 * sizeof(double)), "cudaMallocHost");
+        return pinned_scalars;
+    }
+    cudaEvent_t krylovEvent()
+    {
+        if (krylov_event == nullptr)
+            cudaCheck(cudaEventCreateWithFlags(&krylov_event, cudaEventDisableTiming), "cudaEventCreate");
+        return krylov_event;
+    }
+    double*             workspace(size_t n_doubles)
+    {
+        if (krylov_ws.n < n_doubles)
+        {
+            cudaCheck(cudaStreamSynchronize(stream), "sync");
+            krylov_ws.alloc(n_doubles);
+        }
+        return krylov_ws.ptr;
+    }
     int                 sm_count = 148;
     std::map< std::pair< int, int >, tables::Tables1D > tab1d;
     struct DenseDev
@@ -1355,12 +1387,29 @@ void pcg(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Reduce
          double* x /* device */, double tol, int max_iters, double* achieved, int* iters, bool x0_zero = true)
 {
     // n = owned dofs: dots and updates run over those; p and Ap carry the ghost tail the operator needs
-    DevBuf< double > r(n), z(n), p(n_local), Ap(n_local), minv(n);
-    DevBuf< double > sc_buf(8);
-    PinnedScalars    pinned;
-    Event            read_back;
+    struct Vec
+    {
+        double* ptr;
+        size_t  n;
+        void    zero(cudaStream_t st) const
+        {
+            if (n > 0)
+                cudaCheck(cudaMemsetAsync(ptr, 0, n * sizeof(double), st), "memset");
+        }
+    };
+    // starts staggered by an odd number of 256-byte lines so that the streams of one vector pass do not share a phase
+    const auto       padded = [](long long len, int k) { return static_cast< size_t >((len + 31) / 32 * 32 + 32 * (17 + 2 * k)); };
+    const size_t     total  = padded(n, 0) + padded(n, 1) + padded(n_local, 2) + padded(n_local, 3) + padded(n, 4) + 64;
+    double*          ws     = ctx->workspace(total);
+    const Vec        r{ws, static_cast< size_t >(n)};
+    const Vec        z{r.ptr + padded(n, 0), static_cast< size_t >(n)};
+    const Vec        p{z.ptr + padded(n, 1), static_cast< size_t >(n_local)};
+    const Vec        Ap{p.ptr + padded(n_local, 2), static_cast< size_t >(n_local)};
+    const Vec        minv{Ap.ptr + padded(n_local, 3), static_cast< size_t >(n)};
+    const Vec        sc_buf{minv.ptr + padded(n, 4), 8};
+    const cudaEvent_t read_back_ev = ctx->krylovEvent();
     double*    sc = sc_buf.ptr; // [0] rz, [1] pAp, [2] rr, [3] rz_new
-    double*    h  = pinned.h;
+    double*    h  = ctx->pinnedScalars();
     const auto s  = ctx->stream;
     const auto g  = gridFor(n);
     jacobiInvertKernel<<< g, 256, 0, s >>>(diag, minv.ptr, n, 1., 0.);
@@ -1385,6 +1434,9 @@ void pcg(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Reduce
     cudaCheck(cudaStreamSynchronize(s), "sync");
     double rnorm = std::sqrt(h[0]);
     int    it    = 0;
+    static const bool     trace = [] { const char* e = std::getenv("L3B_PCG_TRACE"); return e != nullptr and e[0] == '1'; }();
+    std::vector< double > stamps;
+    const auto            t_start = std::chrono::steady_clock::now();
     if (rnorm > tol and max_iters > 0)
     {
         cudaCheck(cudaMemcpyAsync(sc, sc + 3, sizeof(double), cudaMemcpyDeviceToDevice, s), "copy"); // rz
@@ -1401,7 +1453,7 @@ void pcg(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Reduce
             cgUpdateKernel<<< g, 256, 0, s >>>(r.ptr, z.ptr, Ap.ptr, minv.ptr, n, sc, sc + 2);
             reduce(sc + 2, 2);
             cudaCheck(cudaMemcpyAsync(h, sc + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, s), "copy");
-            cudaCheck(cudaEventRecord(read_back.ev, s), "event");
+            cudaCheck(cudaEventRecord(read_back_ev, s), "event");
             ++it;
             const bool last = it >= max_iters;
             if (last)
@@ -1412,10 +1464,35 @@ void pcg(l3b_context* ctx, long long n_local, long long n, Apply&& apply, Reduce
                 cudaCheck(cudaMemcpyAsync(sc, sc + 3, sizeof(double), cudaMemcpyDeviceToDevice, s), "copy");
                 applyAndDot();
             }
-            cudaCheck(cudaEventSynchronize(read_back.ev), "sync");
+            cudaCheck(cudaEventSynchronize(read_back_ev), "sync");
+            if (trace)
+                stamps.push_back(std::chrono::duration< double, std::milli >(std::chrono::steady_clock::now() - t_start).count());
             rnorm = std::sqrt(h[0]);
             if (last or not(rnorm > tol))
                 break;
+        }
+        if (trace and stamps.size() > 2)
+        {
+            // L3B_PCG_TRACE=1: distribution of the host-observed iteration periods (diagnostics for run-to-run spread)
+            std::vector< double > d;
+            for (size_t i = 1; i < stamps.size(); ++i)
+                d.push_back(stamps[i] - stamps[i - 1]);
+            std::vector< double > sorted = d;
+            std::sort(sorted.begin(), sorted.end());
+            const auto pct = [&](double q) { return sorted[static_cast< size_t >(q * (sorted.size() - 1))]; };
+            std::fprintf(stderr, "[l3b pcg trace] %zu iterations: period min %.3f, p10 %.3f, median %.3f, p90 %.3f, p99 %.3f, max %.3f ms; first 8:", d.size(),
+                         sorted.front(), pct(.1), pct(.5), pct(.9), pct(.99), sorted.back());
+            for (size_t i = 0; i < std::min< size_t >(8, d.size()); ++i)
+                std::fprintf(stderr, " %.3f", d[i]);
+            std::fprintf(stderr, "; 100-iteration means:");
+            for (size_t i = 0; i + 100 <= d.size(); i += 100)
+            {
+                double m = 0.;
+                for (size_t k = i; k < i + 100; ++k)
+                    m += d[k];
+                std::fprintf(stderr, " %.3f", m / 100);
+            }
+            std::fprintf(stderr, "\n");
         }
         cudaCheck(cudaStreamSynchronize(s), "sync"); // the speculative tail reads buffers this function owns
     }
@@ -1626,6 +1703,11 @@ void l3b_context_destroy(l3b_context* ctx)
     ctx->node_tabs.clear();
     ctx->status.release();
     ctx->scalars.release();
+    ctx->krylov_ws.release();
+    if (ctx->pinned_scalars)
+        cudaFreeHost(ctx->pinned_scalars);
+    if (ctx->krylov_event)
+        cudaEventDestroy(ctx->krylov_event);
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;
