@@ -1154,6 +1154,7 @@ struct l3b_mf
     // more than one rank (l3b_mf_set_halo): the halo of the dof layout [owned | ghost]; elements [0, n_border) touch ghost nodes
     l3b_halo*                halo     = nullptr;
     long long                n_border = 0;
+    int                      reserve_ctas = 0; // set around the launches that must leave room for the halo's NCCL kernels
     long long                ownedDofs() const { return static_cast< long long >(mesh->n_owned_nodes) * dpn; }
     l3b_comm*                comm() const { return halo ? halo->comm : nullptr; }
 };
@@ -1252,6 +1253,7 @@ int applyUse(l3b_mf* sys, const KernelUse& use, const double* x, double* y, int 
     a.n_cols         = n_cols;
     a.alpha          = alpha;
     a.energy         = energy;
+    a.reserve_ctas   = sys->reserve_ctas;
     a.dir_mask       = sys->has_bc and masked ? sys->dir_mask.ptr : nullptr;
     a.elem_dir       = sys->has_bc and masked ? sys->elem_dir.ptr : nullptr;
     bool contiguous  = info.n_unknowns == sys->dpn and reinterpret_cast< uintptr_t >(x) % 16 == 0 and sys->n_dofs % 2 == 0;
@@ -1321,10 +1323,10 @@ void mfApplyPhases(l3b_mf* sys, const double* x, double* y, int n_cols, double a
     sys->last_launches = launches; // of this call
 }
 // The whole operator apply. One rank: one pass over all elements. With a halo (MatrixFreeSystem::applyImpl, :1019-1140):
-//     pack + post the Import of x | y <- beta y (the pass over y hides the Import) | wait | border elements + boundary kernels |
-//     post the Export of y | interior elements (hide the Export) | wait + unpack-add | Dirichlet rows
-// The reference runs interior elements first and polls for the Import; here the zeroing of y covers the Import and the long interior
-// launch covers the Export, so neither transfer is exposed. The ghost block of x is overwritten by the Import.
+//     pack + post the Import of x | y <- beta y | first half of the interior elements | wait | border elements + boundary kernels |
+//     post the Export of y | second half of the interior elements | wait + unpack-add | Dirichlet rows
+// The reference runs its interior elements while it polls for the Import and exposes the Export; here each transfer hides behind half
+// of the interior work. The ghost block of x is overwritten by the Import.
 void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta, double* energy = nullptr)
 {
     const ProfileRegion region{"Evaluate matrix-free operator"}; // MatrixFreeSystem.hpp:1032-1139
@@ -1336,15 +1338,47 @@ void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double a
     }
     int        launches = haloImportBegin(h, const_cast< double* >(x), n_cols);
     const auto n_elems  = sys->mesh->n_elems;
+    // Two schedules. Border-first: Import behind the pass that zeroes y, border elements, Export behind ALL interior elements — the
+    // cheapest (one interior launch), but the Import has only ~80 us of slack. Split: half of the interior elements before the border
+    // elements (hiding the Import), half after (hiding the Export) — either exchange may lag by half an apply before anybody waits.
+    // A rank with a single neighbour (2 ranks; the ends of a chain) runs border-first, a rank with several — whose neighbours drift
+    // against each other — runs split. Measured, 64^3 hex p=4 per GPU, ms per apply: 2 GPUs 1.48 border-first / 1.67 split;
+    // 8 GPUs 1.70 - 2.26 border-first / 1.51 split (1.43 on one GPU). L3B_APPLY_SPLIT=0 / 1 forces one schedule on every rank.
+    static const int forced = [] {
+        const char* e = std::getenv("L3B_APPLY_SPLIT");
+        return e == nullptr ? -1 : e[0] != '0';
+    }();
+    int n_nbrs = static_cast< int >(h->owned_nbrs.size());
+    for (int r : h->shared_nbrs)
+        n_nbrs += std::find(h->owned_nbrs.begin(), h->owned_nbrs.end(), r) == h->owned_nbrs.end();
+    const bool split = forced >= 0 ? forced != 0 : n_nbrs >= 2;
+    const long long half = split ? sys->n_border + (n_elems - sys->n_border) / 2 : sys->n_border;
+    // The persistent element kernel fills every resident CTA slot; an NCCL send / recv kernel queued while it runs would wait for it to
+    // finish (registers, not SMs, are what is full). Leaving a few slots free lets the transfers start at once.
+    static const int reserve = [] {
+        const char* e = std::getenv("L3B_HALO_RESERVE_CTAS");
+        return e != nullptr ? std::atoi(e) : 0; // measured on 2 and 8 GPUs: no gain from 8 free slots (NCCL's kernel gets in anyway)
+    }();
+    struct ReserveScope
+    {
+        l3b_mf* s;
+        ReserveScope(l3b_mf* s_, int r) : s{s_} { s->reserve_ctas = r; }
+        ~ReserveScope() { s->reserve_ctas = 0; }
+    } const reserve_scope{sys, reserve};
     mfApplyPhases(sys, x, y, n_cols, alpha, beta, L3B_APPLY_INIT, 0, 0);
     launches += sys->last_launches;
+    if (half > sys->n_border)
+    {
+        mfApplyPhases(sys, x, y, n_cols, alpha, beta, L3B_APPLY_ELEMENTS, sys->n_border, half, energy);
+        launches += sys->last_launches;
+    }
     haloImportEnd(h);
     mfApplyPhases(sys, x, y, n_cols, alpha, beta, L3B_APPLY_ELEMENTS | L3B_APPLY_BOUNDARY, 0, sys->n_border, energy);
     launches += sys->last_launches;
     haloExportBegin(h, y, n_cols);
-    if (sys->n_border < n_elems)
+    if (half < n_elems)
     {
-        mfApplyPhases(sys, x, y, n_cols, alpha, beta, L3B_APPLY_ELEMENTS, sys->n_border, n_elems, energy);
+        mfApplyPhases(sys, x, y, n_cols, alpha, beta, L3B_APPLY_ELEMENTS, half, n_elems, energy);
         launches += sys->last_launches;
     }
     launches += haloExportEnd(h, y, n_cols);

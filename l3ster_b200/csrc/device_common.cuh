@@ -58,6 +58,9 @@ struct ElemArgs
     // operator apply only, may be null: x^T A x of operand column 0 over the elements of this launch is added here (for CG's p.Ap:
     // sum_q w |B_q x_e|^2 falls out of the point stage, which saves the separate dot-product pass over both vectors)
     double* energy;
+    // host-side launch hint (not read on the device): resident CTA slots a persistent launch leaves free, so that a communication
+    // kernel queued on another stream (NCCL send / recv) can start while it runs
+    int reserve_ctas;
     // Dirichlet mask per local dof (may be null) and prescribed values (ld-strided, may be null)
     const uint8_t* dir_mask;
     const double*  dir_vals;

@@ -92,7 +92,7 @@ cudaError_t launchMfHexImpl(const void* obj, const ElemArgs& args, const SumFact
         return std::max(1, sms * std::max(1, per_sm));
     }();
     const long long n_batches = (args.n_work + Cfg::EPB - 1) / Cfg::EPB;
-    const auto      grid      = static_cast< unsigned >(std::min< long long >((n_batches + Cfg::WG - 1) / Cfg::WG, resident));
+    const auto      grid      = static_cast< unsigned >(std::min< long long >((n_batches + Cfg::WG - 1) / Cfg::WG, std::max(1, resident - args.reserve_ctas)));
     fn<<< grid, Cfg::launch_threads, Cfg::launch_smem, stream >>>(*static_cast< const KernelT* >(obj), args, tab);
     return cudaGetLastError();
 }
