@@ -1,5 +1,6 @@
 """Per-phase table of an `ncu --page source --csv --print-source cuda,sass` dump of mfHexPlanesKernel: share of the stall samples,
-of the executed instructions, static SASS instructions (code size) and the top stall reasons. Usage: ncu_phase_table.py dump.csv"""
+of the executed instructions, static SASS instructions (code size) and the top stall reasons.
+Usage: ncu_phase_table.py dump.csv [name:first_line ...]   (phase marks are read from the current source unless given)"""
 import csv
 import re
 import sys
@@ -15,6 +16,8 @@ for i, line in enumerate(open(SRC), 1):
     elif "for (int it = 0; it < n_it" in line:
         marks.append((i, "loop head"))
 marks.append((10**9, "end"))
+if len(sys.argv) > 2:  # explicit marks for a capture of an older revision of the source: name:first_line ...
+    marks = [(int(a.split(":")[1]), a.split(":")[0]) for a in sys.argv[2:]] + [(10**9, "end")]
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = cur = curfile = None
 agg, static = defaultdict(lambda: defaultdict(float)), defaultdict(int)
