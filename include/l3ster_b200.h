@@ -298,6 +298,23 @@ int l3b_mf_download(l3b_mf* sys, double* diag, double* rhs);
  * host version: copies x (and y if beta != 0) in, y out. */
 int l3b_mf_apply_device(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta);
 int l3b_mf_apply(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha, double beta);
+/* How the host version moves its vectors. The reference's Krylov vectors live in host memory, so this is the call a drop-in makes per
+ * iteration, and at the benchmark's size its two PCIe copies cost 14 x the apply. mode 0: serial (x in, apply, y out). mode 1 (default):
+ * streamed when beta == 0, only domain kernels are registered, x and y do not overlap and the vectors are at least 8 MB — the interior
+ * elements are cut into n_chunks chunks; x travels in blocks of block_nodes nodes on a copy-in stream in the order the chunks first
+ * touch them, chunk k runs when its blocks have landed, and every y block leaves on a copy-out stream once the last chunk that adds to
+ * it has run and its Dirichlet rows are set; with a halo the border elements and the exchange form the last item. Any element order is
+ * legal (no locality = serial behaviour). mode 2: streamed whenever legal, whatever the size. Defaults: 48 chunks, 8192 nodes. */
+int l3b_mf_set_host_apply(l3b_mf* sys, int mode, int n_chunks, int64_t block_nodes);
+/* info = {1 if the last l3b_mf_apply ran streamed, items, upload ranges, download ranges of the current schedule} */
+int l3b_mf_host_apply_info(const l3b_mf* sys, int64_t info[4]);
+/* the schedule itself (host only, csrc/apply_plan_host.hpp): items = chunks of chunk_elems interior elements [n_border_elems, n_elems),
+ * then — with border elements, halo nodes or ghost nodes — one item for the border elements + exchange. item_elems[2 k .. 2 k + 1]:
+ * element range of item k; up_ranges / down_ranges [2 r .. 2 r + 1]: node ranges to copy in before / out after the item, CSR offsets
+ * in up_ptr / down_ptr [n_items + 1]. Arrays are malloc'ed by the library; release with l3b_free. */
+int l3b_host_apply_plan(int64_t n_nodes, int64_t n_owned_nodes, int64_t n_elems, int nodes_per_elem, const uint32_t* nodes,
+                        int64_t n_border_elems, const int32_t* halo_nodes, int64_t n_halo_nodes, int64_t chunk_elems, int64_t block_nodes,
+                        int* n_items, int64_t** item_elems, int64_t** up_ptr, int64_t** up_ranges, int64_t** down_ptr, int64_t** down_ranges);
 /* single-column apply that also adds this rank's share of x^T A x (its elements, its owned Dirichlet dofs) to the device scalar
  * `energy`: CG takes p.Ap from the quadrature-point stage instead of a dot-product pass (see l3b_mf_apply_phase_device) */
 int l3b_mf_apply_energy_device(l3b_mf* sys, const double* x, double* y, double alpha, double beta, double* energy);

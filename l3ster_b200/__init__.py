@@ -80,6 +80,7 @@ EXPORTED_SYMBOLS = [
     "l3b_partition_rank_halo", "l3b_partition_rank_graph", "l3b_asm_export_shared_rows",
     "l3b_mesh_set_element_domains", "l3b_dofmap_create", "l3b_dofmap_destroy", "l3b_dofmap_info", "l3b_dofmap_get", "l3b_asm_set_dofmap",
     "l3b_asm_download_compact", "l3b_compute_values_at_nodes", "l3b_update_solution", "l3b_fields_device",
+    "l3b_mf_set_host_apply", "l3b_mf_host_apply_info", "l3b_host_apply_plan",
 ]
 
 
@@ -218,6 +219,9 @@ def lib():
         getattr(L, f).argtypes = [vp, i32, dbl, i32, i32, i32, vp, i32, C.POINTER(dbl), C.POINTER(i32)]
     L.l3b_vec_scatter_add.argtypes = [vp, vp, i64, vp, i64, i32, vp]
     L.l3b_mf_apply.argtypes = [vp, vp, vp, i32, dbl, dbl]
+    L.l3b_mf_set_host_apply.argtypes = [vp, i32, i32, i64]
+    L.l3b_mf_host_apply_info.argtypes = [vp, vp]
+    L.l3b_host_apply_plan.argtypes = [i64, i64, i64, i32, vp, i64, vp, i64, i64, i64, C.POINTER(i32)] + [C.POINTER(vp)] * 5
     L.l3b_mf_solve_cg.argtypes = [vp, dbl, i32, vp, C.POINTER(dbl), C.POINTER(i32)]
     L.l3b_mf_num_dofs.argtypes = [vp]
     L.l3b_mf_num_dofs.restype = i64
@@ -384,6 +388,31 @@ def node_graph(n_nodes, nodes):
         lib().l3b_free(ptr)
         lib().l3b_free(nbr)
     return p, n
+
+
+def host_apply_plan(n_nodes, nodes, chunk_elems, block_nodes, n_owned_nodes=None, n_border_elems=0, halo_nodes=None):
+    """Schedule of the streamed host-buffer apply (csrc/apply_plan_host.hpp): returns (item_elems [n_items, 2], up, down) with up / down
+    = per item the list of node ranges (begin, end) to copy in before / out after the item."""
+    nodes = np.ascontiguousarray(nodes, dtype=np.uint32).reshape(-1, np.shape(nodes)[-1] if np.ndim(nodes) == 2 else 1)
+    halo = np.zeros(0, dtype=np.int32) if halo_nodes is None else np.ascontiguousarray(halo_nodes, dtype=np.int32)
+    n_items = C.c_int()
+    out = [C.c_void_p() for _ in range(5)]
+    rc = lib().l3b_host_apply_plan(n_nodes, n_nodes if n_owned_nodes is None else n_owned_nodes, nodes.shape[0], nodes.shape[1], _p(nodes),
+                                   n_border_elems, _p(halo), len(halo), chunk_elems, block_nodes, C.byref(n_items), *[C.byref(o) for o in out])
+    if rc != 0:
+        raise L3BError(rc, lib().l3b_global_error().decode())
+    try:
+        k = n_items.value
+        arr = lambda ptr, n: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int64)), shape=(max(n, 1),)).copy()[:n]  # noqa: E731
+        items = arr(out[0], 2 * k).reshape(k, 2)
+        up_ptr, down_ptr = arr(out[1], k + 1), arr(out[3], k + 1)
+        up_r, down_r = arr(out[2], 2 * int(up_ptr[-1])).reshape(-1, 2), arr(out[4], 2 * int(down_ptr[-1])).reshape(-1, 2)
+    finally:
+        for o in out:
+            lib().l3b_free(o)
+    up = [[tuple(map(int, r)) for r in up_r[up_ptr[i]:up_ptr[i + 1]]] for i in range(k)]
+    down = [[tuple(map(int, r)) for r in down_r[down_ptr[i]:down_ptr[i + 1]]] for i in range(k)]
+    return items, up, down
 
 
 def expand_graph(ptr, nbr, dofs_per_node, with_cols=True):
@@ -931,6 +960,16 @@ class MatrixFreeSystem:
     def apply_raw(self, xf, yf, n_cols=1, alpha=1.0, beta=0.0):
         """host buffers already in the C ABI layout (column-major, contiguous): no numpy copies in the timed region"""
         self.ctx._chk(lib().l3b_mf_apply(self._h, xf.ctypes.data, yf.ctypes.data, n_cols, alpha, beta))
+
+    def set_host_apply(self, mode=1, n_chunks=48, block_nodes=8192):
+        """how `apply` / `apply_raw` move their host vectors (l3b_mf_set_host_apply): 0 serial, 1 streamed when it pays, 2 streamed
+        whenever legal"""
+        self.ctx._chk(lib().l3b_mf_set_host_apply(self._h, mode, n_chunks, block_nodes))
+
+    def host_apply_info(self):
+        info = np.zeros(4, dtype=np.int64)
+        self.ctx._chk(lib().l3b_mf_host_apply_info(self._h, _p(info)))
+        return {"streamed": bool(info[0]), "items": int(info[1]), "up_ranges": int(info[2]), "down_ranges": int(info[3])}
 
     def apply_device(self, x_ptr, y_ptr, n_cols=1, alpha=1.0, beta=0.0, energy_ptr=None):
         if energy_ptr is None:

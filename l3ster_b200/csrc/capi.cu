@@ -5,6 +5,7 @@
 #include "comm.cuh"
 #include "mesh_host.hpp"
 #include "partition_host.hpp"
+#include "apply_plan_host.hpp"
 #include "dofmap_host.hpp"
 #include "mf_hex_planes.cuh"
 #include "condense.cuh"
@@ -1134,6 +1135,31 @@ struct l3b_asm
     }
 };
 
+// state of the streamed host-buffer apply (apply_plan_host.hpp): the schedule, the two copy streams and one event pair per item
+struct HostApplyPipe
+{
+    l3b::host::ApplyPlan       plan;
+    cudaStream_t               up = nullptr, down = nullptr; // copy-in / copy-out streams
+    cudaEvent_t                begin = nullptr;
+    std::vector< cudaEvent_t > landed, done; // per item: its x blocks are on the device / its final y blocks may leave
+    HostApplyPipe()                                = default;
+    HostApplyPipe(const HostApplyPipe&)            = delete;
+    HostApplyPipe& operator=(const HostApplyPipe&) = delete;
+    ~HostApplyPipe()
+    {
+        for (auto ev : landed)
+            cudaEventDestroy(ev);
+        for (auto ev : done)
+            cudaEventDestroy(ev);
+        if (begin)
+            cudaEventDestroy(begin);
+        if (up)
+            cudaStreamDestroy(up);
+        if (down)
+            cudaStreamDestroy(down);
+    }
+};
+
 struct l3b_mf
 {
     l3b_context*             ctx  = nullptr;
@@ -1150,6 +1176,12 @@ struct l3b_mf
     bool                     has_bc = false, closed = false;
     std::vector< KernelUse > uses;
     DevBuf< double >         work_x, work_y; // staging for the host-buffer apply
+    std::vector< int32_t >   dir_list_host;  // host copy of dir_list (the streamed host-buffer apply cuts it by node range)
+    // host-buffer apply: 0 = serial (copy in, apply, copy out), 1 = streamed when it pays (the default), 2 = streamed whenever legal
+    int                              host_apply_mode = 1, host_apply_chunks = 48;
+    long long                        host_apply_block_nodes = 8192;
+    std::unique_ptr< HostApplyPipe > pipe;
+    bool                             last_host_apply_streamed = false;
     int                      last_launches = 0;
     // more than one rank (l3b_mf_set_halo): the halo of the dof layout [owned | ghost]; elements [0, n_border) touch ghost nodes
     l3b_halo*                halo     = nullptr;
@@ -1384,6 +1416,153 @@ void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double a
     launches += haloExportEnd(h, y, n_cols);
     mfApplyPhases(sys, x, y, n_cols, alpha, beta, L3B_APPLY_FINISH, 0, 0, energy);
     sys->last_launches += launches;
+}
+
+// ---- streamed host-buffer apply (apply_plan_host.hpp): x over PCIe, the element chunks and y over PCIe as three concurrent streams
+HostApplyPipe& hostApplyPipe(l3b_mf* sys)
+{
+    if (sys->pipe)
+        return *sys->pipe;
+    auto        p    = std::make_unique< HostApplyPipe >();
+    auto* const mesh = sys->mesh;
+    const auto  S    = sys->ctx->stream;
+    const bool  halo = sys->halo != nullptr and sys->halo->active();
+    // the connectivity lives on the device only: one read-back per system (131 MB at 64^3 hex p=4), not per apply
+    std::vector< uint32_t > nodes(static_cast< size_t >(mesh->n_elems) * mesh->nn);
+    mesh->nodes.download(nodes.data(), nodes.size(), S);
+    std::vector< int32_t > halo_nodes;
+    if (halo and sys->halo->owned_ptr.back() > 0)
+    {
+        halo_nodes.resize(static_cast< size_t >(sys->halo->owned_ptr.back()));
+        sys->halo->owned_idx.download(halo_nodes.data(), halo_nodes.size(), S);
+    }
+    cudaCheck(cudaStreamSynchronize(S), "connectivity read-back");
+    for (auto& d : halo_nodes)
+        d /= sys->dpn; // dof index -> node
+    const long long n_border   = halo ? sys->n_border : 0;
+    const long long n_interior = mesh->n_elems - n_border;
+    const long long chunk      = std::max< long long >(1, (n_interior + sys->host_apply_chunks - 1) / std::max(1, sys->host_apply_chunks));
+    try
+    {
+        p->plan = l3b::host::makeApplyPlan(mesh->n_local_nodes, halo ? mesh->n_owned_nodes : mesh->n_local_nodes, mesh->n_elems, mesh->nn, nodes.data(),
+                                           n_border, halo_nodes.data(), static_cast< long long >(halo_nodes.size()), chunk,
+                                           std::max< long long >(1, sys->host_apply_block_nodes));
+    }
+    catch (const std::exception& e)
+    {
+        fail(L3B_ERR_INVALID_ARG, std::string{"host apply plan: "} + e.what());
+    }
+    cudaCheck(cudaStreamCreateWithFlags(&p->up, cudaStreamNonBlocking), "stream create");
+    cudaCheck(cudaStreamCreateWithFlags(&p->down, cudaStreamNonBlocking), "stream create");
+    cudaCheck(cudaEventCreateWithFlags(&p->begin, cudaEventDisableTiming), "event create");
+    p->landed.assign(p->plan.n_items, nullptr);
+    p->done.assign(p->plan.n_items, nullptr);
+    for (int k = 0; k < p->plan.n_items; ++k)
+    {
+        cudaCheck(cudaEventCreateWithFlags(&p->landed[k], cudaEventDisableTiming), "event create");
+        cudaCheck(cudaEventCreateWithFlags(&p->done[k], cudaEventDisableTiming), "event create");
+    }
+    sys->pipe = std::move(p);
+    return *sys->pipe;
+}
+// may this call take the streamed form? y <- alpha A x only (beta y would need y over PCIe in both directions), domain kernels only
+// (the side list of a boundary kernel is not cut into chunks), distinct host vectors (y blocks land in host memory while x blocks are
+// still being read), and — unless forced — vectors large enough for the copies to matter
+bool hostApplyStreams(const l3b_mf* sys, const double* x, const double* y, int n_cols, double beta)
+{
+    if (sys->host_apply_mode == 0 or beta != 0. or not sys->closed)
+        return false;
+    for (const auto& use : sys->uses)
+        if (kernelRegistry()[use.kernel_id].info.is_boundary)
+            return false;
+    const size_t n = static_cast< size_t >(sys->n_dofs) * n_cols;
+    const auto xb = reinterpret_cast< uintptr_t >(x), yb = reinterpret_cast< uintptr_t >(y);
+    if (n == 0 or (xb < yb + n * sizeof(double) and yb < xb + n * sizeof(double)))
+        return false;
+    return sys->host_apply_mode == 2 or n * sizeof(double) >= (size_t{8} << 20);
+}
+void mfApplyHostStreamed(l3b_mf* sys, const double* x, double* y, int n_cols, double alpha)
+{
+    const ProfileRegion region{"Evaluate matrix-free operator"};
+    auto&           pipe = hostApplyPipe(sys);
+    const auto&     plan = pipe.plan;
+    auto* const     ctx  = sys->ctx;
+    const auto      S    = ctx->stream;
+    const long long ld   = sys->n_dofs;
+    const int       dpn  = sys->dpn;
+    double* const   wx   = sys->work_x.ptr;
+    double* const   wy   = sys->work_y.ptr;
+    // both copy streams start behind whatever the context stream still does with the staging vectors
+    cudaCheck(cudaEventRecord(pipe.begin, S), "event record");
+    cudaCheck(cudaStreamWaitEvent(pipe.up, pipe.begin, 0), "event wait");
+    cudaCheck(cudaStreamWaitEvent(pipe.down, pipe.begin, 0), "event wait");
+    for (int k = 0; k < plan.n_items; ++k)
+    {
+        for (long long r = plan.up_ptr[k]; r < plan.up_ptr[k + 1]; ++r)
+        {
+            const long long d0 = plan.up_ranges[2 * r] * dpn, cnt = (plan.up_ranges[2 * r + 1] - plan.up_ranges[2 * r]) * dpn;
+            for (int c = 0; c < n_cols; ++c)
+                cudaCheck(cudaMemcpyAsync(wx + d0 + c * ld, x + d0 + c * ld, cnt * sizeof(double), cudaMemcpyHostToDevice, pipe.up), "H2D copy");
+        }
+        cudaCheck(cudaEventRecord(pipe.landed[k], pipe.up), "event record");
+    }
+    int launches = 0;
+    mfApplyPhases(sys, wx, wy, n_cols, alpha, 0., L3B_APPLY_INIT, 0, 0);
+    launches += sys->last_launches;
+    for (int k = 0; k < plan.n_items; ++k)
+    {
+        cudaCheck(cudaStreamWaitEvent(S, pipe.landed[k], 0), "event wait");
+        const long long e0 = plan.item_elems[2 * k], e1 = plan.item_elems[2 * k + 1];
+        if (plan.halo_item and k == plan.n_items - 1)
+        {
+            // border elements + exchange (MatrixFreeSystem.hpp:1046-1122), after every interior chunk: its blocks leave last
+            launches += haloImportBegin(sys->halo, wx, n_cols);
+            haloImportEnd(sys->halo);
+            if (e1 > e0)
+            {
+                mfApplyPhases(sys, wx, wy, n_cols, alpha, 0., L3B_APPLY_ELEMENTS, e0, e1);
+                launches += sys->last_launches;
+            }
+            haloExportBegin(sys->halo, wy, n_cols);
+            launches += haloExportEnd(sys->halo, wy, n_cols);
+        }
+        else if (e1 > e0)
+        {
+            mfApplyPhases(sys, wx, wy, n_cols, alpha, 0., L3B_APPLY_ELEMENTS, e0, e1);
+            launches += sys->last_launches;
+        }
+        // Dirichlet identity rows (:1087-1103) of the blocks that are final now, then these blocks leave
+        for (long long r = plan.down_ptr[k]; r < plan.down_ptr[k + 1]; ++r)
+        {
+            if (not sys->has_bc or sys->n_dir == 0)
+                break;
+            const long long d0 = plan.down_ranges[2 * r] * dpn, d1 = plan.down_ranges[2 * r + 1] * dpn;
+            const auto&     dl = sys->dir_list_host;
+            const auto      lo = std::lower_bound(dl.begin(), dl.end(), static_cast< int32_t >(std::min< long long >(d0, 0x7fffffff))) - dl.begin();
+            const auto      hi = std::lower_bound(dl.begin(), dl.end(), static_cast< int32_t >(std::min< long long >(d1, 0x7fffffff))) - dl.begin();
+            if (hi > lo)
+            {
+                dirichletRowsListKernel<<< gridFor(hi - lo), 256, 0, S >>>(sys->dir_list.ptr + lo, hi - lo, wx, wy, ld, n_cols, alpha, nullptr,
+                                                                           static_cast< long long >(sys->mesh->n_owned_nodes) * dpn);
+                ++launches;
+            }
+        }
+        cudaCheck(cudaEventRecord(pipe.done[k], S), "event record");
+        cudaCheck(cudaStreamWaitEvent(pipe.down, pipe.done[k], 0), "event wait");
+        for (long long r = plan.down_ptr[k]; r < plan.down_ptr[k + 1]; ++r)
+        {
+            const long long d0 = plan.down_ranges[2 * r] * dpn, cnt = (plan.down_ranges[2 * r + 1] - plan.down_ranges[2 * r]) * dpn;
+            for (int c = 0; c < n_cols; ++c)
+                cudaCheck(cudaMemcpyAsync(y + d0 + c * ld, wy + d0 + c * ld, cnt * sizeof(double), cudaMemcpyDeviceToHost, pipe.down), "D2H copy");
+        }
+    }
+    cudaCheck(cudaGetLastError(), "streamed operator apply");
+    cudaCheck(cudaStreamSynchronize(pipe.down), "apply");
+    cudaCheck(cudaStreamSynchronize(S), "apply");
+    cudaCheck(cudaStreamSynchronize(pipe.up), "apply");
+    ctx->checkStatus();
+    sys->last_launches            = launches;
+    sys->last_host_apply_streamed = true;
 }
 
 // Preconditioned CG, Belos "Block CG" semantics for block size 1 (solve/BelosSolvers.hpp:76-89): left preconditioner,
@@ -1914,6 +2093,7 @@ int l3b_mf_set_halo(l3b_mf* sys, l3b_halo* halo, int64_t n_border_elems)
             fail(L3B_ERR_INVALID_ARG, "l3b_mf_set_halo: border element count out of range");
         sys->halo     = halo;
         sys->n_border = n_border_elems;
+        sys->pipe.reset(); // the schedule of the streamed host-buffer apply depends on both
     });
 }
 int l3b_asm_set_halo(l3b_asm* sys, l3b_halo* halo)
@@ -2461,6 +2641,7 @@ int l3b_mf_create(l3b_context* ctx, l3b_mesh* mesh, int dpn, int n_rhs, const ui
             s->n_dir = static_cast< long long >(list.size());
             s->dir_list.alloc(list.size());
             s->dir_list.upload(list.data(), list.size(), ctx->stream);
+            s->dir_list_host = list;
             s->dir_vals.alloc(s->n_dofs * n_rhs);
             if (vals)
                 s->dir_vals.upload(vals, s->dir_vals.n, ctx->stream);
@@ -2722,6 +2903,12 @@ int l3b_mf_apply(l3b_mf* sys, const double* x, double* y, int n_cols, double alp
             sys->work_x.alloc(n);
             sys->work_y.alloc(n);
         }
+        sys->last_host_apply_streamed = false;
+        if (hostApplyStreams(sys, x, y, n_cols, beta))
+        {
+            mfApplyHostStreamed(sys, x, y, n_cols, alpha);
+            return;
+        }
         sys->work_x.upload(x, n, sys->ctx->stream);
         if (beta != 0.)
             sys->work_y.upload(y, n, sys->ctx->stream);
@@ -2729,6 +2916,55 @@ int l3b_mf_apply(l3b_mf* sys, const double* x, double* y, int n_cols, double alp
         sys->work_y.download(y, n, sys->ctx->stream);
         cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "apply");
         sys->ctx->checkStatus();
+    });
+}
+int l3b_mf_set_host_apply(l3b_mf* sys, int mode, int n_chunks, int64_t block_nodes)
+{
+    return guardedCtx(sys->ctx, [&] {
+        if (mode < 0 or mode > 2 or n_chunks < 1 or block_nodes < 1)
+            fail(L3B_ERR_INVALID_ARG, "l3b_mf_set_host_apply: mode in {0, 1, 2}, n_chunks >= 1, block_nodes >= 1");
+        cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "sync");
+        sys->pipe.reset(); // the schedule is rebuilt by the next streamed call
+        sys->host_apply_mode        = mode;
+        sys->host_apply_chunks      = n_chunks;
+        sys->host_apply_block_nodes = block_nodes;
+    });
+}
+int l3b_mf_host_apply_info(const l3b_mf* sys, int64_t info[4])
+{
+    info[0] = sys->last_host_apply_streamed ? 1 : 0;
+    info[1] = sys->pipe ? sys->pipe->plan.n_items : 0;
+    info[2] = sys->pipe ? static_cast< int64_t >(sys->pipe->plan.up_ranges.size() / 2) : 0;
+    info[3] = sys->pipe ? static_cast< int64_t >(sys->pipe->plan.down_ranges.size() / 2) : 0;
+    return L3B_OK;
+}
+int l3b_host_apply_plan(int64_t n_nodes, int64_t n_owned_nodes, int64_t n_elems, int nn, const uint32_t* nodes, int64_t n_border_elems,
+                        const int32_t* halo_nodes, int64_t n_halo_nodes, int64_t chunk_elems, int64_t block_nodes, int* n_items,
+                        int64_t** item_elems, int64_t** up_ptr, int64_t** up_ranges, int64_t** down_ptr, int64_t** down_ranges)
+{
+    return guardedCtx(nullptr, [&] {
+        l3b::host::ApplyPlan p;
+        try
+        {
+            p = l3b::host::makeApplyPlan(n_nodes, n_owned_nodes, n_elems, nn, nodes, n_border_elems, halo_nodes, n_halo_nodes, chunk_elems, block_nodes);
+        }
+        catch (const std::exception& e)
+        {
+            fail(L3B_ERR_INVALID_ARG, std::string{"host apply plan: "} + e.what());
+        }
+        const auto give = [](const std::vector< long long >& v, int64_t** out) {
+            *out = static_cast< int64_t* >(std::malloc(std::max< size_t >(1, v.size()) * sizeof(int64_t)));
+            if (not *out)
+                fail(L3B_ERR_INVALID_ARG, "out of host memory");
+            for (size_t i = 0; i < v.size(); ++i)
+                (*out)[i] = v[i];
+        };
+        *n_items = p.n_items;
+        give(p.item_elems, item_elems);
+        give(p.up_ptr, up_ptr);
+        give(p.up_ranges, up_ranges);
+        give(p.down_ptr, down_ptr);
+        give(p.down_ranges, down_ranges);
     });
 }
 int l3b_mf_solve_cg(l3b_mf* sys, double tol, int max_iters, double* x, double* achieved_tol, int* iters)

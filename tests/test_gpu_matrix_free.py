@@ -325,3 +325,91 @@ def test_3d_boundary_equation_kernel_matrix_free(ctx, p):
     sob = pm.orc.matrix_free_system(U, 1, None, None)
     sob.add_kernel("robin_bc_3D", boundary_ids=bnd)
     assert rel_err(sb.apply(x), sob.apply(x, n_threads=4)) < TOL
+
+
+STREAMED_CASES = [
+    # kernel, dim, n, order, opts, n_rhs, chunks, block_nodes
+    ("bench_diffusion3d", 3, 3, 4, l3b.AssemblyOptions(), 1, 7, 64),
+    ("bench_diffusion3d", 3, 4, 2, l3b.AssemblyOptions(), 1, 64, 1),
+    ("diffusion_kernel_3D", 3, 2, 3, l3b.AssemblyOptions(value_order=2), 3, 3, 50),
+    ("diffusion_kernel_2D", 2, 5, 4, l3b.AssemblyOptions(value_order=2), 2, 4, 32),
+    ("bench_diffusion3d", 3, 2, 4, l3b.AssemblyOptions(eval_strategy=1), 1, 5, 100),
+]
+
+
+@pytest.mark.parametrize("case", STREAMED_CASES, ids=lambda c: f"{c[0]}-d{c[1]}-n{c[2]}-p{c[3]}-rhs{c[5]}-chunks{c[6]}-block{c[7]}")
+def test_streamed_host_apply_matches_oracle_and_serial_form(ctx, case):
+    """l3b_mf_apply with host vectors, streamed (x blocks in, element chunks, y blocks out on three streams, Dirichlet rows per finished
+    block) against the oracle and against the serial form of the same call"""
+    kname, dim, n, p, opts, n_rhs, chunks, block = case
+    U = l3b.kernel_info(kname)["n_unknowns"]
+    pm = PairedMesh(dim, default_dists(dim, n), p)
+    mesh = pm.upload(ctx)
+    mask, dvals = _dirichlet(pm, U, [1, 2 * dim], [0, U - 1], n_rhs, 3)
+    sys_g = l3b.MatrixFreeSystem(ctx, mesh, U, n_rhs, mask, dvals)
+    sys_g.assembleProblem(kname, asm_opts=opts, time=0.2)
+    sys_g.endAssembly()
+    sys_o = pm.orc.matrix_free_system(U, n_rhs, mask, dvals)
+    sys_o.add_kernel(kname, opts.value_order, opts.derivative_order, opts.eval_strategy, 0.2, None)
+    sys_o.init(n_threads=4)
+    rng = np.random.default_rng(17)
+    for n_cols in sorted({n_rhs, 1}):
+        x = rng.uniform(-1, 1, size=(pm.n_nodes * U, n_cols))
+        y_o = sys_o.apply(x, np.zeros_like(x), -1.3, 0.0, n_threads=4)
+        sys_g.set_host_apply(0)
+        y_serial = sys_g.apply(x, None, -1.3, 0.0)
+        assert not sys_g.host_apply_info()["streamed"]
+        sys_g.set_host_apply(2, chunks, block)
+        for _ in range(2):  # the second call reuses the schedule, the streams and the events
+            y_g = sys_g.apply(x, None, -1.3, 0.0)
+            info = sys_g.host_apply_info()
+            assert info["streamed"] and info["items"] == -(-mesh.n_elems // -(-mesh.n_elems // chunks))
+            assert rel_err(y_g, y_o) < TOL and rel_err(y_g, y_serial) < TOL
+        # beta != 0 needs y over PCIe both ways: the call takes the serial form and stays correct
+        y0 = rng.uniform(-1, 1, size=x.shape)
+        y_b = sys_g.apply(x, y0, 0.5, -0.25)
+        assert not sys_g.host_apply_info()["streamed"]
+        assert rel_err(y_b, sys_o.apply(x, y0, 0.5, -0.25, n_threads=4)) < TOL
+
+
+def test_streamed_host_apply_with_a_numbering_without_locality(ctx):
+    """scrambled node ids and element order: the schedule degenerates (most blocks travel with the first / last item), the result does not"""
+    pm = PairedMesh(3, default_dists(3, 3), 3)
+    rng = np.random.default_rng(23)
+    perm = rng.permutation(pm.n_nodes)
+    eorder = rng.permutation(pm.host.n_elems)
+    nodes = perm[pm.host.nodes.astype(np.int64)][eorder].astype(np.uint32)
+    mesh = l3b.Mesh(ctx, 3, 3, pm.verts[eorder], nodes, pm.host.side_boundaries[eorder], pm.n_nodes, pm.n_nodes)
+    U = 4
+    mask0, _ = _dirichlet(pm, U, [1, 6], [0], 1, 3)
+    mask = np.zeros_like(mask0)
+    mask.reshape(-1, U)[perm] = mask0.reshape(-1, U)
+    sys_g = l3b.MatrixFreeSystem(ctx, mesh, U, 1, mask, None)
+    sys_g.assembleProblem("bench_diffusion3d")
+    sys_g.endAssembly()
+    sys_o = pm.orc.matrix_free_system(U, 1, mask0, None)
+    sys_o.add_kernel("bench_diffusion3d")
+    sys_o.init(n_threads=4)
+    x0 = rng.uniform(-1, 1, size=(pm.n_nodes * U, 1))
+    x = np.zeros_like(x0)
+    x.reshape(-1, U)[perm] = x0.reshape(-1, U)
+    sys_g.set_host_apply(2, 6, 16)
+    y = sys_g.apply(x)
+    assert sys_g.host_apply_info()["streamed"]
+    y_o = sys_o.apply(x0, np.zeros_like(x0), 1.0, 0.0, n_threads=4)
+    assert rel_err(y.reshape(-1, U)[perm].reshape(-1, 1), y_o) < TOL
+
+
+def test_host_apply_with_a_boundary_kernel_takes_the_serial_form(ctx):
+    pm = PairedMesh(2, default_dists(2, 4), 3)
+    mesh = pm.upload(ctx)
+    s = l3b.MatrixFreeSystem(ctx, mesh, 3)
+    s.assembleProblem("example02_domain")
+    s.assembleProblem("example02_bc", boundary_ids=[1, 2, 3, 4])
+    s.endAssembly()
+    x = np.random.default_rng(1).uniform(-1, 1, size=(pm.n_nodes * 3, 1))
+    s.set_host_apply(0)
+    y0 = s.apply(x)
+    s.set_host_apply(2, 4, 8)
+    y1 = s.apply(x)
+    assert not s.host_apply_info()["streamed"] and rel_err(y1, y0) < TOL

@@ -130,3 +130,91 @@ def test_dense_side_tables_match_reference_side_quadratures(dim, p, nq):
         assert np.abs(wts[i] - owts[j]).max() < 1e-15
         assert np.abs(vals[i] - ovals[j]).max() < 1e-13
         assert np.abs(ders[i] - oders[j]).max() < 1e-12
+
+
+def _check_apply_plan(n_nodes, nodes, items, up, down, n_owned=None, halo_nodes=(), block=1):
+    """the invariants of csrc/apply_plan_host.hpp: every node is copied in exactly once, not later than the first item that touches it;
+    copied out exactly once, not before the last item touching it and not before it came in"""
+    k = len(items)
+    came_in, went_out = np.full(n_nodes, -1), np.full(n_nodes, -1)
+    for i in range(k):
+        for a, b in up[i]:
+            assert 0 <= a < b <= n_nodes and (np.all(came_in[a:b] == -1))
+            came_in[a:b] = i
+        for a, b in down[i]:
+            assert 0 <= a < b <= n_nodes and (np.all(went_out[a:b] == -1))
+            went_out[a:b] = i
+    assert np.all(came_in >= 0) and np.all(went_out >= came_in)
+    first, last = np.full(n_nodes, k), np.full(n_nodes, -1)
+    for i, (e0, e1) in enumerate(items):
+        touched = np.unique(nodes[e0:e1])
+        if i == k - 1 and n_owned is not None and (n_owned < n_nodes or len(halo_nodes) or (e0 == 0 and e1 > 0)):
+            touched = np.unique(np.concatenate([touched, np.asarray(halo_nodes, dtype=np.int64), np.arange(n_owned, n_nodes)]))
+        first[touched] = np.minimum(first[touched], i)
+        last[touched] = np.maximum(last[touched], i)
+    seen = last >= 0
+    assert np.all(came_in[seen] <= first[seen]) and np.all(went_out[seen] >= last[seen])
+    # block granularity: every range starts on a block boundary
+    for i in range(k):
+        for a, b in up[i] + down[i]:
+            assert a % block == 0 and (b % block == 0 or b == n_nodes)
+    return came_in, went_out
+
+
+@pytest.mark.parametrize("order,n,chunk,block", [(4, 4, 8, 64), (2, 5, 7, 1), (3, 3, 100, 16), (1, 6, 1, 5)])
+def test_host_apply_plan_streams_a_structured_cube(order, n, chunk, block):
+    host = l3b.make_cube_mesh(np.linspace(0, 1, n + 1), order=order)
+    nodes = host.nodes.astype(np.int64)
+    items, up, down = l3b.host_apply_plan(host.n_nodes, host.nodes, chunk, block)
+    assert len(items) == -(-host.n_elems // chunk) and items[0][0] == 0 and items[-1][1] == host.n_elems
+    assert np.array_equal(items[1:, 0], items[:-1, 1])
+    came_in, went_out = _check_apply_plan(host.n_nodes, nodes, items, up, down, block=block)
+    if len(items) >= 4:
+        # the generator's numbering is monotone along z: the copies really are spread over the items (this is what makes the call overlap)
+        spread = min(len(items), -(-host.n_nodes // block)) // 4
+        assert len(np.unique(came_in)) >= spread and len(np.unique(went_out)) >= spread
+
+
+def test_host_apply_plan_survives_a_numbering_without_locality():
+    host = l3b.make_cube_mesh(np.linspace(0, 1, 4), order=3)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(host.n_nodes)
+    nodes = perm[host.nodes.astype(np.int64)]
+    order = rng.permutation(host.n_elems)
+    nodes = nodes[order]
+    items, up, down = l3b.host_apply_plan(host.n_nodes, nodes, 4, 32)
+    _check_apply_plan(host.n_nodes, nodes, items, up, down, block=32)
+
+
+def test_host_apply_plan_with_border_elements_and_halo_nodes():
+    # a z-slab in the middle of a chain: the lowest node plane is owned and sent to the rank below, the top plane is ghost
+    host = l3b.make_cube_mesh(np.linspace(0, 1, 4), order=2)
+    nodes = host.nodes.astype(np.int64)
+    zmax = host.verts[..., 2].max()
+    border = np.where(np.isclose(host.verts[..., 2].max(axis=1), zmax))[0]
+    ghost_mask = np.zeros(host.n_nodes, dtype=bool)
+    # ghost = nodes on the top plane; found through the elements' local top layer (local nodes 18..26 of a p=2 hex)
+    ghost_mask[np.unique(nodes[border][:, 18:])] = True
+    new_id = np.empty(host.n_nodes, dtype=np.int64)
+    n_owned = int((~ghost_mask).sum())
+    new_id[~ghost_mask] = np.arange(n_owned)
+    new_id[ghost_mask] = n_owned + np.arange(int(ghost_mask.sum()))
+    interior = np.setdiff1d(np.arange(host.n_elems), border)
+    local = new_id[nodes[np.concatenate([border, interior])]]
+    zmin_elems = np.where(np.isclose(host.verts[..., 2].min(axis=1), 0.0))[0]
+    halo_nodes = np.unique(new_id[nodes[zmin_elems][:, :9]])
+    items, up, down = l3b.host_apply_plan(host.n_nodes, local, 5, 8, n_owned_nodes=n_owned, n_border_elems=len(border), halo_nodes=halo_nodes)
+    assert tuple(items[-1]) == (0, len(border)) and items[0][0] == len(border) and items[-2][1] == host.n_elems
+    came_in, went_out = _check_apply_plan(host.n_nodes, local, items, up, down, n_owned=n_owned, halo_nodes=halo_nodes, block=8)
+    last = len(items) - 1
+    # what the exchange reads or writes leaves with the last item only
+    assert np.all(went_out[halo_nodes] == last) and np.all(went_out[n_owned:] == last)
+
+
+def test_host_apply_plan_of_an_empty_rank_and_bad_input():
+    items, up, down = l3b.host_apply_plan(10, np.zeros((0, 8), dtype=np.uint32), 4, 4)
+    assert len(items) == 1 and tuple(items[0]) == (0, 0) and up[0] == [(0, 10)] and down[0] == [(0, 10)]
+    with pytest.raises(l3b.L3BError, match="outside the local node range"):
+        l3b.host_apply_plan(4, np.array([[0, 1, 2, 9]], dtype=np.uint32), 1, 2)
+    with pytest.raises(l3b.L3BError, match="chunk size"):
+        l3b.host_apply_plan(4, np.array([[0, 1, 2, 3]], dtype=np.uint32), 0, 2)
