@@ -304,7 +304,10 @@ int l3b_mf_apply(l3b_mf* sys, const double* x, double* y, int n_cols, double alp
  * elements are cut into n_chunks chunks; x travels in blocks of block_nodes nodes on a copy-in stream in the order the chunks first
  * touch them, chunk k runs when its blocks have landed, and every y block leaves on a copy-out stream once the last chunk that adds to
  * it has run and its Dirichlet rows are set; with a halo the border elements and the exchange form the last item. Any element order is
- * legal (no locality = serial behaviour). mode 2: streamed whenever legal, whatever the size. Defaults: 48 chunks, 8192 nodes. */
+ * legal (no locality = serial behaviour). mode 2: streamed whenever legal, whatever the size. n_chunks 0 (default) = about one chunk per
+ * 22 MB of vector, 2 to 32 (more chunks shorten the tail — the last chunk's y leaves after the last x block landed — but each costs
+ * ~25 us of copy set-up and event hand-over); block_nodes defaults to 65536. Measured, 64^3 hex p=4 (543 MB per vector): 12.7 ms
+ * against 21.1 ms serial and 11.4 ms for the two bare copies run concurrently. */
 int l3b_mf_set_host_apply(l3b_mf* sys, int mode, int n_chunks, int64_t block_nodes);
 /* info = {1 if the last l3b_mf_apply ran streamed, items, upload ranges, download ranges of the current schedule} */
 int l3b_mf_host_apply_info(const l3b_mf* sys, int64_t info[4]);

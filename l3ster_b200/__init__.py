@@ -961,7 +961,7 @@ class MatrixFreeSystem:
         """host buffers already in the C ABI layout (column-major, contiguous): no numpy copies in the timed region"""
         self.ctx._chk(lib().l3b_mf_apply(self._h, xf.ctypes.data, yf.ctypes.data, n_cols, alpha, beta))
 
-    def set_host_apply(self, mode=1, n_chunks=48, block_nodes=8192):
+    def set_host_apply(self, mode=1, n_chunks=0, block_nodes=65536):
         """how `apply` / `apply_raw` move their host vectors (l3b_mf_set_host_apply): 0 serial, 1 streamed when it pays, 2 streamed
         whenever legal"""
         self.ctx._chk(lib().l3b_mf_set_host_apply(self._h, mode, n_chunks, block_nodes))

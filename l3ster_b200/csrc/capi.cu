@@ -1178,8 +1178,8 @@ struct l3b_mf
     DevBuf< double >         work_x, work_y; // staging for the host-buffer apply
     std::vector< int32_t >   dir_list_host;  // host copy of dir_list (the streamed host-buffer apply cuts it by node range)
     // host-buffer apply: 0 = serial (copy in, apply, copy out), 1 = streamed when it pays (the default), 2 = streamed whenever legal
-    int                              host_apply_mode = 1, host_apply_chunks = 48;
-    long long                        host_apply_block_nodes = 8192;
+    int                              host_apply_mode = 1, host_apply_chunks = 0; // 0 = by size, see hostApplyPipe
+    long long                        host_apply_block_nodes = 65536;
     std::unique_ptr< HostApplyPipe > pipe;
     bool                             last_host_apply_streamed = false;
     int                      last_launches = 0;
@@ -1441,7 +1441,14 @@ HostApplyPipe& hostApplyPipe(l3b_mf* sys)
         d /= sys->dpn; // dof index -> node
     const long long n_border   = halo ? sys->n_border : 0;
     const long long n_interior = mesh->n_elems - n_border;
-    const long long chunk      = std::max< long long >(1, (n_interior + sys->host_apply_chunks - 1) / std::max(1, sys->host_apply_chunks));
+    // How many chunks: with K equal chunks the call costs T (1 + 1 / K) + K c — T the slower of the two PCIe directions when both run, the
+    // T / K is the last chunk's y leaving after the last x block has landed (the bytes in flight never drop below one chunk), c the
+    // ~25 us of copy set-up, event hand-over and launch ramp per item. Measured at 543 MB per vector (profiles/r2_host_apply_sweep.jsonl):
+    // K = 12 / 24 / 48 / 96 / 192 -> 12.9 / 12.7 / 13.3 / 14.5 / 16.2 ms against T = 11.4 ms. Hence about one chunk per 22 MB, at most 32.
+    const long long bytes      = sys->n_dofs * static_cast< long long >(sizeof(double));
+    const int       n_chunks   = sys->host_apply_chunks > 0 ? sys->host_apply_chunks
+                                                            : static_cast< int >(std::clamp< long long >(bytes / (22ll << 20), 2, 32));
+    const long long chunk      = std::max< long long >(1, (n_interior + n_chunks - 1) / n_chunks);
     try
     {
         p->plan = l3b::host::makeApplyPlan(mesh->n_local_nodes, halo ? mesh->n_owned_nodes : mesh->n_local_nodes, mesh->n_elems, mesh->nn, nodes.data(),
@@ -2921,8 +2928,8 @@ int l3b_mf_apply(l3b_mf* sys, const double* x, double* y, int n_cols, double alp
 int l3b_mf_set_host_apply(l3b_mf* sys, int mode, int n_chunks, int64_t block_nodes)
 {
     return guardedCtx(sys->ctx, [&] {
-        if (mode < 0 or mode > 2 or n_chunks < 1 or block_nodes < 1)
-            fail(L3B_ERR_INVALID_ARG, "l3b_mf_set_host_apply: mode in {0, 1, 2}, n_chunks >= 1, block_nodes >= 1");
+        if (mode < 0 or mode > 2 or n_chunks < 0 or block_nodes < 1)
+            fail(L3B_ERR_INVALID_ARG, "l3b_mf_set_host_apply: mode in {0, 1, 2}, n_chunks >= 0 (0 = by size), block_nodes >= 1");
         cudaCheck(cudaStreamSynchronize(sys->ctx->stream), "sync");
         sys->pipe.reset(); // the schedule is rebuilt by the next streamed call
         sys->host_apply_mode        = mode;

@@ -401,7 +401,7 @@ def test_streamed_host_apply_with_a_numbering_without_locality(ctx):
 
 
 def test_host_apply_with_a_boundary_kernel_takes_the_serial_form(ctx):
-    pm = PairedMesh(2, default_dists(2, 4), 3)
+    pm = PairedMesh(2, default_dists(2, 4), 4)
     mesh = pm.upload(ctx)
     s = l3b.MatrixFreeSystem(ctx, mesh, 3)
     s.assembleProblem("example02_domain")
