@@ -157,6 +157,36 @@ def cpu_reference(workload, n_threads, budget_s=12.0):
                 sample=f"oracle sum-factorised operator apply on {n}^3 hex p=4 elements ({m.n_nodes * U} DOFs), {reps} applies, {t:.2f} s")
 
 
+def bind_to_gpu_numa_node(device):
+    """Pin this process to the cores of the NUMA node the GPU hangs off, before any host vector is allocated: pinned pages are placed by
+    first touch, and a vector on the far socket crosses the inter-socket link on every PCIe copy. The reference's launch line does the same
+    for its ranks (benchmarks/CMakeLists.txt:38: --map-by package --bind-to package). Returns what it found; does nothing when the box
+    does not say (one node, a container without sysfs, no NVML)."""
+    info = {"bound": False}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]  # sysfs spells the domain with four hex digits
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        info.update(pci=bdf, node=node)
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed))
+    except Exception as exc:  # a placement hint, never a reason to fail
+        info["error"] = str(exc)[:120]
+    return info
+
+
 def physical_cores():
     try:
         import psutil
@@ -524,6 +554,7 @@ def main():
         ctx.synchronize()
         init_s = time.perf_counter() - t0
         n_local, n_owned, n_elems = op.n_local_dofs, op.n_owned_dofs, slab.n_elems
+        numa = bind_to_gpu_numa_node(local_rank)  # before the host vectors are pinned (first touch places them)
         xh = torch.from_numpy(seeded_x(slab)).pin_memory()
         yh = torch.empty(n_local, dtype=torch.float64).pin_memory()
         xd = xh.to("cuda")
@@ -605,7 +636,7 @@ def main():
             "value": owned_total / (ms * 1e-3), "ms_per_step": ms,
             "e2e": {"value": owned_total / (wall_ms * 1e-3), "unit": "DOFs/s", "h2d_bytes_per_step": int(n_local * 8),
                     "d2h_bytes_per_step": int(n_local * 8), "ms_per_step": wall_ms, "streamed": e2e_info, "serial_form_ms_per_step": serial_wall_ms,
-                    "rel_diff_vs_device_apply": e2e_diff, "rel_diff_ok": bool(e2e_diff < 1e-13),
+                    "rel_diff_vs_device_apply": e2e_diff, "rel_diff_ok": bool(e2e_diff < 1e-13), "host_numa_binding": numa,
                     "what": "l3b_mf_apply through the C ABI with pinned HOST vectors, synchronised, wall clock, max over ranks. Streamed form "
                             "(l3b_mf_set_host_apply, the default): x blocks H2D, element chunks and y blocks D2H run as three concurrent "
                             "streams, so the call costs about one PCIe copy instead of two copies plus the apply (serial_form_ms_per_step); "
