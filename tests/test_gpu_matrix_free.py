@@ -413,3 +413,25 @@ def test_host_apply_with_a_boundary_kernel_takes_the_serial_form(ctx):
     s.set_host_apply(2, 4, 8)
     y1 = s.apply(x)
     assert not s.host_apply_info()["streamed"] and rel_err(y1, y0) < TOL
+
+
+def test_streamed_host_apply_with_kernels_restricted_to_element_domains(ctx):
+    """assembleProblem(kernel, domain_ids): each use runs over a sub-list of the elements; the streamed call cuts those lists by chunk"""
+    pm = PairedMesh(3, default_dists(3, 3), 3)
+    mesh = pm.upload(ctx)
+    mesh.set_element_domains(np.arange(pm.host.n_elems, dtype=np.int32) % 3)
+    U = 4
+    mask, _ = _dirichlet(pm, U, [1, 6], [0], 1, 3)
+    whole = l3b.MatrixFreeSystem(ctx, mesh, U, 1, mask, None)
+    whole.assembleProblem("bench_diffusion3d")
+    whole.endAssembly()
+    parts = l3b.MatrixFreeSystem(ctx, mesh, U, 1, mask, None)
+    parts.assembleProblem("bench_diffusion3d", boundary_ids=[0, 2])
+    parts.assembleProblem("bench_diffusion3d", boundary_ids=[1])
+    parts.endAssembly()
+    x = np.random.default_rng(3).uniform(-1, 1, size=(pm.n_nodes * U, 1))
+    whole.set_host_apply(0)
+    y_ref = whole.apply(x)
+    parts.set_host_apply(2, 5, 40)
+    y = parts.apply(x)
+    assert parts.host_apply_info()["streamed"] and rel_err(y, y_ref) < TOL
