@@ -370,6 +370,8 @@ struct QpEval
     }
 };
 
+constexpr int max_unknowns_fill = 16; // unknowns per kernel the batch fill of assembleLocalSystem keeps on the stack
+
 void checkDims(const Kernel& kernel, ElementType et)
 {
     if (kernel.params.dimension != nativeDim(et))
@@ -377,12 +379,17 @@ void checkDims(const Kernel& kernel, ElementType et)
 }
 
 // K_lower += sign * B * B^T, B col-major L x ncols (Eigen selfadjointView<Lower>::rankUpdate, AssembleLocalSystem.hpp:191-208).
-// Register-tiled so that the multi-threaded CPU baseline is a fair stand-in for Eigen's SYRK.
+// Register-tiled so that the multi-threaded CPU baseline is a fair stand-in for Eigen's SYRK: a 4 x 16 accumulator tile (measured best of
+// 3 x 16 ... 14 x 16, 4 x 32, 8 x 24 with 256- and 512-bit vectors: 38.7 GFLOP/s per core with -mprefer-vector-width=512, which the
+// -march=native build of oracle/__init__.py passes; 25.0 with GCC's default 256-bit preference on the same AVX-512 core), the transposed
+// panel in a per-thread buffer, no edge conditionals in the k-loop (rows are padded with zeros).
+constexpr int syrk_rt = 4, syrk_ct = 16;
 void syrkLower(val_t* K, int L, const val_t* B, int ncols, val_t sign)
 {
-    constexpr int        RT = 4, CT = 16;
-    const int            Lp = (L + CT - 1) / CT * CT; // rows padded with zeros: the micro-kernel has no edge conditionals
-    std::vector< val_t > Bt(static_cast< std::size_t >(ncols) * Lp, 0.); // Bt[k][r]
+    constexpr int RT = syrk_rt, CT = syrk_ct;
+    const int     Lp = (L + CT - 1) / CT * CT + RT; // padded: a row tile starting below L may read up to RT - 1 rows past it
+    thread_local std::vector< val_t > Bt;           // Bt[k][r]
+    Bt.assign(static_cast< std::size_t >(ncols) * Lp, 0.);
     for (int k = 0; k < ncols; ++k)
         for (int r = 0; r < L; ++r)
             Bt[static_cast< std::size_t >(k) * Lp + r] = B[static_cast< std::size_t >(r) + static_cast< std::size_t >(k) * L];
@@ -393,17 +400,18 @@ void syrkLower(val_t* K, int L, const val_t* B, int ncols, val_t sign)
         {
             const int cn = std::min(CT, L - c0);
             val_t     acc[RT][CT] = {};
-            for (int k = 0; k < ncols; ++k)
+            const val_t* __restrict__ bk = Bt.data();
+            for (int k = 0; k < ncols; ++k, bk += Lp)
             {
-                const val_t* __restrict__ bk = &Bt[static_cast< std::size_t >(k) * Lp];
                 const val_t* __restrict__ bc = bk + c0;
-#pragma GCC unroll 4
+                const val_t* __restrict__ br = bk + r0;
+#pragma GCC unroll 8
                 for (int i = 0; i < RT; ++i)
                 {
-                    const val_t br = bk[r0 + i];
+                    const val_t bri = br[i];
 #pragma omp simd
                     for (int j = 0; j < CT; ++j)
-                        acc[i][j] += br * bc[j];
+                        acc[i][j] += bri * bc[j];
                 }
             }
             for (int i = 0; i < rn; ++i)
@@ -431,6 +439,8 @@ void assembleLocalSystem(const Kernel&         kernel,
     const int n_bases = numNodes(et, order);
     const int E = kernel.params.n_equations, U = kernel.params.n_unknowns, NRHS = kernel.params.n_rhs;
     const int L = n_bases * U;
+    if (U > max_unknowns_fill)
+        throw std::invalid_argument{"more unknowns per kernel than the oracle's batch fill keeps on the stack"};
     // LocalSystemManager batching (:80-82): target_update_size = 16 * simd_width / sizeof(val_t), simd_width = 32
     constexpr int target_update_size = 16 * 32 / 8;
     const int     updates_per_batch  = (target_update_size + E - 1) / E;
@@ -456,19 +466,37 @@ void assembleLocalSystem(const Kernel&         kernel,
         int&         bn       = positive ? pos_n : neg_n;
         const val_t  wsqrt    = std::sqrt(std::fabs(weight));
         const val_t* bvals    = &rbq.values[static_cast< std::size_t >(q) * n_bases];
-        for (int a = 0; a < n_bases; ++a)
+        // equation-major: column (bn E + e) of the batch is written top to bottom (rows a U + u), the order Eigen's column-major
+        // block assignment takes (:159-166); per row the contributions to F_e still arrive in ascending e
+        for (int e = 0; e < E; ++e)
+        {
+            val_t* __restrict__ col = &buf[static_cast< std::size_t >(bn * E + e) * L];
+            // row e of the operators, per unknown: the same products and the same order as QpEval::block
+            val_t       ce[4][max_unknowns_fill];
+            const int   dim = qp.dim;
             for (int u = 0; u < U; ++u)
+                for (int i = 0; i <= dim; ++i)
+                    ce[i][u] = qp.A[static_cast< std::size_t >(i) * E * U + e + static_cast< std::size_t >(u) * E];
+            const val_t* __restrict__ pd = qp.phys_ders.data();
+            for (int a = 0; a < n_bases; ++a)
             {
-                const int row = a * U + u;
-                for (int e = 0; e < E; ++e)
+                const val_t n = bvals[a];
+                val_t       g[3] = {0., 0., 0.};
+                for (int d = 0; d < dim; ++d)
+                    g[d] = pd[static_cast< std::size_t >(d) * n_bases + a];
+                for (int u = 0; u < U; ++u)
                 {
-                    const val_t b = qp.block(bvals, a, u, e);
+                    const int row = a * U + u;
+                    val_t     b   = n * ce[0][u];
+                    for (int d = 0; d < dim; ++d)
+                        b += g[d] * ce[d + 1][u];
                     for (int r = 0; r < NRHS; ++r)
                         Fout[static_cast< std::size_t >(row) + static_cast< std::size_t >(r) * L] +=
                             b * qp.F[static_cast< std::size_t >(e) + static_cast< std::size_t >(r) * E] * weight;
-                    buf[static_cast< std::size_t >(row) + static_cast< std::size_t >(bn * E + e) * L] = b * wsqrt;
+                    col[row] = b * wsqrt;
                 }
             }
+        }
         if (++bn == updates_per_batch)
             flush(buf, bn, positive ? 1. : -1.);
     }

@@ -3,6 +3,10 @@
 
 #include <algorithm>
 #include <cmath>
+#include <array>
+#include <map>
+#include <tuple>
+#include <utility>
 
 namespace orc
 {
@@ -48,6 +52,43 @@ void sweepStandard(const val_t* in, val_t* out, int n_in, int n_out, int cols, c
             dst        = accumulate ? dst + acc : acc;
         }
 }
+
+// The same sweep with compile-time extents, as the reference instantiates it (Eigen fixed-size maps, :67-86): identical summation order,
+// so the results do not change; it exists so that the CPU baseline timed beside the GPU numbers is not slowed down by run-time loop bounds.
+template < int NI, int NO >
+void sweepStandardFixed(const val_t* __restrict__ in, val_t* __restrict__ out, int cols, const val_t* __restrict__ M, bool accumulate)
+{
+    val_t m[NI * NO];
+    for (int k = 0; k < NI * NO; ++k)
+        m[k] = M[k];
+    for (int c = 0; c < cols; ++c)
+    {
+        val_t v[NI];
+        for (int i = 0; i < NI; ++i)
+            v[i] = in[i + NI * c];
+        for (int o = 0; o < NO; ++o)
+        {
+            val_t acc = 0.;
+            for (int i = 0; i < NI; ++i)
+                acc += v[i] * m[i * NO + o];
+            val_t& dst = out[c + static_cast< std::size_t >(cols) * o];
+            dst        = accumulate ? dst + acc : acc;
+        }
+    }
+}
+using sweep_fn_t = void (*)(const val_t*, val_t*, int, const val_t*, bool);
+constexpr int max_fixed_extent = 10;
+template < int NI, int... NOs >
+constexpr std::array< sweep_fn_t, sizeof...(NOs) > sweepRow(std::integer_sequence< int, NOs... >)
+{
+    return {&sweepStandardFixed< NI, NOs + 1 >...};
+}
+template < int... NIs >
+constexpr std::array< std::array< sweep_fn_t, max_fixed_extent >, sizeof...(NIs) > sweepTable(std::integer_sequence< int, NIs... >)
+{
+    return {sweepRow< NIs + 1 >(std::make_integer_sequence< int, max_fixed_extent >{})...};
+}
+constexpr auto fixed_sweeps = sweepTable(std::make_integer_sequence< int, max_fixed_extent >{});
 
 // odd-even decomposition (:88-258). psi tables are rebuilt per call — this path exists for parity, not for speed.
 void sweepOddEven(const val_t* in, val_t* out, int rows, int colsM, int cols, const val_t* M, bool is_der, bool accumulate)
@@ -120,6 +161,8 @@ void sumFactSweep(const val_t* in, val_t* out, int n_in, int n_out, int cols, co
 {
     if (odd_even)
         sweepOddEven(in, out, n_in, n_out, cols, M, is_der, accumulate);
+    else if (n_in >= 1 and n_in <= max_fixed_extent and n_out >= 1 and n_out <= max_fixed_extent)
+        fixed_sweeps[n_in - 1][n_out - 1](in, out, cols, M, accumulate);
     else
         sweepStandard(in, out, n_in, n_out, cols, M, accumulate);
 }
@@ -209,26 +252,39 @@ void sumFactForward(const SumFactTables& t, int dim, int F, std::array< buf_t, 4
 } // namespace
 
 // evalLocalOperatorSumFact (:882-917) → sumFactImpl (:816-868) → evalAtQuadQPs / evalAtHexQPs (:614-756)
-void evalLocalOperatorSumFact(const Kernel&          kernel,
-                              ElementType            et,
-                              int                    order,
-                              const val_t*           verts,
-                              const AssemblyOptions& opts,
-                              val_t                  time,
-                              int                    n_rhs_actual,
-                              const val_t*           X,
-                              val_t*                 Y)
+// DIM_T, E_T, U_T: compile-time sizes (0 = read them from the kernel). The reference's sizes are all template parameters; the
+// instantiations listed in evalLocalOperatorSumFact give the compiler the same knowledge for the configurations that are timed.
+namespace
 {
-    const int dim = nativeDim(et);
-    if (kernel.params.dimension != dim or dim < 2)
-        throw std::invalid_argument{"sum factorisation needs a quad/hex element matching the kernel dimension"};
-    const int  E = kernel.params.n_equations, U = kernel.params.n_unknowns, NF = kernel.params.n_fields;
+template < int DIM_T, int E_T, int U_T >
+void evalSumFactSized(const Kernel&          kernel,
+                      ElementType            et,
+                      int                    order,
+                      const val_t*           verts,
+                      const AssemblyOptions& opts,
+                      val_t                  time,
+                      int                    n_rhs_actual,
+                      const val_t*           X,
+                      val_t*                 Y)
+{
+    const int  dim = DIM_T > 0 ? DIM_T : nativeDim(et);
+    const int  E = E_T > 0 ? E_T : kernel.params.n_equations, U = U_T > 0 ? U_T : kernel.params.n_unknowns, NF = kernel.params.n_fields;
     const int  n_ops   = U * n_rhs_actual;
     const int  F_total = n_ops + NF;
     const int  quad_order = 2 * opts.order(order); // make_basis_params (:425-430)
     const bool oe         = opts.useOddEven(order);
-    const auto tab        = makeSumFactTables(order, quad_order, oe);
-    const auto gtab       = makeSumFactTables(1, quad_order, oe); // make_geom_basis_params (:431-436)
+    // the reference's tables are compile-time constants (:25-65); rebuilding them per element (the 1-D basis is evaluated through the
+    // generic polynomial code) cost more than the element itself, which made the CPU baseline unfairly slow: one copy per thread
+    const auto cachedTables = [](int basis_order, int qo, bool odd_even) -> const SumFactTables& {
+        thread_local std::map< std::tuple< int, int, bool >, SumFactTables > cache;
+        const auto key = std::make_tuple(basis_order, qo, odd_even);
+        auto       it  = cache.find(key);
+        if (it == cache.end())
+            it = cache.emplace(key, makeSumFactTables(basis_order, qo, odd_even)).first;
+        return it->second;
+    };
+    const auto& tab  = cachedTables(order, quad_order, oe);
+    const auto& gtab = cachedTables(1, quad_order, oe); // make_geom_basis_params (:431-436)
     const int  nq = tab.nq, n_nodes = numNodes(et, order), Q = ipow(nq, dim), nv = 1 << dim;
 
     auto back = sumFactBack(tab, dim, F_total, X, static_cast< std::size_t >(n_nodes) * F_total);
@@ -331,5 +387,30 @@ void evalLocalOperatorSumFact(const Kernel&          kernel,
     buf_t temp(static_cast< std::size_t >(std::max(Q, n_nodes)) * n_ops, 0.);
     sumFactForward(tab, dim, n_ops, fwd, temp);
     std::copy_n(fwd[0].begin(), static_cast< std::size_t >(n_nodes) * n_ops, Y);
+}
+} // namespace
+
+void evalLocalOperatorSumFact(const Kernel&          kernel,
+                              ElementType            et,
+                              int                    order,
+                              const val_t*           verts,
+                              const AssemblyOptions& opts,
+                              val_t                  time,
+                              int                    n_rhs_actual,
+                              const val_t*           X,
+                              val_t*                 Y)
+{
+    const int dim = nativeDim(et);
+    if (kernel.params.dimension != dim or dim < 2)
+        throw std::invalid_argument{"sum factorisation needs a quad/hex element matching the kernel dimension"};
+    const int E = kernel.params.n_equations, U = kernel.params.n_unknowns;
+    if (dim == 3 and E == 7 and U == 4) // benchmarks/Diffusion3D.hpp:50-79, the configuration bench.py times
+        evalSumFactSized< 3, 7, 4 >(kernel, et, order, verts, opts, time, n_rhs_actual, X, Y);
+    else if (dim == 2 and E == 4 and U == 3) // tests/Kernels.hpp diffusion 2D, examples/02
+        evalSumFactSized< 2, 4, 3 >(kernel, et, order, verts, opts, time, n_rhs_actual, X, Y);
+    else if (dim == 3 and E == 8 and U == 7) // benchmarks/Kernels.hpp ns3d
+        evalSumFactSized< 3, 8, 7 >(kernel, et, order, verts, opts, time, n_rhs_actual, X, Y);
+    else
+        evalSumFactSized< 0, 0, 0 >(kernel, et, order, verts, opts, time, n_rhs_actual, X, Y);
 }
 } // namespace orc
