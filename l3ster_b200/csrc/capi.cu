@@ -1383,7 +1383,10 @@ void mfApplyDevice(l3b_mf* sys, const double* x, double* y, int n_cols, double a
     int n_nbrs = static_cast< int >(h->owned_nbrs.size());
     for (int r : h->shared_nbrs)
         n_nbrs += std::find(h->owned_nbrs.begin(), h->owned_nbrs.end(), r) == h->owned_nbrs.end();
-    const bool split = forced >= 0 ? forced != 0 : n_nbrs >= 2;
+    // (round 2, later) with more than two ranks EVERY rank runs split: an end-of-chain rank on border-first stalls whenever its — split —
+    // neighbour posts its sends late, and the stall travels back through the Export: 4 GPUs measured 1.52 ms and 1.73 ms per apply in two
+    // runs of the mixed policy, 8 GPUs 1.51 / 1.52 with split forced everywhere
+    const bool split = forced >= 0 ? forced != 0 : (n_nbrs >= 2 or h->comm->world > 2);
     const long long half = split ? sys->n_border + (n_elems - sys->n_border) / 2 : sys->n_border;
     // The persistent element kernel fills every resident CTA slot; an NCCL send / recv kernel queued while it runs would wait for it to
     // finish (registers, not SMs, are what is full). Leaving a few slots free lets the transfers start at once.

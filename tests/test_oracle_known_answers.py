@@ -417,3 +417,27 @@ def test_static_condensation_is_exact(orc):
     x_full = np.linalg.solve(K, rhs)
     x_cond = recover(np.linalg.solve(S, Fc))
     assert np.abs(x_cond - x_full).max() < 1e-10 * np.abs(x_full).max()
+
+
+# the element routine of the sum-factorised apply is instantiated with compile-time sizes for the timed configurations (oracle/sumfact.cpp:
+# evalLocalOperatorSumFact) and falls back to run-time sizes elsewhere: every branch must reproduce K_e x of the dense assembly
+@pytest.mark.parametrize("kernel,et,p,n_fields", [("ns3d_kernel", HEX, 2, 7), ("example02_domain", QUAD, 3, 0), ("dense_probe_3D", HEX, 2, 2),
+                                                  ("bench_diffusion3d", HEX, 3, 0), ("diffusion_kernel_2D", QUAD, 4, 0)],
+                         ids=["ns3d_8x7", "example02_4x3", "dense_probe_runtime_sizes", "diffusion3d_7x4", "diffusion2d"])
+def test_sized_and_unsized_sum_factorised_routines_agree_with_the_dense_element_matrix(orc, kernel, et, p, n_fields):
+    rng = np.random.default_rng(7)
+    nn = (p + 1) ** et
+    verts = np.array([[x, y, z] for z in (0, 1) for y in (0, 1) for x in (0, 1)], dtype=float)[: 2 ** et]
+    verts[-1] += 0.3  # not affine
+    if et == QUAD:
+        verts[:, 2] = 0.0
+    field = rng.uniform(-1, 1, size=(nn, n_fields)) if n_fields else None
+    K, _ = orc.assemble_local(kernel, et, p, verts, node_vals=field)
+    x = rng.uniform(-1, 1, size=(K.shape[0], 1))
+    # dense_probe_3D reads the point: the hex sum-factorised path hands it z = 0 (SumFactorization.hpp:732), the dense paths the true z —
+    # that kernel depends on x and y only (tests/test_gpu_matrix_free.py pins the quirk)
+    y_sf = orc.eval_sumfact(kernel, et, p, verts, x, node_vals=field)
+    y_lo = orc.eval_local_operator(kernel, et, p, verts, x, node_vals=field)
+    scale = np.linalg.norm(K @ x)
+    assert np.linalg.norm(K @ x - y_lo) < 1e-12 * scale
+    assert np.linalg.norm(K @ x - y_sf) < 1e-12 * scale
