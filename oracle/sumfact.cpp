@@ -155,13 +155,88 @@ void sweepOddEven(const val_t* in, val_t* out, int rows, int colsM, int cols, co
             put(n_second, first[n_first - 1]);
     }
 }
+// sweepOddEven with compile-time extents: the same operations in the same order (the results are bit-identical), tables and temporaries
+// on the stack. This is the sweep the reference picks for 2 <= p <= 6 (AssembleLocalSystem.hpp:43-48), i.e. the one the CPU baseline runs
+// at p = 4: with run-time extents and four heap allocations per call it cost more than the standard sweep it is meant to beat.
+template < int ROWS, int COLSM, bool DER >
+void sweepOddEvenFixed(const val_t* __restrict__ in, val_t* __restrict__ out, int cols, const val_t* __restrict__ M, bool accumulate)
+{
+    constexpr int PPR = (ROWS + 1) / 2, PMR = ROWS / 2;
+    constexpr int PPC = DER ? COLSM / 2 : (COLSM + 1) / 2, PMC = DER ? (COLSM + 1) / 2 : COLSM / 2;
+    constexpr int N_FIRST = DER ? PMC : PPC, N_SECOND = DER ? PPC : PMC, FULL = N_FIRST + N_SECOND;
+    val_t psi_p[(PPR * PPC > 0 ? PPR * PPC : 1)], psi_m[(PMR * PMC > 0 ? PMR * PMC : 1)];
+    for (int r = 0; r < ROWS / 2; ++r)
+        for (int c = 0; c < PPC; ++c)
+            psi_p[r * PPC + c] = M[r * COLSM + c] + M[(ROWS - r - 1) * COLSM + c];
+    if constexpr (ROWS % 2 != 0)
+        for (int c = 0; c < PPC; ++c)
+            psi_p[(PPR - 1) * PPC + c] = M[(ROWS / 2) * COLSM + c];
+    for (int r = 0; r < PMR; ++r)
+        for (int c = 0; c < PMC; ++c)
+            psi_m[r * PMC + c] = M[r * COLSM + c] - M[(ROWS - r - 1) * COLSM + c];
+    for (int c = 0; c < cols; ++c)
+    {
+        const val_t* v = in + static_cast< std::size_t >(ROWS) * c;
+        val_t        e[PPR > 0 ? PPR : 1], o[PMR > 0 ? PMR : 1], ep[PPC > 0 ? PPC : 1], op[PMC > 0 ? PMC : 1];
+        for (int r = 0; r < PMR; ++r)
+        {
+            const val_t v1 = v[r], v2 = v[ROWS - r - 1];
+            e[r] = .5 * (v1 + v2);
+            o[r] = .5 * (v1 - v2);
+        }
+        if constexpr (PMR < PPR)
+            e[PMR] = v[PMR];
+        for (int j = 0; j < PPC; ++j)
+        {
+            val_t acc = 0.;
+            for (int r = 0; r < PPR; ++r)
+                acc += e[r] * psi_p[r * PPC + j];
+            ep[j] = acc;
+        }
+        for (int j = 0; j < PMC; ++j)
+        {
+            val_t acc = 0.;
+            for (int r = 0; r < PMR; ++r)
+                acc += o[r] * psi_m[r * PMC + j];
+            op[j] = acc;
+        }
+        const val_t* first  = DER ? op : ep;
+        const val_t* second = DER ? ep : op;
+        const auto   put    = [&](int col, val_t val) {
+            val_t& dst = out[c + static_cast< std::size_t >(cols) * col];
+            dst        = accumulate ? dst + val : val;
+        };
+        for (int j = 0; j < N_SECOND; ++j)
+        {
+            put(j, first[j] + second[j]);
+            put(FULL - j - 1, first[j] - second[j]);
+        }
+        if constexpr (N_FIRST > N_SECOND)
+            put(N_SECOND, first[N_FIRST - 1]);
+    }
+}
+template < bool DER, int NI, int... NOs >
+constexpr std::array< sweep_fn_t, sizeof...(NOs) > oddEvenRow(std::integer_sequence< int, NOs... >)
+{
+    return {&sweepOddEvenFixed< NI, NOs + 1, DER >...};
+}
+template < bool DER, int... NIs >
+constexpr std::array< std::array< sweep_fn_t, max_fixed_extent >, sizeof...(NIs) > oddEvenTable(std::integer_sequence< int, NIs... >)
+{
+    return {oddEvenRow< DER, NIs + 1 >(std::make_integer_sequence< int, max_fixed_extent >{})...};
+}
+constexpr auto fixed_odd_even_interp = oddEvenTable< false >(std::make_integer_sequence< int, max_fixed_extent >{});
+constexpr auto fixed_odd_even_der    = oddEvenTable< true >(std::make_integer_sequence< int, max_fixed_extent >{});
 } // namespace
 
 void sumFactSweep(const val_t* in, val_t* out, int n_in, int n_out, int cols, const val_t* M, bool is_der, bool accumulate, bool odd_even)
 {
-    if (odd_even)
+    const bool fixed = n_in >= 1 and n_in <= max_fixed_extent and n_out >= 1 and n_out <= max_fixed_extent;
+    if (odd_even and fixed)
+        (is_der ? fixed_odd_even_der : fixed_odd_even_interp)[n_in - 1][n_out - 1](in, out, cols, M, accumulate);
+    else if (odd_even)
         sweepOddEven(in, out, n_in, n_out, cols, M, is_der, accumulate);
-    else if (n_in >= 1 and n_in <= max_fixed_extent and n_out >= 1 and n_out <= max_fixed_extent)
+    else if (fixed)
         fixed_sweeps[n_in - 1][n_out - 1](in, out, cols, M, accumulate);
     else
         sweepStandard(in, out, n_in, n_out, cols, M, accumulate);
