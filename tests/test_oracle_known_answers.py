@@ -441,3 +441,57 @@ def test_sized_and_unsized_sum_factorised_routines_agree_with_the_dense_element_
     scale = np.linalg.norm(K @ x)
     assert np.linalg.norm(K @ x - y_lo) < 1e-12 * scale
     assert np.linalg.norm(K @ x - y_sf) < 1e-12 * scale
+
+
+# tests/Diffusion2D.hpp:23-120 (the fixture of Diffusion2DAssembledTest / Diffusion2DMFTest / Diffusion2DMFSFTest): 4 x 4 quads p = 2 on the
+# unit square, first-order diffusion system (T, qx, qy), T = x on the left / right sides as Dirichlet values, adiabatic top / bottom through
+# the boundary kernel; the exact solution T = x, q = (1, 0) must come out to 1e-8 — here through the ORACLE's global assembly (scatter, dof
+# numbering, algebraic Dirichlet rows) and its matrix-free system (lifting, Jacobi-CG), so that the checker's global half is pinned by the
+# reference's own end-to-end answer without a GPU
+def _diffusion2d_fixture(orc):
+    node_dist = np.linspace(0.0, 1.0, 5)
+    mesh = orc.mesh_square(node_dist, order=2)
+    host_nodes = mesh.elem_nodes.astype(np.int64)
+    gll = orc.lobatto(3)
+    xs = np.zeros(mesh.n_nodes)
+    for e in range(host_nodes.shape[0]):
+        for a in range(9):
+            xs[host_nodes[e, a]] = orc.map_to_physical(2, mesh.elem_verts[e], [gll[a % 3], gll[a // 3]])[0]
+    bc_nodes = np.where((np.abs(xs) < 1e-14) | (np.abs(xs - 1.0) < 1e-14))[0]
+    return mesh, xs, bc_nodes
+
+
+def _check_diffusion2d_solution(sol, xs):
+    assert np.abs(sol[0::3] - xs).max() < 1e-8
+    assert np.abs(sol[1::3] - 1.0).max() < 1e-8
+    assert np.abs(sol[2::3]).max() < 1e-8
+
+
+def test_diffusion2d_end_to_end_assembled(orc):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    mesh, xs, bc_nodes = _diffusion2d_fixture(orc)
+    s = mesh.assembled_system(3)
+    s.assemble("diffusion_kernel_2D")
+    s.assemble("adiabatic_bc_2D", boundary_ids=[1, 2])
+    s.apply_dirichlet((bc_nodes * 3).astype(np.int32), xs[bc_nodes][:, None])
+    vals, rhs = s.get()
+    A = sp.csr_matrix((vals, s.col_ind, s.row_ptr), shape=(s.n_dofs,) * 2).tocsc()
+    _check_diffusion2d_solution(spla.spsolve(A, rhs[:, 0]), xs)
+
+
+@pytest.mark.parametrize("strategy", [1, 2], ids=["local_element", "sum_factorisation"])
+def test_diffusion2d_end_to_end_matrix_free(orc, strategy):
+    mesh, xs, bc_nodes = _diffusion2d_fixture(orc)
+    mask = np.zeros(mesh.n_nodes * 3, dtype=np.uint8)
+    mask[bc_nodes * 3] = 1
+    vals = np.zeros((mesh.n_nodes * 3, 1))
+    vals[bc_nodes * 3, 0] = xs[bc_nodes]
+    s = mesh.matrix_free_system(3, 1, mask, vals)
+    s.add_kernel("diffusion_kernel_2D", eval_strategy=strategy)
+    s.add_kernel("adiabatic_bc_2D", boundary_ids=[1, 2])
+    s.init()
+    sol, res, iters = s.cg(tol=1e-12, max_iters=5000)
+    assert res <= 1e-12 and iters < 5000
+    _check_diffusion2d_solution(sol, xs)
