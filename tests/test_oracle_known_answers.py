@@ -495,3 +495,21 @@ def test_diffusion2d_end_to_end_matrix_free(orc, strategy):
     sol, res, iters = s.cg(tol=1e-12, max_iters=5000)
     assert res <= 1e-12 and iters < 5000
     _check_diffusion2d_solution(sol, xs)
+
+
+# the same identity over every extent the compile-time sweep tables hold (1 .. 10 in both directions), odd and even sizes, all four kinds
+@pytest.mark.parametrize("EO", [1, 2, 3, 4, 5, 6, 8, 9])
+def test_odd_even_and_standard_sweeps_equal_the_matrix_product_for_all_tabulated_extents(orc, EO):
+    rng = np.random.default_rng(100 + EO)
+    nb = EO + 1
+    for QO in (0, 1, 2, 3, 5, 6, 9, 12, 15, 18):
+        nq = QO // 2 + 1
+        interp, der = orc.sumfact_tables(EO, QO)
+        assert interp.shape == (nb, nq)
+        for kind in range(4):
+            x = rng.uniform(-1, 1, size=(nb if kind < 2 else nq, 7))
+            y0 = rng.uniform(-1, 1, size=(7, nb)) if kind == 3 else None
+            ref = x.T @ [interp, der, interp.T, der.T][kind] + (y0 if y0 is not None else 0)
+            for odd_even in (False, True):
+                y = orc.sumfact_sweep(EO, QO, kind, odd_even, x, y0)
+                assert np.linalg.norm(y - ref) < 1e-12 * max(1.0, np.linalg.norm(ref)), (EO, QO, kind, odd_even)
